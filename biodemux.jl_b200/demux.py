@@ -1,0 +1,206 @@
+"""Host streaming pipeline around the hot path: ``execute_demultiplexing``.
+
+Mirrors the reference's orchestration (src/core.jl:43-224, 360-631): FASTQ chunks
+in, per-barcode output files out, same option names and defaults, same output
+naming and append semantics.  The per-chunk classification (the body of
+``worker_task``, core.jl:235-269) is done by the CUDA engine through the C ABI
+(``capi.Engine``); there is no CPU classification path in this package.
+"""
+from __future__ import annotations
+
+import gzip
+import os
+import re
+from typing import Callable, Dict, List, Optional, Sequence
+
+import numpy as np
+
+from .config import DemuxConfig, build_config
+from .fileio import fastq_records
+
+# bdx_result (include/bdx.h)
+RESULT_DTYPE = np.dtype([("status", "<i4"), ("bc1", "<i4"), ("bc2", "<i4"),
+                         ("keep_start", "<i4"), ("keep_end", "<i4")])
+# bdx_pass_detail (include/bdx.h)
+DETAIL_DTYPE = np.dtype([("status", "<i4"), ("bc", "<i4"), ("dist", "<i4"), ("norm", "<i4"),
+                         ("start", "<i4"), ("end", "<i4")])
+MATCH, UNKNOWN, AMBIGUOUS = 0, 1, 2
+
+
+class Chunk:
+    """core.jl:5-39 -- up to ``chunk_size`` FASTQ records (and their mates)."""
+
+    __slots__ = ("id", "headers", "seqs", "pluses", "quals", "mate")
+
+    def __init__(self, cid: int):
+        self.id = cid
+        self.headers: List[bytes] = []
+        self.seqs: List[bytes] = []
+        self.pluses: List[bytes] = []
+        self.quals: List[bytes] = []
+        self.mate: Optional["Chunk"] = None
+
+    def __len__(self):
+        return len(self.headers)
+
+
+def iter_chunks(fastq1: str, fastq2: Optional[str], chunk_size: int):
+    """reader_task (core.jl:43-110)."""
+    it1 = fastq_records(fastq1)
+    it2 = fastq_records(fastq2) if fastq2 is not None else None
+    cid = 1
+    while True:
+        c1 = Chunk(cid)
+        c2 = Chunk(cid) if it2 is not None else None
+        for _ in range(chunk_size):
+            try:
+                rec1 = next(it1)
+                rec2 = next(it2) if it2 is not None else None
+            except StopIteration:
+                break
+            c1.headers.append(rec1[0]); c1.seqs.append(rec1[1]); c1.pluses.append(rec1[2]); c1.quals.append(rec1[3])
+            if c2 is not None:
+                c2.headers.append(rec2[0]); c2.seqs.append(rec2[1]); c2.pluses.append(rec2[2]); c2.quals.append(rec2[3])
+        if len(c1) == 0:
+            return
+        c1.mate = c2
+        yield c1
+        cid += 1
+        if len(c1) < chunk_size:
+            return
+
+
+def pack_reads(seqs: Sequence[bytes]):
+    """Packed batch layout of the C ABI: concatenated bytes + int32 offsets (n+1)."""
+    off = np.zeros(len(seqs) + 1, dtype=np.int32)
+    if len(seqs):
+        off[1:] = np.cumsum([len(s) for s in seqs])
+    blob = np.frombuffer(b"".join(seqs), dtype=np.uint8) if len(seqs) else np.zeros(0, np.uint8)
+    return blob, off
+
+
+def output_filename(cfg: DemuxConfig, status: int, bc1: int, bc2: int) -> str:
+    """classification.jl:877-900 -- a pure function of (status, bc1, bc2)."""
+    suffix = ".fastq.gz" if cfg.gzip_output else ".fastq"
+    if status == UNKNOWN:
+        return "unknown" + suffix
+    if status == AMBIGUOUS:
+        return "ambiguous_classification" + suffix
+    if cfg.is_dual:
+        return f"{cfg.ids[bc1 - 1]}.{cfg.ids2[bc2 - 1]}{suffix}"
+    return f"{cfg.ids[bc1 - 1]}{suffix}"
+
+
+class Writer:
+    """writer_task (core.jl:118-224): append-mode handle cache, trimming of read 1,
+    routing of mates by the read-1 classification."""
+
+    def __init__(self, output_dir: str, prefix1: str, prefix2: str, cfg: DemuxConfig):
+        self.dir, self.p1, self.p2, self.cfg = output_dir, prefix1, prefix2, cfg
+        self.handles: Dict[str, object] = {}
+        self.do_trim = cfg.trim_side is not None or cfg.trim_side2 is not None
+
+    def _handle(self, filename: str):
+        h = self.handles.get(filename)
+        if h is None:
+            path = os.path.join(self.dir, filename)
+            if self.cfg.gzip_output or path.lower().endswith(".gz"):
+                h = gzip.open(path, "ab")
+            else:
+                h = open(path, "ab")
+            self.handles[filename] = h
+        return h
+
+    def write_chunk(self, chunk: Chunk, results: np.ndarray):
+        cfg = self.cfg
+        for i in range(len(chunk)):
+            st, b1, b2 = int(results["status"][i]), int(results["bc1"][i]), int(results["bc2"][i])
+            filename = output_filename(cfg, st, b1, b2)
+            h1, s1, p1, q1 = chunk.headers[i], chunk.seqs[i], chunk.pluses[i], chunk.quals[i]
+            # trim_ranges[i] === nothing when t_start == -1 (core.jl:250-254)
+            if self.do_trim and int(results["keep_start"][i]) != -1:
+                lo = max(int(results["keep_start"][i]), 1)
+                hi = min(int(results["keep_end"][i]), len(s1))
+                if lo <= hi:
+                    s1, q1 = s1[lo - 1:hi], q1[lo - 1:hi]
+                else:
+                    s1, q1 = b"", b""
+            mate = chunk.mate
+            if cfg.classify_both and mate is not None:
+                self._handle(self.p1 + "." + filename).write(b"\n".join((h1, s1, p1, q1, b"")))
+                self._handle(self.p2 + "." + filename).write(
+                    b"\n".join((mate.headers[i], mate.seqs[i], mate.pluses[i], mate.quals[i], b"")))
+            elif mate is not None:
+                self._handle(self.p2 + "." + filename).write(
+                    b"\n".join((mate.headers[i], mate.seqs[i], mate.pluses[i], mate.quals[i], b"")))
+            else:
+                self._handle(self.p1 + "." + filename).write(b"\n".join((h1, s1, p1, q1, b"")))
+
+    def close(self):
+        for h in self.handles.values():
+            h.close()
+        self.handles.clear()
+
+
+def run_pipeline(cfg: DemuxConfig, classify_chunk: Callable[[Sequence[bytes]], np.ndarray],
+                 fastq1: str, fastq2: Optional[str], output_dir: str, prefix1: str, prefix2: str,
+                 chunk_size: int = 4000):
+    """reader -> classify -> writer, in chunk order (core.jl:139-148)."""
+    os.makedirs(output_dir, exist_ok=True)
+    w = Writer(output_dir, prefix1, prefix2, cfg)
+    try:
+        for chunk in iter_chunks(fastq1, fastq2, chunk_size):
+            w.write_chunk(chunk, classify_chunk(chunk.seqs))
+    finally:
+        w.close()
+
+
+def _strip_fastq_ext(path: str) -> str:
+    return re.sub(r"\.fastq(\.gz)?$", "", os.path.basename(path))
+
+
+def execute_demultiplexing(fastq1: str, a: str, b: str, c: Optional[str] = None, *,
+                           barcode_file2: Optional[str] = None,
+                           output_prefix: str = "", output_prefix1: str = "", output_prefix2: str = "",
+                           gzip_output: Optional[bool] = None,
+                           max_error_rate: float = 0.2, min_delta: float = 0.0,
+                           match: int = 0, mismatch: int = 1, indel: int = 1, nindel: Optional[int] = None,
+                           classify_both: bool = False, bc_complement: bool = False, bc_rev: bool = False,
+                           ref_search_range: str = "1:end", barcode_start_range: str = "1:end",
+                           barcode_end_range: str = "1:end", ref_search_range2: str = "1:end",
+                           barcode_start_range2: str = "1:end", barcode_end_range2: str = "1:end",
+                           chunk_size: int = 4000, channel_capacity: int = 64,
+                           trim_side: Optional[int] = None, trim_side2: Optional[int] = None,
+                           summary: bool = False, summary_format: str = "html",
+                           matching_algorithm: str = "semiglobal", log: bool = False,
+                           device: int = 0):
+    """Both reference methods (core.jl:360-392 paired, :500-529 single):
+
+        execute_demultiplexing(FASTQ_file, barcode_file, output_directory; ...)
+        execute_demultiplexing(FASTQ_file1, FASTQ_file2, barcode_file, output_directory; ...)
+
+    Returns the DemuxStats-like dict when ``summary`` is set, else None.
+    """
+    from .capi import Engine  # needs libbdx + a CUDA device; fails loudly otherwise
+
+    if c is None:
+        fastq2, barcode_file, output_directory = None, a, b
+        prefix1 = output_prefix or output_prefix1 or _strip_fastq_ext(fastq1)
+        prefix2 = ""
+        fastqs = [fastq1]
+        classify_both = False  # core.jl:559
+    else:
+        fastq2, barcode_file, output_directory = a, b, c
+        prefix1 = output_prefix1 or _strip_fastq_ext(fastq1)
+        prefix2 = output_prefix2 or _strip_fastq_ext(fastq2)
+        fastqs = [fastq1, fastq2]
+    cfg = build_config(barcode_file, barcode_file2, fastqs, gzip_output, bc_complement, bc_rev,
+                       classify_both, max_error_rate, min_delta, match, mismatch, indel, nindel,
+                       ref_search_range, barcode_start_range, barcode_end_range,
+                       ref_search_range2, barcode_start_range2, barcode_end_range2,
+                       trim_side, trim_side2, summary, summary_format, matching_algorithm)
+    with Engine(cfg, device=device, max_reads=chunk_size) as eng:
+        run_pipeline(cfg, eng.classify_reads, fastq1, fastq2, output_directory, prefix1, prefix2, chunk_size)
+        if cfg.summary:
+            return eng.demux_stats()
+    return None

@@ -1,0 +1,223 @@
+/*
+ * bdx.h -- C ABI of libbdx, the B200-native barcode-assignment engine.
+ *
+ * Drop-in boundary: the body of BioDemuX.jl's `worker_task`
+ * (reference src/core.jl:226-279): given a chunk of read-1 sequences and an
+ * immutable DemuxConfig, produce per read (status, barcode index/indices,
+ * keep range) and -- when a summary is requested -- the per-worker DemuxStats
+ * counters.  The reference has no FFI of its own; INTEGRATION.md shows the
+ * `ccall` shim a BioDemuX maintainer adds to replace that loop body.
+ *
+ * Conventions
+ *  - plain C types only; every call returns BDX_OK (0) or a negative bdx_status
+ *    and never throws, aborts or exits;  bdx_last_error() gives the message of
+ *    the last failure on the calling thread;
+ *  - there is NO CPU fallback: if no sm_100 device/driver is usable the calls
+ *    that need one return BDX_ERR_CUDA;
+ *  - positions are 1-based inclusive, barcode indices are 1-based (0 = none),
+ *    exactly as in the reference;
+ *  - a bdx_config is immutable and may be shared by any number of streams and
+ *    threads; a bdx_stream is owned by one thread at a time (it mirrors the
+ *    per-worker SemiGlobalWorkspace, core.jl:229-233).
+ */
+#ifndef BDX_H
+#define BDX_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BDX_ABI_VERSION 1
+
+typedef enum bdx_status {
+    BDX_OK = 0,
+    BDX_ERR_INVALID = -1,     /* bad argument / unsupported option value */
+    BDX_ERR_CUDA = -2,        /* CUDA runtime error or no usable device */
+    BDX_ERR_NOMEM = -3,
+    BDX_ERR_STATE = -4,       /* call sequence error (fetch with nothing in flight, ...) */
+    BDX_ERR_TOO_LARGE = -5    /* batch exceeds the stream's max_reads / max_bytes */
+} bdx_status;
+
+/* matching_algorithm (classification.jl:57, :639-649) */
+typedef enum bdx_algorithm {
+    BDX_SEMIGLOBAL = 0, /* semiglobal_alignment[_N]   classification.jl:238-477 */
+    BDX_HAMMING = 1,    /* hamming_align              classification.jl:557-625 */
+    BDX_EXACT = 2       /* exact_align                classification.jl:485-548 */
+} bdx_algorithm;
+
+/* per-read status: match_barcode_pass' :match / :unknown / :ambiguous
+ * (classification.jl:805-824) folded over both passes (:879-897) */
+typedef enum bdx_read_status {
+    BDX_MATCH = 0,
+    BDX_UNKNOWN = 1,   /* file "unknown.fastq[.gz]" */
+    BDX_AMBIGUOUS = 2  /* file "ambiguous_classification.fastq[.gz]" */
+} bdx_read_status;
+
+/* DynamicRange (classification.jl:9-14), produced by parse_dynamic_range (:83-94) */
+typedef struct bdx_range {
+    int64_t start_offset;
+    int32_t start_from_end;
+    int32_t end_from_end;
+    int64_t end_offset;
+} bdx_range;
+
+/* One barcode set with the per-pass options match_barcode_pass selects
+ * (classification.jl:778-792).  Barcodes are the byte strings returned by
+ * preprocess_bc_file (fileio.jl:7-72): already B-filtered, upper-cased, U->T,
+ * complemented/reversed. */
+typedef struct bdx_barcode_set {
+    int32_t n_barcodes;
+    int32_t trim_side;            /* 0 = nothing, 3, 5  (core.jl:308-313) */
+    const uint8_t *bytes;         /* concatenated barcode bytes */
+    const int32_t *offsets;       /* n_barcodes + 1 */
+    const int32_t *lengths_no_n;  /* bc_lengths_no_N; may be NULL unless has_nindel */
+    bdx_range ref_search_range;
+    bdx_range barcode_start_range;
+    bdx_range barcode_end_range;
+} bdx_barcode_set;
+
+/* Hot-path fields of DemuxConfig (classification.jl:16-58). */
+typedef struct bdx_params {
+    uint32_t struct_size;  /* = sizeof(bdx_params) */
+    uint32_t abi_version;  /* = BDX_ABI_VERSION */
+    double max_error_rate;
+    double min_delta;
+    int64_t match, mismatch, indel, nindel;
+    int32_t has_nindel;    /* nindel !== nothing */
+    int32_t algorithm;     /* bdx_algorithm */
+    int32_t is_dual;
+    int32_t want_stats;    /* summary=true: alignment positions are tracked for every
+                              matched pass (classification.jl:812) and the device keeps
+                              the DemuxStats counters */
+    bdx_barcode_set set1;
+    bdx_barcode_set set2;  /* ignored unless is_dual */
+} bdx_params;
+
+/* What worker_task stores per read (core.jl:243-267). */
+typedef struct bdx_result {
+    int32_t status;     /* bdx_read_status */
+    int32_t bc1;        /* 1-based index into set 1; 0 unless status == BDX_MATCH */
+    int32_t bc2;        /* 1-based index into set 2 (dual), else 0 */
+    int32_t keep_start; /* keep range; -1,-1 when status != BDX_MATCH (=> trim_ranges[i] = */
+    int32_t keep_end;   /* nothing, core.jl:250-254); 1,0 = empty keep (classification.jl:932-935) */
+} bdx_result;
+
+/* Optional per-pass detail (what match_barcode_pass feeds the stats Dicts,
+ * classification.jl:827-865).  score = dist / norm as Float64. */
+typedef struct bdx_pass_detail {
+    int32_t status; /* bdx_read_status of this pass; -1 = pass not run */
+    int32_t bc;
+    int32_t dist;   /* integer numerator of the score (weighted distance / mismatches) */
+    int32_t norm;   /* normalisation length */
+    int32_t start;  /* alignment start / end; -1 when positions were not tracked */
+    int32_t end;
+} bdx_pass_detail;
+
+typedef struct bdx_config bdx_config;
+typedef struct bdx_stream bdx_stream;
+
+const char *bdx_last_error(void);
+int bdx_abi_version(void);
+/* number of visible CUDA devices (0 if none / driver missing) */
+int bdx_device_count(void);
+
+/* Copies everything it needs; the caller keeps ownership of its buffers.
+ * Validation mirrors the reference (trim_side in {0,3,5}); additionally rejects
+ * what the device encoding cannot express: empty barcodes, zero gap costs
+ * (Julia raises DivideError), |cost| > 2^20, more than 65535 barcodes per set. */
+int bdx_config_create(const bdx_params *params, bdx_config **out);
+void bdx_config_destroy(bdx_config *cfg);
+
+/* One per host worker.  Owns a CUDA stream pair, double-buffered pinned staging
+ * for max_reads reads / max_bytes sequence bytes per batch, and device scratch. */
+int bdx_stream_create(const bdx_config *cfg, int device, int32_t max_reads, int64_t max_bytes,
+                      bdx_stream **out);
+void bdx_stream_destroy(bdx_stream *s);
+
+/* Queue one batch: packed read-1 sequences, raw bytes exactly as read (no case
+ * folding; equality is bytewise like codeunits, classification.jl:185).
+ * offsets has n_reads + 1 entries, offsets[0] = 0.  Returns after the bytes are in pinned
+ * staging, so the caller may reuse its buffers.  At most 2 batches may be in
+ * flight per stream (BDX_ERR_STATE otherwise). */
+int bdx_submit(bdx_stream *s, const uint8_t *seq_bytes, const int32_t *offsets, int32_t n_reads,
+               uint64_t tag);
+/* Zero-copy variant: borrow the next pinned staging buffers, fill them, commit. */
+int bdx_acquire(bdx_stream *s, uint8_t **seq_bytes, int32_t **offsets);
+int bdx_commit(bdx_stream *s, int32_t n_reads, uint64_t tag);
+
+/* Blocks until the oldest in-flight batch is done and copies its results out.
+ * details may be NULL; otherwise it receives 2 * n_reads entries laid out
+ * [pass][read] (pass 1 block then pass 2 block). */
+int bdx_fetch(bdx_stream *s, uint64_t *tag, int32_t *n_reads, bdx_result *results,
+              bdx_pass_detail *details);
+
+/* submit + fetch of a single batch */
+int bdx_classify(bdx_stream *s, const uint8_t *seq_bytes, const int32_t *offsets, int32_t n_reads,
+                 bdx_result *results, bdx_pass_detail *details);
+
+/* Device-resident path: inputs and outputs are device pointers on the stream's
+ * device; the kernels are enqueued on the stream's compute CUDA stream and the
+ * call returns without waiting (bdx_stream_sync waits).  n_reads is not limited
+ * by max_reads here, scratch grows on demand.  d_details may be NULL. */
+int bdx_classify_device(bdx_stream *s, const uint8_t *d_seq_bytes, const int32_t *d_offsets,
+                        int32_t n_reads, bdx_result *d_results, bdx_pass_detail *d_details);
+int bdx_stream_sync(bdx_stream *s);
+/* cudaStream_t of the compute stream, for callers that record their own events */
+void *bdx_stream_cuda_stream(bdx_stream *s);
+/* number of kernel launches this stream has issued so far */
+int64_t bdx_stream_launch_count(const bdx_stream *s);
+
+/* ---- DemuxStats counters (classification.jl:736-767) ----------------------
+ * A flat int64 buffer per stream, accumulated on the device when want_stats:
+ *   [0] total  [1] matched  [2] unmatched  [3] ambiguous
+ *   sample_counts[(B1+1) * (B2+1)]            index bc1 * (B2+1) + bc2
+ *   per pass p in {1,2}:  pos[B_p+1][POS_BINS]  len[B_p+1][LEN_BINS]  dist[B_p+1][DIST_BINS]
+ *     row 0 of each is the global histogram, row b the per-barcode one;
+ *     pos bin = start + pos_bias, len bin = end - start + 1, dist bin = integer
+ *     distance (host converts to round(dist / norm_b, digits=2) keys).
+ * bdx_stats_layout describes the offsets; sum the buffers of all streams / GPUs
+ * (e.g. one ncclAllReduce(sum, int64)) before converting to DemuxStats. */
+typedef struct bdx_stats_layout {
+    int64_t total_len;       /* number of int64 entries */
+    int64_t sample_off;      /* (B1+1)*(B2+1) entries */
+    int32_t b1, b2;          /* set sizes (b2 = 0 when not dual) */
+    int32_t pos_bins, len_bins, dist_bins, pos_bias;
+    int64_t pos_off[2], len_off[2], dist_off[2];
+} bdx_stats_layout;
+
+int bdx_stats_layout_get(const bdx_config *cfg, bdx_stats_layout *out);
+/* copies the stream's device counters to host (after syncing the stream) */
+int bdx_stats_fetch(bdx_stream *s, int64_t *out, int64_t out_len);
+/* device pointer of the counters (for an in-place NCCL all-reduce by the host) */
+void *bdx_stats_device_ptr(bdx_stream *s);
+int bdx_stats_reset(bdx_stream *s);
+
+/* ---- bench / test utilities (not part of the reference boundary) ----------
+ * Synthetic reads of SURVEY.md section 8(d): fixed-length reads over ACGT with a
+ * barcode of set 1 (and set 2 when dual) planted after k random edits.  Philox-style
+ * counter RNG keyed by (seed, read index): any sub-range can be regenerated
+ * independently.  Writes n_reads * read_len bytes and n_reads + 1 offsets. */
+typedef struct bdx_synth_spec {
+    uint64_t seed;
+    int64_t first_read;       /* global index of the first read generated */
+    int32_t read_len;
+    int32_t plant_permille;   /* probability (per 1000) that set-1 barcode is planted */
+    int32_t start_lo, start_hi; /* planted start position range (1-based, inclusive) */
+    int32_t n_permille_x10;   /* probability (per 10000) of one base replaced by N */
+    int32_t set2_mode;        /* 0 none, 1 plant set-2 barcode ending end_lo..end_hi before read end */
+    int32_t end_lo, end_hi;
+} bdx_synth_spec;
+int bdx_synth_reads_device(bdx_stream *s, const bdx_synth_spec *spec, int32_t n_reads,
+                           uint8_t *d_seq_bytes, int32_t *d_offsets);
+
+/* Integer-ALU peak microbenchmark (roofline denominator): independent LOP3/IADD3
+ * chains at full occupancy on `device`; returns lane-ops per second. */
+int bdx_int_alu_peak(int device, double *ops_per_second);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BDX_H */

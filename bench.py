@@ -1,0 +1,408 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the barcode-assignment hot path.
+
+Workload (BASELINE.json configs[1], SURVEY.md section 8d "config 2"): synthetic 10 M x 150 bp
+single-end reads per GPU, 96 barcodes of 24 nt with injected indels/mismatches,
+:semiglobal with the reference's default options.  A "step" = one pass of the hot
+path over the whole 10 M-read batch.
+
+  value : reads/s, whole job, reads already resident in HBM (kernels only)
+  e2e   : reads/s through the C ABI with HOST (pinned) buffers: H2D of every batch,
+          kernels, D2H of the per-read results, all inside the timed region
+  --impl reference : the reference's CPU algorithm (oracle port, all host threads)
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from concurrent.futures import ThreadPoolExecutor
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+READ_LEN = 150
+N_BARCODES = 96
+BARCODE_LEN = 24
+SEED = 0x42444D58  # "BDMX"
+CU_PER_READ = N_BARCODES * BARCODE_LEN * READ_LEN          # full-matrix cell updates
+OPS_PER_READ = 17 * N_BARCODES * ((BARCODE_LEN + 31) // 32) * READ_LEN   # algorithmic int-ops
+BYTES_PER_READ = READ_LEN + 4 + 20                         # sequence + offset in, bdx_result out
+CHUNK = 4000                                               # reference chunk_size (core.jl:521)
+
+
+def make_config():
+    import bdx_b200 as bdx
+    rng = np.random.default_rng(SEED)
+    alpha = np.frombuffer(b"ACGT", dtype=np.uint8)
+    bcs = [bytes(alpha[rng.integers(0, 4, BARCODE_LEN)]).decode() for _ in range(N_BARCODES)]
+    return bdx.DemuxConfig(bc_seqs=bcs, bc_lengths_no_N=[BARCODE_LEN] * N_BARCODES,
+                           ids=[f"bc{i:03d}" for i in range(N_BARCODES)])
+
+
+def synth_spec(first_read: int):
+    from bdx_b200 import capi
+    return capi.SynthSpec(seed=SEED, first_read=first_read, read_len=READ_LEN, plant_permille=900,
+                          start_lo=1, start_hi=120, n_permille_x10=50, set2_mode=0, end_lo=0, end_hi=0)
+
+
+def numpy_reads(cfg, n, seed):
+    """CPU stand-in for the device generator (same distribution, used only when no GPU is visible)."""
+    import synth
+    rng = np.random.default_rng(seed)
+    reads = synth.random_reads(rng, n, cfg.bc_seqs, min_len=READ_LEN, plant=0.9, start_hi=119, n_prob=0.005)
+    blob = np.frombuffer(b"".join(reads), dtype=np.uint8).copy()
+    off = np.arange(n + 1, dtype=np.int64) * READ_LEN
+    return blob, off
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); power.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def oracle_rate(cfg, blob, off64, threads):
+    """reads/s of the oracle port over (blob, off64) with `threads` workers, chunked like
+    the reference (4000 reads per task)."""
+    import orc
+    o = orc.Oracle(cfg)
+    n = len(off64) - 1
+    spans = [(a, min(a + CHUNK, n)) for a in range(0, n, CHUNK)]
+
+    def work(span):
+        a, b = span
+        sub_off = off64[a:b + 1] - off64[a]
+        o.classify(blob[off64[a]:off64[b]], sub_off)
+        return b - a
+
+    t0 = time.perf_counter()
+    if threads == 1:
+        done = sum(work(s) for s in spans)
+    else:
+        with ThreadPoolExecutor(threads) as ex:
+            done = sum(ex.map(work, spans))
+    dt = time.perf_counter() - t0
+    return done / dt, dt
+
+
+def sample_reads_host(cfg, n_sample, rank=0):
+    """First n_sample reads of the workload, on the host, as (uint8 blob, int64 offsets)."""
+    try:
+        import torch
+        from bdx_b200 import capi
+        if not torch.cuda.is_available():
+            raise RuntimeError("no cuda")
+        torch.cuda.set_device(0)
+        config = capi.Config(cfg)
+        st = capi.Stream(config, device=0, max_reads=0, max_bytes=0)
+        d_seq = torch.empty(n_sample * READ_LEN, dtype=torch.uint8, device="cuda")
+        d_off = torch.empty(n_sample + 1, dtype=torch.int32, device="cuda")
+        st.synth_device(synth_spec(0), n_sample, d_seq.data_ptr(), d_off.data_ptr())
+        st.sync()
+        blob = d_seq.cpu().numpy()
+        off = d_off.cpu().numpy().astype(np.int64)
+        st.close()
+        return blob, off, "device generator (Philox), first reads of the workload"
+    except Exception as exc:  # no GPU visible: same distribution from numpy
+        blob, off = numpy_reads(cfg, n_sample, SEED)
+        return blob, off, f"numpy generator, same distribution ({type(exc).__name__})"
+
+
+def calibrate_sample(cfg, threads, seconds, lo=20000, hi=2_000_000):
+    blob, off, _ = sample_reads_host(cfg, 8000)
+    r1, _ = oracle_rate(cfg, blob, off, 1)
+    n = int(r1 * threads * seconds * 0.8)
+    n = max(lo, min(hi, n))
+    return (n + CHUNK - 1) // CHUNK * CHUNK, r1
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cfg = make_config()
+    threads = os.cpu_count() or 1
+    per_step_s = 6.0
+    n_sample, r1 = calibrate_sample(cfg, threads, per_step_s)
+    blob, off, how = sample_reads_host(cfg, n_sample)
+    times = []
+    for i in range(args.warmup + args.steps):
+        _, dt = oracle_rate(cfg, blob, off, threads)
+        if i >= args.warmup:
+            times.append(dt)
+    total = sum(times)
+    value = n_sample * len(times) / total
+    line = {
+        "impl": "reference", "metric": "reads_per_sec", "value": value, "unit": "reads/s",
+        "gcups": value * CU_PER_READ / 1e9, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "int64", "data": "synthetic",
+        "config": {"workload": f"config2: {n_sample} x {READ_LEN}bp reads (bounded sample of the 10M-read job), "
+                               f"{N_BARCODES} barcodes x {BARCODE_LEN}nt, :semiglobal defaults",
+                   "note": "C restatement of BioDemuX.jl classification.jl (oracle port), all host threads; "
+                           "Julia is not installed in this image so the reference itself cannot run"},
+        "cpu_baseline": {"value": value, "unit": "reads/s", "cores": threads, "kind": "port",
+                         "sample": f"{n_sample} reads per step; {how}", "single_thread_reads_per_s": r1},
+        "e2e": {"value": value, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import bdx_b200 as bdx
+    from bdx_b200 import capi
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product has no CPU path")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    n = args.reads
+    cfg = make_config()
+    config = capi.Config(cfg)
+    stream = capi.Stream(config, device=local, max_reads=args.e2e_batch, max_bytes=args.e2e_batch * READ_LEN)
+    ext = torch.cuda.ExternalStream(stream.cuda_stream, device=torch.device("cuda", local))
+
+    d_seq = torch.empty(n * READ_LEN, dtype=torch.uint8, device="cuda")
+    d_off = torch.empty(n + 1, dtype=torch.int32, device="cuda")
+    d_res = torch.empty(n * bdx.RESULT_DTYPE.itemsize, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    stream.synth_device(synth_spec(rank * n), n, d_seq.data_ptr(), d_off.data_ptr())
+    stream.sync()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        stream.classify_device(d_seq.data_ptr(), d_off.data_ptr(), n, d_res.data_ptr())
+
+    # ---- device-resident: value + roofline of the dominant kernel -------------------------
+    for _ in range(args.warmup):
+        step()
+    stream.sync()
+    peak_ops = capi.C.c_double()
+    capi._check(stream.lib.bdx_int_alu_peak(local, capi.C.byref(peak_ops)))
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    stream.profile(True)
+    l0 = stream.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(ext)
+    for _ in range(args.steps):
+        step()
+    e1.record(ext)
+    stream.sync()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = stream.launch_count - l0
+    filt_ms, filt_n = stream.profile_read()
+    stream.profile(False)
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = world * n * args.steps / (ms_max * 1e-3)
+
+    # ---- sanity on the timed results (parity proper lives in tests/) -----------------------
+    res = np.frombuffer(d_res.cpu().numpy().tobytes(), dtype=bdx.RESULT_DTYPE)
+    matched = int((res["status"] == 0).sum())
+
+    # ---- e2e through the C ABI with host buffers ------------------------------------------
+    B = args.e2e_batch
+    nb = n // B
+    h_seq = torch.empty(n * READ_LEN, dtype=torch.uint8, pin_memory=True)
+    h_seq.copy_(d_seq)
+    h_off = torch.empty(B + 1, dtype=torch.int32, pin_memory=True)
+    h_off.copy_(d_off[:B + 1])
+    torch.cuda.synchronize()
+    seq_np, off_np = h_seq.numpy(), h_off.numpy()
+    e2e_matched = 0
+
+    def e2e_step():
+        nonlocal e2e_matched
+        m = 0
+        stream.submit(seq_np[0:B * READ_LEN], off_np, tag=0, pinned=True)
+        for k in range(1, nb):
+            stream.submit(seq_np[k * B * READ_LEN:(k + 1) * B * READ_LEN], off_np, tag=k, pinned=True)
+            _, r = stream.fetch()
+            m += int((r["status"] == 0).sum())
+        _, r = stream.fetch()
+        m += int((r["status"] == 0).sum())
+        e2e_matched = m
+
+    for _ in range(max(1, min(args.warmup, 2))):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * nb * B * args.steps / float(t.item())
+    assert e2e_matched == int((res["status"][:nb * B] == 0).sum()), "e2e and device-resident results disagree"
+
+    # ---- N > 1: the one collective of the path -- DemuxStats counters summed over GPUs ------
+    stats_ms = None
+    if world > 1:
+        scfg = capi.Config(cfg, want_stats=True)
+        sst = capi.Stream(scfg, device=local, max_reads=0, max_bytes=0)
+        ns = min(n, 1_000_000)
+        d_det = torch.empty(2 * ns * bdx.DETAIL_DTYPE.itemsize, dtype=torch.uint8, device="cuda")
+        sst.classify_device(d_seq.data_ptr(), d_off.data_ptr(), ns, d_res.data_ptr(), d_det.data_ptr())
+        sst.sync()
+        L = scfg.layout.total_len
+
+        class _DevBuf:  # zero-copy torch view of the stream's device counters
+            __cuda_array_interface__ = {"shape": (L,), "typestr": "<i8", "version": 2,
+                                        "data": (sst.stats_device_ptr, False)}
+
+        counters = torch.as_tensor(_DevBuf(), device="cuda")
+        torch.cuda.synchronize()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        dist.all_reduce(counters, op=dist.ReduceOp.SUM)
+        c1.record()
+        torch.cuda.synchronize()
+        stats_ms = c0.elapsed_time(c1)
+        assert int(counters[0].item()) == world * ns
+        sst.close()
+
+    if rank == 0:
+        filt_s = filt_ms * 1e-3 / max(filt_n, 1)          # average duration of one filter launch
+        achieved_ops = OPS_PER_READ * n / filt_s if filt_s > 0 else 0.0
+        hbm_peak = None
+        try:
+            hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+            hbm_src = "MEASURED_PEAKS.json"
+        except Exception:
+            hbm_peak, hbm_src = 6650.0, "fallback (B200_PROFILING.md)"
+        hbm_gbs = BYTES_PER_READ * n / filt_s / 1e9 if filt_s > 0 else 0.0
+        line = {
+            "metric": "reads_per_sec", "value": value, "unit": "reads/s", "gcups": value * CU_PER_READ / 1e9,
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32",
+            "data": "synthetic",
+            "config": {"workload": f"config2: {n} x {READ_LEN}bp reads per GPU, {N_BARCODES} barcodes x "
+                                   f"{BARCODE_LEN}nt, :semiglobal defaults (max_error_rate 0.2, unit costs)",
+                       "reads_per_gpu": n, "l2": "inputs (1.5 GB of reads per step) exceed the 126 MB L2",
+                       "matched_fraction": matched / n, "e2e_batch_reads": B},
+            "roofline": {"bound": "int_alu", "achieved": achieved_ops / 1e12, "peak": peak_ops.value / 1e12,
+                         "unit": "Tint-op/s", "frac": achieved_ops / peak_ops.value if peak_ops.value else None,
+                         "traffic": None, "kernel": "k_filter<1,3>", "kernel_ms": filt_s * 1e3,
+                         "kernel_share_of_step": filt_ms / ms if ms else None,
+                         "ops_per_read": OPS_PER_READ,
+                         "peak_source": "bdx_int_alu_peak: LOP3/IADD3 chains measured live on this GPU",
+                         "hbm": {"achieved": hbm_gbs, "peak": hbm_peak, "unit": "GB/s",
+                                 "frac": hbm_gbs / hbm_peak, "peak_source": hbm_src,
+                                 "bytes_per_read": BYTES_PER_READ}},
+            "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": nb * (B * READ_LEN + 4 * (B + 1)),
+                    "d2h_bytes_per_step": nb * B * bdx.RESULT_DTYPE.itemsize,
+                    "api": "bdx_submit_pinned / bdx_fetch_view, 2 batches in flight"},
+            "gpu_launches": launches, "clocks": clocks,
+        }
+        if stats_ms is not None:
+            line["stats_allreduce_ms"] = stats_ms
+        if world == 1 and not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            n_sample, r1 = calibrate_sample(cfg, threads, 12.0)
+            blob = seq_np[:n_sample * READ_LEN]
+            off64 = np.arange(n_sample + 1, dtype=np.int64) * READ_LEN
+            rate, dt = oracle_rate(cfg, blob, off64, threads)
+            line["cpu_baseline"] = {"value": rate, "unit": "reads/s", "cores": threads, "kind": "port",
+                                    "sample": f"first {n_sample} reads of the same workload, {dt:.1f} s, "
+                                              f"chunks of {CHUNK}; C restatement of classification.jl "
+                                              "(Julia unavailable in image)",
+                                    "gcups": rate * CU_PER_READ / 1e9, "single_thread_reads_per_s": r1}
+        print(json.dumps(line))
+    stream.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--reads", type=int, default=10_000_000, help="reads per GPU (config 2: 10 M)")
+    ap.add_argument("--e2e-batch", type=int, default=1_000_000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.reads % args.e2e_batch:
+        args.e2e_batch = args.reads
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,336 @@
+"""ctypes binding of libbdx (include/bdx.h) and the ``Engine`` convenience wrapper.
+
+This is the Python twin of the ``ccall`` shim in ``julia/BioDemuXB200.jl``: it fills
+``bdx_params`` from a ``DemuxConfig`` and drives submit / fetch.  It never classifies
+on the CPU -- if the shared library or a CUDA device is missing it raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from typing import Optional, Sequence
+
+import numpy as np
+
+from .config import DemuxConfig
+from .demux import DETAIL_DTYPE, RESULT_DTYPE, pack_reads
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libbdx.so")
+ABI_VERSION = 1
+
+BDX_OK, BDX_ERR_INVALID, BDX_ERR_CUDA, BDX_ERR_NOMEM, BDX_ERR_STATE, BDX_ERR_TOO_LARGE = 0, -1, -2, -3, -4, -5
+
+# every symbol include/bdx.h declares (tests check that the library exports all of them)
+EXPORTS = [
+    "bdx_last_error", "bdx_abi_version", "bdx_device_count", "bdx_config_create", "bdx_config_destroy",
+    "bdx_stream_create", "bdx_stream_destroy", "bdx_submit", "bdx_acquire", "bdx_commit",
+    "bdx_submit_pinned", "bdx_host_alloc", "bdx_host_free", "bdx_stream_enable_details",
+    "bdx_fetch", "bdx_fetch_view", "bdx_classify", "bdx_classify_device", "bdx_stream_sync",
+    "bdx_stream_cuda_stream", "bdx_stream_launch_count", "bdx_stream_profile", "bdx_stream_profile_read", "bdx_stats_layout_get", "bdx_stats_fetch",
+    "bdx_stats_device_ptr", "bdx_stats_reset", "bdx_synth_reads_device", "bdx_int_alu_peak",
+]
+
+
+class BdxError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"libbdx error {code}: {msg}")
+        self.code = code
+
+
+class Range(C.Structure):
+    _fields_ = [("start_offset", C.c_int64), ("start_from_end", C.c_int32), ("end_from_end", C.c_int32),
+                ("end_offset", C.c_int64)]
+
+
+class BarcodeSet(C.Structure):
+    _fields_ = [("n_barcodes", C.c_int32), ("trim_side", C.c_int32), ("bytes", C.c_void_p),
+                ("offsets", C.c_void_p), ("lengths_no_n", C.c_void_p), ("ref_search_range", Range),
+                ("barcode_start_range", Range), ("barcode_end_range", Range)]
+
+
+class Params(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("abi_version", C.c_uint32), ("max_error_rate", C.c_double),
+                ("min_delta", C.c_double), ("match", C.c_int64), ("mismatch", C.c_int64),
+                ("indel", C.c_int64), ("nindel", C.c_int64), ("has_nindel", C.c_int32),
+                ("algorithm", C.c_int32), ("is_dual", C.c_int32), ("want_stats", C.c_int32),
+                ("set1", BarcodeSet), ("set2", BarcodeSet)]
+
+
+class StatsLayout(C.Structure):
+    _fields_ = [("total_len", C.c_int64), ("sample_off", C.c_int64), ("b1", C.c_int32), ("b2", C.c_int32),
+                ("pos_bins", C.c_int32), ("len_bins", C.c_int32), ("dist_bins", C.c_int32),
+                ("pos_bias", C.c_int32), ("pos_off", C.c_int64 * 2), ("len_off", C.c_int64 * 2),
+                ("dist_off", C.c_int64 * 2)]
+
+
+class SynthSpec(C.Structure):
+    _fields_ = [("seed", C.c_uint64), ("first_read", C.c_int64), ("read_len", C.c_int32),
+                ("plant_permille", C.c_int32), ("start_lo", C.c_int32), ("start_hi", C.c_int32),
+                ("n_permille_x10", C.c_int32), ("set2_mode", C.c_int32), ("end_lo", C.c_int32),
+                ("end_hi", C.c_int32)]
+
+
+_LIB = None
+
+
+def build_library(force: bool = False) -> str:
+    """Compile csrc/ with nvcc for sm_100a (works without a GPU)."""
+    if force or not os.path.exists(LIB_PATH):
+        subprocess.run(["make", "-s", "-C", os.path.join(_HERE, "csrc")], check=True,
+                       stdout=subprocess.DEVNULL)
+    return LIB_PATH
+
+
+def load_library():
+    """Loads libbdx.so; raises if it is missing (no fallback)."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if not os.path.exists(LIB_PATH):
+        raise BdxError(BDX_ERR_CUDA, f"{LIB_PATH} not built: run `make -C biodemux.jl_b200/csrc` "
+                                     "(or __graft_entry__.build()); there is no CPU fallback")
+    L = C.CDLL(LIB_PATH)
+    vp, i32, i64, u64 = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64
+    L.bdx_last_error.restype = C.c_char_p
+    L.bdx_abi_version.restype = C.c_int
+    L.bdx_device_count.restype = C.c_int
+    L.bdx_config_create.argtypes = [C.POINTER(Params), C.POINTER(vp)]
+    L.bdx_config_destroy.argtypes = [vp]
+    L.bdx_config_destroy.restype = None
+    L.bdx_stream_create.argtypes = [vp, C.c_int, i32, i64, C.POINTER(vp)]
+    L.bdx_stream_destroy.argtypes = [vp]
+    L.bdx_stream_destroy.restype = None
+    L.bdx_submit.argtypes = [vp, vp, vp, i32, u64]
+    L.bdx_submit_pinned.argtypes = [vp, vp, vp, i32, u64]
+    L.bdx_acquire.argtypes = [vp, C.POINTER(vp), C.POINTER(vp)]
+    L.bdx_commit.argtypes = [vp, i32, u64]
+    L.bdx_host_alloc.argtypes = [C.c_size_t]
+    L.bdx_host_alloc.restype = vp
+    L.bdx_host_free.argtypes = [vp]
+    L.bdx_host_free.restype = None
+    L.bdx_stream_enable_details.argtypes = [vp, C.c_int]
+    L.bdx_fetch.argtypes = [vp, C.POINTER(u64), C.POINTER(i32), vp, vp]
+    L.bdx_fetch_view.argtypes = [vp, C.POINTER(u64), C.POINTER(i32), C.POINTER(vp), C.POINTER(vp)]
+    L.bdx_classify.argtypes = [vp, vp, vp, i32, vp, vp]
+    L.bdx_classify_device.argtypes = [vp, vp, vp, i32, vp, vp]
+    L.bdx_stream_sync.argtypes = [vp]
+    L.bdx_stream_cuda_stream.argtypes = [vp]
+    L.bdx_stream_cuda_stream.restype = vp
+    L.bdx_stream_launch_count.argtypes = [vp]
+    L.bdx_stream_launch_count.restype = i64
+    L.bdx_stream_profile.argtypes = [vp, C.c_int]
+    L.bdx_stream_profile_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(i32)]
+    L.bdx_stats_layout_get.argtypes = [vp, C.POINTER(StatsLayout)]
+    L.bdx_stats_fetch.argtypes = [vp, vp, i64]
+    L.bdx_stats_device_ptr.argtypes = [vp]
+    L.bdx_stats_device_ptr.restype = vp
+    L.bdx_stats_reset.argtypes = [vp]
+    L.bdx_synth_reads_device.argtypes = [vp, C.POINTER(SynthSpec), i32, vp, vp]
+    L.bdx_int_alu_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]
+    _LIB = L
+    return L
+
+
+def _check(rc: int):
+    if rc != BDX_OK:
+        raise BdxError(rc, load_library().bdx_last_error().decode("utf-8", "replace"))
+
+
+def _range(dr) -> Range:
+    return Range(dr.start_offset, int(dr.start_from_end), int(dr.end_from_end), dr.end_offset)
+
+
+class Config:
+    """Owns a ``bdx_config`` (immutable; shareable across streams)."""
+
+    def __init__(self, cfg: DemuxConfig, want_stats: Optional[bool] = None):
+        self.lib = load_library()
+        self.cfg = cfg
+        self._keep = []
+        p = Params()
+        p.struct_size = C.sizeof(Params)
+        p.abi_version = ABI_VERSION
+        p.max_error_rate = float(cfg.max_error_rate)
+        p.min_delta = float(cfg.min_delta)
+        p.match, p.mismatch, p.indel = int(cfg.match), int(cfg.mismatch), int(cfg.indel)
+        p.has_nindel = 0 if cfg.nindel is None else 1
+        p.nindel = 0 if cfg.nindel is None else int(cfg.nindel)
+        p.algorithm = cfg.algorithm_code
+        p.is_dual = int(bool(cfg.is_dual))
+        p.want_stats = int(bool(cfg.summary if want_stats is None else want_stats))
+        p.set1 = self._set(cfg.bc_seqs, cfg.bc_lengths_no_N, cfg.ref_search_range, cfg.barcode_start_range,
+                           cfg.barcode_end_range, cfg.trim_side)
+        if cfg.is_dual:
+            p.set2 = self._set(cfg.bc_seqs2, cfg.bc_lengths_no_N2, cfg.ref_search_range2,
+                               cfg.barcode_start_range2, cfg.barcode_end_range2, cfg.trim_side2)
+        self.params = p
+        self.handle = C.c_void_p()
+        _check(self.lib.bdx_config_create(C.byref(p), C.byref(self.handle)))
+        self.layout = StatsLayout()
+        _check(self.lib.bdx_stats_layout_get(self.handle, C.byref(self.layout)))
+
+    def _set(self, seqs: Sequence[str], lens: Sequence[int], rs, bs, be, trim) -> BarcodeSet:
+        raw = [s.encode("latin-1") if isinstance(s, str) else bytes(s) for s in seqs]
+        blob = np.frombuffer(b"".join(raw) + b"\0", dtype=np.uint8).copy()
+        off = np.zeros(len(raw) + 1, dtype=np.int32)
+        off[1:] = np.cumsum([len(x) for x in raw])
+        ln = np.asarray(list(lens), dtype=np.int32) if len(lens) else np.zeros(1, np.int32)
+        self._keep += [blob, off, ln]
+        s = BarcodeSet()
+        s.n_barcodes = len(raw)
+        s.trim_side = 0 if trim is None else int(trim)
+        s.bytes = blob.ctypes.data
+        s.offsets = off.ctypes.data
+        s.lengths_no_n = ln.ctypes.data
+        s.ref_search_range = _range(rs)
+        s.barcode_start_range = _range(bs)
+        s.barcode_end_range = _range(be)
+        return s
+
+    def close(self):
+        if self.handle:
+            self.lib.bdx_config_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Stream:
+    """Owns a ``bdx_stream`` (one per host worker)."""
+
+    def __init__(self, config: Config, device: int = 0, max_reads: int = 4000, max_bytes: Optional[int] = None):
+        self.lib = config.lib
+        self.config = config
+        self.max_reads = int(max_reads)
+        self.max_bytes = int(max_bytes if max_bytes is not None else max(self.max_reads, 1) * 1024)
+        self.handle = C.c_void_p()
+        _check(self.lib.bdx_stream_create(config.handle, device, self.max_reads, self.max_bytes,
+                                          C.byref(self.handle)))
+        self.details = bool(config.params.want_stats)
+
+    def enable_details(self, on: bool = True):
+        _check(self.lib.bdx_stream_enable_details(self.handle, int(on)))
+        self.details = bool(on)
+
+    def submit(self, seq: np.ndarray, off: np.ndarray, tag: int = 0, pinned: bool = False):
+        n = len(off) - 1
+        fn = self.lib.bdx_submit_pinned if pinned else self.lib.bdx_submit
+        _check(fn(self.handle, seq.ctypes.data, off.ctypes.data, n, tag))
+
+    def fetch(self, want_details: bool = False):
+        tag, n = C.c_uint64(), C.c_int32()
+        res_p, det_p = C.c_void_p(), C.c_void_p()
+        _check(self.lib.bdx_fetch_view(self.handle, C.byref(tag), C.byref(n), C.byref(res_p), C.byref(det_p)))
+        nn = n.value
+        if nn == 0:
+            res = np.zeros(0, RESULT_DTYPE)
+            det = np.zeros((2, 0), DETAIL_DTYPE)
+        else:
+            buf = (C.c_char * (nn * RESULT_DTYPE.itemsize)).from_address(res_p.value)
+            res = np.frombuffer(buf, dtype=RESULT_DTYPE, count=nn).copy()
+            det = None
+            if want_details:
+                if not det_p.value:
+                    raise BdxError(BDX_ERR_STATE, "details not enabled on this stream")
+                dbuf = (C.c_char * (2 * nn * DETAIL_DTYPE.itemsize)).from_address(det_p.value)
+                det = np.frombuffer(dbuf, dtype=DETAIL_DTYPE, count=2 * nn).reshape(2, nn).copy()
+        return (tag.value, res, det) if want_details else (tag.value, res)
+
+    def classify(self, seq: np.ndarray, off: np.ndarray, want_details: bool = False):
+        """One batch through bdx_classify (host buffers in, host results out)."""
+        seq = np.ascontiguousarray(seq, dtype=np.uint8)
+        off = np.ascontiguousarray(off, dtype=np.int32)
+        n = len(off) - 1
+        res = np.zeros(n, RESULT_DTYPE)
+        det = np.zeros((2, n), DETAIL_DTYPE) if want_details else None
+        if seq.size == 0:
+            seq = np.zeros(1, np.uint8)
+        _check(self.lib.bdx_classify(self.handle, seq.ctypes.data, off.ctypes.data, n, res.ctypes.data,
+                                     det.ctypes.data if det is not None else None))
+        return (res, det) if want_details else res
+
+    def classify_device(self, d_seq: int, d_off: int, n: int, d_res: int, d_det: int = 0):
+        _check(self.lib.bdx_classify_device(self.handle, d_seq, d_off, n, d_res, d_det or None))
+
+    def synth_device(self, spec: SynthSpec, n: int, d_seq: int, d_off: int):
+        _check(self.lib.bdx_synth_reads_device(self.handle, C.byref(spec), n, d_seq, d_off))
+
+    def sync(self):
+        _check(self.lib.bdx_stream_sync(self.handle))
+
+    @property
+    def cuda_stream(self) -> int:
+        return int(self.lib.bdx_stream_cuda_stream(self.handle) or 0)
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.bdx_stream_launch_count(self.handle))
+
+    def profile(self, on: bool):
+        _check(self.lib.bdx_stream_profile(self.handle, int(on)))
+
+    def profile_read(self):
+        ms, n = C.c_double(), C.c_int32()
+        _check(self.lib.bdx_stream_profile_read(self.handle, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+    def stats(self) -> np.ndarray:
+        out = np.zeros(self.config.layout.total_len, dtype=np.int64)
+        _check(self.lib.bdx_stats_fetch(self.handle, out.ctypes.data, out.size))
+        return out
+
+    @property
+    def stats_device_ptr(self) -> int:
+        return int(self.lib.bdx_stats_device_ptr(self.handle) or 0)
+
+    def stats_reset(self):
+        _check(self.lib.bdx_stats_reset(self.handle))
+
+    def close(self):
+        if self.handle:
+            self.lib.bdx_stream_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Engine:
+    """Config + one stream: what a single reference worker thread would own."""
+
+    def __init__(self, cfg: DemuxConfig, device: int = 0, max_reads: int = 4000,
+                 max_bytes: Optional[int] = None, want_stats: Optional[bool] = None):
+        self.cfg = cfg
+        self.config = Config(cfg, want_stats=want_stats)
+        self.stream = Stream(self.config, device=device, max_reads=max_reads, max_bytes=max_bytes)
+
+    def classify_reads(self, seqs: Sequence[bytes]) -> np.ndarray:
+        blob, off = pack_reads(seqs)
+        return self.stream.classify(blob, off)
+
+    def classify_packed(self, blob: np.ndarray, off: np.ndarray, want_details: bool = False):
+        return self.stream.classify(blob, off, want_details=want_details)
+
+    def demux_stats(self):
+        from .stats import stats_from_counters
+        return stats_from_counters(self.stream.stats(), self.config.layout, self.cfg)
+
+    def close(self):
+        self.stream.close()
+        self.config.close()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+        return False

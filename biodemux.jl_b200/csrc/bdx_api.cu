@@ -1,0 +1,801 @@
+// bdx_api.cu -- C ABI of libbdx (include/bdx.h): configuration, per-worker streams with
+// pinned double-buffered staging, batch submission / retrieval, DemuxStats counters.
+// Replaces the body of the reference's worker_task (src/core.jl:226-279).
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "bdx_internal.h"
+
+using namespace bdx;
+
+namespace bdx {
+size_t filter_smem_bytes_for(const DevSet &S);
+}
+
+// ---------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------
+static thread_local std::string g_err;
+
+static int fail(int code, const std::string &msg)
+{
+    g_err = msg;
+    return code;
+}
+static int cuda_fail(cudaError_t e, const char *what)
+{
+    g_err = std::string(what) + ": " + cudaGetErrorString(e);
+    return BDX_ERR_CUDA;
+}
+#define CU(call)                                              \
+    do {                                                      \
+        cudaError_t e__ = (call);                             \
+        if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
+    } while (0)
+
+extern "C" const char *bdx_last_error(void) { return g_err.c_str(); }
+extern "C" int bdx_abi_version(void) { return BDX_ABI_VERSION; }
+extern "C" int bdx_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+// ---------------------------------------------------------------------------
+// configuration
+// ---------------------------------------------------------------------------
+struct HostSet {
+    int n_bc = 0, n_bc_pad = 0, max_m = 0, trim_side = 0, words = 0, n_classes = 1;
+    DevRange rs{}, bs{}, be{};
+    std::vector<uint8_t> bytes;
+    std::vector<int> off, norm, filt_allowed, allowed0;
+    std::vector<uint32_t> peq;
+    uint8_t class_of[256];
+};
+
+struct DeviceTables {
+    DevParams P;
+    std::vector<void *> allocs;
+    int sm_count = 0;
+};
+
+struct bdx_config {
+    DevParams base{};  // device pointers unset
+    HostSet set[2];
+    bdx_stats_layout lay{};
+    std::mutex mu;
+    std::map<int, DeviceTables *> per_device;
+};
+
+static int narrow_range(const bdx_range &in, DevRange &out, const char *name)
+{
+    const int64_t lim = 1ll << 30;
+    if (in.start_offset > lim || in.start_offset < -lim || in.end_offset > lim || in.end_offset < -lim)
+        return fail(BDX_ERR_INVALID, std::string(name) + ": range offset out of bounds");
+    out.start_off = (int)in.start_offset;
+    out.start_from_end = in.start_from_end ? 1 : 0;
+    out.end_off = (int)in.end_offset;
+    out.end_from_end = in.end_from_end ? 1 : 0;
+    return BDX_OK;
+}
+
+static int host_allowed(double max_error, int norm)
+{
+    // floor(Int, max_error * normalization_length), classification.jl:254 (same clamp as the device)
+    volatile double prod = max_error * (double)norm;
+    double x = std::floor(prod);
+    if (!(x < 268435456.0)) return 268435456;
+    if (x < -268435456.0) return -268435456;
+    return (int)x;
+}
+
+static int build_set(const bdx_params &p, const bdx_barcode_set &in, HostSet &hs, bool disable_filter,
+                     const char *name)
+{
+    if (in.n_barcodes <= 0 || !in.bytes || !in.offsets)
+        return fail(BDX_ERR_INVALID, std::string(name) + ": empty barcode set");
+    if (in.n_barcodes > 65535) return fail(BDX_ERR_INVALID, std::string(name) + ": more than 65535 barcodes");
+    if (in.trim_side != 0 && in.trim_side != 3 && in.trim_side != 5)
+        return fail(BDX_ERR_INVALID, "trim_side must be 3 or 5");  // core.jl:308-313
+    if (p.has_nindel && !in.lengths_no_n)
+        return fail(BDX_ERR_INVALID, std::string(name) + ": lengths_no_n required with nindel");
+    hs.n_bc = in.n_barcodes;
+    hs.trim_side = in.trim_side;
+    int rc;
+    if ((rc = narrow_range(in.ref_search_range, hs.rs, name))) return rc;
+    if ((rc = narrow_range(in.barcode_start_range, hs.bs, name))) return rc;
+    if ((rc = narrow_range(in.barcode_end_range, hs.be, name))) return rc;
+    if (in.offsets[0] != 0) return fail(BDX_ERR_INVALID, std::string(name) + ": offsets[0] must be 0");
+    hs.off.assign(in.offsets, in.offsets + in.n_barcodes + 1);
+    hs.max_m = 0;
+    for (int b = 0; b < hs.n_bc; b++) {
+        const int m = hs.off[b + 1] - hs.off[b];
+        if (m <= 0) return fail(BDX_ERR_INVALID, std::string(name) + ": empty barcode (not supported)");
+        if (m > kMaxBarcodeLen) return fail(BDX_ERR_INVALID, std::string(name) + ": barcode longer than 256");
+        hs.max_m = std::max(hs.max_m, m);
+    }
+    hs.bytes.assign(in.bytes, in.bytes + hs.off[hs.n_bc]);
+    hs.norm.resize(hs.n_bc);
+    for (int b = 0; b < hs.n_bc; b++) {
+        const int m = hs.off[b + 1] - hs.off[b];
+        // semiglobal: m, or bc_lengths_no_N under NScoring (classification.jl:460, :476, :647);
+        // hamming: m (:567, :607)
+        hs.norm[b] = (p.algorithm == BDX_SEMIGLOBAL && p.has_nindel) ? in.lengths_no_n[b] : m;
+        if (hs.norm[b] < 0) return fail(BDX_ERR_INVALID, std::string(name) + ": negative lengths_no_n");
+    }
+
+    // ---- bit-parallel filter tables (semiglobal only) ----
+    const int groups = (hs.n_bc + 31) / 32;
+    int gpad = groups;
+    if (groups > 4) {
+        const int m3 = (groups + 2) / 3 * 3, m4 = (groups + 3) / 4 * 4;
+        gpad = m4 <= m3 ? m4 : m3;
+    }
+    hs.n_bc_pad = gpad * 32;
+    memset(hs.class_of, 0, sizeof(hs.class_of));
+    hs.n_classes = 1;
+    for (uint8_t c : hs.bytes)
+        if (!hs.class_of[c]) hs.class_of[c] = (uint8_t)hs.n_classes++;
+    hs.words = hs.max_m <= 32 ? 1 : (hs.max_m <= 32 * kMaxFilterWords ? 2 : 0);
+    const bool benign = p.match >= 0 && p.mismatch >= 1 && p.indel >= 1 && (!p.has_nindel || p.nindel >= p.indel);
+    if (p.algorithm != BDX_SEMIGLOBAL || !benign || disable_filter || hs.n_classes > 64) hs.words = 0;
+
+    hs.allowed0.assign(hs.n_bc_pad, -1);
+    hs.filt_allowed.assign(hs.n_bc_pad, -1);
+    int64_t min_cost = std::min(p.mismatch, p.indel);
+    if (p.has_nindel) min_cost = std::min(min_cost, p.nindel);
+    for (int b = 0; b < hs.n_bc; b++) {
+        hs.allowed0[b] = host_allowed(p.max_error_rate, hs.norm[b]);
+        if (benign) hs.filt_allowed[b] = hs.allowed0[b] < 0 ? -1 : (int)(hs.allowed0[b] / min_cost);
+    }
+    if (hs.words) {
+        const int W = hs.words;
+        const size_t plane = (size_t)hs.n_classes * hs.n_bc_pad;
+        hs.peq.assign((size_t)W * plane, 0u);
+        for (int b = 0; b < hs.n_bc_pad; b++) {
+            const int m = b < hs.n_bc ? hs.off[b + 1] - hs.off[b] : 0;
+            const int first_row_bit = W * 32 - m;  // bit of barcode row 1; lower bits are phantom rows
+            for (int c = 0; c < hs.n_classes; c++) {
+                uint64_t v = first_row_bit >= 64 ? ~0ull : ((1ull << first_row_bit) - 1);  // phantom rows match
+                if (W == 1) v &= 0xFFFFFFFFull;
+                for (int i = 0; i < m; i++) {
+                    const uint8_t q = hs.bytes[hs.off[b] + i];
+                    const bool is_n = p.has_nindel && q == (uint8_t)'N';   // NScoring wildcard (:196-203)
+                    if (is_n || (c != 0 && hs.class_of[q] == c)) v |= 1ull << (first_row_bit + i);
+                }
+                hs.peq[0 * plane + (size_t)c * hs.n_bc_pad + b] = (uint32_t)v;
+                if (W == 2) hs.peq[1 * plane + (size_t)c * hs.n_bc_pad + b] = (uint32_t)(v >> 32);
+            }
+        }
+    }
+    return BDX_OK;
+}
+
+extern "C" int bdx_config_create(const bdx_params *p, bdx_config **out)
+{
+    if (!p || !out) return fail(BDX_ERR_INVALID, "null argument");
+    *out = nullptr;
+    if (p->struct_size != sizeof(bdx_params) || p->abi_version != BDX_ABI_VERSION)
+        return fail(BDX_ERR_INVALID, "bdx_params: struct_size / abi_version mismatch");
+    if (p->algorithm < BDX_SEMIGLOBAL || p->algorithm > BDX_EXACT) return fail(BDX_ERR_INVALID, "unknown algorithm");
+    const int64_t costs[4] = {p->match, p->mismatch, p->indel, p->has_nindel ? p->nindel : 1};
+    for (int64_t c : costs)
+        if (c > kMaxCost || c < -kMaxCost) return fail(BDX_ERR_INVALID, "cost magnitude above 2^20");
+    if (p->algorithm == BDX_SEMIGLOBAL && (p->indel == 0 || (p->has_nindel && p->nindel == 0)))
+        return fail(BDX_ERR_INVALID, "zero gap cost (the reference raises DivideError, classification.jl:170-176)");
+    if (std::isnan(p->max_error_rate) || std::isnan(p->min_delta)) return fail(BDX_ERR_INVALID, "NaN option");
+
+    bdx_config *cfg = new (std::nothrow) bdx_config();
+    if (!cfg) return fail(BDX_ERR_NOMEM, "out of memory");
+    const char *env = getenv("BDX_DISABLE_FILTER");
+    const bool disable_filter = env && env[0] == '1';
+    int rc = build_set(*p, p->set1, cfg->set[0], disable_filter, "set1");
+    if (rc == BDX_OK && p->is_dual) rc = build_set(*p, p->set2, cfg->set[1], disable_filter, "set2");
+    if (rc != BDX_OK) {
+        delete cfg;
+        return rc;
+    }
+    DevParams &P = cfg->base;
+    P.max_error_rate = p->max_error_rate;
+    P.min_delta = p->min_delta;
+    P.match = (int)p->match;
+    P.mismatch = (int)p->mismatch;
+    P.indel = (int)p->indel;
+    P.nindel = p->has_nindel ? (int)p->nindel : 0;
+    P.has_n = p->has_nindel ? 1 : 0;
+    P.algo = p->algorithm;
+    P.is_dual = p->is_dual ? 1 : 0;
+    P.want_stats = p->want_stats ? 1 : 0;
+    P.filter_ok = cfg->set[0].words > 0 && (!p->is_dual || cfg->set[1].words > 0);
+    P.unit_costs = p->match == 0 && p->mismatch == 1 && p->indel == 1 && (!p->has_nindel || p->nindel == 1);
+
+    // stats layout (classification.jl:736-758)
+    bdx_stats_layout &L = cfg->lay;
+    const int b1 = cfg->set[0].n_bc, b2 = p->is_dual ? cfg->set[1].n_bc : 0;
+    const int max_m = std::max(cfg->set[0].max_m, p->is_dual ? cfg->set[1].max_m : 0);
+    int max_allowed = 0;
+    for (int s = 0; s < (p->is_dual ? 2 : 1); s++)
+        for (int b = 0; b < cfg->set[s].n_bc; b++) max_allowed = std::max(max_allowed, cfg->set[s].allowed0[b]);
+    L.b1 = b1;
+    L.b2 = b2;
+    L.pos_bias = max_m;
+    L.pos_bins = 1024 + max_m + 2;
+    L.len_bins = 2 * max_m + 2;
+    L.dist_bins = std::min(max_allowed, 4095) + 1;
+    int64_t o = 4;
+    L.sample_off = o;
+    o += (int64_t)(b1 + 1) * (b2 + 1);
+    const int bsz[2] = {b1, b2};
+    for (int s = 0; s < 2; s++) {
+        L.pos_off[s] = o;
+        o += (int64_t)(bsz[s] + 1) * L.pos_bins;
+        L.len_off[s] = o;
+        o += (int64_t)(bsz[s] + 1) * L.len_bins;
+        L.dist_off[s] = o;
+        o += (int64_t)(bsz[s] + 1) * L.dist_bins;
+    }
+    L.total_len = o;
+    *out = cfg;
+    return BDX_OK;
+}
+
+static void free_tables(DeviceTables *t)
+{
+    for (void *p : t->allocs) cudaFree(p);
+    delete t;
+}
+
+extern "C" void bdx_config_destroy(bdx_config *cfg)
+{
+    if (!cfg) return;
+    for (auto &kv : cfg->per_device) {
+        cudaSetDevice(kv.first);
+        free_tables(kv.second);
+    }
+    delete cfg;
+}
+
+template <typename T>
+static cudaError_t upload(DeviceTables *t, const std::vector<T> &v, const T **out)
+{
+    *out = nullptr;
+    if (v.empty()) return cudaSuccess;
+    void *d = nullptr;
+    cudaError_t e = cudaMalloc(&d, v.size() * sizeof(T));
+    if (e != cudaSuccess) return e;
+    t->allocs.push_back(d);
+    e = cudaMemcpy(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
+    *out = (const T *)d;
+    return e;
+}
+
+static int get_tables(bdx_config *cfg, int device, DeviceTables **out)
+{
+    std::lock_guard<std::mutex> lk(cfg->mu);
+    auto it = cfg->per_device.find(device);
+    if (it != cfg->per_device.end()) {
+        *out = it->second;
+        return BDX_OK;
+    }
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return fail(BDX_ERR_CUDA, "libbdx is built for sm_100a only; device compute capability too low");
+    DeviceTables *t = new DeviceTables();
+    t->P = cfg->base;
+    t->sm_count = prop.multiProcessorCount;
+    for (int s = 0; s < (cfg->base.is_dual ? 2 : 1); s++) {
+        HostSet &hs = cfg->set[s];
+        DevSet &D = t->P.set[s];
+        D.n_bc = hs.n_bc;
+        D.n_bc_pad = hs.n_bc_pad;
+        D.max_m = hs.max_m;
+        D.trim_side = hs.trim_side;
+        D.words = hs.words;
+        D.n_classes = hs.n_classes;
+        D.rs = hs.rs;
+        D.bs = hs.bs;
+        D.be = hs.be;
+        std::vector<uint8_t> cls(hs.class_of, hs.class_of + 256);
+        cudaError_t e = upload(t, hs.bytes, &D.bc_bytes);
+        if (e == cudaSuccess) e = upload(t, hs.off, &D.bc_off);
+        if (e == cudaSuccess) e = upload(t, hs.norm, &D.norm);
+        if (e == cudaSuccess) e = upload(t, hs.peq, &D.peq);
+        if (e == cudaSuccess) e = upload(t, hs.filt_allowed, &D.filt_allowed);
+        if (e == cudaSuccess) e = upload(t, hs.allowed0, &D.allowed0);
+        if (e == cudaSuccess) e = upload(t, cls, &D.class_of);
+        if (e != cudaSuccess) {
+            free_tables(t);
+            return cuda_fail(e, "uploading barcode tables");
+        }
+        if (D.words && filter_smem_bytes_for(D) > (size_t)prop.sharedMemPerBlockOptin) D.words = 0;
+    }
+    t->P.filter_ok = t->P.set[0].words > 0 && (!t->P.is_dual || t->P.set[1].words > 0);
+    cfg->per_device[device] = t;
+    *out = t;
+    return BDX_OK;
+}
+
+// ---------------------------------------------------------------------------
+// streams
+// ---------------------------------------------------------------------------
+struct Slot {
+    uint8_t *h_seq = nullptr;
+    int32_t *h_off = nullptr;
+    bdx_result *h_res = nullptr;
+    bdx_pass_detail *h_det = nullptr;
+    uint8_t *d_seq = nullptr;
+    int32_t *d_off = nullptr;
+    bdx_result *d_res = nullptr;
+    bdx_pass_detail *d_det = nullptr;
+    cudaEvent_t ev_h2d = nullptr, ev_kern = nullptr, ev_done = nullptr;
+    int32_t n = 0;
+    uint64_t tag = 0;
+    bool busy = false;
+};
+
+struct bdx_stream {
+    bdx_config *cfg = nullptr;
+    DeviceTables *tab = nullptr;
+    int device = 0;
+    int32_t max_reads = 0;
+    int64_t max_bytes = 0;
+    bool details = false;
+    cudaStream_t st_copy = nullptr, st_comp = nullptr, st_d2h = nullptr;
+    Slot slot[2];
+    int head = 0;      // next slot to submit into
+    int tail = 0;      // oldest in-flight slot
+    int in_flight = 0;
+    bool acquired = false;
+    Scratch sc{};
+    int64_t sc_cap = 0;
+    unsigned long long *d_stats = nullptr;
+    int64_t launches = 0;
+    // optional per-kernel timing of the dominant (filter) kernel, for roofline reporting
+    bool profile = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
+};
+
+static int ensure_scratch(bdx_stream *s, int64_t n)
+{
+    if (n <= s->sc_cap) return BDX_OK;
+    // in-order on the compute stream: earlier kernels still own the old buffers
+    CU(cudaStreamSynchronize(s->st_comp));
+    cudaFree(s->sc.pass[0]);
+    cudaFree(s->sc.pass[1]);
+    cudaFree(s->sc.cand);
+    cudaFree(s->sc.cand_cnt);
+    s->sc = Scratch{};
+    s->sc_cap = 0;
+    const int64_t cap = n + n / 8 + 1024;
+    CU(cudaMalloc(&s->sc.pass[0], cap * sizeof(PassOut)));
+    CU(cudaMalloc(&s->sc.pass[1], cap * sizeof(PassOut)));
+    CU(cudaMalloc(&s->sc.cand, cap * kCandMax * sizeof(uint16_t)));
+    CU(cudaMalloc(&s->sc.cand_cnt, cap));
+    s->sc_cap = cap;
+    return BDX_OK;
+}
+
+extern "C" void bdx_stream_destroy(bdx_stream *s)
+{
+    if (!s) return;
+    cudaSetDevice(s->device);
+    if (s->st_comp) cudaStreamSynchronize(s->st_comp);
+    if (s->st_copy) cudaStreamSynchronize(s->st_copy);
+    if (s->st_d2h) cudaStreamSynchronize(s->st_d2h);
+    for (Slot &sl : s->slot) {
+        cudaFreeHost(sl.h_seq);
+        cudaFreeHost(sl.h_off);
+        cudaFreeHost(sl.h_res);
+        cudaFreeHost(sl.h_det);
+        cudaFree(sl.d_seq);
+        cudaFree(sl.d_off);
+        cudaFree(sl.d_res);
+        cudaFree(sl.d_det);
+        if (sl.ev_h2d) cudaEventDestroy(sl.ev_h2d);
+        if (sl.ev_kern) cudaEventDestroy(sl.ev_kern);
+        if (sl.ev_done) cudaEventDestroy(sl.ev_done);
+    }
+    cudaFree(s->sc.pass[0]);
+    cudaFree(s->sc.pass[1]);
+    cudaFree(s->sc.cand);
+    cudaFree(s->sc.cand_cnt);
+    cudaFree(s->d_stats);
+    for (auto &pr : s->prof_events) {
+        cudaEventDestroy(pr.first);
+        cudaEventDestroy(pr.second);
+    }
+    if (s->st_copy) cudaStreamDestroy(s->st_copy);
+    if (s->st_comp) cudaStreamDestroy(s->st_comp);
+    if (s->st_d2h) cudaStreamDestroy(s->st_d2h);
+    delete s;
+}
+
+static int stream_create_impl(bdx_stream *s)
+{
+    CU(cudaSetDevice(s->device));
+    CU(cudaStreamCreateWithFlags(&s->st_copy, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&s->st_comp, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&s->st_d2h, cudaStreamNonBlocking));
+    if (s->max_reads > 0) {
+        for (Slot &sl : s->slot) {
+            CU(cudaHostAlloc(&sl.h_seq, (size_t)std::max<int64_t>(s->max_bytes, 16), cudaHostAllocDefault));
+            CU(cudaHostAlloc(&sl.h_off, ((size_t)s->max_reads + 1) * 4, cudaHostAllocDefault));
+            CU(cudaHostAlloc(&sl.h_res, (size_t)s->max_reads * sizeof(bdx_result), cudaHostAllocDefault));
+            CU(cudaHostAlloc(&sl.h_det, (size_t)s->max_reads * 2 * sizeof(bdx_pass_detail), cudaHostAllocDefault));
+            CU(cudaMalloc(&sl.d_seq, (size_t)std::max<int64_t>(s->max_bytes, 16)));
+            CU(cudaMalloc(&sl.d_off, ((size_t)s->max_reads + 1) * 4));
+            CU(cudaMalloc(&sl.d_res, (size_t)s->max_reads * sizeof(bdx_result)));
+            CU(cudaMalloc(&sl.d_det, (size_t)s->max_reads * 2 * sizeof(bdx_pass_detail)));
+            CU(cudaEventCreateWithFlags(&sl.ev_h2d, cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&sl.ev_kern, cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&sl.ev_done, cudaEventDisableTiming));
+        }
+        int rc = ensure_scratch(s, s->max_reads);
+        if (rc) return rc;
+    }
+    if (s->cfg->base.want_stats) {
+        CU(cudaMalloc(&s->d_stats, (size_t)s->cfg->lay.total_len * 8));
+        CU(cudaMemset(s->d_stats, 0, (size_t)s->cfg->lay.total_len * 8));
+    }
+    return BDX_OK;
+}
+
+extern "C" int bdx_stream_create(const bdx_config *cfg_c, int device, int32_t max_reads, int64_t max_bytes,
+                                 bdx_stream **out)
+{
+    if (!cfg_c || !out || max_reads < 0 || max_bytes < 0) return fail(BDX_ERR_INVALID, "bad argument");
+    *out = nullptr;
+    if (max_bytes > 0x7FFFFFF0ll) return fail(BDX_ERR_TOO_LARGE, "max_bytes must stay below 2^31 (int32 offsets)");
+    bdx_config *cfg = const_cast<bdx_config *>(cfg_c);
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(BDX_ERR_CUDA, "no CUDA device available (libbdx has no CPU fallback)");
+    }
+    if (device < 0 || device >= ndev) return fail(BDX_ERR_INVALID, "device index out of range");
+    DeviceTables *tab = nullptr;
+    int rc = get_tables(cfg, device, &tab);
+    if (rc) return rc;
+    bdx_stream *s = new (std::nothrow) bdx_stream();
+    if (!s) return fail(BDX_ERR_NOMEM, "out of memory");
+    s->cfg = cfg;
+    s->tab = tab;
+    s->device = device;
+    s->max_reads = max_reads;
+    s->max_bytes = max_bytes;
+    s->details = cfg->base.want_stats != 0;
+    rc = stream_create_impl(s);
+    if (rc) {
+        std::string keep = g_err;
+        bdx_stream_destroy(s);
+        g_err = keep;
+        return rc;
+    }
+    *out = s;
+    return BDX_OK;
+}
+
+extern "C" int bdx_stream_enable_details(bdx_stream *s, int on)
+{
+    if (!s) return fail(BDX_ERR_INVALID, "null stream");
+    if (s->in_flight) return fail(BDX_ERR_STATE, "batches in flight");
+    s->details = on != 0;
+    return BDX_OK;
+}
+
+// Enqueue the classification kernels for n reads resident on the device.
+static int enqueue_classify(bdx_stream *s, const uint8_t *d_seq, const int32_t *d_off, int32_t n,
+                            bdx_result *d_res, bdx_pass_detail *d_det)
+{
+    if (n == 0) return BDX_OK;
+    int rc = ensure_scratch(s, n);
+    if (rc) return rc;
+    const DevParams &P = s->tab->P;
+    const int passes = P.is_dual ? 2 : 1;
+    for (int pass = 0; pass < passes; pass++) {
+        if (P.algo == BDX_SEMIGLOBAL && P.set[pass].words > 0) {
+            cudaEvent_t e0 = nullptr, e1 = nullptr;
+            if (s->profile) {
+                CU(cudaEventCreate(&e0));
+                CU(cudaEventCreate(&e1));
+                CU(cudaEventRecord(e0, s->st_comp));
+            }
+            CU(launch_filter(P, pass, d_seq, d_off, n, s->sc, s->tab->sm_count, s->st_comp));
+            s->launches++;
+            if (s->profile) {
+                CU(cudaEventRecord(e1, s->st_comp));
+                s->prof_events.emplace_back(e0, e1);
+            }
+            // the exact regime finishes inside the filter kernel; anything else leaves
+            // kBcPending reads with candidate lists for the literal kernel
+            const bool may_finish = P.unit_costs && P.set[pass].trim_side == 0 && !P.want_stats;
+            const DevRange &bs = P.set[pass].bs, &be = P.set[pass].be;
+            const bool default_geometry = bs.start_off <= 1 && !bs.start_from_end && bs.end_from_end &&
+                                          bs.end_off >= 0 && be.start_off <= 1 && !be.start_from_end;
+            if (!(may_finish && default_geometry)) {
+                CU(launch_literal(P, pass, 1, d_seq, d_off, n, s->sc, s->st_comp));
+                s->launches++;
+            }
+        } else {
+            CU(launch_literal(P, pass, 0, d_seq, d_off, n, s->sc, s->st_comp));
+            s->launches++;
+        }
+    }
+    StatsDev sd{s->d_stats, s->cfg->lay};
+    CU(launch_finalize(P, d_off, n, s->sc, d_res, d_det, sd, s->st_comp));
+    s->launches++;
+    return BDX_OK;
+}
+
+static int launch_slot(bdx_stream *s, Slot &sl, const uint8_t *h_seq, const int32_t *h_off)
+{
+    CU(cudaSetDevice(s->device));
+    const int32_t n = sl.n;
+    const size_t bytes = n ? (size_t)h_off[n] : 0;
+    if (n) {
+        CU(cudaMemcpyAsync(sl.d_off, h_off, ((size_t)n + 1) * 4, cudaMemcpyHostToDevice, s->st_copy));
+        if (bytes) CU(cudaMemcpyAsync(sl.d_seq, h_seq, bytes, cudaMemcpyHostToDevice, s->st_copy));
+    }
+    CU(cudaEventRecord(sl.ev_h2d, s->st_copy));
+    CU(cudaStreamWaitEvent(s->st_comp, sl.ev_h2d, 0));
+    int rc = enqueue_classify(s, sl.d_seq, sl.d_off, n, sl.d_res, s->details ? sl.d_det : nullptr);
+    if (rc) return rc;
+    CU(cudaEventRecord(sl.ev_kern, s->st_comp));
+    CU(cudaStreamWaitEvent(s->st_d2h, sl.ev_kern, 0));
+    if (n) {
+        CU(cudaMemcpyAsync(sl.h_res, sl.d_res, (size_t)n * sizeof(bdx_result), cudaMemcpyDeviceToHost, s->st_d2h));
+        if (s->details)
+            CU(cudaMemcpyAsync(sl.h_det, sl.d_det, (size_t)n * 2 * sizeof(bdx_pass_detail),
+                               cudaMemcpyDeviceToHost, s->st_d2h));
+    }
+    CU(cudaEventRecord(sl.ev_done, s->st_d2h));
+    sl.busy = true;
+    s->head ^= 1;
+    s->in_flight++;
+    return BDX_OK;
+}
+
+static int check_batch(bdx_stream *s, const int32_t *offsets, int32_t n)
+{
+    if (n < 0) return fail(BDX_ERR_INVALID, "negative n_reads");
+    if (n > s->max_reads) return fail(BDX_ERR_TOO_LARGE, "batch exceeds max_reads of the stream");
+    if (n && offsets[0] != 0) return fail(BDX_ERR_INVALID, "offsets[0] must be 0");
+    if (n && (offsets[n] < 0 || (int64_t)offsets[n] > s->max_bytes))
+        return fail(BDX_ERR_TOO_LARGE, "batch exceeds max_bytes of the stream");
+    return BDX_OK;
+}
+
+extern "C" int bdx_submit(bdx_stream *s, const uint8_t *seq, const int32_t *offsets, int32_t n, uint64_t tag)
+{
+    if (!s || (n > 0 && (!seq || !offsets))) return fail(BDX_ERR_INVALID, "null argument");
+    if (s->max_reads <= 0) return fail(BDX_ERR_STATE, "stream has no staging (max_reads = 0)");
+    if (s->acquired) return fail(BDX_ERR_STATE, "bdx_acquire pending; call bdx_commit");
+    if (s->in_flight >= 2) return fail(BDX_ERR_STATE, "two batches already in flight; call bdx_fetch");
+    int rc = check_batch(s, offsets, n);
+    if (rc) return rc;
+    Slot &sl = s->slot[s->head];
+    if (n) {
+        memcpy(sl.h_off, offsets, ((size_t)n + 1) * 4);
+        memcpy(sl.h_seq, seq, (size_t)offsets[n]);
+    }
+    sl.n = n;
+    sl.tag = tag;
+    return launch_slot(s, sl, sl.h_seq, sl.h_off);
+}
+
+extern "C" int bdx_submit_pinned(bdx_stream *s, const uint8_t *seq, const int32_t *offsets, int32_t n,
+                                 uint64_t tag)
+{
+    if (!s || (n > 0 && (!seq || !offsets))) return fail(BDX_ERR_INVALID, "null argument");
+    if (s->max_reads <= 0) return fail(BDX_ERR_STATE, "stream has no staging (max_reads = 0)");
+    if (s->acquired) return fail(BDX_ERR_STATE, "bdx_acquire pending; call bdx_commit");
+    if (s->in_flight >= 2) return fail(BDX_ERR_STATE, "two batches already in flight; call bdx_fetch");
+    int rc = check_batch(s, offsets, n);
+    if (rc) return rc;
+    Slot &sl = s->slot[s->head];
+    sl.n = n;
+    sl.tag = tag;
+    return launch_slot(s, sl, seq, offsets);
+}
+
+extern "C" int bdx_acquire(bdx_stream *s, uint8_t **seq, int32_t **offsets)
+{
+    if (!s || !seq || !offsets) return fail(BDX_ERR_INVALID, "null argument");
+    if (s->max_reads <= 0) return fail(BDX_ERR_STATE, "stream has no staging (max_reads = 0)");
+    if (s->acquired) return fail(BDX_ERR_STATE, "already acquired");
+    if (s->in_flight >= 2) return fail(BDX_ERR_STATE, "two batches already in flight; call bdx_fetch");
+    Slot &sl = s->slot[s->head];
+    *seq = sl.h_seq;
+    *offsets = sl.h_off;
+    s->acquired = true;
+    return BDX_OK;
+}
+
+extern "C" int bdx_commit(bdx_stream *s, int32_t n, uint64_t tag)
+{
+    if (!s) return fail(BDX_ERR_INVALID, "null stream");
+    if (!s->acquired) return fail(BDX_ERR_STATE, "bdx_commit without bdx_acquire");
+    Slot &sl = s->slot[s->head];
+    int rc = check_batch(s, sl.h_off, n);
+    if (rc) return rc;
+    s->acquired = false;
+    sl.n = n;
+    sl.tag = tag;
+    return launch_slot(s, sl, sl.h_seq, sl.h_off);
+}
+
+extern "C" int bdx_fetch(bdx_stream *s, uint64_t *tag, int32_t *n_reads, bdx_result *results,
+                         bdx_pass_detail *details)
+{
+    if (!s) return fail(BDX_ERR_INVALID, "null stream");
+    if (s->in_flight == 0) return fail(BDX_ERR_STATE, "nothing in flight");
+    if (details && !s->details) return fail(BDX_ERR_STATE, "details not enabled on this stream");
+    Slot &sl = s->slot[s->tail];
+    CU(cudaEventSynchronize(sl.ev_done));
+    if (tag) *tag = sl.tag;
+    if (n_reads) *n_reads = sl.n;
+    if (results && sl.n) memcpy(results, sl.h_res, (size_t)sl.n * sizeof(bdx_result));
+    if (details && sl.n) memcpy(details, sl.h_det, (size_t)sl.n * 2 * sizeof(bdx_pass_detail));
+    sl.busy = false;
+    s->tail ^= 1;
+    s->in_flight--;
+    return BDX_OK;
+}
+
+// zero-copy retrieval: pointers into the pinned result staging of the oldest batch,
+// valid until the next bdx_submit / bdx_commit that reuses the slot
+extern "C" int bdx_fetch_view(bdx_stream *s, uint64_t *tag, int32_t *n_reads, const bdx_result **results,
+                              const bdx_pass_detail **details)
+{
+    if (!s) return fail(BDX_ERR_INVALID, "null stream");
+    if (s->in_flight == 0) return fail(BDX_ERR_STATE, "nothing in flight");
+    Slot &sl = s->slot[s->tail];
+    CU(cudaEventSynchronize(sl.ev_done));
+    if (tag) *tag = sl.tag;
+    if (n_reads) *n_reads = sl.n;
+    if (results) *results = sl.h_res;
+    if (details) *details = s->details ? sl.h_det : nullptr;
+    sl.busy = false;
+    s->tail ^= 1;
+    s->in_flight--;
+    return BDX_OK;
+}
+
+extern "C" int bdx_classify(bdx_stream *s, const uint8_t *seq, const int32_t *offsets, int32_t n,
+                            bdx_result *results, bdx_pass_detail *details)
+{
+    if (s && s->in_flight) return fail(BDX_ERR_STATE, "batches in flight");
+    int rc = bdx_submit(s, seq, offsets, n, 0);
+    if (rc) return rc;
+    return bdx_fetch(s, nullptr, nullptr, results, details);
+}
+
+extern "C" int bdx_classify_device(bdx_stream *s, const uint8_t *d_seq, const int32_t *d_off, int32_t n,
+                                   bdx_result *d_res, bdx_pass_detail *d_det)
+{
+    if (!s || n < 0 || (n > 0 && (!d_seq || !d_off || !d_res))) return fail(BDX_ERR_INVALID, "bad argument");
+    CU(cudaSetDevice(s->device));
+    return enqueue_classify(s, d_seq, d_off, n, d_res, d_det);
+}
+
+extern "C" int bdx_stream_sync(bdx_stream *s)
+{
+    if (!s) return fail(BDX_ERR_INVALID, "null stream");
+    CU(cudaSetDevice(s->device));
+    CU(cudaStreamSynchronize(s->st_comp));
+    return BDX_OK;
+}
+
+extern "C" int bdx_stream_profile(bdx_stream *s, int on)
+{
+    if (!s) return fail(BDX_ERR_INVALID, "null stream");
+    s->profile = on != 0;
+    return BDX_OK;
+}
+
+extern "C" int bdx_stream_profile_read(bdx_stream *s, double *filter_ms, int32_t *n_launches)
+{
+    if (!s || !filter_ms || !n_launches) return fail(BDX_ERR_INVALID, "null argument");
+    CU(cudaSetDevice(s->device));
+    CU(cudaStreamSynchronize(s->st_comp));
+    double total = 0.0;
+    for (auto &pr : s->prof_events) {
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, pr.first, pr.second));
+        total += ms;
+        cudaEventDestroy(pr.first);
+        cudaEventDestroy(pr.second);
+    }
+    *filter_ms = total;
+    *n_launches = (int32_t)s->prof_events.size();
+    s->prof_events.clear();
+    return BDX_OK;
+}
+
+extern "C" void *bdx_stream_cuda_stream(bdx_stream *s) { return s ? (void *)s->st_comp : nullptr; }
+extern "C" int64_t bdx_stream_launch_count(const bdx_stream *s) { return s ? s->launches : 0; }
+
+// ---------------------------------------------------------------------------
+// stats
+// ---------------------------------------------------------------------------
+extern "C" int bdx_stats_layout_get(const bdx_config *cfg, bdx_stats_layout *out)
+{
+    if (!cfg || !out) return fail(BDX_ERR_INVALID, "null argument");
+    *out = cfg->lay;
+    return BDX_OK;
+}
+
+extern "C" int bdx_stats_fetch(bdx_stream *s, int64_t *out, int64_t out_len)
+{
+    if (!s || !out) return fail(BDX_ERR_INVALID, "null argument");
+    if (!s->d_stats) return fail(BDX_ERR_STATE, "config was created without want_stats");
+    if (out_len < s->cfg->lay.total_len) return fail(BDX_ERR_INVALID, "stats buffer too small");
+    CU(cudaSetDevice(s->device));
+    CU(cudaStreamSynchronize(s->st_comp));
+    CU(cudaMemcpy(out, s->d_stats, (size_t)s->cfg->lay.total_len * 8, cudaMemcpyDeviceToHost));
+    return BDX_OK;
+}
+
+extern "C" void *bdx_stats_device_ptr(bdx_stream *s) { return s ? (void *)s->d_stats : nullptr; }
+
+extern "C" int bdx_stats_reset(bdx_stream *s)
+{
+    if (!s) return fail(BDX_ERR_INVALID, "null stream");
+    if (!s->d_stats) return BDX_OK;
+    CU(cudaSetDevice(s->device));
+    CU(cudaMemsetAsync(s->d_stats, 0, (size_t)s->cfg->lay.total_len * 8, s->st_comp));
+    return BDX_OK;
+}
+
+// ---------------------------------------------------------------------------
+// utilities
+// ---------------------------------------------------------------------------
+extern "C" int bdx_synth_reads_device(bdx_stream *s, const bdx_synth_spec *spec, int32_t n, uint8_t *d_seq,
+                                      int32_t *d_off)
+{
+    if (!s || !spec || n < 0 || !d_seq || !d_off) return fail(BDX_ERR_INVALID, "bad argument");
+    if (spec->read_len <= 0 || (int64_t)spec->read_len * n > 0x7FFFFFF0ll)
+        return fail(BDX_ERR_TOO_LARGE, "n_reads * read_len must stay below 2^31");
+    if (spec->start_lo < 1 || spec->start_hi < spec->start_lo || spec->end_hi < spec->end_lo)
+        return fail(BDX_ERR_INVALID, "bad plant range");
+    CU(cudaSetDevice(s->device));
+    CU(launch_synth(s->tab->P, *spec, n, d_seq, d_off, s->st_comp));
+    s->launches++;
+    return BDX_OK;
+}
+
+extern "C" int bdx_int_alu_peak(int device, double *ops_per_second)
+{
+    if (!ops_per_second) return fail(BDX_ERR_INVALID, "null argument");
+    cudaError_t e = run_int_alu_peak(device, ops_per_second);
+    if (e != cudaSuccess) return cuda_fail(e, "int alu peak microbenchmark");
+    return BDX_OK;
+}
+
+extern "C" void *bdx_host_alloc(size_t bytes)
+{
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+extern "C" void bdx_host_free(void *p)
+{
+    if (p) cudaFreeHost(p);
+}

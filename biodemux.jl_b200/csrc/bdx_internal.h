@@ -1,0 +1,87 @@
+// bdx_internal.h -- device-visible parameter blocks shared by the kernels and the
+// C-ABI host code of libbdx.  Not installed; include/bdx.h is the public surface.
+#pragma once
+
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "../../include/bdx.h"
+
+namespace bdx {
+
+constexpr int kMaxBarcodeLen = 256;   // literal kernel DP workspace bound
+constexpr int kMaxFilterWords = 2;    // bit-parallel filter: barcodes up to 64 nt
+constexpr int kCandMax = 8;           // candidate slots per read and pass
+constexpr int kCandOverflow = 255;    // cand_cnt value: scan every barcode
+constexpr int kInf = 1 << 29;         // INF_INT stand-in for int32 cells (classification.jl:7)
+constexpr int kMaxCost = 1 << 20;
+
+// pass-state codes stored in PassOut.bc when no barcode index applies
+constexpr int kBcUnknown = 0;     // :unknown   (classification.jl:806, :821)
+constexpr int kBcAmbiguous = -1;  // :ambiguous (classification.jl:823)
+constexpr int kBcPending = -2;    // filter kernel left candidates for the literal kernel
+constexpr int kBcNotRun = -3;     // pass 2 skipped because pass 1 did not match
+
+// DynamicRange with offsets narrowed to int32 (validated at config creation)
+struct DevRange {
+    int start_off, start_from_end, end_off, end_from_end;
+};
+
+struct DevSet {
+    int n_bc;
+    int n_bc_pad;     // n_bc rounded up to a multiple of 32
+    int max_m;
+    int trim_side;    // 0, 3, 5
+    int words;        // 32-bit words per barcode in the filter tables; 0 = no filter for this set
+    int n_classes;    // byte classes incl. class 0 = "byte absent from every barcode"
+    int pad0, pad1;
+    DevRange rs, bs, be;          // ref_search_range, barcode_start_range, barcode_end_range
+    const uint8_t *bc_bytes;      // concatenated barcodes
+    const int *bc_off;            // n_bc + 1
+    const int *norm;              // normalisation length per barcode (classification.jl:460, :476)
+    const uint32_t *peq;          // [words][n_classes][n_bc_pad], barcode rows top-aligned
+    const int *filt_allowed;      // [n_bc_pad] unit-cost candidate threshold, -1 = padding
+    const int *allowed0;          // [n_bc_pad] floor(max_error_rate * norm) at the initial threshold
+    const uint8_t *class_of;      // [256] byte -> class
+};
+
+struct DevParams {
+    double max_error_rate, min_delta;
+    int match, mismatch, indel, nindel, has_n;
+    int algo, is_dual, want_stats;
+    int filter_ok;    // costs allow the unit-cost filter to be a superset
+    int unit_costs;   // match 0, mismatch 1, indel 1 (and nindel 1): filter distance is the score
+    int pad0, pad1;
+    DevSet set[2];
+};
+
+// per read and pass
+struct PassOut {
+    int bc;     // > 0 matched barcode (1-based) or one of kBc*
+    int dist;   // integer score numerator
+    int start, end;
+};
+
+struct StatsDev {
+    unsigned long long *buf;  // layout: bdx_stats_layout
+    bdx_stats_layout lay;
+};
+
+struct Scratch {
+    PassOut *pass[2];
+    uint16_t *cand;       // [n][kCandMax]
+    uint8_t *cand_cnt;    // [n]
+};
+
+// ---- launch wrappers (kernels.cu / filter.cu) ----
+cudaError_t launch_literal(const DevParams &P, int pass, int from_filter, const uint8_t *seq,
+                           const int *off, int n, const Scratch &sc, cudaStream_t st);
+cudaError_t launch_filter(const DevParams &P, int pass, const uint8_t *seq, const int *off, int n,
+                          const Scratch &sc, int sm_count, cudaStream_t st);
+cudaError_t launch_finalize(const DevParams &P, const int *off, int n, const Scratch &sc,
+                            bdx_result *res, bdx_pass_detail *det, StatsDev stats, cudaStream_t st);
+cudaError_t launch_synth(const DevParams &P, const bdx_synth_spec &spec, int n, uint8_t *seq, int *off,
+                         cudaStream_t st);
+cudaError_t run_int_alu_peak(int device, double *ops_per_second);
+
+}  // namespace bdx

@@ -1,0 +1,330 @@
+// filter.cu -- bit-parallel semi-global kernel (the hot kernel of the :semiglobal path).
+//
+// One warp per read, one lane per barcode: every lane advances a Myers/Hyyro
+// bit-vector column automaton (unit costs, free start and end in the read) for
+// its barcode over the read's search range, G independent barcodes per lane for
+// ILP.  The barcode match tables (Peq) live in shared memory, transposed so that
+// a warp's 32 lanes read 32 consecutive words; the read is streamed once per warp,
+// translated to table offsets and broadcast from shared memory.
+//
+// Barcode rows are TOP-ALIGNED in the W*32-bit vector (row m = the MSB).  The
+// unused low bits are "phantom" rows that match every byte and start with a zero
+// vertical delta, which keeps them at distance 0 forever, i.e. they are the free
+// row 0 of the reference DP (classification.jl:215, :288-295).  With row m in
+// the MSB the +-1 update of D[m][j] is the carry-out of the shifts Ph+Ph / Mh+Mh
+// (add.cc / addc / subc), so a column costs 13 integer instructions per word.
+//
+// What the kernel produces per read (DESIGN.md "filter + literal split"):
+//   * d_b = min_j D_unit[m_b][j]  for every barcode -- a lower bound of the
+//     reference's weighted distance whenever the costs are "benign", so
+//     {b : d_b <= floor(allowed_b / min_cost)} is a superset of the barcodes the
+//     reference can accept under ANY running threshold (classification.jl:661);
+//   * in the exact regime (unit costs, no start/end constraint, score-only) d_b is
+//     the reference's distance itself and the running-threshold selection
+//     (classification.jl:632-713) is replayed in-warp over the candidates;
+//   * otherwise the candidates are queued for the literal kernel.
+#include <math_constants.h>
+
+#include "bdx_internal.h"
+#include "literal.cuh"
+
+namespace bdx {
+
+constexpr int kFilterWarps = 4;
+constexpr int kTile = 256;  // columns staged per pass over the read
+
+template <int W>
+struct BV {
+    uint32_t w[W];
+};
+
+// One column of the automaton for one barcode.  Eq: match mask of this read byte.
+__device__ __forceinline__ void myers_col(const BV<1> &Eq, BV<1> &Pv, BV<1> &Mv, int &score)
+{
+    const uint32_t eq = Eq.w[0], pv = Pv.w[0], mv = Mv.w[0];
+    const uint32_t xv = eq | mv;
+    const uint32_t xh = ((((eq & pv) + pv) ^ pv) | eq);
+    const uint32_t ph = mv | ~(xh | pv);
+    const uint32_t mh = pv & xh;
+    uint32_t phs, mhs;
+    asm("{\n\t"
+        "add.cc.u32 %0, %3, %3;\n\t"   // Ph << 1, carry = horizontal delta +1 at row m
+        "addc.u32 %2, %2, 0;\n\t"
+        "add.cc.u32 %1, %4, %4;\n\t"   // Mh << 1, carry = horizontal delta -1 at row m
+        "subc.u32 %2, %2, 0;\n\t"
+        "}"
+        : "=&r"(phs), "=r"(mhs), "+r"(score)
+        : "r"(ph), "r"(mh));
+    Pv.w[0] = mhs | ~(xv | phs);
+    Mv.w[0] = phs & xv;
+}
+
+__device__ __forceinline__ void myers_col(const BV<2> &Eq, BV<2> &Pv, BV<2> &Mv, int &score)
+{
+    const uint32_t eq0 = Eq.w[0], eq1 = Eq.w[1], pv0 = Pv.w[0], pv1 = Pv.w[1], mv0 = Mv.w[0], mv1 = Mv.w[1];
+    const uint32_t xv0 = eq0 | mv0, xv1 = eq1 | mv1;
+    uint32_t t0, t1;
+    asm("{\n\t"
+        "add.cc.u32 %0, %2, %3;\n\t"
+        "addc.u32 %1, %4, %5;\n\t"
+        "}"
+        : "=&r"(t0), "=r"(t1)
+        : "r"(eq0 & pv0), "r"(pv0), "r"(eq1 & pv1), "r"(pv1));
+    const uint32_t xh0 = (t0 ^ pv0) | eq0, xh1 = (t1 ^ pv1) | eq1;
+    const uint32_t ph0 = mv0 | ~(xh0 | pv0), ph1 = mv1 | ~(xh1 | pv1);
+    const uint32_t mh0 = pv0 & xh0, mh1 = pv1 & xh1;
+    uint32_t phs0, phs1, mhs0, mhs1;
+    asm("{\n\t"
+        "add.cc.u32 %0, %5, %5;\n\t"
+        "addc.cc.u32 %1, %6, %6;\n\t"
+        "addc.u32 %4, %4, 0;\n\t"
+        "add.cc.u32 %2, %7, %7;\n\t"
+        "addc.cc.u32 %3, %8, %8;\n\t"
+        "subc.u32 %4, %4, 0;\n\t"
+        "}"
+        : "=&r"(phs0), "=&r"(phs1), "=&r"(mhs0), "=r"(mhs1), "+r"(score)
+        : "r"(ph0), "r"(ph1), "r"(mh0), "r"(mh1));
+    Pv.w[0] = mhs0 | ~(xv0 | phs0);
+    Pv.w[1] = mhs1 | ~(xv1 | phs1);
+    Mv.w[0] = phs0 & xv0;
+    Mv.w[1] = phs1 & xv1;
+}
+
+template <int W>
+__device__ __forceinline__ void init_rows(int m, BV<W> &Pv, BV<W> &Mv)
+{
+    // vertical delta +1 on the m real rows (D[i][start-1] = i, classification.jl:278-279
+    // with indel = 1), 0 on the phantom rows below them
+    if (W == 1) {
+        Pv.w[0] = m <= 0 ? 0u : (m >= 32 ? 0xFFFFFFFFu : (0xFFFFFFFFu << (32 - m)));
+    } else {
+        if (m <= 32) {
+            Pv.w[1] = m <= 0 ? 0u : (m == 32 ? 0xFFFFFFFFu : (0xFFFFFFFFu << (32 - m)));
+            Pv.w[0] = 0u;
+        } else {
+            Pv.w[1] = 0xFFFFFFFFu;
+            Pv.w[0] = m >= 64 ? 0xFFFFFFFFu : (0xFFFFFFFFu << (64 - m));
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < W; k++) Mv.w[k] = 0u;
+}
+
+// Shared memory carve-up (dynamic):
+//   uint32 peq[W][n_classes][n_bc_pad] | uint32 stage[kFilterWarps][kTile] |
+//   int16 fa[n_bc_pad] | uint8 len[n_bc_pad] | uint8 class_of[256]
+template <int W, int G>
+__global__ void __launch_bounds__(kFilterWarps * 32)
+k_filter(const __grid_constant__ DevParams P, const int pass, const uint8_t *__restrict__ seq,
+         const int *__restrict__ off, const int n_reads, PassOut *__restrict__ out,
+         const PassOut *__restrict__ prev_pass, uint16_t *__restrict__ cand,
+         uint8_t *__restrict__ cand_cnt)
+{
+    extern __shared__ __align__(16) uint32_t smem[];
+    const DevSet &S = P.set[pass];
+    const int n_pad = S.n_bc_pad;
+    const int plane = S.n_classes * n_pad;          // words per bit-vector word plane
+    uint32_t *peq_s = smem;
+    uint32_t *stage_all = peq_s + W * plane;
+    int16_t *fa_s = reinterpret_cast<int16_t *>(stage_all + kFilterWarps * kTile);
+    uint8_t *len_s = reinterpret_cast<uint8_t *>(fa_s + n_pad);
+    uint8_t *class_s = len_s + n_pad;
+
+    for (int k = threadIdx.x; k < W * plane; k += blockDim.x) peq_s[k] = S.peq[k];
+    for (int k = threadIdx.x; k < n_pad; k += blockDim.x) {
+        fa_s[k] = (int16_t)max(-1, min(S.filt_allowed[k], 32767));
+        len_s[k] = (uint8_t)(k < S.n_bc ? S.bc_off[k + 1] - S.bc_off[k] : 0);
+    }
+    for (int k = threadIdx.x; k < 256; k += blockDim.x) class_s[k] = S.class_of[k];
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    uint32_t *stage = stage_all + warp * kTile;
+    const int warps_total = gridDim.x * kFilterWarps;
+    const bool with_delta = P.min_delta != 0.0;
+    const bool need_tb = S.trim_side != 0 || P.want_stats;
+    const uint32_t row_bytes = (uint32_t)n_pad * 4u;
+
+    for (int read = blockIdx.x * kFilterWarps + warp; read < n_reads; read += warps_total) {
+        if (pass == 1 && prev_pass[read].bc <= 0) {             // classification.jl:879-888
+            if (lane == 0) out[read] = PassOut{kBcNotRun, 0, -1, -1};
+            continue;
+        }
+        const int base = off[read];
+        const int n = off[read + 1] - base;
+        const uint8_t *r = seq + base;
+        const Geometry g = pass_geometry(S, n);
+        if (!g.valid) {                                          // :805-807
+            if (lane == 0) out[read] = PassOut{kBcUnknown, 0, -1, -1};
+            continue;
+        }
+        // exact regime: the filter distance IS the reference's distance
+        const bool fast = P.unit_costs && !need_tb && g.max_start_pos >= n && g.min_end_pos <= g.start_j;
+        const int first_tracked = max(g.start_j, g.min_end_pos);  // hits need j >= min_end_pos (:419)
+
+        BestState bs;
+        best_init(bs, P.max_error_rate);
+        int n_cand = 0;
+
+        for (int chunk = 0; chunk < n_pad; chunk += 32 * G) {
+            BV<W> Pv[G], Mv[G];
+            int score[G], best[G];
+#pragma unroll
+            for (int q = 0; q < G; q++) {
+                const int m = len_s[chunk + q * 32 + lane];
+                init_rows<W>(m, Pv[q], Mv[q]);
+                score[q] = m;
+                best[q] = kInf;
+            }
+            const uint32_t *lane_base = peq_s + chunk + lane;
+
+            for (int tile0 = g.start_j; tile0 <= g.end_j; tile0 += kTile) {
+                const int tlen = min(kTile, g.end_j - tile0 + 1);
+                __syncwarp();
+                for (int t = lane; t < tlen; t += 32)
+                    stage[t] = (uint32_t)class_s[r[tile0 - 1 + t]] * row_bytes;
+                __syncwarp();
+                // columns before min_end_pos advance the automaton but are not hits
+                int t = 0;
+                const int untracked = min(tlen, max(0, first_tracked - tile0));
+                for (; t < untracked; t++) {
+                    const uint32_t *p = reinterpret_cast<const uint32_t *>(
+                        reinterpret_cast<const char *>(lane_base) + stage[t]);
+#pragma unroll
+                    for (int q = 0; q < G; q++) {
+                        BV<W> Eq;
+#pragma unroll
+                        for (int k = 0; k < W; k++) Eq.w[k] = p[k * plane + q * 32];
+                        myers_col(Eq, Pv[q], Mv[q], score[q]);
+                    }
+                }
+                // align to 4 so that the staged offsets can be fetched as one 128-bit load
+                for (; t < tlen && (t & 3); t++) {
+                    const uint32_t *p = reinterpret_cast<const uint32_t *>(
+                        reinterpret_cast<const char *>(lane_base) + stage[t]);
+#pragma unroll
+                    for (int q = 0; q < G; q++) {
+                        BV<W> Eq;
+#pragma unroll
+                        for (int k = 0; k < W; k++) Eq.w[k] = p[k * plane + q * 32];
+                        myers_col(Eq, Pv[q], Mv[q], score[q]);
+                        best[q] = min(best[q], score[q]);
+                    }
+                }
+                for (; t + 4 <= tlen; t += 4) {
+                    const uint4 o4 = *reinterpret_cast<const uint4 *>(stage + t);
+                    const uint32_t o[4] = {o4.x, o4.y, o4.z, o4.w};
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        const uint32_t *p = reinterpret_cast<const uint32_t *>(
+                            reinterpret_cast<const char *>(lane_base) + o[u]);
+#pragma unroll
+                        for (int q = 0; q < G; q++) {
+                            BV<W> Eq;
+#pragma unroll
+                            for (int k = 0; k < W; k++) Eq.w[k] = p[k * plane + q * 32];
+                            myers_col(Eq, Pv[q], Mv[q], score[q]);
+                            best[q] = min(best[q], score[q]);
+                        }
+                    }
+                }
+                for (; t < tlen; t++) {
+                    const uint32_t *p = reinterpret_cast<const uint32_t *>(
+                        reinterpret_cast<const char *>(lane_base) + stage[t]);
+#pragma unroll
+                    for (int q = 0; q < G; q++) {
+                        BV<W> Eq;
+#pragma unroll
+                        for (int k = 0; k < W; k++) Eq.w[k] = p[k * plane + q * 32];
+                        myers_col(Eq, Pv[q], Mv[q], score[q]);
+                        best[q] = min(best[q], score[q]);
+                    }
+                }
+            }
+
+            // candidates of this chunk, visited in barcode (file) order
+#pragma unroll
+            for (int q = 0; q < G; q++) {
+                const int b0 = chunk + q * 32;
+                uint32_t mask = __ballot_sync(0xFFFFFFFFu, best[q] <= (int)fa_s[b0 + lane]);
+                while (mask) {
+                    const int l = __ffs(mask) - 1;
+                    mask &= mask - 1;
+                    const int b = b0 + l;
+                    if (fast) {
+                        const int d = __shfl_sync(0xFFFFFFFFu, best[q], l);
+                        const int norm = S.norm[b];
+                        const int allowed = allowed_from(bs.thr, norm);                      // :254
+                        const double score_b = d <= allowed ? __ddiv_rn((double)d, (double)norm) : CUDART_INF;
+                        best_consider(bs, with_delta, score_b, d, b + 1, -1, -1);
+                    } else {
+                        if (n_cand < kCandMax && lane == 0) cand[(size_t)read * kCandMax + n_cand] = (uint16_t)b;
+                        n_cand++;
+                    }
+                }
+            }
+        }
+
+        if (lane == 0) {
+            if (fast) {
+                out[read] = best_finish(bs, with_delta, P.min_delta);
+            } else if (n_cand == 0) {
+                out[read] = PassOut{kBcUnknown, 0, -1, -1};   // every barcode returns Inf (:820-821)
+            } else {
+                cand_cnt[read] = (uint8_t)(n_cand > kCandMax ? kCandOverflow : n_cand);
+                out[read] = PassOut{kBcPending, 0, -1, -1};
+            }
+        }
+    }
+}
+
+static size_t filter_smem_bytes(const DevSet &S)
+{
+    const size_t n_pad = (size_t)S.n_bc_pad;
+    size_t b = (size_t)S.words * S.n_classes * n_pad * 4;
+    b += (size_t)kFilterWarps * kTile * 4;
+    b += n_pad * 2 + n_pad + 256;
+    return (b + 15) & ~(size_t)15;
+}
+
+template <int W, int G>
+static cudaError_t launch_wg(const DevParams &P, int pass, const uint8_t *seq, const int *off, int n,
+                             const Scratch &sc, int sm_count, cudaStream_t st)
+{
+    const size_t smem = filter_smem_bytes(P.set[pass]);
+    auto kern = k_filter<W, G>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kFilterWarps * 32, smem);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) per_sm = 1;
+    // persistent grid: a whole number of resident blocks per SM, capped by the work
+    long long blocks = (long long)sm_count * per_sm;
+    const long long need = ((long long)n + kFilterWarps - 1) / kFilterWarps;
+    if (blocks > need) blocks = need;
+    if (blocks < 1) blocks = 1;
+    kern<<<(unsigned)blocks, kFilterWarps * 32, smem, st>>>(P, pass, seq, off, n, sc.pass[pass], sc.pass[0],
+                                                            sc.cand, sc.cand_cnt);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_filter(const DevParams &P, int pass, const uint8_t *seq, const int *off, int n,
+                          const Scratch &sc, int sm_count, cudaStream_t st)
+{
+    if (n <= 0) return cudaSuccess;
+    const DevSet &S = P.set[pass];
+    const int groups = S.n_bc_pad / 32;
+    const int G = groups >= 4 && groups % 4 == 0 ? 4 : (groups % 3 == 0 ? 3 : (groups % 2 == 0 ? 2 : 1));
+#define BDX_CASE(W_, G_) \
+    if (S.words == W_ && G == G_) return launch_wg<W_, G_>(P, pass, seq, off, n, sc, sm_count, st);
+    BDX_CASE(1, 1) BDX_CASE(1, 2) BDX_CASE(1, 3) BDX_CASE(1, 4)
+    BDX_CASE(2, 1) BDX_CASE(2, 2) BDX_CASE(2, 3) BDX_CASE(2, 4)
+#undef BDX_CASE
+    return cudaErrorInvalidValue;
+}
+
+size_t filter_smem_bytes_for(const DevSet &S) { return filter_smem_bytes(S); }
+
+}  // namespace bdx

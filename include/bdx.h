@@ -148,11 +148,27 @@ int bdx_submit(bdx_stream *s, const uint8_t *seq_bytes, const int32_t *offsets, 
 int bdx_acquire(bdx_stream *s, uint8_t **seq_bytes, int32_t **offsets);
 int bdx_commit(bdx_stream *s, int32_t n_reads, uint64_t tag);
 
+/* Like bdx_submit, but the caller guarantees that seq_bytes / offsets are page-locked
+ * (bdx_host_alloc or cudaHostRegister) and stay untouched until the batch has been
+ * fetched: the H2D copies read them directly, no staging memcpy. */
+int bdx_submit_pinned(bdx_stream *s, const uint8_t *seq_bytes, const int32_t *offsets, int32_t n_reads,
+                      uint64_t tag);
+void *bdx_host_alloc(size_t bytes);
+void bdx_host_free(void *p);
+
+/* Per-pass details are copied back only when enabled (default: on iff want_stats). */
+int bdx_stream_enable_details(bdx_stream *s, int on);
+
 /* Blocks until the oldest in-flight batch is done and copies its results out.
  * details may be NULL; otherwise it receives 2 * n_reads entries laid out
  * [pass][read] (pass 1 block then pass 2 block). */
 int bdx_fetch(bdx_stream *s, uint64_t *tag, int32_t *n_reads, bdx_result *results,
               bdx_pass_detail *details);
+
+/* Zero-copy variant of bdx_fetch: pointers into the stream's pinned result staging,
+ * valid until the slot is reused by the second-next submit / commit. */
+int bdx_fetch_view(bdx_stream *s, uint64_t *tag, int32_t *n_reads, const bdx_result **results,
+                   const bdx_pass_detail **details);
 
 /* submit + fetch of a single batch */
 int bdx_classify(bdx_stream *s, const uint8_t *seq_bytes, const int32_t *offsets, int32_t n_reads,
@@ -167,6 +183,12 @@ int bdx_classify_device(bdx_stream *s, const uint8_t *d_seq_bytes, const int32_t
 int bdx_stream_sync(bdx_stream *s);
 /* cudaStream_t of the compute stream, for callers that record their own events */
 void *bdx_stream_cuda_stream(bdx_stream *s);
+/* Per-kernel timing of the dominant (bit-parallel semiglobal) kernel: while enabled,
+ * every launch of it is bracketed by CUDA events on the compute stream;
+ * bdx_stream_profile_read syncs, returns the summed milliseconds and launch count
+ * since the last read, and clears the list. */
+int bdx_stream_profile(bdx_stream *s, int on);
+int bdx_stream_profile_read(bdx_stream *s, double *filter_ms, int32_t *n_launches);
 /* number of kernel launches this stream has issued so far */
 int64_t bdx_stream_launch_count(const bdx_stream *s);
 

@@ -1,0 +1,129 @@
+"""CPU-side checks of the C-ABI library and the host mirror (no compute calls)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import bdx_b200 as bdx
+from bdx_b200 import capi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    capi.build_library()
+    return capi.load_library()
+
+
+def test_library_exports_every_declared_symbol(lib):
+    header = open(os.path.join(ROOT, "include", "bdx.h")).read()
+    declared = set(re.findall(r"\b(bdx_[a-z_0-9]+)\s*\(", header))
+    assert declared == set(capi.EXPORTS), declared ^ set(capi.EXPORTS)
+    for name in declared:
+        assert hasattr(lib, name), f"libbdx.so does not export {name}"
+    assert lib.bdx_abi_version() == capi.ABI_VERSION
+
+
+def test_struct_layouts_match_header():
+    # sizes the C compiler gives include/bdx.h (LP64)
+    assert C.sizeof(capi.Range) == 24
+    assert C.sizeof(capi.BarcodeSet) == 8 + 3 * 8 + 3 * 24
+    assert C.sizeof(capi.Params) == 8 + 16 + 32 + 16 + 2 * C.sizeof(capi.BarcodeSet)
+    assert bdx.RESULT_DTYPE.itemsize == 20 and bdx.DETAIL_DTYPE.itemsize == 24
+
+
+def _cfg(**kw):
+    base = dict(bc_seqs=["ACGTACGTAC", "TTTTGGGGCC"], bc_lengths_no_N=[10, 10], ids=["a", "b"])
+    base.update(kw)
+    return bdx.DemuxConfig(**base)
+
+
+def test_config_create_and_stats_layout(lib):
+    c = capi.Config(_cfg(summary=True))
+    L = c.layout
+    assert (L.b1, L.b2) == (2, 0)
+    assert L.dist_bins == 3            # floor(0.2 * 10) + 1
+    assert L.pos_bias == 10 and L.len_bins == 22
+    assert L.sample_off == 4 and L.pos_off[0] == 4 + 3
+    assert L.total_len == L.dist_off[1] + L.dist_bins
+    c.close()
+
+
+@pytest.mark.parametrize("kw,msg", [
+    (dict(trim_side=4), "trim_side"),
+    (dict(bc_seqs=["ACGT", ""], bc_lengths_no_N=[4, 0]), "empty barcode"),
+    (dict(indel=0), "zero gap cost"),
+    (dict(mismatch=1 << 21), "cost magnitude"),
+    (dict(bc_seqs=["A" * 300, "C"], bc_lengths_no_N=[300, 1]), "longer than 256"),
+])
+def test_config_validation_errors(lib, kw, msg):
+    with pytest.raises(capi.BdxError) as ei:
+        capi.Config(_cfg(**kw))
+    assert ei.value.code == capi.BDX_ERR_INVALID and msg in str(ei.value)
+
+
+def test_no_cpu_fallback(lib, refdata, tmp_path):
+    if lib.bdx_device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    c = capi.Config(_cfg())
+    with pytest.raises(capi.BdxError) as ei:
+        capi.Stream(c)
+    assert ei.value.code == capi.BDX_ERR_CUDA and "no CPU fallback" in str(ei.value)
+    with pytest.raises(capi.BdxError):
+        fq = os.path.join(refdata, "FASTQ_files", "demo1_R1", "demo-001_R1.fastq")
+        bdx.execute_demultiplexing(fq, os.path.join(refdata, "reference_files", "demo1.tsv"), str(tmp_path / "o"))
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "biodemux.jl_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".jl", "Makefile")):
+                text = open(os.path.join(dirpath, f), errors="replace").read()
+                assert "liboracle" not in text and "bdx_oracle" not in text and "import orc" not in text, f
+
+
+def test_barcode_table_loader(refdata):
+    seqs, lens, ids = bdx.preprocess_bc_file(os.path.join(refdata, "reference_files", "demo1.tsv"), False, False)
+    assert len(seqs) == 24 and all(len(s) == 24 for s in seqs) and lens == [24] * 24
+    assert ids[0] == "barcode_001" and seqs[0] == "TGACAGGTAACTACTGACCGTCCT"
+    s2, _, _ = bdx.preprocess_bc_file(os.path.join(refdata, "reference_files", "demo2.csv"), True, True)
+    comp = {"A": "T", "T": "A", "G": "C", "C": "G"}
+    full, ann = "TGGATGGGAGAGATCGACCTGGTCCCCCC", "XXXBBBBBBBBBBBBBBBBBBBBBBBBXX"   # demo2.csv row 1
+    kept = "".join(c for c, a in zip(full, ann) if a == "B")
+    assert s2[0] == "".join(comp[c] for c in kept)[::-1]
+
+
+def test_fasta_loader_and_filenames(tmp_path):
+    p = tmp_path / "bc.fasta"
+    p.write_text(">BC1 some description\nANNC\n>BC2\nuuTT\n")
+    seqs, lens, ids = bdx.preprocess_bc_file(str(p), False, False)
+    assert (seqs, lens, ids) == (["ANNC", "TTTT"], [2, 4], ["BC1", "BC2"])
+    cfg = bdx.DemuxConfig(bc_seqs=seqs, bc_lengths_no_N=lens, ids=ids, gzip_output=True)
+    assert bdx.output_filename(cfg, bdx.MATCH, 2, 0) == "BC2.fastq.gz"
+    assert bdx.output_filename(cfg, bdx.UNKNOWN, 0, 0) == "unknown.fastq.gz"
+    assert bdx.output_filename(cfg, bdx.AMBIGUOUS, 0, 0) == "ambiguous_classification.fastq.gz"
+    bad = tmp_path / "bad.csv"
+    bad.write_text("ID,Full_seq,Full_annotation\nx,ACGT,BBB\n")
+    with pytest.raises(ValueError, match="Length mismatch"):
+        bdx.preprocess_bc_file(str(bad), False, False)
+
+
+def test_build_config_validation(refdata):
+    bc = os.path.join(refdata, "reference_files", "demo1.tsv")
+    with pytest.raises(ValueError, match="trim_side must be 3 or 5"):
+        import hostref
+        hostref.build_cfg(bc, ["x.fastq"], trim_side=4)
+    import hostref
+    cfg = hostref.build_cfg(bc, ["x.fastq.gz"])
+    assert cfg.gzip_output is True          # core.jl:316
+    with pytest.raises(ValueError, match="Invalid range format"):
+        hostref.build_cfg(bc, ["x.fastq"], ref_search_range="1-10")
+
+
+def test_stats_roundtrip_helpers():
+    from bdx_b200.stats import julia_round2
+    assert julia_round2(1 / 3) == 0.33 and julia_round2(0.125) == 0.12 and julia_round2(1 / 6) == 0.17

@@ -1,0 +1,211 @@
+"""GPU parity tests (run on the B200 box): the CUDA path, called through the C ABI,
+against the oracle on the same seeded inputs -- bit-exact on every output field."""
+import os
+
+import numpy as np
+import pytest
+
+import bdx_b200 as bdx
+import hostref
+import synth
+from gpu_common import compare, run_cuda
+from bdx_b200 import capi
+
+pytestmark = pytest.mark.gpu
+R = bdx.parse_dynamic_range
+
+
+def _cfg(bcs, **kw):
+    lens = [sum(1 for c in b if c != "N") for b in bcs]
+    return bdx.DemuxConfig(bc_seqs=bcs, bc_lengths_no_N=lens, ids=[f"bc{i}" for i in range(len(bcs))], **kw)
+
+
+def _dual(bcs1, bcs2, **kw):
+    c = _cfg(bcs1, **kw)
+    c.is_dual = True
+    c.bc_seqs2 = bcs2
+    c.bc_lengths_no_N2 = [sum(1 for ch in b if ch != "N") for b in bcs2]
+    c.ids2 = [f"x{i}" for i in range(len(bcs2))]
+    return c
+
+
+@pytest.mark.parametrize("idx", [0, 1, 2])
+def test_golden_files_through_cuda(refdata, tmp_path, idx):
+    """Config 1: the reference's fixtures -> byte-identical output files via the CUDA path."""
+    case = hostref.demo_cases(refdata)[idx]
+
+    engines = []
+
+    def make(cfg):
+        for e in engines:
+            e.close()
+        engines.clear()
+        engines.append(capi.Engine(cfg, max_reads=4000))
+        return engines[0].classify_reads
+
+    assert hostref.run_case(case, str(tmp_path / "out"), make) == {0: 24, 1: 24, 2: 76}[idx]
+    for e in engines:
+        e.close()
+
+
+def test_unit_vectors_through_cuda():
+    cfg = _cfg(["TTTTT"], trim_side=3)
+    res, _ = compare(cfg, [b"AAAAATTTTTCCCCC"])
+    assert (res["keep_start"][0], res["keep_end"][0]) == (1, 5)
+    cfg = _cfg(["TTTTT"], trim_side=5)
+    res, _ = compare(cfg, [b"AAAAATTTTTCCCCC"])
+    assert (res["keep_start"][0], res["keep_end"][0]) == (11, 15)
+    cfg = _dual(["TTTTT"], ["GGGGG"], trim_side=5, trim_side2=3)
+    res, _ = compare(cfg, [b"AAAAATTTTTCCCCCGGGGGTTTTT"])
+    assert tuple(res[0]) == (0, 1, 1, 11, 15)
+    cfg = _cfg(["ANNC", "TTTT"], max_error_rate=0.6, nindel=1)
+    res, _ = compare(cfg, [b"ATTC", b"TTTT", b"ATTG", b"GGGG"])
+    assert list(res["bc1"]) == [1, 2, 1, 0]
+    cfg = _cfg(["GGACGT"], max_error_rate=0.34, trim_side=3)   # start label <= 0
+    res, _ = compare(cfg, [b"ACGTTTTT"])
+    assert tuple(res[0]) == (0, 1, 0, 1, 0)
+    bcs = ["CGCA", "TAAGGTTTTTT", "CAAACCG", "CGCAC", "TAGAT", "TCGA"]  # order dependence
+    cfg = _cfg(bcs, max_error_rate=0.5, mismatch=1, indel=2, ref_search_range=R("2:17"),
+               barcode_start_range=R("1:7"), barcode_end_range=R("9:end"))
+    res, _ = compare(cfg, [b"CCGAGTTTCCGACGTGG"])
+    assert res["bc1"][0] == 4
+
+
+def test_edge_cases():
+    cfg = _cfg(["ACGTAC", "TTGGCCAA"])
+    reads = [b"", b"A", b"ACGTA", b"ACGTAC", b"N" * 20, b"acgtacacgtac", b"TTGGCCAA" * 3, b"ACGTAC" + b"G" * 300]
+    for algo in ("semiglobal", "hamming", "exact"):
+        cfg.matching_algorithm = algo
+        compare(cfg, reads, label=algo)
+        compare(cfg, [], label=algo + "-empty")
+    cfg.matching_algorithm = "semiglobal"
+    # degenerate ranges
+    for rs, bs, be in (("10:5", "1:end", "1:end"), ("1:end", "end+3:end", "1:end"), ("1:end", "1:end", "end+1:end"),
+                       ("end-3:end", "1:2", "1:end"), ("1:3", "1:end", "end:end")):
+        c = _cfg(["ACGTAC", "TTGGCCAA"], ref_search_range=R(rs), barcode_start_range=R(bs), barcode_end_range=R(be),
+                 trim_side=3)
+        compare(c, reads, label=f"{rs}|{bs}|{be}")
+
+
+CONFIGS = {
+    "default96": dict(n_bc=96, m=(24, 24)),
+    "delta": dict(n_bc=96, m=(24, 24), min_delta=0.1),
+    "weighted": dict(n_bc=48, m=(24, 24), max_error_rate=0.25, min_delta=0.15, mismatch=1, indel=2),
+    "mismatch3": dict(n_bc=40, m=(16, 28), max_error_rate=0.3, mismatch=3, indel=1),
+    "match1": dict(n_bc=20, m=(12, 20), max_error_rate=0.4, match=1, mismatch=2, indel=2),
+    "negmatch": dict(n_bc=20, m=(12, 20), max_error_rate=0.3, match=-1, mismatch=2, indel=2),
+    "varlen": dict(n_bc=100, m=(8, 32), max_error_rate=0.22),
+    "long": dict(n_bc=33, m=(33, 64), max_error_rate=0.15, min_delta=0.05),
+    "verylong": dict(n_bc=5, m=(65, 120), max_error_rate=0.1),
+    "nindel": dict(n_bc=64, m=(20, 26), nindel=1, n_frac=0.15, max_error_rate=0.3),
+    "nindel2": dict(n_bc=30, m=(20, 26), nindel=2, indel=1, n_frac=0.15, max_error_rate=0.3),
+    "nindel_lt": dict(n_bc=30, m=(10, 16), nindel=1, indel=2, n_frac=0.2, max_error_rate=0.5),
+    "trim3": dict(n_bc=96, m=(24, 24), trim_side=3),
+    "trim5": dict(n_bc=96, m=(24, 24), trim_side=5, min_delta=0.05),
+    "stats": dict(n_bc=50, m=(18, 24), want_stats=True),
+    "startrange": dict(n_bc=96, m=(16, 28), ref_search_range=R("1:40"), barcode_start_range=R("1:6"), min_delta=0.1,
+                       start_hi=5, max_error_rate=0.3),
+    "endrange": dict(n_bc=64, m=(16, 28), ref_search_range=R("end-39:end"), barcode_end_range=R("end-5:end"),
+                     trim_side=3),
+    "subrange": dict(n_bc=64, m=(20, 24), ref_search_range=R("5:60"), barcode_start_range=R("3:30"),
+                     barcode_end_range=R("20:end-10"), trim_side=5, want_stats=True),
+    "iupac": dict(n_bc=24, m=(20, 24), alphabet=b"ACGTRYKM", max_error_rate=0.3),
+    "big1536": dict(n_bc=1536, m=(24, 24), n_reads=600),
+    "hamming": dict(n_bc=96, m=(24, 24), matching_algorithm="hamming", n_frac=0.05),
+    "hamming_trim3": dict(n_bc=40, m=(6, 12), matching_algorithm="hamming", trim_side=3, max_error_rate=0.34,
+                          min_delta=0.1, barcode_start_range=R("1:40"), barcode_end_range=R("10:end")),
+    "exact": dict(n_bc=96, m=(24, 24), matching_algorithm="exact"),
+    "exact_trim3": dict(n_bc=30, m=(4, 8), matching_algorithm="exact", trim_side=3, min_delta=0.5,
+                        barcode_start_range=R("1:60"), barcode_end_range=R("8:end")),
+}
+
+
+@pytest.mark.parametrize("name", sorted(CONFIGS))
+def test_random_parity(name):
+    spec = dict(CONFIGS[name])
+    rng = np.random.default_rng(abs(hash(name)) % (2 ** 31) if False else sum(map(ord, name)))
+    n_bc, (m_lo, m_hi) = spec.pop("n_bc"), spec.pop("m")
+    n_reads = spec.pop("n_reads", 3000)
+    want_stats = spec.pop("want_stats", False)
+    start_hi = spec.pop("start_hi", None)
+    bcs = synth.random_barcodes(rng, n_bc, m_lo, m_hi, alphabet=spec.pop("alphabet", b"ACGT"),
+                                n_frac=spec.pop("n_frac", 0.0))
+    cfg = _cfg(bcs, **spec)
+    reads = synth.random_reads(rng, n_reads, bcs, min_len=60, max_len=160, start_hi=start_hi, lower_prob=0.02)
+    reads += [b"", b"ACG"]
+    compare(cfg, reads, want_stats=want_stats, label=name)
+
+
+DUAL = {
+    "dual_default": dict(),
+    "dual_trim": dict(trim_side=5, trim_side2=3, min_delta=0.1),
+    "dual_ranges": dict(ref_search_range=R("1:40"), barcode_start_range=R("1:6"),
+                        ref_search_range2=R("end-39:end"), barcode_end_range2=R("end-5:end"), min_delta=0.1,
+                        max_error_rate=0.25),
+    "dual_stats": dict(want_stats=True, trim_side2=5),
+    "dual_hamming": dict(matching_algorithm="hamming", trim_side=5),
+    "dual_adapter": dict(ref_search_range=R("1:32"), trim_side=5, trim_side2=3, adapter=True),
+}
+
+
+@pytest.mark.parametrize("name", sorted(DUAL))
+def test_random_parity_dual(name):
+    spec = dict(DUAL[name])
+    rng = np.random.default_rng(sum(map(ord, name)))
+    want_stats = spec.pop("want_stats", False)
+    adapter = spec.pop("adapter", False)
+    b1 = synth.random_barcodes(rng, 96 if adapter else 60, 16, 28)
+    b2 = ["AGATCGGAAGAGCACACGTCTGAACTCCAGTCA"] if adapter else synth.random_barcodes(rng, 70, 16, 28)
+    cfg = _dual(b1, b2, **spec)
+    reads = synth.random_reads(rng, 3000, b1, barcodes2=b2, min_len=100, max_len=150, start_hi=4,
+                               at_end2=not adapter)
+    compare(cfg, reads, want_stats=want_stats, label=name)
+
+
+def test_filter_matches_literal_only(monkeypatch):
+    """The bit-parallel filter path and the literal-only path must agree read for read."""
+    rng = np.random.default_rng(7)
+    bcs = synth.random_barcodes(rng, 96, 24)
+    reads = synth.random_reads(rng, 4000, bcs, min_len=150)
+    for kw in (dict(), dict(min_delta=0.1), dict(trim_side=3), dict(mismatch=2, indel=3, max_error_rate=0.3)):
+        cfg = _cfg(bcs, **kw)
+        a, _, _, _ = run_cuda(cfg, reads)
+        monkeypatch.setenv("BDX_DISABLE_FILTER", "1")
+        b, _, _, _ = run_cuda(cfg, reads)
+        monkeypatch.delenv("BDX_DISABLE_FILTER")
+        assert (a == b).all(), kw
+
+
+def test_streaming_double_buffer_and_errors():
+    rng = np.random.default_rng(11)
+    bcs = synth.random_barcodes(rng, 96, 24)
+    cfg = _cfg(bcs)
+    batches = [synth.random_reads(rng, 500 + 37 * i, bcs, min_len=150) for i in range(5)]
+    import orc
+    o = orc.Oracle(cfg)
+    with capi.Engine(cfg, max_reads=1000, max_bytes=1000 * 160) as eng:
+        st = eng.stream
+        packed = [bdx.pack_reads(b) for b in batches]
+        got = {}
+        st.submit(packed[0][0], packed[0][1], tag=100)
+        for i in range(1, 5):
+            st.submit(packed[i][0], packed[i][1], tag=100 + i)
+            tag, res = st.fetch()
+            got[tag] = res
+        with pytest.raises(capi.BdxError):          # third batch in flight is refused
+            st.submit(packed[0][0], packed[0][1]); st.submit(packed[0][0], packed[0][1])
+        while True:
+            try:
+                tag, res = st.fetch()
+                got.setdefault(tag, res)
+            except capi.BdxError:
+                break
+        for i in range(5):
+            ref = o.classify_reads(batches[i])
+            for f in ("status", "bc1", "bc2", "keep_start", "keep_end"):
+                assert (got[100 + i][f] == ref[f]).all()
+        big = bdx.pack_reads(synth.random_reads(rng, 1001, bcs, min_len=10))
+        with pytest.raises(capi.BdxError) as ei:
+            st.submit(big[0], big[1])
+        assert ei.value.code == capi.BDX_ERR_TOO_LARGE
+        assert st.launch_count > 0

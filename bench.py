@@ -271,6 +271,16 @@ def run_ours(args):
     res = np.frombuffer(d_res.cpu().numpy().tobytes(), dtype=bdx.RESULT_DTYPE)
     matched = int((res["status"] == 0).sum())
 
+    if args.no_e2e:
+        if rank == 0:
+            filt_s = filt_ms * 1e-3 / max(filt_n, 1)
+            print(json.dumps({"value": value, "ms_per_step": ms_max / args.steps, "kernel_ms": filt_s * 1e3,
+                              "matched_fraction": matched / n, "peak_Tops": peak_ops.value / 1e12,
+                              "achieved_Tops": OPS_PER_READ * n / filt_s / 1e12, "clocks": clocks,
+                              "variant": os.environ.get("BDX_FILTER_VARIANT")}))
+        stream.close()
+        return
+
     # ---- e2e through the C ABI with host buffers ------------------------------------------
     B = args.e2e_batch
     nb = n // B
@@ -395,6 +405,7 @@ def main():
     ap.add_argument("--reads", type=int, default=10_000_000, help="reads per GPU (config 2: 10 M)")
     ap.add_argument("--e2e-batch", type=int, default=1_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="device-resident timing only (kernel experiments)")
     args = ap.parse_args()
     if args.reads % args.e2e_batch:
         args.e2e_batch = args.reads

@@ -218,6 +218,7 @@ extern "C" int bdx_config_create(const bdx_params *p, bdx_config **out)
     P.is_dual = p->is_dual ? 1 : 0;
     P.want_stats = p->want_stats ? 1 : 0;
     P.filter_ok = cfg->set[0].words > 0 && (!p->is_dual || cfg->set[1].words > 0);
+    P.two = 2;
     P.unit_costs = p->match == 0 && p->mismatch == 1 && p->indel == 1 && (!p->has_nindel || p->nindel == 1);
 
     // stats layout (classification.jl:736-758)

@@ -51,7 +51,8 @@ struct DevParams {
     int algo, is_dual, want_stats;
     int filter_ok;    // costs allow the unit-cost filter to be a superset
     int unit_costs;   // match 0, mismatch 1, indel 1 (and nindel 1): filter distance is the score
-    int pad0, pad1;
+    int two;          // the constant 2, opaque to ptxas (keeps IMAD.HI on the fma pipe, filter.cu)
+    int pad1;
     DevSet set[2];
 };
 

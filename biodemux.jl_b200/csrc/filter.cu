@@ -23,6 +23,7 @@
 //     the reference's distance itself and the running-threshold selection
 //     (classification.jl:632-713) is replayed in-warp over the candidates;
 //   * otherwise the candidates are queued for the literal kernel.
+#include <cstdlib>
 #include <math_constants.h>
 
 #include "bdx_internal.h"
@@ -38,8 +39,52 @@ struct BV {
     uint32_t w[W];
 };
 
+// ---- score update + shift of the horizontal delta vectors -------------------------------
+// D[m][j] - D[m][j-1] is +1 when the MSB of Ph is set, -1 when the MSB of Mh is set.
+// `mid` = score - msb(mh) is min(D[m][j-1], D[m][j]) (the score moves by at most one per
+// column), so taking the running minimum of `mid` at every SECOND column covers both.
+// Codings of "mid = score - msb(mh); score = mid + msb(ph); ph <<= 1; mh <<= 1",
+// selectable for measurement (BDX_FILTER_VARIANT); they differ in how the work splits
+// between the alu pipe (LOP3/IADD3/LEA) and the fma pipe (IMAD*):
+//   kPlain : plain C, the compiler picks (LEA.HI on the alu pipe)
+//   kCarry : add.cc ph+ph / addc, sub.cc 0x7fffffff-mh / subc (borrow = msb(mh))
+//   kMadHi : mad.hi.s32(mh, two, score) subtracts msb(mh) (the signed high half of 2*mh is
+//            -1 exactly when the MSB is set), mad.hi.u32(ph, two, mid) adds msb(ph); `two`
+//            is a kernel parameter (DevParams::two) so that ptxas cannot fold it into LEA.HI
+enum { kPlain = 0, kCarry = 1, kMadHi = 2 };
+
+template <int CODING>
+__device__ __forceinline__ void shift_score(uint32_t ph, uint32_t mh, uint32_t two, uint32_t &phs,
+                                            uint32_t &mhs, int &score, int &mid)
+{
+    if (CODING == kMadHi) {
+        asm("mad.hi.s32 %0, %1, %2, %3;" : "=r"(mid) : "r"(mh), "r"(two), "r"(score));
+        asm("mad.hi.u32 %0, %1, %2, %3;" : "=r"(score) : "r"(ph), "r"(two), "r"(mid));
+        phs = ph << 1;
+        mhs = mh << 1;
+    } else if (CODING == kCarry) {
+        uint32_t dummy;
+        asm("{\n\t"
+            "sub.cc.u32 %1, 0x7fffffff, %5;\n\t"
+            "subc.u32 %3, %2, 0;\n\t"
+            "add.cc.u32 %0, %4, %4;\n\t"
+            "addc.u32 %2, %3, 0;\n\t"
+            "}"
+            : "=&r"(phs), "=&r"(dummy), "+r"(score), "=&r"(mid)
+            : "r"(ph), "r"(mh));
+        mhs = mh << 1;
+    } else {
+        mid = score - (int)(mh >> 31);
+        score = mid + (int)(ph >> 31);
+        phs = ph << 1;
+        mhs = mh << 1;
+    }
+}
+
 // One column of the automaton for one barcode.  Eq: match mask of this read byte.
-__device__ __forceinline__ void myers_col(const BV<1> &Eq, BV<1> &Pv, BV<1> &Mv, int &score)
+template <int CODING>
+__device__ __forceinline__ void myers_col(const BV<1> &Eq, BV<1> &Pv, BV<1> &Mv, uint32_t two, int &score,
+                                          int &mid)
 {
     const uint32_t eq = Eq.w[0], pv = Pv.w[0], mv = Mv.w[0];
     const uint32_t xv = eq | mv;
@@ -47,19 +92,14 @@ __device__ __forceinline__ void myers_col(const BV<1> &Eq, BV<1> &Pv, BV<1> &Mv,
     const uint32_t ph = mv | ~(xh | pv);
     const uint32_t mh = pv & xh;
     uint32_t phs, mhs;
-    asm("{\n\t"
-        "add.cc.u32 %0, %3, %3;\n\t"   // Ph << 1, carry = horizontal delta +1 at row m
-        "addc.u32 %2, %2, 0;\n\t"
-        "add.cc.u32 %1, %4, %4;\n\t"   // Mh << 1, carry = horizontal delta -1 at row m
-        "subc.u32 %2, %2, 0;\n\t"
-        "}"
-        : "=&r"(phs), "=r"(mhs), "+r"(score)
-        : "r"(ph), "r"(mh));
+    shift_score<CODING>(ph, mh, two, phs, mhs, score, mid);
     Pv.w[0] = mhs | ~(xv | phs);
     Mv.w[0] = phs & xv;
 }
 
-__device__ __forceinline__ void myers_col(const BV<2> &Eq, BV<2> &Pv, BV<2> &Mv, int &score)
+template <int CODING>
+__device__ __forceinline__ void myers_col(const BV<2> &Eq, BV<2> &Pv, BV<2> &Mv, uint32_t two, int &score,
+                                          int &mid)
 {
     const uint32_t eq0 = Eq.w[0], eq1 = Eq.w[1], pv0 = Pv.w[0], pv1 = Pv.w[1], mv0 = Mv.w[0], mv1 = Mv.w[1];
     const uint32_t xv0 = eq0 | mv0, xv1 = eq1 | mv1;
@@ -73,17 +113,11 @@ __device__ __forceinline__ void myers_col(const BV<2> &Eq, BV<2> &Pv, BV<2> &Mv,
     const uint32_t xh0 = (t0 ^ pv0) | eq0, xh1 = (t1 ^ pv1) | eq1;
     const uint32_t ph0 = mv0 | ~(xh0 | pv0), ph1 = mv1 | ~(xh1 | pv1);
     const uint32_t mh0 = pv0 & xh0, mh1 = pv1 & xh1;
-    uint32_t phs0, phs1, mhs0, mhs1;
-    asm("{\n\t"
-        "add.cc.u32 %0, %5, %5;\n\t"
-        "addc.cc.u32 %1, %6, %6;\n\t"
-        "addc.u32 %4, %4, 0;\n\t"
-        "add.cc.u32 %2, %7, %7;\n\t"
-        "addc.cc.u32 %3, %8, %8;\n\t"
-        "subc.u32 %4, %4, 0;\n\t"
-        "}"
-        : "=&r"(phs0), "=&r"(phs1), "=&r"(mhs0), "=r"(mhs1), "+r"(score)
-        : "r"(ph0), "r"(ph1), "r"(mh0), "r"(mh1));
+    uint32_t phs1, mhs1;
+    shift_score<CODING>(ph1, mh1, two, phs1, mhs1, score, mid);   // row m = MSB of the high word
+    phs1 |= ph0 >> 31;
+    mhs1 |= mh0 >> 31;
+    const uint32_t phs0 = ph0 << 1, mhs0 = mh0 << 1;
     Pv.w[0] = mhs0 | ~(xv0 | phs0);
     Pv.w[1] = mhs1 | ~(xv1 | phs1);
     Mv.w[0] = phs0 & xv0;
@@ -110,10 +144,30 @@ __device__ __forceinline__ void init_rows(int m, BV<W> &Pv, BV<W> &Mv)
     for (int k = 0; k < W; k++) Mv.w[k] = 0u;
 }
 
+// One read column for the G barcodes of a lane.  TRACK: 0 = automaton only (column before
+// min_end_pos), 1 = best = min(best, D[m][j]), 2 = best = min(best, mid) which covers
+// columns j-1 and j at once.
+template <int W, int G, int CODING, int TRACK>
+__device__ __forceinline__ void column(const uint32_t *lane_base, uint32_t byte_off, int plane, uint32_t two,
+                                       BV<W> (&Pv)[G], BV<W> (&Mv)[G], int (&score)[G], int (&best)[G])
+{
+    const uint32_t *p = reinterpret_cast<const uint32_t *>(reinterpret_cast<const char *>(lane_base) + byte_off);
+#pragma unroll
+    for (int q = 0; q < G; q++) {
+        BV<W> Eq;
+#pragma unroll
+        for (int k = 0; k < W; k++) Eq.w[k] = p[k * plane + q * 32];
+        int mid;
+        myers_col<CODING>(Eq, Pv[q], Mv[q], two, score[q], mid);
+        if (TRACK == 1) best[q] = min(best[q], score[q]);
+        if (TRACK == 2) best[q] = min(best[q], mid);
+    }
+}
+
 // Shared memory carve-up (dynamic):
 //   uint32 peq[W][n_classes][n_bc_pad] | uint32 stage[kFilterWarps][kTile] |
 //   int16 fa[n_bc_pad] | uint8 len[n_bc_pad] | uint8 class_of[256]
-template <int W, int G>
+template <int W, int G, int CODING, bool PAIR>
 __global__ void __launch_bounds__(kFilterWarps * 32)
 k_filter(const __grid_constant__ DevParams P, const int pass, const uint8_t *__restrict__ seq,
          const int *__restrict__ off, const int n_reads, PassOut *__restrict__ out,
@@ -145,6 +199,7 @@ k_filter(const __grid_constant__ DevParams P, const int pass, const uint8_t *__r
     const bool with_delta = P.min_delta != 0.0;
     const bool need_tb = S.trim_side != 0 || P.want_stats;
     const uint32_t row_bytes = (uint32_t)n_pad * 4u;
+    const uint32_t two = (uint32_t)P.two;
 
     for (int read = blockIdx.x * kFilterWarps + warp; read < n_reads; read += warps_total) {
         if (pass == 1 && prev_pass[read].bc <= 0) {             // classification.jl:879-888
@@ -188,59 +243,27 @@ k_filter(const __grid_constant__ DevParams P, const int pass, const uint8_t *__r
                 // columns before min_end_pos advance the automaton but are not hits
                 int t = 0;
                 const int untracked = min(tlen, max(0, first_tracked - tile0));
-                for (; t < untracked; t++) {
-                    const uint32_t *p = reinterpret_cast<const uint32_t *>(
-                        reinterpret_cast<const char *>(lane_base) + stage[t]);
-#pragma unroll
-                    for (int q = 0; q < G; q++) {
-                        BV<W> Eq;
-#pragma unroll
-                        for (int k = 0; k < W; k++) Eq.w[k] = p[k * plane + q * 32];
-                        myers_col(Eq, Pv[q], Mv[q], score[q]);
-                    }
-                }
+                for (; t < untracked; t++)
+                    column<W, G, CODING, 0>(lane_base, stage[t], plane, two, Pv, Mv, score, best);
                 // align to 4 so that the staged offsets can be fetched as one 128-bit load
-                for (; t < tlen && (t & 3); t++) {
-                    const uint32_t *p = reinterpret_cast<const uint32_t *>(
-                        reinterpret_cast<const char *>(lane_base) + stage[t]);
-#pragma unroll
-                    for (int q = 0; q < G; q++) {
-                        BV<W> Eq;
-#pragma unroll
-                        for (int k = 0; k < W; k++) Eq.w[k] = p[k * plane + q * 32];
-                        myers_col(Eq, Pv[q], Mv[q], score[q]);
-                        best[q] = min(best[q], score[q]);
-                    }
-                }
+                for (; t < tlen && (t & 3); t++)
+                    column<W, G, CODING, 1>(lane_base, stage[t], plane, two, Pv, Mv, score, best);
                 for (; t + 4 <= tlen; t += 4) {
                     const uint4 o4 = *reinterpret_cast<const uint4 *>(stage + t);
-                    const uint32_t o[4] = {o4.x, o4.y, o4.z, o4.w};
-#pragma unroll
-                    for (int u = 0; u < 4; u++) {
-                        const uint32_t *p = reinterpret_cast<const uint32_t *>(
-                            reinterpret_cast<const char *>(lane_base) + o[u]);
-#pragma unroll
-                        for (int q = 0; q < G; q++) {
-                            BV<W> Eq;
-#pragma unroll
-                            for (int k = 0; k < W; k++) Eq.w[k] = p[k * plane + q * 32];
-                            myers_col(Eq, Pv[q], Mv[q], score[q]);
-                            best[q] = min(best[q], score[q]);
-                        }
+                    if (PAIR) {
+                        column<W, G, CODING, 0>(lane_base, o4.x, plane, two, Pv, Mv, score, best);
+                        column<W, G, CODING, 2>(lane_base, o4.y, plane, two, Pv, Mv, score, best);
+                        column<W, G, CODING, 0>(lane_base, o4.z, plane, two, Pv, Mv, score, best);
+                        column<W, G, CODING, 2>(lane_base, o4.w, plane, two, Pv, Mv, score, best);
+                    } else {
+                        column<W, G, CODING, 1>(lane_base, o4.x, plane, two, Pv, Mv, score, best);
+                        column<W, G, CODING, 1>(lane_base, o4.y, plane, two, Pv, Mv, score, best);
+                        column<W, G, CODING, 1>(lane_base, o4.z, plane, two, Pv, Mv, score, best);
+                        column<W, G, CODING, 1>(lane_base, o4.w, plane, two, Pv, Mv, score, best);
                     }
                 }
-                for (; t < tlen; t++) {
-                    const uint32_t *p = reinterpret_cast<const uint32_t *>(
-                        reinterpret_cast<const char *>(lane_base) + stage[t]);
-#pragma unroll
-                    for (int q = 0; q < G; q++) {
-                        BV<W> Eq;
-#pragma unroll
-                        for (int k = 0; k < W; k++) Eq.w[k] = p[k * plane + q * 32];
-                        myers_col(Eq, Pv[q], Mv[q], score[q]);
-                        best[q] = min(best[q], score[q]);
-                    }
-                }
+                for (; t < tlen; t++)
+                    column<W, G, CODING, 1>(lane_base, stage[t], plane, two, Pv, Mv, score, best);
             }
 
             // candidates of this chunk, visited in barcode (file) order
@@ -288,12 +311,12 @@ static size_t filter_smem_bytes(const DevSet &S)
     return (b + 15) & ~(size_t)15;
 }
 
-template <int W, int G>
-static cudaError_t launch_wg(const DevParams &P, int pass, const uint8_t *seq, const int *off, int n,
-                             const Scratch &sc, int sm_count, cudaStream_t st)
+template <int W, int G, int CODING, bool PAIR>
+static cudaError_t launch_wgv(const DevParams &P, int pass, const uint8_t *seq, const int *off, int n,
+                              const Scratch &sc, int sm_count, cudaStream_t st)
 {
     const size_t smem = filter_smem_bytes(P.set[pass]);
-    auto kern = k_filter<W, G>;
+    auto kern = k_filter<W, G, CODING, PAIR>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int per_sm = 0;
@@ -308,6 +331,36 @@ static cudaError_t launch_wg(const DevParams &P, int pass, const uint8_t *seq, c
     kern<<<(unsigned)blocks, kFilterWarps * 32, smem, st>>>(P, pass, seq, off, n, sc.pass[pass], sc.pass[0],
                                                             sc.cand, sc.cand_cnt);
     return cudaGetLastError();
+}
+
+// BDX_FILTER_VARIANT (measurement only): 0 plain, 1 plain+pair, 2 carry, 3 carry+pair,
+// 4 mad.hi, 5 mad.hi+pair.  Variants other than the default exist for one word per barcode.
+constexpr int kDefaultVariant = 1;
+static int filter_variant()
+{
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("BDX_FILTER_VARIANT");
+        v = (e && e[0] >= '0' && e[0] <= '5') ? e[0] - '0' : kDefaultVariant;
+    }
+    return v;
+}
+
+template <int W, int G>
+static cudaError_t launch_wg(const DevParams &P, int pass, const uint8_t *seq, const int *off, int n,
+                             const Scratch &sc, int sm_count, cudaStream_t st)
+{
+    if (W == 1) {
+        switch (filter_variant()) {
+        case 0: return launch_wgv<W, G, kPlain, false>(P, pass, seq, off, n, sc, sm_count, st);
+        case 2: return launch_wgv<W, G, kCarry, false>(P, pass, seq, off, n, sc, sm_count, st);
+        case 3: return launch_wgv<W, G, kCarry, true>(P, pass, seq, off, n, sc, sm_count, st);
+        case 4: return launch_wgv<W, G, kMadHi, false>(P, pass, seq, off, n, sc, sm_count, st);
+        case 5: return launch_wgv<W, G, kMadHi, true>(P, pass, seq, off, n, sc, sm_count, st);
+        default: break;
+        }
+    }
+    return launch_wgv<W, G, kPlain, true>(P, pass, seq, off, n, sc, sm_count, st);
 }
 
 cudaError_t launch_filter(const DevParams &P, int pass, const uint8_t *seq, const int *off, int n,

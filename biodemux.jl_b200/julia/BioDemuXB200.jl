@@ -1,0 +1,238 @@
+# BioDemuXB200.jl -- ccall shim that swaps BioDemuX.jl's CPU worker loop for libbdx.
+#
+# NOT EXECUTED IN THIS REPOSITORY'S CI: Julia is not installed in the build image, so
+# this file is delivered as the reference-side binding a BioDemuX maintainer would add
+# (see INTEGRATION.md).  The same call sequence is exercised from Python (ctypes) in
+# biodemux.jl_b200/capi.py and tests/test_gpu_parity.py.
+#
+# It replaces the body of `worker_task` (BioDemuX src/core.jl:226-279): for every Chunk it
+# packs the read-1 sequences, lets the GPU classify them and rebuilds exactly what the
+# CPU loop produced -- `filenames::Vector{String}` and `trim_ranges` -- so reader_task,
+# writer_task and generate_summary_report stay untouched.
+module BioDemuXB200
+
+using BioDemuX
+using BioDemuX: DemuxConfig, DemuxStats, DynamicRange, Chunk, ResultChunk
+
+const libbdx = get(ENV, "LIBBDX", joinpath(@__DIR__, "..", "csrc", "libbdx.so"))
+const BDX_ABI_VERSION = UInt32(1)
+
+# ---- struct mirrors of include/bdx.h (field order and widths must match) -----------------
+struct BdxRange            # bdx_range  <- DynamicRange (classification.jl:9-14)
+    start_offset::Int64
+    start_from_end::Int32
+    end_from_end::Int32
+    end_offset::Int64
+end
+BdxRange(r::DynamicRange) = BdxRange(r.start_offset, r.start_from_end, r.end_from_end, r.end_offset)
+
+struct BdxBarcodeSet       # bdx_barcode_set
+    n_barcodes::Int32
+    trim_side::Int32
+    bytes::Ptr{UInt8}
+    offsets::Ptr{Int32}
+    lengths_no_n::Ptr{Int32}
+    ref_search_range::BdxRange
+    barcode_start_range::BdxRange
+    barcode_end_range::BdxRange
+end
+
+struct BdxParams           # bdx_params <- DemuxConfig (classification.jl:16-58)
+    struct_size::UInt32
+    abi_version::UInt32
+    max_error_rate::Float64
+    min_delta::Float64
+    match::Int64
+    mismatch::Int64
+    indel::Int64
+    nindel::Int64
+    has_nindel::Int32
+    algorithm::Int32
+    is_dual::Int32
+    want_stats::Int32
+    set1::BdxBarcodeSet
+    set2::BdxBarcodeSet
+end
+
+struct BdxResult           # bdx_result
+    status::Int32
+    bc1::Int32
+    bc2::Int32
+    keep_start::Int32
+    keep_end::Int32
+end
+
+struct BdxStatsLayout      # bdx_stats_layout
+    total_len::Int64
+    sample_off::Int64
+    b1::Int32
+    b2::Int32
+    pos_bins::Int32
+    len_bins::Int32
+    dist_bins::Int32
+    pos_bias::Int32
+    pos_off::NTuple{2,Int64}
+    len_off::NTuple{2,Int64}
+    dist_off::NTuple{2,Int64}
+end
+
+bdx_error() = unsafe_string(ccall((:bdx_last_error, libbdx), Cstring, ()))
+check(rc) = rc == 0 ? nothing : error("libbdx: $(bdx_error()) (code $rc)")
+
+algorithm_code(s::Symbol) = s == :hamming ? Int32(1) : s == :exact ? Int32(2) : Int32(0)  # classification.jl:639-649
+
+# Keeps the Julia arrays the C structs point into alive.
+mutable struct GpuConfig
+    handle::Ptr{Cvoid}
+    config::DemuxConfig
+    keep::Vector{Any}
+end
+
+function pack_set(keep, seqs::Vector{String}, lens::Vector{Int}, rs, bs, be, trim)
+    bytes = Vector{UInt8}(join(seqs))
+    offsets = Int32[0; cumsum(ncodeunits.(seqs))]
+    lens32 = isempty(lens) ? Int32[0] : Int32.(lens)
+    push!(keep, bytes, offsets, lens32)
+    BdxBarcodeSet(length(seqs), isnothing(trim) ? 0 : trim, pointer(bytes), pointer(offsets), pointer(lens32),
+                  BdxRange(rs), BdxRange(bs), BdxRange(be))
+end
+
+function GpuConfig(c::DemuxConfig)
+    keep = Any[]
+    set1 = pack_set(keep, c.bc_seqs, c.bc_lengths_no_N, c.ref_search_range, c.barcode_start_range,
+                    c.barcode_end_range, c.trim_side)
+    set2 = c.is_dual ?
+        pack_set(keep, c.bc_seqs2, c.bc_lengths_no_N2, c.ref_search_range2, c.barcode_start_range2,
+                 c.barcode_end_range2, c.trim_side2) : set1
+    p = Ref(BdxParams(sizeof(BdxParams), BDX_ABI_VERSION, c.max_error_rate, c.min_delta, c.match, c.mismatch,
+                      c.indel, something(c.nindel, 0), isnothing(c.nindel) ? 0 : 1,
+                      algorithm_code(c.matching_algorithm), c.is_dual ? 1 : 0, c.summary ? 1 : 0, set1, set2))
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    GC.@preserve keep check(ccall((:bdx_config_create, libbdx), Cint, (Ref{BdxParams}, Ref{Ptr{Cvoid}}), p, h))
+    g = GpuConfig(h[], c, keep)
+    finalizer(x -> ccall((:bdx_config_destroy, libbdx), Cvoid, (Ptr{Cvoid},), x.handle), g)
+    g
+end
+
+# classification.jl:877-900 -- filename is a pure function of (status, bc1, bc2)
+function filename_of(c::DemuxConfig, r::BdxResult)
+    suffix = c.gzip_output ? ".fastq.gz" : ".fastq"
+    r.status == 1 && return "unknown" * suffix
+    r.status == 2 && return "ambiguous_classification" * suffix
+    c.is_dual ? string(c.ids[r.bc1]) * "." * string(c.ids2[r.bc2]) * suffix : string(c.ids[r.bc1]) * suffix
+end
+
+"""
+    gpu_worker_task(input_channel, output_channel, gcfg; device=0, chunk_size=4000)
+
+Drop-in for `BioDemuX.worker_task` (core.jl:226-279).  One bdx_stream per worker task;
+two chunks are kept in flight so H2D copies overlap the kernels.  Returns the stream's
+DemuxStats (from the device counters) when `config.summary`, else `nothing`.
+"""
+function gpu_worker_task(input_channel::Channel{Chunk}, output_channel::Channel{ResultChunk}, g::GpuConfig;
+                         device::Int=0, chunk_size::Int=4000, max_read_len::Int=1024)
+    c = g.config
+    sref = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:bdx_stream_create, libbdx), Cint, (Ptr{Cvoid}, Cint, Int32, Int64, Ref{Ptr{Cvoid}}),
+                g.handle, device, chunk_size, chunk_size * max_read_len, sref))
+    s = sref[]
+    do_trim = !isnothing(c.trim_side) || !isnothing(c.trim_side2)
+    pending = Chunk[]
+    results = Vector{BdxResult}(undef, chunk_size)
+
+    function finish_oldest()
+        chunk = popfirst!(pending)
+        n = length(chunk.data.headers)
+        tag = Ref{UInt64}(0); nn = Ref{Int32}(0)
+        check(ccall((:bdx_fetch, libbdx), Cint, (Ptr{Cvoid}, Ref{UInt64}, Ref{Int32}, Ptr{BdxResult}, Ptr{Cvoid}),
+                    s, tag, nn, results, C_NULL))
+        filenames = Vector{String}(undef, n)
+        trim_ranges = do_trim ? Vector{Union{UnitRange{Int},Nothing}}(undef, n) : nothing
+        @inbounds for i in 1:n
+            r = results[i]
+            filenames[i] = filename_of(c, r)
+            if do_trim                                   # core.jl:249-255
+                trim_ranges[i] = r.keep_start != -1 ? (Int(r.keep_start):Int(r.keep_end)) : nothing
+            end
+        end
+        put!(output_channel, ResultChunk(chunk, filenames, trim_ranges))
+    end
+
+    try
+        for chunk in input_channel
+            seqs = chunk.data.seqs
+            n = length(seqs)
+            # zero-copy: write straight into the stream's pinned staging
+            pseq = Ref{Ptr{UInt8}}(C_NULL); poff = Ref{Ptr{Int32}}(C_NULL)
+            check(ccall((:bdx_acquire, libbdx), Cint, (Ptr{Cvoid}, Ref{Ptr{UInt8}}, Ref{Ptr{Int32}}), s, pseq, poff))
+            off = 0
+            unsafe_store!(poff[], Int32(0), 1)
+            @inbounds for i in 1:n
+                len = ncodeunits(seqs[i])
+                GC.@preserve seqs unsafe_copyto!(pseq[] + off, pointer(seqs[i]), len)
+                off += len
+                unsafe_store!(poff[], Int32(off), i + 1)
+            end
+            check(ccall((:bdx_commit, libbdx), Cint, (Ptr{Cvoid}, Int32, UInt64), s, n, chunk.id))
+            push!(pending, chunk)
+            length(pending) == 2 && finish_oldest()
+        end
+        while !isempty(pending)
+            finish_oldest()
+        end
+        return c.summary ? fetch_stats(s, g) : nothing
+    finally
+        ccall((:bdx_stream_destroy, libbdx), Cvoid, (Ptr{Cvoid},), s)
+    end
+end
+
+"Device counters -> DemuxStats (classification.jl:736-767); score keys are round(dist / norm, digits=2)."
+function fetch_stats(s::Ptr{Cvoid}, g::GpuConfig)
+    c = g.config
+    lay = Ref{BdxStatsLayout}()
+    check(ccall((:bdx_stats_layout_get, libbdx), Cint, (Ptr{Cvoid}, Ref{BdxStatsLayout}), g.handle, lay))
+    L = lay[]
+    buf = Vector{Int64}(undef, L.total_len)
+    check(ccall((:bdx_stats_fetch, libbdx), Cint, (Ptr{Cvoid}, Ptr{Int64}, Int64), s, buf, length(buf)))
+    st = DemuxStats()
+    st.total_reads, st.matched_reads, st.unmatched_reads, st.ambiguous_reads = buf[1], buf[2], buf[3], buf[4]
+    for b1 in 0:L.b1, b2 in 0:L.b2
+        v = buf[L.sample_off + b1 * (L.b2 + 1) + b2 + 1]
+        v > 0 && (st.sample_counts[(b1, b2)] = v)
+    end
+    norm_of(pass, b) = begin
+        seqs = pass == 1 ? c.bc_seqs : c.bc_seqs2
+        lens = pass == 1 ? c.bc_lengths_no_N : c.bc_lengths_no_N2
+        (c.matching_algorithm != :hamming && c.matching_algorithm != :exact && !isnothing(c.nindel)) ?
+            lens[b] : ncodeunits(seqs[b])
+    end
+    for pass in 1:(c.is_dual ? 2 : 1)
+        nb = pass == 1 ? L.b1 : L.b2
+        gpos, glen, gsc, pbs, pbp, pbl = pass == 1 ?
+            (st.bc1_pos_counts, st.bc1_len_counts, st.bc1_score_counts, st.bc1_per_bc_score_counts,
+             st.bc1_per_bc_pos_counts, st.bc1_per_bc_len_counts) :
+            (st.bc2_pos_counts, st.bc2_len_counts, st.bc2_score_counts, st.bc2_per_bc_score_counts,
+             st.bc2_per_bc_pos_counts, st.bc2_per_bc_len_counts)
+        for b in 0:nb
+            for k in 0:L.pos_bins-1
+                v = buf[L.pos_off[pass] + b * L.pos_bins + k + 1]; v == 0 && continue
+                b == 0 ? (gpos[k - L.pos_bias] = v) : (get!(() -> Dict{Int,Int}(), pbp, b)[k - L.pos_bias] = v)
+            end
+            for k in 0:L.len_bins-1
+                v = buf[L.len_off[pass] + b * L.len_bins + k + 1]; v == 0 && continue
+                b == 0 ? (glen[k] = v) : (get!(() -> Dict{Int,Int}(), pbl, b)[k] = v)
+            end
+            b == 0 && continue
+            for d in 0:L.dist_bins-1
+                v = buf[L.dist_off[pass] + b * L.dist_bins + d + 1]; v == 0 && continue
+                key = round(d / norm_of(pass, b), digits=2)
+                dd = get!(() -> Dict{Float64,Int}(), pbs, b)
+                dd[key] = get(dd, key, 0) + v
+                gsc[key] = get(gsc, key, 0) + v
+            end
+        end
+    end
+    st
+end
+
+end # module

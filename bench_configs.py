@@ -1,0 +1,127 @@
+#!/usr/bin/env python
+"""Throughput + sampled parity of the other BASELINE.json configs (3, 4, 5) at reduced N.
+
+These are parity-test configurations, not the headline bench line (bench.py = config 2).
+Each config prints one JSON line: device-resident reads/s, full-matrix GCUPS, and whether the
+first --check reads are bit-identical to the oracle.
+Usage: python bench_configs.py [--reads 2000000] [--check 20000] [--only 3 4 5s 5h 5e]
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+READ_LEN = 150
+SEED = 0x42444D58
+ADAPTER = "AGATCGGAAGAGCACACGTCTGAACTCCAGTCA"
+
+
+def barcodes(rng, n, lo, hi):
+    alpha = np.frombuffer(b"ACGT", dtype=np.uint8)
+    return [bytes(alpha[rng.integers(0, 4, int(rng.integers(lo, hi + 1)))]).decode() for _ in range(n)]
+
+
+def configs():
+    import bdx_b200 as bdx
+    R = bdx.parse_dynamic_range
+    rng = np.random.default_rng(SEED)
+    out = {}
+    b1, b2 = barcodes(rng, 384, 16, 28), barcodes(rng, 384, 16, 28)
+    out["3"] = (bdx.DemuxConfig(bc_seqs=b1, bc_lengths_no_N=[len(x) for x in b1], ids=[f"a{i}" for i in range(384)],
+                                is_dual=True, bc_seqs2=b2, bc_lengths_no_N2=[len(x) for x in b2],
+                                ids2=[f"b{i}" for i in range(384)], ref_search_range=R("1:40"),
+                                barcode_start_range=R("1:6"), ref_search_range2=R("end-39:end"),
+                                barcode_end_range2=R("end-5:end"), min_delta=0.1),
+                dict(start_lo=1, start_hi=5, set2_mode=1, end_lo=0, end_hi=4),
+                "config3: dual 384x384, variable-length barcodes 16..28, custom search ranges, min_delta 0.1")
+    b = barcodes(rng, 96, 24, 24)
+    out["4"] = (bdx.DemuxConfig(bc_seqs=b, bc_lengths_no_N=[24] * 96, ids=[f"a{i}" for i in range(96)], is_dual=True,
+                                bc_seqs2=[ADAPTER], bc_lengths_no_N2=[len(ADAPTER)], ids2=["adapter"],
+                                ref_search_range=R("1:32"), trim_side=5, trim_side2=3),
+                dict(start_lo=1, start_hi=4, set2_mode=2, end_lo=55, end_hi=135),
+                "config4: 96 barcodes (trim 5') + 33-nt adapter match and 3' trimming")
+    b = barcodes(rng, 1536, 24, 24)
+    for key, algo in (("5s", "semiglobal"), ("5h", "hamming"), ("5e", "exact")):
+        out[key] = (bdx.DemuxConfig(bc_seqs=b, bc_lengths_no_N=[24] * 1536, ids=[f"a{i}" for i in range(1536)],
+                                    matching_algorithm=algo),
+                    dict(start_lo=1, start_hi=120, set2_mode=0, end_lo=0, end_hi=0),
+                    f"config5: 1536 barcodes x 24nt, :{algo}")
+    return out
+
+
+def cell_updates(cfg, n=READ_LEN):
+    """Full-matrix cell updates per read: sum over sets of m_b x L_set."""
+    import bdx_b200 as bdx
+    total = 0
+    for seqs, rs, bs, be in ((cfg.bc_seqs, cfg.ref_search_range, cfg.barcode_start_range, cfg.barcode_end_range),
+                             (cfg.bc_seqs2, cfg.ref_search_range2, cfg.barcode_start_range2, cfg.barcode_end_range2)):
+        if not seqs:
+            continue
+        r, b, e = bdx.resolve(rs, n), bdx.resolve(bs, n), bdx.resolve(be, n)
+        L = max(0, min(r[1], e[1], n) - max(r[0], b[0], 1) + 1)
+        total += sum(len(s) for s in seqs) * L
+    return total
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--reads", type=int, default=2_000_000)
+    ap.add_argument("--check", type=int, default=20_000)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--only", nargs="*", default=None)
+    args = ap.parse_args()
+    import torch
+    import bdx_b200 as bdx
+    from bdx_b200 import capi
+    import orc
+    torch.cuda.set_device(0)
+    n = args.reads
+    for key, (cfg, sp, name) in configs().items():
+        if args.only and key not in args.only:
+            continue
+        config = capi.Config(cfg)
+        st = capi.Stream(config, device=0, max_reads=0, max_bytes=0)
+        ext = torch.cuda.ExternalStream(st.cuda_stream)
+        d_seq = torch.empty(n * READ_LEN, dtype=torch.uint8, device="cuda")
+        d_off = torch.empty(n + 1, dtype=torch.int32, device="cuda")
+        d_res = torch.empty(n * bdx.RESULT_DTYPE.itemsize, dtype=torch.uint8, device="cuda")
+        spec = capi.SynthSpec(seed=SEED, first_read=0, read_len=READ_LEN, plant_permille=900, n_permille_x10=50, **sp)
+        st.synth_device(spec, n, d_seq.data_ptr(), d_off.data_ptr())
+        for _ in range(2):
+            st.classify_device(d_seq.data_ptr(), d_off.data_ptr(), n, d_res.data_ptr())
+        st.sync()
+        l0 = st.launch_count
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(ext)
+        for _ in range(args.steps):
+            st.classify_device(d_seq.data_ptr(), d_off.data_ptr(), n, d_res.data_ptr())
+        e1.record(ext)
+        st.sync()
+        ms = e0.elapsed_time(e1) / args.steps
+        launches = (st.launch_count - l0) // args.steps
+        res = np.frombuffer(d_res.cpu().numpy().tobytes(), dtype=bdx.RESULT_DTYPE)
+        k = min(args.check, n)
+        blob = d_seq[:k * READ_LEN].cpu().numpy()
+        off = np.arange(k + 1, dtype=np.int64) * READ_LEN
+        ref = orc.Oracle(cfg).classify(blob, off)
+        ok = all((res[f][:k] == ref[f]).all() for f in ("status", "bc1", "bc2", "keep_start", "keep_end"))
+        rate = n / (ms * 1e-3)
+        print(json.dumps({"config": name, "reads": n, "reads_per_sec": rate, "ms_per_step": ms,
+                          "gcups": rate * cell_updates(cfg) / 1e9, "launches_per_step": launches,
+                          "matched_fraction": float((res["status"] == 0).mean()),
+                          "ambiguous_fraction": float((res["status"] == 2).mean()),
+                          "parity_checked_reads": k, "parity_bit_exact": bool(ok)}), flush=True)
+        st.close()
+        del d_seq, d_off, d_res
+
+
+if __name__ == "__main__":
+    main()

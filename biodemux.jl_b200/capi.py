@@ -223,7 +223,9 @@ class Stream:
         fn = self.lib.bdx_submit_pinned if pinned else self.lib.bdx_submit
         _check(fn(self.handle, seq.ctypes.data, off.ctypes.data, n, tag))
 
-    def fetch(self, want_details: bool = False):
+    def fetch(self, want_details: bool = False, copy: bool = True):
+        """Oldest in-flight batch.  copy=False returns views into the stream's pinned result
+        staging (valid until BDX_MAX_IN_FLIGHT - 1 further submits)."""
         tag, n = C.c_uint64(), C.c_int32()
         res_p, det_p = C.c_void_p(), C.c_void_p()
         _check(self.lib.bdx_fetch_view(self.handle, C.byref(tag), C.byref(n), C.byref(res_p), C.byref(det_p)))
@@ -233,13 +235,17 @@ class Stream:
             det = np.zeros((2, 0), DETAIL_DTYPE)
         else:
             buf = (C.c_char * (nn * RESULT_DTYPE.itemsize)).from_address(res_p.value)
-            res = np.frombuffer(buf, dtype=RESULT_DTYPE, count=nn).copy()
+            res = np.frombuffer(buf, dtype=RESULT_DTYPE, count=nn)
+            if copy:
+                res = res.copy()
             det = None
             if want_details:
                 if not det_p.value:
                     raise BdxError(BDX_ERR_STATE, "details not enabled on this stream")
                 dbuf = (C.c_char * (2 * nn * DETAIL_DTYPE.itemsize)).from_address(det_p.value)
-                det = np.frombuffer(dbuf, dtype=DETAIL_DTYPE, count=2 * nn).reshape(2, nn).copy()
+                det = np.frombuffer(dbuf, dtype=DETAIL_DTYPE, count=2 * nn).reshape(2, nn)
+                if copy:
+                    det = det.copy()
         return (tag.value, res, det) if want_details else (tag.value, res)
 
     def classify(self, seq: np.ndarray, off: np.ndarray, want_details: bool = False):

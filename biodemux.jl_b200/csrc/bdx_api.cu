@@ -149,7 +149,11 @@ static int build_set(const bdx_params &p, const bdx_barcode_set &in, HostSet &hs
         if (!hs.class_of[c]) hs.class_of[c] = (uint8_t)hs.n_classes++;
     hs.words = hs.max_m <= 32 ? 1 : (hs.max_m <= 32 * kMaxFilterWords ? 2 : 0);
     const bool benign = p.match >= 0 && p.mismatch >= 1 && p.indel >= 1 && (!p.has_nindel || p.nindel >= p.indel);
-    if (p.algorithm != BDX_SEMIGLOBAL || !benign || disable_filter || hs.n_classes > 64) hs.words = 0;
+    // The unit-cost filter is also a superset filter for :hamming (Hamming distance >= edit
+    // distance; a barcode N is a wildcard there, classification.jl:597) and :exact (distance 0).
+    // Tiny sets are cheaper to scan with the literal kernel than to spread over 32 lanes.
+    const bool sg = p.algorithm == BDX_SEMIGLOBAL;
+    if ((sg && !benign) || disable_filter || hs.n_classes > 64 || hs.n_bc < 8) hs.words = 0;
 
     hs.allowed0.assign(hs.n_bc_pad, -1);
     hs.filt_allowed.assign(hs.n_bc_pad, -1);
@@ -157,7 +161,12 @@ static int build_set(const bdx_params &p, const bdx_barcode_set &in, HostSet &hs
     if (p.has_nindel) min_cost = std::min(min_cost, p.nindel);
     for (int b = 0; b < hs.n_bc; b++) {
         hs.allowed0[b] = host_allowed(p.max_error_rate, hs.norm[b]);
-        if (benign) hs.filt_allowed[b] = hs.allowed0[b] < 0 ? -1 : (int)(hs.allowed0[b] / min_cost);
+        if (p.algorithm == BDX_EXACT)
+            hs.filt_allowed[b] = p.max_error_rate >= 0.0 ? 0 : -1;          // score 0.0 <= thr (:658, :696)
+        else if (p.algorithm == BDX_HAMMING)
+            hs.filt_allowed[b] = hs.allowed0[b] < 0 ? -1 : hs.allowed0[b];  // floor(thr * m) (:567)
+        else if (benign)
+            hs.filt_allowed[b] = hs.allowed0[b] < 0 ? -1 : (int)(hs.allowed0[b] / min_cost);
     }
     if (hs.words) {
         const int W = hs.words;
@@ -171,7 +180,8 @@ static int build_set(const bdx_params &p, const bdx_barcode_set &in, HostSet &hs
                 if (W == 1) v &= 0xFFFFFFFFull;
                 for (int i = 0; i < m; i++) {
                     const uint8_t q = hs.bytes[hs.off[b] + i];
-                    const bool is_n = p.has_nindel && q == (uint8_t)'N';   // NScoring wildcard (:196-203)
+                    // wildcard rows: NScoring (:196-203) and hamming_align (:597); literal in :exact
+                    const bool is_n = q == (uint8_t)'N' && ((sg && p.has_nindel) || p.algorithm == BDX_HAMMING);
                     if (is_n || (c != 0 && hs.class_of[q] == c)) v |= 1ull << (first_row_bit + i);
                 }
                 hs.peq[0 * plane + (size_t)c * hs.n_bc_pad + b] = (uint32_t)v;
@@ -355,7 +365,8 @@ struct bdx_stream {
     int64_t max_bytes = 0;
     bool details = false;
     cudaStream_t st_copy = nullptr, st_comp = nullptr, st_d2h = nullptr;
-    Slot slot[2];
+    Slot slot[BDX_MAX_IN_FLIGHT];
+    bool host_staging = false;  // pinned h_seq / h_off are allocated on first use
     int head = 0;      // next slot to submit into
     int tail = 0;      // oldest in-flight slot
     int in_flight = 0;
@@ -432,8 +443,6 @@ static int stream_create_impl(bdx_stream *s)
     CU(cudaStreamCreateWithFlags(&s->st_d2h, cudaStreamNonBlocking));
     if (s->max_reads > 0) {
         for (Slot &sl : s->slot) {
-            CU(cudaHostAlloc(&sl.h_seq, (size_t)std::max<int64_t>(s->max_bytes, 16), cudaHostAllocDefault));
-            CU(cudaHostAlloc(&sl.h_off, ((size_t)s->max_reads + 1) * 4, cudaHostAllocDefault));
             CU(cudaHostAlloc(&sl.h_res, (size_t)s->max_reads * sizeof(bdx_result), cudaHostAllocDefault));
             CU(cudaHostAlloc(&sl.h_det, (size_t)s->max_reads * 2 * sizeof(bdx_pass_detail), cudaHostAllocDefault));
             CU(cudaMalloc(&sl.d_seq, (size_t)std::max<int64_t>(s->max_bytes, 16)));
@@ -508,7 +517,7 @@ static int enqueue_classify(bdx_stream *s, const uint8_t *d_seq, const int32_t *
     const DevParams &P = s->tab->P;
     const int passes = P.is_dual ? 2 : 1;
     for (int pass = 0; pass < passes; pass++) {
-        if (P.algo == BDX_SEMIGLOBAL && P.set[pass].words > 0) {
+        if (P.set[pass].words > 0) {
             cudaEvent_t e0 = nullptr, e1 = nullptr;
             if (s->profile) {
                 CU(cudaEventCreate(&e0));
@@ -523,7 +532,8 @@ static int enqueue_classify(bdx_stream *s, const uint8_t *d_seq, const int32_t *
             }
             // the exact regime finishes inside the filter kernel; anything else leaves
             // kBcPending reads with candidate lists for the literal kernel
-            const bool may_finish = P.unit_costs && P.set[pass].trim_side == 0 && !P.want_stats;
+            const bool may_finish = P.algo == BDX_SEMIGLOBAL && P.unit_costs && P.set[pass].trim_side == 0 &&
+                                    !P.want_stats;
             const DevRange &bs = P.set[pass].bs, &be = P.set[pass].be;
             const bool default_geometry = bs.start_off <= 1 && !bs.start_from_end && bs.end_from_end &&
                                           bs.end_off >= 0 && be.start_off <= 1 && !be.start_from_end;
@@ -565,8 +575,21 @@ static int launch_slot(bdx_stream *s, Slot &sl, const uint8_t *h_seq, const int3
     }
     CU(cudaEventRecord(sl.ev_done, s->st_d2h));
     sl.busy = true;
-    s->head ^= 1;
+    s->head = (s->head + 1) % BDX_MAX_IN_FLIGHT;
     s->in_flight++;
+    return BDX_OK;
+}
+
+// pinned input staging (only bdx_submit / bdx_acquire need it; bdx_submit_pinned does not)
+static int ensure_host_staging(bdx_stream *s)
+{
+    if (s->host_staging) return BDX_OK;
+    CU(cudaSetDevice(s->device));
+    for (Slot &sl : s->slot) {
+        CU(cudaHostAlloc(&sl.h_seq, (size_t)std::max<int64_t>(s->max_bytes, 16), cudaHostAllocDefault));
+        CU(cudaHostAlloc(&sl.h_off, ((size_t)s->max_reads + 1) * 4, cudaHostAllocDefault));
+    }
+    s->host_staging = true;
     return BDX_OK;
 }
 
@@ -585,9 +608,10 @@ extern "C" int bdx_submit(bdx_stream *s, const uint8_t *seq, const int32_t *offs
     if (!s || (n > 0 && (!seq || !offsets))) return fail(BDX_ERR_INVALID, "null argument");
     if (s->max_reads <= 0) return fail(BDX_ERR_STATE, "stream has no staging (max_reads = 0)");
     if (s->acquired) return fail(BDX_ERR_STATE, "bdx_acquire pending; call bdx_commit");
-    if (s->in_flight >= 2) return fail(BDX_ERR_STATE, "two batches already in flight; call bdx_fetch");
+    if (s->in_flight >= BDX_MAX_IN_FLIGHT) return fail(BDX_ERR_STATE, "BDX_MAX_IN_FLIGHT batches already in flight; call bdx_fetch");
     int rc = check_batch(s, offsets, n);
     if (rc) return rc;
+    if ((rc = ensure_host_staging(s))) return rc;
     Slot &sl = s->slot[s->head];
     if (n) {
         memcpy(sl.h_off, offsets, ((size_t)n + 1) * 4);
@@ -604,7 +628,7 @@ extern "C" int bdx_submit_pinned(bdx_stream *s, const uint8_t *seq, const int32_
     if (!s || (n > 0 && (!seq || !offsets))) return fail(BDX_ERR_INVALID, "null argument");
     if (s->max_reads <= 0) return fail(BDX_ERR_STATE, "stream has no staging (max_reads = 0)");
     if (s->acquired) return fail(BDX_ERR_STATE, "bdx_acquire pending; call bdx_commit");
-    if (s->in_flight >= 2) return fail(BDX_ERR_STATE, "two batches already in flight; call bdx_fetch");
+    if (s->in_flight >= BDX_MAX_IN_FLIGHT) return fail(BDX_ERR_STATE, "BDX_MAX_IN_FLIGHT batches already in flight; call bdx_fetch");
     int rc = check_batch(s, offsets, n);
     if (rc) return rc;
     Slot &sl = s->slot[s->head];
@@ -618,7 +642,9 @@ extern "C" int bdx_acquire(bdx_stream *s, uint8_t **seq, int32_t **offsets)
     if (!s || !seq || !offsets) return fail(BDX_ERR_INVALID, "null argument");
     if (s->max_reads <= 0) return fail(BDX_ERR_STATE, "stream has no staging (max_reads = 0)");
     if (s->acquired) return fail(BDX_ERR_STATE, "already acquired");
-    if (s->in_flight >= 2) return fail(BDX_ERR_STATE, "two batches already in flight; call bdx_fetch");
+    if (s->in_flight >= BDX_MAX_IN_FLIGHT) return fail(BDX_ERR_STATE, "BDX_MAX_IN_FLIGHT batches already in flight; call bdx_fetch");
+    int rc = ensure_host_staging(s);
+    if (rc) return rc;
     Slot &sl = s->slot[s->head];
     *seq = sl.h_seq;
     *offsets = sl.h_off;
@@ -652,7 +678,7 @@ extern "C" int bdx_fetch(bdx_stream *s, uint64_t *tag, int32_t *n_reads, bdx_res
     if (results && sl.n) memcpy(results, sl.h_res, (size_t)sl.n * sizeof(bdx_result));
     if (details && sl.n) memcpy(details, sl.h_det, (size_t)sl.n * 2 * sizeof(bdx_pass_detail));
     sl.busy = false;
-    s->tail ^= 1;
+    s->tail = (s->tail + 1) % BDX_MAX_IN_FLIGHT;
     s->in_flight--;
     return BDX_OK;
 }
@@ -671,7 +697,7 @@ extern "C" int bdx_fetch_view(bdx_stream *s, uint64_t *tag, int32_t *n_reads, co
     if (results) *results = sl.h_res;
     if (details) *details = s->details ? sl.h_det : nullptr;
     sl.busy = false;
-    s->tail ^= 1;
+    s->tail = (s->tail + 1) % BDX_MAX_IN_FLIGHT;
     s->in_flight--;
     return BDX_OK;
 }

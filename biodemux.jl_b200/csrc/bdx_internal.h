@@ -11,7 +11,7 @@ namespace bdx {
 
 constexpr int kMaxBarcodeLen = 256;   // literal kernel DP workspace bound
 constexpr int kMaxFilterWords = 2;    // bit-parallel filter: barcodes up to 64 nt
-constexpr int kCandMax = 8;           // candidate slots per read and pass
+constexpr int kCandMax = 16;          // candidate slots per read and pass
 constexpr int kCandOverflow = 255;    // cand_cnt value: scan every barcode
 constexpr int kInf = 1 << 29;         // INF_INT stand-in for int32 cells (classification.jl:7)
 constexpr int kMaxCost = 1 << 20;

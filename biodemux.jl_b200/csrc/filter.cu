@@ -215,8 +215,12 @@ k_filter(const __grid_constant__ DevParams P, const int pass, const uint8_t *__r
             continue;
         }
         // exact regime: the filter distance IS the reference's distance
-        const bool fast = P.unit_costs && !need_tb && g.max_start_pos >= n && g.min_end_pos <= g.start_j;
+        const bool fast = P.algo == BDX_SEMIGLOBAL && P.unit_costs && !need_tb && g.max_start_pos >= n &&
+                          g.min_end_pos <= g.start_j;
         const int first_tracked = max(g.start_j, g.min_end_pos);  // hits need j >= min_end_pos (:419)
+        // :hamming / :exact constrain the START to the search range; the match itself may run
+        // past its end (classification.jl:490-491, :570-571)
+        const int last_col = P.algo == BDX_SEMIGLOBAL ? g.end_j : min(n, g.end_j + S.max_m - 1);
 
         BestState bs;
         best_init(bs, P.max_error_rate);
@@ -234,8 +238,8 @@ k_filter(const __grid_constant__ DevParams P, const int pass, const uint8_t *__r
             }
             const uint32_t *lane_base = peq_s + chunk + lane;
 
-            for (int tile0 = g.start_j; tile0 <= g.end_j; tile0 += kTile) {
-                const int tlen = min(kTile, g.end_j - tile0 + 1);
+            for (int tile0 = g.start_j; tile0 <= last_col; tile0 += kTile) {
+                const int tlen = min(kTile, last_col - tile0 + 1);
                 __syncwarp();
                 for (int t = lane; t < tlen; t += 32)
                     stage[t] = (uint32_t)class_s[r[tile0 - 1 + t]] * row_bytes;

@@ -323,10 +323,11 @@ k_synth(const __grid_constant__ DevParams P, const bdx_synth_spec spec, const in
         const int start = spec.start_lo + (int)g.below((uint32_t)(spec.start_hi - spec.start_lo + 1));
         for (int k = 0; k < len && start - 1 + k < L; k++)
             if (start - 1 + k >= 0) r[start - 1 + k] = buf[k];
-        if (spec.set2_mode == 1 && P.is_dual) {
+        if (spec.set2_mode != 0 && P.is_dual) {
             const int len2 = synth_mutate(g, P.set[1], buf);
-            const int gap = spec.end_lo + (int)g.below((uint32_t)(spec.end_hi - spec.end_lo + 1));
-            const int s2 = L - gap - len2;  // 0-based start so that the barcode ends `gap` before the end
+            const int v = spec.end_lo + (int)g.below((uint32_t)(spec.end_hi - spec.end_lo + 1));
+            // mode 1: the barcode ends `v` bases before the read end; mode 2: it starts at 1-based position v
+            const int s2 = spec.set2_mode == 1 ? L - v - len2 : v - 1;
             for (int k = 0; k < len2; k++)
                 if (s2 + k >= 0 && s2 + k < L) r[s2 + k] = buf[k];
         }

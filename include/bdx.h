@@ -31,6 +31,7 @@ extern "C" {
 #endif
 
 #define BDX_ABI_VERSION 1
+#define BDX_MAX_IN_FLIGHT 4 /* batches a stream keeps in flight (ring of staging slots) */
 
 typedef enum bdx_status {
     BDX_OK = 0,
@@ -131,8 +132,9 @@ int bdx_device_count(void);
 int bdx_config_create(const bdx_params *params, bdx_config **out);
 void bdx_config_destroy(bdx_config *cfg);
 
-/* One per host worker.  Owns a CUDA stream pair, double-buffered pinned staging
- * for max_reads reads / max_bytes sequence bytes per batch, and device scratch. */
+/* One per host worker.  Owns three CUDA streams (H2D / kernels / D2H), a ring of
+ * BDX_MAX_IN_FLIGHT staging slots (pinned host + device buffers for max_reads reads /
+ * max_bytes sequence bytes per batch) and device scratch. */
 int bdx_stream_create(const bdx_config *cfg, int device, int32_t max_reads, int64_t max_bytes,
                       bdx_stream **out);
 void bdx_stream_destroy(bdx_stream *s);
@@ -140,8 +142,8 @@ void bdx_stream_destroy(bdx_stream *s);
 /* Queue one batch: packed read-1 sequences, raw bytes exactly as read (no case
  * folding; equality is bytewise like codeunits, classification.jl:185).
  * offsets has n_reads + 1 entries, offsets[0] = 0.  Returns after the bytes are in pinned
- * staging, so the caller may reuse its buffers.  At most 2 batches may be in
- * flight per stream (BDX_ERR_STATE otherwise). */
+ * staging, so the caller may reuse its buffers.  At most BDX_MAX_IN_FLIGHT batches may
+ * be in flight per stream (BDX_ERR_STATE otherwise). */
 int bdx_submit(bdx_stream *s, const uint8_t *seq_bytes, const int32_t *offsets, int32_t n_reads,
                uint64_t tag);
 /* Zero-copy variant: borrow the next pinned staging buffers, fill them, commit. */
@@ -166,7 +168,7 @@ int bdx_fetch(bdx_stream *s, uint64_t *tag, int32_t *n_reads, bdx_result *result
               bdx_pass_detail *details);
 
 /* Zero-copy variant of bdx_fetch: pointers into the stream's pinned result staging,
- * valid until the slot is reused by the second-next submit / commit. */
+ * valid until BDX_MAX_IN_FLIGHT - 1 further batches have been submitted. */
 int bdx_fetch_view(bdx_stream *s, uint64_t *tag, int32_t *n_reads, const bdx_result **results,
                    const bdx_pass_detail **details);
 
@@ -229,7 +231,8 @@ typedef struct bdx_synth_spec {
     int32_t plant_permille;   /* probability (per 1000) that set-1 barcode is planted */
     int32_t start_lo, start_hi; /* planted start position range (1-based, inclusive) */
     int32_t n_permille_x10;   /* probability (per 10000) of one base replaced by N */
-    int32_t set2_mode;        /* 0 none, 1 plant set-2 barcode ending end_lo..end_hi before read end */
+    int32_t set2_mode;        /* 0 none; 1 set-2 barcode ends end_lo..end_hi bases before the read end;
+                                 2 set-2 barcode starts at 1-based position end_lo..end_hi */
     int32_t end_lo, end_hi;
 } bdx_synth_spec;
 int bdx_synth_reads_device(bdx_stream *s, const bdx_synth_spec *spec, int32_t n_reads,

@@ -1,0 +1,98 @@
+"""Full-size checks at BASELINE.json's config-2 size (10 M x 150 bp, 96 barcodes) through
+size-independent properties, plus oracle parity on sampled windows."""
+import hashlib
+import os
+import sys
+
+import numpy as np
+import pytest
+
+import bdx_b200 as bdx
+from bdx_b200 import capi
+import orc
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+N = 10_000_000
+L = 150
+
+
+@pytest.fixture(scope="module")
+def workload():
+    import torch
+    sys.path.insert(0, ROOT)
+    import bench
+    cfg = bench.make_config()
+    config = capi.Config(cfg)
+    st = capi.Stream(config, device=0, max_reads=0, max_bytes=0)
+    d_seq = torch.empty(N * L, dtype=torch.uint8, device="cuda")
+    d_off = torch.empty(N + 1, dtype=torch.int32, device="cuda")
+    st.synth_device(bench.synth_spec(0), N, d_seq.data_ptr(), d_off.data_ptr())
+    st.sync()
+    yield cfg, config, st, d_seq, d_off
+    st.close()
+
+
+def _classify(st, d_seq_ptr, d_off_ptr, n):
+    import torch
+    d_res = torch.empty(n * bdx.RESULT_DTYPE.itemsize, dtype=torch.uint8, device="cuda")
+    st.classify_device(d_seq_ptr, d_off_ptr, n, d_res.data_ptr())
+    st.sync()
+    return np.frombuffer(d_res.cpu().numpy().tobytes(), dtype=bdx.RESULT_DTYPE)
+
+
+def test_full_size_properties(workload):
+    import torch
+    cfg, config, st, d_seq, d_off = workload
+    whole = _classify(st, d_seq.data_ptr(), d_off.data_ptr(), N)
+    # determinism / idempotence
+    again = _classify(st, d_seq.data_ptr(), d_off.data_ptr(), N)
+    assert hashlib.sha256(whole.tobytes()).digest() == hashlib.sha256(again.tobytes()).digest()
+    # shard invariance: 10 contiguous shards (what a host dispatcher hands to 10 streams / GPUs)
+    # give the same per-read records as the single launch -- checksum of checksums
+    shard = N // 10
+    d_off_shard = d_off[:shard + 1].contiguous()       # fixed-length reads: offsets repeat
+    h_whole, h_parts = hashlib.sha256(), hashlib.sha256()
+    for k in range(10):
+        part = _classify(st, d_seq.data_ptr() + k * shard * L, d_off_shard.data_ptr(), shard)
+        h_parts.update(hashlib.sha256(part.tobytes()).digest())
+        h_whole.update(hashlib.sha256(whole[k * shard:(k + 1) * shard].tobytes()).digest())
+    assert h_whole.digest() == h_parts.digest()
+    # domain sanity: 90 % of reads carry a barcode with <= 5 edits, threshold is 4 edits
+    frac = float((whole["status"] == 0).mean())
+    assert 0.86 < frac < 0.90, frac
+    assert (whole["bc1"][whole["status"] == 0] >= 1).all() and (whole["bc1"] <= 96).all()
+    assert (whole["keep_start"][whole["status"] == 0] == 1).all()       # no trimming: keep 1:n
+    assert (whole["keep_end"][whole["status"] == 0] == L).all()
+    assert (whole["keep_start"][whole["status"] != 0] == -1).all()
+    # oracle parity on sampled windows of the full-size run
+    rng = np.random.default_rng(3)
+    o = orc.Oracle(cfg)
+    for start in [0, N - 4000] + [int(x) for x in rng.integers(0, N - 4000, 3)]:
+        blob = d_seq[start * L:(start + 4000) * L].cpu().numpy()
+        ref = o.classify(blob, np.arange(4001, dtype=np.int64) * L)
+        for f in ("status", "bc1", "bc2", "keep_start", "keep_end"):
+            assert (whole[f][start:start + 4000] == ref[f]).all(), (start, f)
+
+
+def test_host_path_equals_device_path(workload):
+    """bdx_submit (host buffers, staged) == bdx_submit_pinned == bdx_classify_device on 1 M reads."""
+    cfg, config, st, d_seq, d_off = workload
+    n = 1_000_000
+    dev = _classify(st, d_seq.data_ptr(), d_off.data_ptr(), n)
+    blob = d_seq[:n * L].cpu().numpy()
+    off = np.arange(n + 1, dtype=np.int32) * L
+    s2 = capi.Stream(config, device=0, max_reads=250_000, max_bytes=250_000 * L)
+    got = []
+    q = 0
+    sub_off = off[:250_001]
+    for k in range(4):
+        s2.submit(blob[k * 250_000 * L:(k + 1) * 250_000 * L], sub_off, tag=k)
+        q += 1
+    while q:
+        tag, r = s2.fetch()
+        assert tag == len(got)
+        got.append(r)
+        q -= 1
+    s2.close()
+    assert (np.concatenate(got) == dev).all()

@@ -192,8 +192,10 @@ def test_streaming_double_buffer_and_errors():
             st.submit(packed[i][0], packed[i][1], tag=100 + i)
             tag, res = st.fetch()
             got[tag] = res
-        with pytest.raises(capi.BdxError):          # third batch in flight is refused
-            st.submit(packed[0][0], packed[0][1]); st.submit(packed[0][0], packed[0][1])
+        with pytest.raises(capi.BdxError) as ei:    # more than BDX_MAX_IN_FLIGHT batches are refused
+            for _ in range(5):
+                st.submit(packed[0][0], packed[0][1])
+        assert ei.value.code == capi.BDX_ERR_STATE
         while True:
             try:
                 tag, res = st.fetch()

@@ -108,7 +108,7 @@ def main():
         ms = e0.elapsed_time(e1) / args.steps
         launches = (st.launch_count - l0) // args.steps
         res = np.frombuffer(d_res.cpu().numpy().tobytes(), dtype=bdx.RESULT_DTYPE)
-        k = min(args.check, n)
+        k = min(args.check if len(cfg.bc_seqs) < 1000 else args.check // 5, n)
         blob = d_seq[:k * READ_LEN].cpu().numpy()
         off = np.arange(k + 1, dtype=np.int64) * READ_LEN
         ref = orc.Oracle(cfg).classify(blob, off)

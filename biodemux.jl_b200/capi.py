@@ -17,7 +17,7 @@ from .config import DemuxConfig
 from .demux import DETAIL_DTYPE, RESULT_DTYPE, pack_reads
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libbdx.so")
+LIB_PATH = os.environ.get("BDX_LIB") or os.path.join(_HERE, "csrc", "libbdx.so")
 ABI_VERSION = 1
 
 BDX_OK, BDX_ERR_INVALID, BDX_ERR_CUDA, BDX_ERR_NOMEM, BDX_ERR_STATE, BDX_ERR_TOO_LARGE = 0, -1, -2, -3, -4, -5

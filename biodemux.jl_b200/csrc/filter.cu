@@ -51,7 +51,8 @@ struct BV {
 //   kMadHi : mad.hi.s32(mh, two, score) subtracts msb(mh) (the signed high half of 2*mh is
 //            -1 exactly when the MSB is set), mad.hi.u32(ph, two, mid) adds msb(ph); `two`
 //            is a kernel parameter (DevParams::two) so that ptxas cannot fold it into LEA.HI
-enum { kPlain = 0, kCarry = 1, kMadHi = 2 };
+enum { kPlain = 0, kCarry = 1, kMadHi = 2, kMadHiP = 3, kMadHiM = 4,  // 3/4: only one of the two on the fma pipe
+       kShiftAnd = 5 };  // :exact -- Shift-And automaton instead of the edit-distance automaton
 
 template <int CODING>
 __device__ __forceinline__ void shift_score(uint32_t ph, uint32_t mh, uint32_t two, uint32_t &phs,
@@ -60,6 +61,16 @@ __device__ __forceinline__ void shift_score(uint32_t ph, uint32_t mh, uint32_t t
     if (CODING == kMadHi) {
         asm("mad.hi.s32 %0, %1, %2, %3;" : "=r"(mid) : "r"(mh), "r"(two), "r"(score));
         asm("mad.hi.u32 %0, %1, %2, %3;" : "=r"(score) : "r"(ph), "r"(two), "r"(mid));
+        phs = ph << 1;
+        mhs = mh << 1;
+    } else if (CODING == kMadHiP) {
+        mid = score - (int)(mh >> 31);
+        asm("mad.hi.u32 %0, %1, %2, %3;" : "=r"(score) : "r"(ph), "r"(two), "r"(mid));
+        phs = ph << 1;
+        mhs = mh << 1;
+    } else if (CODING == kMadHiM) {
+        asm("mad.hi.s32 %0, %1, %2, %3;" : "=r"(mid) : "r"(mh), "r"(two), "r"(score));
+        score = mid + (int)(ph >> 31);
         phs = ph << 1;
         mhs = mh << 1;
     } else if (CODING == kCarry) {
@@ -157,18 +168,37 @@ __device__ __forceinline__ void column(const uint32_t *lane_base, uint32_t byte_
         BV<W> Eq;
 #pragma unroll
         for (int k = 0; k < W; k++) Eq.w[k] = p[k * plane + q * 32];
-        int mid;
-        myers_col<CODING>(Eq, Pv[q], Mv[q], two, score[q], mid);
-        if (TRACK == 1) best[q] = min(best[q], score[q]);
-        if (TRACK == 2) best[q] = min(best[q], mid);
+        if constexpr (CODING == kShiftAnd) {
+            // R = ((R << 1) | 1) & Eq: bit i = "barcode prefix of length i+1 ends at this column".
+            // The phantom low bits are all ones (Eq and the initial state), so the shifted-in
+            // bit of row 1 is always 1; the MSB says "the whole barcode ends here".  best[]
+            // ORs the states of the tracked columns; its sign bit marks a candidate.
+            BV<W> &R = Pv[q];
+            if (W == 1) {
+                R.w[0] = (R.w[0] * 2u + 1u) & Eq.w[0];
+            } else {
+                const uint32_t hi = (R.w[W - 1] << 1) | (R.w[0] >> 31);
+                R.w[0] = (R.w[0] * 2u + 1u) & Eq.w[0];
+                R.w[W - 1] = hi & Eq.w[W - 1];
+            }
+            if (TRACK != 0) best[q] |= (int)R.w[W - 1];
+        } else {
+            int mid;
+            myers_col<CODING>(Eq, Pv[q], Mv[q], two, score[q], mid);
+            if (TRACK == 1) best[q] = min(best[q], score[q]);
+            if (TRACK == 2) best[q] = min(best[q], mid);
+        }
     }
 }
 
 // Shared memory carve-up (dynamic):
 //   uint32 peq[W][n_classes][n_bc_pad] | uint32 stage[kFilterWarps][kTile] |
 //   int16 fa[n_bc_pad] | uint8 len[n_bc_pad] | uint8 class_of[256]
+#ifndef BDX_FILTER_MINBLOCKS
+#define BDX_FILTER_MINBLOCKS 1
+#endif
 template <int W, int G, int CODING, bool PAIR>
-__global__ void __launch_bounds__(kFilterWarps * 32)
+__global__ void __launch_bounds__(kFilterWarps * 32, BDX_FILTER_MINBLOCKS)
 k_filter(const __grid_constant__ DevParams P, const int pass, const uint8_t *__restrict__ seq,
          const int *__restrict__ off, const int n_reads, PassOut *__restrict__ out,
          const PassOut *__restrict__ prev_pass, uint16_t *__restrict__ cand,
@@ -235,6 +265,11 @@ k_filter(const __grid_constant__ DevParams P, const int pass, const uint8_t *__r
                 init_rows<W>(m, Pv[q], Mv[q]);
                 score[q] = m;
                 best[q] = kInf;
+                if constexpr (CODING == kShiftAnd) {
+#pragma unroll
+                    for (int k = 0; k < W; k++) Pv[q].w[k] = ~Pv[q].w[k];   // phantom rows = 1, real rows = 0
+                    best[q] = 0;
+                }
             }
             const uint32_t *lane_base = peq_s + chunk + lane;
 
@@ -274,7 +309,9 @@ k_filter(const __grid_constant__ DevParams P, const int pass, const uint8_t *__r
 #pragma unroll
             for (int q = 0; q < G; q++) {
                 const int b0 = chunk + q * 32;
-                uint32_t mask = __ballot_sync(0xFFFFFFFFu, best[q] <= (int)fa_s[b0 + lane]);
+                const bool is_cand = CODING == kShiftAnd ? (best[q] < 0 && fa_s[b0 + lane] >= 0)
+                                                         : best[q] <= (int)fa_s[b0 + lane];
+                uint32_t mask = __ballot_sync(0xFFFFFFFFu, is_cand);
                 while (mask) {
                     const int l = __ffs(mask) - 1;
                     mask &= mask - 1;
@@ -338,14 +375,14 @@ static cudaError_t launch_wgv(const DevParams &P, int pass, const uint8_t *seq, 
 }
 
 // BDX_FILTER_VARIANT (measurement only): 0 plain, 1 plain+pair, 2 carry, 3 carry+pair,
-// 4 mad.hi, 5 mad.hi+pair.  Variants other than the default exist for one word per barcode.
+// 4 mad.hi, 5 mad.hi+pair, 6 mad.hi for +msb(ph) only (+pair), 7 mad.hi for -msb(mh) only (+pair).  Variants other than the default exist for one word per barcode.
 constexpr int kDefaultVariant = 1;
 static int filter_variant()
 {
     static int v = -1;
     if (v < 0) {
         const char *e = getenv("BDX_FILTER_VARIANT");
-        v = (e && e[0] >= '0' && e[0] <= '5') ? e[0] - '0' : kDefaultVariant;
+        v = (e && e[0] >= '0' && e[0] <= '7') ? e[0] - '0' : kDefaultVariant;
     }
     return v;
 }
@@ -354,6 +391,8 @@ template <int W, int G>
 static cudaError_t launch_wg(const DevParams &P, int pass, const uint8_t *seq, const int *off, int n,
                              const Scratch &sc, int sm_count, cudaStream_t st)
 {
+    if (P.algo == BDX_EXACT && !getenv("BDX_EXACT_VIA_MYERS"))
+        return launch_wgv<W, G, kShiftAnd, false>(P, pass, seq, off, n, sc, sm_count, st);
     if (W == 1) {
         switch (filter_variant()) {
         case 0: return launch_wgv<W, G, kPlain, false>(P, pass, seq, off, n, sc, sm_count, st);
@@ -361,6 +400,8 @@ static cudaError_t launch_wg(const DevParams &P, int pass, const uint8_t *seq, c
         case 3: return launch_wgv<W, G, kCarry, true>(P, pass, seq, off, n, sc, sm_count, st);
         case 4: return launch_wgv<W, G, kMadHi, false>(P, pass, seq, off, n, sc, sm_count, st);
         case 5: return launch_wgv<W, G, kMadHi, true>(P, pass, seq, off, n, sc, sm_count, st);
+        case 6: return launch_wgv<W, G, kMadHiP, true>(P, pass, seq, off, n, sc, sm_count, st);
+        case 7: return launch_wgv<W, G, kMadHiM, true>(P, pass, seq, off, n, sc, sm_count, st);
         default: break;
         }
     }

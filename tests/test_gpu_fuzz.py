@@ -1,0 +1,65 @@
+"""Randomised differential fuzz: random option combinations (costs, thresholds, ranges,
+trims, algorithms, dual sets, N wildcards, odd alphabets) -- CUDA path vs oracle, bit-exact."""
+import numpy as np
+import pytest
+
+import bdx_b200 as bdx
+import synth
+from gpu_common import compare
+
+pytestmark = pytest.mark.gpu
+R = bdx.parse_dynamic_range
+
+
+def _range(rng, kind):
+    """A random 'start:end' expression (mix of absolute and end-relative parts)."""
+    if kind == "any" and rng.random() < 0.4:
+        return "1:end"
+    a = int(rng.integers(1, 40))
+    b = int(rng.integers(a, a + 60))
+    forms = [f"{a}:{b}", f"{a}:end", f"1:{b}", f"end-{b}:end", f"end-{b}:end-{max(a - 1, 0)}", f"{a}:end-{a}"]
+    return forms[int(rng.integers(0, len(forms)))]
+
+
+def _random_case(seed):
+    rng = np.random.default_rng(seed)
+    algo = ["semiglobal", "semiglobal", "semiglobal", "hamming", "exact"][int(rng.integers(0, 5))]
+    n1 = int(rng.choice([1, 3, 9, 24, 40, 97]))
+    m_lo = int(rng.choice([4, 8, 16, 24, 30, 40]))
+    m_hi = m_lo + int(rng.choice([0, 0, 3, 8, 30]))
+    n_frac = float(rng.choice([0.0, 0.0, 0.1]))
+    alphabet = [b"ACGT", b"ACGT", b"ACGTN", b"ACGTRY"][int(rng.integers(0, 4))]
+    b1 = synth.random_barcodes(rng, n1, m_lo, m_hi, alphabet=alphabet, n_frac=n_frac)
+    kw = dict(matching_algorithm=algo,
+              max_error_rate=float(rng.choice([0.0, 0.1, 0.2, 0.25, 0.34, 0.5])),
+              min_delta=float(rng.choice([0.0, 0.0, 0.05, 0.15, 0.3])),
+              match=int(rng.choice([0, 0, 0, 1, -1])), mismatch=int(rng.choice([1, 1, 2, 3])),
+              indel=int(rng.choice([1, 1, 2, 3])),
+              nindel=(None if rng.random() < 0.6 else int(rng.choice([1, 2, 3]))),
+              trim_side=[None, 3, 5][int(rng.integers(0, 3))],
+              ref_search_range=R(_range(rng, "any")), barcode_start_range=R(_range(rng, "any")),
+              barcode_end_range=R(_range(rng, "any")))
+    cfg = bdx.DemuxConfig(bc_seqs=b1, bc_lengths_no_N=[sum(c != "N" for c in x) for x in b1],
+                          ids=[f"a{i}" for i in range(n1)], **kw)
+    b2 = None
+    if rng.random() < 0.4:
+        n2 = int(rng.choice([1, 5, 33, 70]))
+        b2 = synth.random_barcodes(rng, n2, m_lo, m_hi, alphabet=alphabet, n_frac=n_frac)
+        cfg.is_dual = True
+        cfg.bc_seqs2, cfg.bc_lengths_no_N2 = b2, [sum(c != "N" for c in x) for x in b2]
+        cfg.ids2 = [f"b{i}" for i in range(n2)]
+        cfg.trim_side2 = [None, 3, 5][int(rng.integers(0, 3))]
+        cfg.ref_search_range2 = R(_range(rng, "any"))
+        cfg.barcode_start_range2 = R(_range(rng, "any"))
+        cfg.barcode_end_range2 = R(_range(rng, "any"))
+    want_stats = bool(rng.random() < 0.3)
+    reads = synth.random_reads(rng, 500, b1, barcodes2=b2, min_len=int(rng.choice([20, 60, 100])),
+                               max_len=int(rng.choice([100, 150, 260])), max_edits=5, lower_prob=0.02,
+                               at_end2=bool(rng.random() < 0.5))
+    return cfg, reads, want_stats
+
+
+@pytest.mark.parametrize("seed", range(80))
+def test_fuzz_random_config(seed):
+    cfg, reads, want_stats = _random_case(1000 + seed)
+    compare(cfg, reads, want_stats=want_stats, label=f"seed{seed}: {cfg.matching_algorithm}")

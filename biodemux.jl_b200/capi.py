@@ -30,6 +30,7 @@ EXPORTS = [
     "bdx_fetch", "bdx_fetch_view", "bdx_classify", "bdx_classify_device", "bdx_stream_sync",
     "bdx_stream_cuda_stream", "bdx_stream_launch_count", "bdx_stream_profile", "bdx_stream_profile_read", "bdx_stats_layout_get", "bdx_stats_fetch",
     "bdx_stats_device_ptr", "bdx_stats_reset", "bdx_synth_reads_device", "bdx_int_alu_peak",
+    "bdx_fastq_scan", "bdx_fastq_pack",
 ]
 
 
@@ -61,7 +62,8 @@ class Params(C.Structure):
 class StatsLayout(C.Structure):
     _fields_ = [("total_len", C.c_int64), ("sample_off", C.c_int64), ("b1", C.c_int32), ("b2", C.c_int32),
                 ("pos_bins", C.c_int32), ("len_bins", C.c_int32), ("dist_bins", C.c_int32),
-                ("pos_bias", C.c_int32), ("pos_off", C.c_int64 * 2), ("len_off", C.c_int64 * 2),
+                ("pos_bias", C.c_int32), ("dist_bias", C.c_int32), ("reserved", C.c_int32),
+                ("pos_off", C.c_int64 * 2), ("len_off", C.c_int64 * 2),
                 ("dist_off", C.c_int64 * 2)]
 
 
@@ -71,6 +73,9 @@ class SynthSpec(C.Structure):
                 ("n_permille_x10", C.c_int32), ("set2_mode", C.c_int32), ("end_lo", C.c_int32),
                 ("end_hi", C.c_int32)]
 
+
+FASTQ_REC_DTYPE = np.dtype([("header_off", "<i8"), ("seq_off", "<i8"), ("plus_off", "<i8"), ("qual_off", "<i8"),
+                            ("header_len", "<i4"), ("seq_len", "<i4"), ("plus_len", "<i4"), ("qual_len", "<i4")])
 
 _LIB = None
 
@@ -129,6 +134,8 @@ def load_library():
     L.bdx_stats_reset.argtypes = [vp]
     L.bdx_synth_reads_device.argtypes = [vp, C.POINTER(SynthSpec), i32, vp, vp]
     L.bdx_int_alu_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]
+    L.bdx_fastq_scan.argtypes = [vp, i64, C.c_int, i32, vp, C.POINTER(i32), C.POINTER(i64)]
+    L.bdx_fastq_pack.argtypes = [vp, vp, i32, vp, i64, vp]
     _LIB = L
     return L
 
@@ -140,6 +147,27 @@ def _check(rc: int):
 
 def _range(dr) -> Range:
     return Range(dr.start_offset, int(dr.start_from_end), int(dr.end_from_end), dr.end_offset)
+
+
+def fastq_scan(buf: np.ndarray, final_block: bool, max_records: int):
+    """bdx_fastq_scan over a uint8 array -> (records structured array, bytes consumed)."""
+    recs = np.zeros(max_records, dtype=FASTQ_REC_DTYPE)
+    n, consumed = C.c_int32(), C.c_int64()
+    _check(load_library().bdx_fastq_scan(buf.ctypes.data if buf.size else None, buf.size, int(final_block),
+                                         max_records, recs.ctypes.data, C.byref(n), C.byref(consumed)))
+    return recs[:n.value], consumed.value
+
+
+def fastq_pack(buf: np.ndarray, recs: np.ndarray, seq_out: Optional[np.ndarray] = None):
+    """bdx_fastq_pack -> (packed sequence bytes, int32 offsets)."""
+    recs = np.ascontiguousarray(recs)
+    total = int(recs["seq_len"].sum())
+    if seq_out is None:
+        seq_out = np.zeros(max(total, 1), dtype=np.uint8)
+    off = np.zeros(len(recs) + 1, dtype=np.int32)
+    _check(load_library().bdx_fastq_pack(buf.ctypes.data if buf.size else None, recs.ctypes.data, len(recs),
+                                         seq_out.ctypes.data, seq_out.size, off.ctypes.data))
+    return seq_out[:total], off
 
 
 class Config:

@@ -242,8 +242,10 @@ extern "C" int bdx_config_create(const bdx_params *p, bdx_config **out)
     L.b2 = b2;
     L.pos_bias = max_m;
     L.pos_bins = 1024 + max_m + 2;
-    L.len_bins = 2 * max_m + 2;
-    L.dist_bins = std::min(max_allowed, 4095) + 1;
+    // e - s + 1 with s >= 1 - m (origin labels of the init column, classification.jl:281) and e <= n
+    L.len_bins = 1024 + max_m + 2;
+    L.dist_bias = (int)std::min<int64_t>(std::max<int64_t>(0, -p->match) * max_m, 4096);
+    L.dist_bins = L.dist_bias + std::min(std::max(max_allowed, 0), 4095) + 1;
     int64_t o = 4;
     L.sample_off = o;
     o += (int64_t)(b1 + 1) * (b2 + 1);

@@ -131,7 +131,7 @@ __device__ void stats_pass(const DevParams &P, const StatsDev &st, int pass, con
     const bdx_stats_layout &L = st.lay;
     const int pos = min(max(o.start + L.pos_bias, 0), L.pos_bins - 1);
     const int len = min(max(o.end - o.start + 1, 0), L.len_bins - 1);
-    const int d = min(max(o.dist, 0), L.dist_bins - 1);
+    const int d = min(max(o.dist + L.dist_bias, 0), L.dist_bins - 1);
     unsigned long long *bp = st.buf + L.pos_off[pass], *bl = st.buf + L.len_off[pass],
                        *bd = st.buf + L.dist_off[pass];
     stat_add(bp + pos);

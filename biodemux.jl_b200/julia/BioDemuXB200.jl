@@ -71,6 +71,8 @@ struct BdxStatsLayout      # bdx_stats_layout
     len_bins::Int32
     dist_bins::Int32
     pos_bias::Int32
+    dist_bias::Int32
+    reserved::Int32
     pos_off::NTuple{2,Int64}
     len_off::NTuple{2,Int64}
     dist_off::NTuple{2,Int64}
@@ -225,7 +227,7 @@ function fetch_stats(s::Ptr{Cvoid}, g::GpuConfig)
             b == 0 && continue
             for d in 0:L.dist_bins-1
                 v = buf[L.dist_off[pass] + b * L.dist_bins + d + 1]; v == 0 && continue
-                key = round(d / norm_of(pass, b), digits=2)
+                key = round((d - L.dist_bias) / norm_of(pass, b), digits=2)
                 dd = get!(() -> Dict{Float64,Int}(), pbs, b)
                 dd[key] = get(dd, key, 0) + v
                 gsc[key] = get(gsc, key, 0) + v

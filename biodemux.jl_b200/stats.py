@@ -82,7 +82,8 @@ def stats_from_counters(buf: np.ndarray, lay, cfg) -> DemuxStats:
             for k in np.nonzero(ln[b])[0]:
                 _bump(pb_len.setdefault(b, {}), int(k), int(ln[b, k]))
             for d in np.nonzero(ds[b])[0]:
-                key = julia_round2(float(d) / float(norms[b - 1])) if norms[b - 1] else float("nan")
+                dist = int(d) - lay.dist_bias
+                key = julia_round2(float(dist) / float(norms[b - 1])) if norms[b - 1] else float("nan")
                 _bump(pb_sc.setdefault(b, {}), key, int(ds[b, d]))
                 _bump(g_sc, key, int(ds[b, d]))
     return st

@@ -200,8 +200,9 @@ int64_t bdx_stream_launch_count(const bdx_stream *s);
  *   sample_counts[(B1+1) * (B2+1)]            index bc1 * (B2+1) + bc2
  *   per pass p in {1,2}:  pos[B_p+1][POS_BINS]  len[B_p+1][LEN_BINS]  dist[B_p+1][DIST_BINS]
  *     row 0 of each is the global histogram, row b the per-barcode one;
- *     pos bin = start + pos_bias, len bin = end - start + 1, dist bin = integer
- *     distance (host converts to round(dist / norm_b, digits=2) keys).
+ *     pos bin = start + pos_bias (start can be <= 0), len bin = end - start + 1 (up to n + m),
+ *     dist bin = integer distance + dist_bias (host converts to round(dist / norm_b, digits=2) keys).
+ *     pos/len histograms cover reads up to 1024 bases; longer reads land in the last bin.
  * bdx_stats_layout describes the offsets; sum the buffers of all streams / GPUs
  * (e.g. one ncclAllReduce(sum, int64)) before converting to DemuxStats. */
 typedef struct bdx_stats_layout {
@@ -209,6 +210,8 @@ typedef struct bdx_stats_layout {
     int64_t sample_off;      /* (B1+1)*(B2+1) entries */
     int32_t b1, b2;          /* set sizes (b2 = 0 when not dual) */
     int32_t pos_bins, len_bins, dist_bins, pos_bias;
+    int32_t dist_bias;       /* dist bin = distance + dist_bias (distances are negative when match < 0) */
+    int32_t reserved;
     int64_t pos_off[2], len_off[2], dist_off[2];
 } bdx_stats_layout;
 
@@ -218,6 +221,25 @@ int bdx_stats_fetch(bdx_stream *s, int64_t *out, int64_t out_len);
 /* device pointer of the counters (for an in-place NCCL all-reduce by the host) */
 void *bdx_stats_device_ptr(bdx_stream *s);
 int bdx_stats_reset(bdx_stream *s);
+
+/* ---- host-side FASTQ block scanner / packer ---------------------
+ * CPU helpers for the data format in front of the hot path; they keep the record semantics
+ * of reader_task (core.jl:43-110): a record = four readline()s, each stripping one trailing
+ * "\n" or "\r\n"; at end of input missing lines read as "". */
+typedef struct bdx_fastq_record {   /* byte ranges inside the scanned buffer, terminators stripped */
+    int64_t header_off, seq_off, plus_off, qual_off;
+    int32_t header_len, seq_len, plus_len, qual_len;
+} bdx_fastq_record;
+/* Scans up to max_records records from buf[0, len).  final_block = 0: stop before a record whose
+ * four lines are not all terminated inside the buffer (re-present buf + *consumed with the next
+ * block); final_block != 0: no data follows, a trailing partial record is completed with empty
+ * lines.  Thread-safe; needs no CUDA device. */
+int bdx_fastq_scan(const uint8_t *buf, int64_t len, int final_block, int32_t max_records,
+                   bdx_fastq_record *recs, int32_t *n_records, int64_t *consumed);
+/* Packs the sequence lines of recs[0, n) back to back into seq_out (capacity seq_cap bytes) and
+ * writes the n + 1 offsets: exactly the batch layout of bdx_submit / bdx_acquire. */
+int bdx_fastq_pack(const uint8_t *buf, const bdx_fastq_record *recs, int32_t n, uint8_t *seq_out,
+                   int64_t seq_cap, int32_t *offsets_out);
 
 /* ---- bench / test utilities (not part of the reference boundary) ----------
  * Synthetic reads of SURVEY.md section 8(d): fixed-length reads over ACGT with a

@@ -46,7 +46,7 @@ def test_config_create_and_stats_layout(lib):
     L = c.layout
     assert (L.b1, L.b2) == (2, 0)
     assert L.dist_bins == 3            # floor(0.2 * 10) + 1
-    assert L.pos_bias == 10 and L.len_bins == 22
+    assert L.pos_bias == 10 and L.len_bins == 1036 and L.pos_bins == 1036
     assert L.sample_off == 4 and L.pos_off[0] == 4 + 3
     assert L.total_len == L.dist_off[1] + L.dist_bins
     c.close()

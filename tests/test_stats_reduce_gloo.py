@@ -28,7 +28,7 @@ def _counters(layout, cfg, ref):
             d = int(round(float(ps["score"]) * norm))
             pos = min(max(s + L.pos_bias, 0), L.pos_bins - 1)
             ln = min(max(e - s + 1, 0), L.len_bins - 1)
-            d = min(max(d, 0), L.dist_bins - 1)
+            d = min(max(d + L.dist_bias, 0), L.dist_bins - 1)
             for row in (0, b):
                 buf[L.pos_off[p] + row * L.pos_bins + pos] += 1
                 buf[L.len_off[p] + row * L.len_bins + ln] += 1

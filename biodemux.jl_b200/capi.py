@@ -28,7 +28,7 @@ EXPORTS = [
     "bdx_stream_create", "bdx_stream_destroy", "bdx_submit", "bdx_acquire", "bdx_commit",
     "bdx_submit_pinned", "bdx_host_alloc", "bdx_host_free", "bdx_stream_enable_details",
     "bdx_fetch", "bdx_fetch_view", "bdx_classify", "bdx_classify_device", "bdx_stream_sync",
-    "bdx_stream_cuda_stream", "bdx_stream_launch_count", "bdx_stream_profile", "bdx_stream_profile_read", "bdx_stats_layout_get", "bdx_stats_fetch",
+    "bdx_stream_cuda_stream", "bdx_stream_launch_count", "bdx_stream_profile", "bdx_stream_profile_read", "bdx_stream_path_counters", "bdx_stats_layout_get", "bdx_stats_fetch",
     "bdx_stats_device_ptr", "bdx_stats_reset", "bdx_synth_reads_device", "bdx_int_alu_peak",
     "bdx_fastq_scan", "bdx_fastq_pack",
 ]
@@ -127,6 +127,7 @@ def load_library():
     L.bdx_stream_launch_count.restype = i64
     L.bdx_stream_profile.argtypes = [vp, C.c_int]
     L.bdx_stream_profile_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(i32)]
+    L.bdx_stream_path_counters.argtypes = [vp, C.POINTER(i64), C.POINTER(i64), C.c_int]
     L.bdx_stats_layout_get.argtypes = [vp, C.POINTER(StatsLayout)]
     L.bdx_stats_fetch.argtypes = [vp, vp, i64]
     L.bdx_stats_device_ptr.argtypes = [vp]
@@ -313,6 +314,12 @@ class Stream:
         ms, n = C.c_double(), C.c_int32()
         _check(self.lib.bdx_stream_profile_read(self.handle, C.byref(ms), C.byref(n)))
         return ms.value, n.value
+
+    def path_counters(self, reset: bool = False):
+        """(reads resolved by the perfect-occurrence prefilter, reads that ran the automaton)."""
+        a, b = C.c_int64(), C.c_int64()
+        _check(self.lib.bdx_stream_path_counters(self.handle, C.byref(a), C.byref(b), int(reset)))
+        return a.value, b.value
 
     def stats(self) -> np.ndarray:
         out = np.zeros(self.config.layout.total_len, dtype=np.int64)

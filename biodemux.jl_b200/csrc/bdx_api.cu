@@ -62,6 +62,11 @@ struct HostSet {
     std::vector<int> off, norm, filt_allowed, allowed0;
     std::vector<uint32_t> peq;
     uint8_t class_of[256];
+    // perfect-occurrence prefilter
+    int pf_enabled = 0, pf_seed = 0, pf_log2 = 0;
+    uint32_t pf_pow = 0;
+    std::vector<uint32_t> pf_keys, pf_vals;
+    std::vector<uint8_t> bc_cls;
 };
 
 struct DeviceTables {
@@ -188,6 +193,45 @@ static int build_set(const bdx_params &p, const bdx_barcode_set &in, HostSet &hs
                 if (W == 2) hs.peq[1 * plane + (size_t)c * hs.n_bc_pad + b] = (uint32_t)(v >> 32);
             }
         }
+    }
+    // ---- perfect-occurrence prefilter table (semiglobal, no wildcard rows) ----
+    hs.bc_cls.resize(hs.bytes.size());
+    for (size_t k = 0; k < hs.bytes.size(); k++) hs.bc_cls[k] = hs.class_of[hs.bytes[k]];
+    int min_m = hs.max_m;
+    for (int b = 0; b < hs.n_bc; b++) min_m = std::min(min_m, hs.off[b + 1] - hs.off[b]);
+    if (hs.words && sg && !p.has_nindel && min_m >= kPfMinSeed && !getenv("BDX_DISABLE_PREFILTER")) {
+        const int seed = std::min(min_m, kPfMaxSeed);
+        hs.pf_seed = seed;
+        uint32_t pw = 1;
+        for (int i = 1; i < seed; i++) pw *= kPfBase;
+        hs.pf_pow = pw;
+        int lg = 4;
+        while ((1 << lg) < 2 * hs.n_bc) lg++;
+        hs.pf_log2 = lg;
+        const uint32_t size = 1u << lg;
+        hs.pf_keys.assign(size, 0u);
+        hs.pf_vals.assign(size, kPfEmpty);
+        for (int b = 0; b < hs.n_bc; b++) {            // ascending: the lowest index of identical sequences stays
+            const int m = hs.off[b + 1] - hs.off[b];
+            uint32_t h = 0;
+            for (int i = 0; i < seed; i++) h = h * kPfBase + (uint32_t)(hs.bc_cls[hs.off[b] + i] + 1);
+            uint32_t slot = pf_slot(h, lg);
+            bool dup = false;
+            while (hs.pf_vals[slot] != kPfEmpty) {
+                const uint32_t v = hs.pf_vals[slot];
+                const int ob = (int)(v & 0xFFFFu);
+                if ((int)(v >> 16) == m && memcmp(&hs.bytes[hs.off[ob]], &hs.bytes[hs.off[b]], (size_t)m) == 0) {
+                    dup = true;
+                    break;
+                }
+                slot = (slot + 1) & (size - 1);
+            }
+            if (!dup) {
+                hs.pf_keys[slot] = h;
+                hs.pf_vals[slot] = ((uint32_t)m << 16) | (uint32_t)b;
+            }
+        }
+        hs.pf_enabled = 1;
     }
     return BDX_OK;
 }
@@ -329,11 +373,21 @@ static int get_tables(bdx_config *cfg, int device, DeviceTables **out)
         if (e == cudaSuccess) e = upload(t, hs.filt_allowed, &D.filt_allowed);
         if (e == cudaSuccess) e = upload(t, hs.allowed0, &D.allowed0);
         if (e == cudaSuccess) e = upload(t, cls, &D.class_of);
+        D.pf_enabled = hs.pf_enabled;
+        D.pf_seed = hs.pf_seed;
+        D.pf_pow = hs.pf_pow;
+        D.pf_log2 = hs.pf_log2;
+        if (e == cudaSuccess) e = upload(t, hs.pf_keys, &D.pf_keys);
+        if (e == cudaSuccess) e = upload(t, hs.pf_vals, &D.pf_vals);
+        if (e == cudaSuccess) e = upload(t, hs.bc_cls, &D.bc_cls);
         if (e != cudaSuccess) {
             free_tables(t);
             return cuda_fail(e, "uploading barcode tables");
         }
-        if (D.words && filter_smem_bytes_for(D) > (size_t)prop.sharedMemPerBlockOptin) D.words = 0;
+        if (D.words && filter_smem_bytes_for(D) > (size_t)prop.sharedMemPerBlockOptin) {
+            D.pf_enabled = 0;   // drop the prefilter table first, then the filter itself
+            if (filter_smem_bytes_for(D) > (size_t)prop.sharedMemPerBlockOptin) D.words = 0;
+        }
     }
     t->P.filter_ok = t->P.set[0].words > 0 && (!t->P.is_dual || t->P.set[1].words > 0);
     cfg->per_device[device] = t;
@@ -376,6 +430,8 @@ struct bdx_stream {
     Scratch sc{};
     int64_t sc_cap = 0;
     unsigned long long *d_stats = nullptr;
+    unsigned long long *d_counters = nullptr;  // [0] reads resolved by the perfect-occurrence prefilter,
+                                               // [1] reads that ran the bit-parallel automaton
     int64_t launches = 0;
     // optional per-kernel timing of the dominant (filter) kernel, for roofline reporting
     bool profile = false;
@@ -427,6 +483,7 @@ extern "C" void bdx_stream_destroy(bdx_stream *s)
     cudaFree(s->sc.cand);
     cudaFree(s->sc.cand_cnt);
     cudaFree(s->d_stats);
+    cudaFree(s->d_counters);
     for (auto &pr : s->prof_events) {
         cudaEventDestroy(pr.first);
         cudaEventDestroy(pr.second);
@@ -458,6 +515,8 @@ static int stream_create_impl(bdx_stream *s)
         int rc = ensure_scratch(s, s->max_reads);
         if (rc) return rc;
     }
+    CU(cudaMalloc(&s->d_counters, 4 * sizeof(unsigned long long)));
+    CU(cudaMemset(s->d_counters, 0, 4 * sizeof(unsigned long long)));
     if (s->cfg->base.want_stats) {
         CU(cudaMalloc(&s->d_stats, (size_t)s->cfg->lay.total_len * 8));
         CU(cudaMemset(s->d_stats, 0, (size_t)s->cfg->lay.total_len * 8));
@@ -526,7 +585,7 @@ static int enqueue_classify(bdx_stream *s, const uint8_t *d_seq, const int32_t *
                 CU(cudaEventCreate(&e1));
                 CU(cudaEventRecord(e0, s->st_comp));
             }
-            CU(launch_filter(P, pass, d_seq, d_off, n, s->sc, s->tab->sm_count, s->st_comp));
+            CU(launch_filter(P, pass, d_seq, d_off, n, s->sc, s->tab->sm_count, s->d_counters, s->st_comp));
             s->launches++;
             if (s->profile) {
                 CU(cudaEventRecord(e1, s->st_comp));
@@ -752,6 +811,20 @@ extern "C" int bdx_stream_profile_read(bdx_stream *s, double *filter_ms, int32_t
     *filter_ms = total;
     *n_launches = (int32_t)s->prof_events.size();
     s->prof_events.clear();
+    return BDX_OK;
+}
+
+extern "C" int bdx_stream_path_counters(bdx_stream *s, int64_t *prefilter_reads, int64_t *automaton_reads,
+                                        int reset)
+{
+    if (!s) return fail(BDX_ERR_INVALID, "null stream");
+    CU(cudaSetDevice(s->device));
+    CU(cudaStreamSynchronize(s->st_comp));
+    unsigned long long h[4];
+    CU(cudaMemcpy(h, s->d_counters, sizeof(h), cudaMemcpyDeviceToHost));
+    if (prefilter_reads) *prefilter_reads = (int64_t)h[0];
+    if (automaton_reads) *automaton_reads = (int64_t)h[1];
+    if (reset) CU(cudaMemset(s->d_counters, 0, sizeof(h)));
     return BDX_OK;
 }
 

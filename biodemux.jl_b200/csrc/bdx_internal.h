@@ -43,7 +43,26 @@ struct DevSet {
     const int *filt_allowed;      // [n_bc_pad] unit-cost candidate threshold, -1 = padding
     const int *allowed0;          // [n_bc_pad] floor(max_error_rate * norm) at the initial threshold
     const uint8_t *class_of;      // [256] byte -> class
+    // perfect-occurrence prefilter (filter.cu): open-addressing table of barcode hashes
+    int pf_enabled;               // 0 = off (N wildcard rows, barcodes shorter than kPfMinSeed, ...)
+    int pf_seed;                  // hashed prefix length = min(shortest barcode, kPfMaxSeed)
+    uint32_t pf_pow;              // kPfBase^(pf_seed-1)
+    int pf_log2;                  // table size = 1 << pf_log2
+    const uint32_t *pf_keys;      // [size] hash of the first pf_seed class codes
+    const uint32_t *pf_vals;      // [size] (len << 16) | barcode index (lowest of identical sequences); kPfEmpty
+    const uint8_t *bc_cls;        // barcode bytes mapped through class_of (same offsets as bc_bytes)
 };
+
+constexpr int kPfMaxSeed = 12;
+constexpr int kPfMinSeed = 6;
+constexpr uint32_t kPfBase = 0x9E3779B1u;
+constexpr uint32_t kPfMix = 0x85EBCA6Bu;
+constexpr uint32_t kPfEmpty = 0xFFFFFFFFu;
+
+__host__ __device__ inline uint32_t pf_slot(uint32_t h, int log2size)
+{
+    return (h * kPfMix) >> (32 - log2size);
+}
 
 struct DevParams {
     double max_error_rate, min_delta;
@@ -78,7 +97,7 @@ struct Scratch {
 cudaError_t launch_literal(const DevParams &P, int pass, int from_filter, const uint8_t *seq,
                            const int *off, int n, const Scratch &sc, cudaStream_t st);
 cudaError_t launch_filter(const DevParams &P, int pass, const uint8_t *seq, const int *off, int n,
-                          const Scratch &sc, int sm_count, cudaStream_t st);
+                          const Scratch &sc, int sm_count, unsigned long long *counters, cudaStream_t st);
 cudaError_t launch_finalize(const DevParams &P, const int *off, int n, const Scratch &sc,
                             bdx_result *res, bdx_pass_detail *det, StatsDev stats, cudaStream_t st);
 cudaError_t launch_synth(const DevParams &P, const bdx_synth_spec &spec, int n, uint8_t *seq, int *off,

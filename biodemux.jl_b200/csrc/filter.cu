@@ -202,7 +202,7 @@ __global__ void __launch_bounds__(kFilterWarps * 32, BDX_FILTER_MINBLOCKS)
 k_filter(const __grid_constant__ DevParams P, const int pass, const uint8_t *__restrict__ seq,
          const int *__restrict__ off, const int n_reads, PassOut *__restrict__ out,
          const PassOut *__restrict__ prev_pass, uint16_t *__restrict__ cand,
-         uint8_t *__restrict__ cand_cnt)
+         uint8_t *__restrict__ cand_cnt, unsigned long long *__restrict__ counters)
 {
     extern __shared__ __align__(16) uint32_t smem[];
     const DevSet &S = P.set[pass];
@@ -213,6 +213,11 @@ k_filter(const __grid_constant__ DevParams P, const int pass, const uint8_t *__r
     int16_t *fa_s = reinterpret_cast<int16_t *>(stage_all + kFilterWarps * kTile);
     uint8_t *len_s = reinterpret_cast<uint8_t *>(fa_s + n_pad);
     uint8_t *class_s = len_s + n_pad;
+    uint8_t *stage8_all = class_s + 256;                       // class code per staged column
+    const int pf_size = S.pf_enabled ? (1 << S.pf_log2) : 0;
+    uint32_t *pf_keys_s = reinterpret_cast<uint32_t *>(
+        (reinterpret_cast<uintptr_t>(stage8_all + kFilterWarps * kTile) + 15) & ~(uintptr_t)15);
+    uint32_t *pf_vals_s = pf_keys_s + pf_size;
 
     for (int k = threadIdx.x; k < W * plane; k += blockDim.x) peq_s[k] = S.peq[k];
     for (int k = threadIdx.x; k < n_pad; k += blockDim.x) {
@@ -220,11 +225,17 @@ k_filter(const __grid_constant__ DevParams P, const int pass, const uint8_t *__r
         len_s[k] = (uint8_t)(k < S.n_bc ? S.bc_off[k + 1] - S.bc_off[k] : 0);
     }
     for (int k = threadIdx.x; k < 256; k += blockDim.x) class_s[k] = S.class_of[k];
+    for (int k = threadIdx.x; k < pf_size; k += blockDim.x) {
+        pf_keys_s[k] = S.pf_keys[k];
+        pf_vals_s[k] = S.pf_vals[k];
+    }
     __syncthreads();
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     uint32_t *stage = stage_all + warp * kTile;
+    uint8_t *stage8 = stage8_all + warp * kTile;
+    unsigned int n_prefilter = 0, n_automaton = 0;
     const int warps_total = gridDim.x * kFilterWarps;
     const bool with_delta = P.min_delta != 0.0;
     const bool need_tb = S.trim_side != 0 || P.want_stats;
@@ -256,6 +267,68 @@ k_filter(const __grid_constant__ DevParams P, const int pass, const uint8_t *__r
         best_init(bs, P.max_error_rate);
         int n_cand = 0;
 
+        // Reads whose columns fit one tile are staged once (not once per barcode chunk).
+        const bool single_tile = last_col - g.start_j + 1 <= kTile;
+        if (single_tile) {
+            const int tlen = last_col - g.start_j + 1;
+            __syncwarp();
+            for (int t = lane; t < tlen; t += 32) {
+                const uint32_t c = class_s[r[g.start_j - 1 + t]];
+                stage[t] = c * row_bytes;
+                stage8[t] = (uint8_t)c;
+            }
+            __syncwarp();
+        }
+
+        // ---- perfect-occurrence prefilter --------------------------------------------------
+        // In the exact regime without min_delta, a barcode that occurs verbatim inside the
+        // search range scores 0, the running threshold drops to 0 and no later barcode can be
+        // accepted (score < min_score is strict, classification.jl:658); earlier barcodes win
+        // only with a score of 0 themselves, i.e. if THEY occur verbatim.  So the answer is the
+        // lowest-index barcode with a verbatim occurrence, found by hashing a seed-length window
+        // at every column (rolling polynomial hash over class codes, table of barcode-prefix
+        // hashes in shared memory, full byte-wise verification on a hit).  No DP is run for
+        // such reads.
+        if (CODING != kShiftAnd && fast && !with_delta && S.pf_enabled && single_tile && P.max_error_rate >= 0.0) {
+            int found = 0x7FFFFFFF;
+            const int ncols = g.end_j - g.start_j + 1;
+            const int seed = S.pf_seed;                 // hashed prefix length (<= every barcode length)
+            const int nwin = ncols - seed + 1;
+            const int per = (nwin + 31) >> 5;           // contiguous block of windows per lane
+            const int w0 = lane * per, w1 = min(w0 + per, nwin);
+            if (w0 < w1) {
+                const uint32_t pw = S.pf_pow;
+                uint32_t h = 0;
+                for (int i = 0; i < seed; i++) h = h * kPfBase + (uint32_t)(stage8[w0 + i] + 1);
+                for (int w = w0;;) {
+                    uint32_t slot = pf_slot(h, S.pf_log2);
+                    for (;;) {
+                        const uint32_t v = pf_vals_s[slot];
+                        if (v == kPfEmpty) break;
+                        const int len = (int)(v >> 16);
+                        if (pf_keys_s[slot] == h && w + len <= ncols) {
+                            const int b = (int)(v & 0xFFFFu);
+                            const uint8_t *qc = S.bc_cls + S.bc_off[b];
+                            bool same = true;
+                            for (int i = 0; i < len; i++)
+                                if (qc[i] != stage8[w + i]) { same = false; break; }
+                            if (same) found = min(found, b);
+                        }
+                        slot = (slot + 1) & (uint32_t)(pf_size - 1);
+                    }
+                    if (++w >= w1) break;
+                    h = (h - (uint32_t)(stage8[w - 1] + 1) * pw) * kPfBase + (uint32_t)(stage8[w - 1 + seed] + 1);
+                }
+            }
+            found = __reduce_min_sync(0xFFFFFFFFu, found);
+            if (found != 0x7FFFFFFF) {
+                if (lane == 0) out[read] = PassOut{found + 1, 0, -1, -1};
+                n_prefilter++;
+                continue;
+            }
+        }
+        n_automaton++;
+
         for (int chunk = 0; chunk < n_pad; chunk += 32 * G) {
             BV<W> Pv[G], Mv[G];
             int score[G], best[G];
@@ -275,10 +348,12 @@ k_filter(const __grid_constant__ DevParams P, const int pass, const uint8_t *__r
 
             for (int tile0 = g.start_j; tile0 <= last_col; tile0 += kTile) {
                 const int tlen = min(kTile, last_col - tile0 + 1);
-                __syncwarp();
-                for (int t = lane; t < tlen; t += 32)
-                    stage[t] = (uint32_t)class_s[r[tile0 - 1 + t]] * row_bytes;
-                __syncwarp();
+                if (!single_tile) {
+                    __syncwarp();
+                    for (int t = lane; t < tlen; t += 32)
+                        stage[t] = (uint32_t)class_s[r[tile0 - 1 + t]] * row_bytes;
+                    __syncwarp();
+                }
                 // columns before min_end_pos advance the automaton but are not hits
                 int t = 0;
                 const int untracked = min(tlen, max(0, first_tracked - tile0));
@@ -341,6 +416,10 @@ k_filter(const __grid_constant__ DevParams P, const int pass, const uint8_t *__r
             }
         }
     }
+    if (counters && lane == 0) {
+        if (n_prefilter) atomicAdd(counters + 0, (unsigned long long)n_prefilter);
+        if (n_automaton) atomicAdd(counters + 1, (unsigned long long)n_automaton);
+    }
 }
 
 static size_t filter_smem_bytes(const DevSet &S)
@@ -349,12 +428,14 @@ static size_t filter_smem_bytes(const DevSet &S)
     size_t b = (size_t)S.words * S.n_classes * n_pad * 4;
     b += (size_t)kFilterWarps * kTile * 4;
     b += n_pad * 2 + n_pad + 256;
+    b += (size_t)kFilterWarps * kTile + 16;                   // stage8 + alignment slack
+    if (S.pf_enabled) b += (size_t)8 << S.pf_log2;            // prefilter keys + vals
     return (b + 15) & ~(size_t)15;
 }
 
 template <int W, int G, int CODING, bool PAIR>
 static cudaError_t launch_wgv(const DevParams &P, int pass, const uint8_t *seq, const int *off, int n,
-                              const Scratch &sc, int sm_count, cudaStream_t st)
+                              const Scratch &sc, int sm_count, unsigned long long *counters, cudaStream_t st)
 {
     const size_t smem = filter_smem_bytes(P.set[pass]);
     auto kern = k_filter<W, G, CODING, PAIR>;
@@ -370,7 +451,7 @@ static cudaError_t launch_wgv(const DevParams &P, int pass, const uint8_t *seq, 
     if (blocks > need) blocks = need;
     if (blocks < 1) blocks = 1;
     kern<<<(unsigned)blocks, kFilterWarps * 32, smem, st>>>(P, pass, seq, off, n, sc.pass[pass], sc.pass[0],
-                                                            sc.cand, sc.cand_cnt);
+                                                            sc.cand, sc.cand_cnt, counters);
     return cudaGetLastError();
 }
 
@@ -389,34 +470,34 @@ static int filter_variant()
 
 template <int W, int G>
 static cudaError_t launch_wg(const DevParams &P, int pass, const uint8_t *seq, const int *off, int n,
-                             const Scratch &sc, int sm_count, cudaStream_t st)
+                             const Scratch &sc, int sm_count, unsigned long long *counters, cudaStream_t st)
 {
     if (P.algo == BDX_EXACT && !getenv("BDX_EXACT_VIA_MYERS"))
-        return launch_wgv<W, G, kShiftAnd, false>(P, pass, seq, off, n, sc, sm_count, st);
+        return launch_wgv<W, G, kShiftAnd, false>(P, pass, seq, off, n, sc, sm_count, counters, st);
     if (W == 1) {
         switch (filter_variant()) {
-        case 0: return launch_wgv<W, G, kPlain, false>(P, pass, seq, off, n, sc, sm_count, st);
-        case 2: return launch_wgv<W, G, kCarry, false>(P, pass, seq, off, n, sc, sm_count, st);
-        case 3: return launch_wgv<W, G, kCarry, true>(P, pass, seq, off, n, sc, sm_count, st);
-        case 4: return launch_wgv<W, G, kMadHi, false>(P, pass, seq, off, n, sc, sm_count, st);
-        case 5: return launch_wgv<W, G, kMadHi, true>(P, pass, seq, off, n, sc, sm_count, st);
-        case 6: return launch_wgv<W, G, kMadHiP, true>(P, pass, seq, off, n, sc, sm_count, st);
-        case 7: return launch_wgv<W, G, kMadHiM, true>(P, pass, seq, off, n, sc, sm_count, st);
+        case 0: return launch_wgv<W, G, kPlain, false>(P, pass, seq, off, n, sc, sm_count, counters, st);
+        case 2: return launch_wgv<W, G, kCarry, false>(P, pass, seq, off, n, sc, sm_count, counters, st);
+        case 3: return launch_wgv<W, G, kCarry, true>(P, pass, seq, off, n, sc, sm_count, counters, st);
+        case 4: return launch_wgv<W, G, kMadHi, false>(P, pass, seq, off, n, sc, sm_count, counters, st);
+        case 5: return launch_wgv<W, G, kMadHi, true>(P, pass, seq, off, n, sc, sm_count, counters, st);
+        case 6: return launch_wgv<W, G, kMadHiP, true>(P, pass, seq, off, n, sc, sm_count, counters, st);
+        case 7: return launch_wgv<W, G, kMadHiM, true>(P, pass, seq, off, n, sc, sm_count, counters, st);
         default: break;
         }
     }
-    return launch_wgv<W, G, kPlain, true>(P, pass, seq, off, n, sc, sm_count, st);
+    return launch_wgv<W, G, kPlain, true>(P, pass, seq, off, n, sc, sm_count, counters, st);
 }
 
 cudaError_t launch_filter(const DevParams &P, int pass, const uint8_t *seq, const int *off, int n,
-                          const Scratch &sc, int sm_count, cudaStream_t st)
+                          const Scratch &sc, int sm_count, unsigned long long *counters, cudaStream_t st)
 {
     if (n <= 0) return cudaSuccess;
     const DevSet &S = P.set[pass];
     const int groups = S.n_bc_pad / 32;
     const int G = groups >= 4 && groups % 4 == 0 ? 4 : (groups % 3 == 0 ? 3 : (groups % 2 == 0 ? 2 : 1));
 #define BDX_CASE(W_, G_) \
-    if (S.words == W_ && G == G_) return launch_wg<W_, G_>(P, pass, seq, off, n, sc, sm_count, st);
+    if (S.words == W_ && G == G_) return launch_wg<W_, G_>(P, pass, seq, off, n, sc, sm_count, counters, st);
     BDX_CASE(1, 1) BDX_CASE(1, 2) BDX_CASE(1, 3) BDX_CASE(1, 4)
     BDX_CASE(2, 1) BDX_CASE(2, 2) BDX_CASE(2, 3) BDX_CASE(2, 4)
 #undef BDX_CASE

@@ -211,3 +211,36 @@ def test_streaming_double_buffer_and_errors():
             st.submit(big[0], big[1])
         assert ei.value.code == capi.BDX_ERR_TOO_LARGE
         assert st.launch_count > 0
+
+
+def test_prefilter_edge_cases(monkeypatch):
+    """Perfect-occurrence prefilter: duplicate barcodes (lowest index wins), barcodes that are
+    substrings of longer ones, several lengths, occurrences cut by the search range, and the
+    prefilter-off path must agree."""
+    rng = np.random.default_rng(21)
+    base = synth.random_barcodes(rng, 40, 12, 12)
+    bcs = base + [base[3], base[7] + "ACGTAC", "TT" + base[9], base[11][:8]] + synth.random_barcodes(rng, 30, 16, 18)
+    reads = synth.random_reads(rng, 3000, bcs, min_len=30, max_len=120, max_edits=2)
+    reads += [b"", b"ACGT", bcs[0].encode(), (bcs[43][:-1]).encode(), ("GG" + bcs[41] + "GG").encode()]
+    for kw in (dict(), dict(ref_search_range=R("5:60")), dict(ref_search_range=R("end-30:end")),
+               dict(max_error_rate=0.0), dict(min_delta=0.1)):
+        cfg = _cfg(bcs, **kw)
+        res, _ = compare(cfg, reads, label=f"prefilter {kw}")
+        monkeypatch.setenv("BDX_DISABLE_PREFILTER", "1")
+        off, _, _, _ = run_cuda(cfg, reads)
+        monkeypatch.delenv("BDX_DISABLE_PREFILTER")
+        assert (res == off).all(), kw
+
+
+def test_prefilter_counters():
+    rng = np.random.default_rng(22)
+    bcs = synth.random_barcodes(rng, 96, 24)
+    reads = [(b"ACGTTGCA" * 3 + bcs[i % 96].encode() + b"TTGACCAT" * 4) for i in range(1000)]
+    reads += synth.random_reads(rng, 1000, bcs, min_len=100, plant=0.0)
+    cfg = _cfg(bcs)
+    blob, off = bdx.pack_reads(reads)
+    with capi.Engine(cfg, max_reads=len(reads), max_bytes=int(off[-1])) as eng:
+        res = eng.classify_packed(blob, off)
+        pre, auto = eng.stream.path_counters()
+    assert (res["bc1"][:1000] == (np.arange(1000) % 96) + 1).all()
+    assert pre >= 1000 and pre + auto == 2000

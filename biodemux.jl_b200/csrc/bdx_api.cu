@@ -63,7 +63,8 @@ struct HostSet {
     std::vector<uint32_t> peq;
     uint8_t class_of[256];
     // perfect-occurrence prefilter
-    int pf_enabled = 0, pf_seed = 0, pf_log2 = 0;
+    int pf_enabled = 0, pf_seed = 0, pf_log2 = 0, pf_bm_log2 = 0;
+    std::vector<uint32_t> pf_bitmap;
     uint32_t pf_pow = 0;
     std::vector<uint32_t> pf_keys, pf_vals;
     std::vector<uint8_t> bc_cls;
@@ -211,10 +212,16 @@ static int build_set(const bdx_params &p, const bdx_barcode_set &in, HostSet &hs
         const uint32_t size = 1u << lg;
         hs.pf_keys.assign(size, 0u);
         hs.pf_vals.assign(size, kPfEmpty);
+        int bl = 13;                                    // >= 512 bits per barcode, 8 KB .. 32 KB
+        while (bl < 18 && (1 << bl) < 512 * hs.n_bc) bl++;
+        hs.pf_bm_log2 = bl;
+        hs.pf_bitmap.assign((size_t)1 << (bl - 5), 0u);
         for (int b = 0; b < hs.n_bc; b++) {            // ascending: the lowest index of identical sequences stays
             const int m = hs.off[b + 1] - hs.off[b];
             uint32_t h = 0;
-            for (int i = 0; i < seed; i++) h = h * kPfBase + (uint32_t)(hs.bc_cls[hs.off[b] + i] + 1);
+            for (int i = 0; i < seed; i++) h = h * kPfBase + (uint32_t)hs.bytes[hs.off[b] + i];
+            const uint32_t bit = h >> (32 - bl);
+            hs.pf_bitmap[bit >> 5] |= 1u << (bit & 31);
             uint32_t slot = pf_slot(h, lg);
             bool dup = false;
             while (hs.pf_vals[slot] != kPfEmpty) {
@@ -377,6 +384,8 @@ static int get_tables(bdx_config *cfg, int device, DeviceTables **out)
         D.pf_seed = hs.pf_seed;
         D.pf_pow = hs.pf_pow;
         D.pf_log2 = hs.pf_log2;
+        D.pf_bm_log2 = hs.pf_bm_log2;
+        if (e == cudaSuccess) e = upload(t, hs.pf_bitmap, &D.pf_bitmap);
         if (e == cudaSuccess) e = upload(t, hs.pf_keys, &D.pf_keys);
         if (e == cudaSuccess) e = upload(t, hs.pf_vals, &D.pf_vals);
         if (e == cudaSuccess) e = upload(t, hs.bc_cls, &D.bc_cls);
@@ -447,6 +456,8 @@ static int ensure_scratch(bdx_stream *s, int64_t n)
     cudaFree(s->sc.pass[1]);
     cudaFree(s->sc.cand);
     cudaFree(s->sc.cand_cnt);
+    cudaFree(s->sc.worklist);
+    cudaFree(s->sc.n_work);
     s->sc = Scratch{};
     s->sc_cap = 0;
     const int64_t cap = n + n / 8 + 1024;
@@ -454,6 +465,8 @@ static int ensure_scratch(bdx_stream *s, int64_t n)
     CU(cudaMalloc(&s->sc.pass[1], cap * sizeof(PassOut)));
     CU(cudaMalloc(&s->sc.cand, cap * kCandMax * sizeof(uint16_t)));
     CU(cudaMalloc(&s->sc.cand_cnt, cap));
+    CU(cudaMalloc(&s->sc.worklist, cap * sizeof(int)));
+    CU(cudaMalloc(&s->sc.n_work, sizeof(int)));
     s->sc_cap = cap;
     return BDX_OK;
 }
@@ -482,6 +495,8 @@ extern "C" void bdx_stream_destroy(bdx_stream *s)
     cudaFree(s->sc.pass[1]);
     cudaFree(s->sc.cand);
     cudaFree(s->sc.cand_cnt);
+    cudaFree(s->sc.worklist);
+    cudaFree(s->sc.n_work);
     cudaFree(s->d_stats);
     cudaFree(s->d_counters);
     for (auto &pr : s->prof_events) {
@@ -579,13 +594,18 @@ static int enqueue_classify(bdx_stream *s, const uint8_t *d_seq, const int32_t *
     const int passes = P.is_dual ? 2 : 1;
     for (int pass = 0; pass < passes; pass++) {
         if (P.set[pass].words > 0) {
+            const bool pre = prefilter_applies(P, pass);
+            if (pre) {
+                CU(launch_prefilter(P, pass, d_seq, d_off, n, s->sc, s->tab->sm_count, s->d_counters, s->st_comp));
+                s->launches++;
+            }
             cudaEvent_t e0 = nullptr, e1 = nullptr;
             if (s->profile) {
                 CU(cudaEventCreate(&e0));
                 CU(cudaEventCreate(&e1));
                 CU(cudaEventRecord(e0, s->st_comp));
             }
-            CU(launch_filter(P, pass, d_seq, d_off, n, s->sc, s->tab->sm_count, s->d_counters, s->st_comp));
+            CU(launch_filter(P, pass, d_seq, d_off, n, s->sc, s->tab->sm_count, s->d_counters, pre, s->st_comp));
             s->launches++;
             if (s->profile) {
                 CU(cudaEventRecord(e1, s->st_comp));

@@ -48,6 +48,9 @@ struct DevSet {
     int pf_seed;                  // hashed prefix length = min(shortest barcode, kPfMaxSeed)
     uint32_t pf_pow;              // kPfBase^(pf_seed-1)
     int pf_log2;                  // table size = 1 << pf_log2
+    int pf_bm_log2;               // bitmap of 1 << pf_bm_log2 bits indexed by the top hash bits
+    int pad2;
+    const uint32_t *pf_bitmap;    // "some barcode prefix has this hash" (first-level reject)
     const uint32_t *pf_keys;      // [size] hash of the first pf_seed class codes
     const uint32_t *pf_vals;      // [size] (len << 16) | barcode index (lowest of identical sequences); kPfEmpty
     const uint8_t *bc_cls;        // barcode bytes mapped through class_of (same offsets as bc_bytes)
@@ -91,13 +94,19 @@ struct Scratch {
     PassOut *pass[2];
     uint16_t *cand;       // [n][kCandMax]
     uint8_t *cand_cnt;    // [n]
+    int *worklist;        // [n] reads the prefilter left for the bit-parallel kernel
+    int *n_work;          // [1]
 };
 
 // ---- launch wrappers (kernels.cu / filter.cu) ----
 cudaError_t launch_literal(const DevParams &P, int pass, int from_filter, const uint8_t *seq,
                            const int *off, int n, const Scratch &sc, cudaStream_t st);
 cudaError_t launch_filter(const DevParams &P, int pass, const uint8_t *seq, const int *off, int n,
-                          const Scratch &sc, int sm_count, unsigned long long *counters, cudaStream_t st);
+                          const Scratch &sc, int sm_count, unsigned long long *counters, bool use_worklist,
+                          cudaStream_t st);
+cudaError_t launch_prefilter(const DevParams &P, int pass, const uint8_t *seq, const int *off, int n,
+                             const Scratch &sc, int sm_count, unsigned long long *counters, cudaStream_t st);
+bool prefilter_applies(const DevParams &P, int pass);
 cudaError_t launch_finalize(const DevParams &P, const int *off, int n, const Scratch &sc,
                             bdx_result *res, bdx_pass_detail *det, StatsDev stats, cudaStream_t st);
 cudaError_t launch_synth(const DevParams &P, const bdx_synth_spec &spec, int n, uint8_t *seq, int *off,

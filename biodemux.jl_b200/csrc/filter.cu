@@ -23,6 +23,7 @@
 //     the reference's distance itself and the running-threshold selection
 //     (classification.jl:632-713) is replayed in-warp over the candidates;
 //   * otherwise the candidates are queued for the literal kernel.
+#include <algorithm>
 #include <cstdlib>
 #include <math_constants.h>
 
@@ -202,7 +203,8 @@ __global__ void __launch_bounds__(kFilterWarps * 32, BDX_FILTER_MINBLOCKS)
 k_filter(const __grid_constant__ DevParams P, const int pass, const uint8_t *__restrict__ seq,
          const int *__restrict__ off, const int n_reads, PassOut *__restrict__ out,
          const PassOut *__restrict__ prev_pass, uint16_t *__restrict__ cand,
-         uint8_t *__restrict__ cand_cnt, unsigned long long *__restrict__ counters)
+         uint8_t *__restrict__ cand_cnt, unsigned long long *__restrict__ counters,
+         const int *__restrict__ worklist, const int *__restrict__ n_work)
 {
     extern __shared__ __align__(16) uint32_t smem[];
     const DevSet &S = P.set[pass];
@@ -213,11 +215,6 @@ k_filter(const __grid_constant__ DevParams P, const int pass, const uint8_t *__r
     int16_t *fa_s = reinterpret_cast<int16_t *>(stage_all + kFilterWarps * kTile);
     uint8_t *len_s = reinterpret_cast<uint8_t *>(fa_s + n_pad);
     uint8_t *class_s = len_s + n_pad;
-    uint8_t *stage8_all = class_s + 256;                       // class code per staged column
-    const int pf_size = S.pf_enabled ? (1 << S.pf_log2) : 0;
-    uint32_t *pf_keys_s = reinterpret_cast<uint32_t *>(
-        (reinterpret_cast<uintptr_t>(stage8_all + kFilterWarps * kTile) + 15) & ~(uintptr_t)15);
-    uint32_t *pf_vals_s = pf_keys_s + pf_size;
 
     for (int k = threadIdx.x; k < W * plane; k += blockDim.x) peq_s[k] = S.peq[k];
     for (int k = threadIdx.x; k < n_pad; k += blockDim.x) {
@@ -225,24 +222,22 @@ k_filter(const __grid_constant__ DevParams P, const int pass, const uint8_t *__r
         len_s[k] = (uint8_t)(k < S.n_bc ? S.bc_off[k + 1] - S.bc_off[k] : 0);
     }
     for (int k = threadIdx.x; k < 256; k += blockDim.x) class_s[k] = S.class_of[k];
-    for (int k = threadIdx.x; k < pf_size; k += blockDim.x) {
-        pf_keys_s[k] = S.pf_keys[k];
-        pf_vals_s[k] = S.pf_vals[k];
-    }
     __syncthreads();
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     uint32_t *stage = stage_all + warp * kTile;
-    uint8_t *stage8 = stage8_all + warp * kTile;
-    unsigned int n_prefilter = 0, n_automaton = 0;
+    unsigned int n_automaton = 0;
     const int warps_total = gridDim.x * kFilterWarps;
     const bool with_delta = P.min_delta != 0.0;
     const bool need_tb = S.trim_side != 0 || P.want_stats;
     const uint32_t row_bytes = (uint32_t)n_pad * 4u;
     const uint32_t two = (uint32_t)P.two;
 
-    for (int read = blockIdx.x * kFilterWarps + warp; read < n_reads; read += warps_total) {
+    // With a worklist (left by k_prefilter) only the unresolved reads are visited.
+    const int n_items = worklist ? *n_work : n_reads;
+    for (int item = blockIdx.x * kFilterWarps + warp; item < n_items; item += warps_total) {
+        const int read = worklist ? worklist[item] : item;
         if (pass == 1 && prev_pass[read].bc <= 0) {             // classification.jl:879-888
             if (lane == 0) out[read] = PassOut{kBcNotRun, 0, -1, -1};
             continue;
@@ -272,61 +267,11 @@ k_filter(const __grid_constant__ DevParams P, const int pass, const uint8_t *__r
         if (single_tile) {
             const int tlen = last_col - g.start_j + 1;
             __syncwarp();
-            for (int t = lane; t < tlen; t += 32) {
-                const uint32_t c = class_s[r[g.start_j - 1 + t]];
-                stage[t] = c * row_bytes;
-                stage8[t] = (uint8_t)c;
-            }
+            for (int t = lane; t < tlen; t += 32)
+                stage[t] = (uint32_t)class_s[r[g.start_j - 1 + t]] * row_bytes;
             __syncwarp();
         }
 
-        // ---- perfect-occurrence prefilter --------------------------------------------------
-        // In the exact regime without min_delta, a barcode that occurs verbatim inside the
-        // search range scores 0, the running threshold drops to 0 and no later barcode can be
-        // accepted (score < min_score is strict, classification.jl:658); earlier barcodes win
-        // only with a score of 0 themselves, i.e. if THEY occur verbatim.  So the answer is the
-        // lowest-index barcode with a verbatim occurrence, found by hashing a seed-length window
-        // at every column (rolling polynomial hash over class codes, table of barcode-prefix
-        // hashes in shared memory, full byte-wise verification on a hit).  No DP is run for
-        // such reads.
-        if (CODING != kShiftAnd && fast && !with_delta && S.pf_enabled && single_tile && P.max_error_rate >= 0.0) {
-            int found = 0x7FFFFFFF;
-            const int ncols = g.end_j - g.start_j + 1;
-            const int seed = S.pf_seed;                 // hashed prefix length (<= every barcode length)
-            const int nwin = ncols - seed + 1;
-            const int per = (nwin + 31) >> 5;           // contiguous block of windows per lane
-            const int w0 = lane * per, w1 = min(w0 + per, nwin);
-            if (w0 < w1) {
-                const uint32_t pw = S.pf_pow;
-                uint32_t h = 0;
-                for (int i = 0; i < seed; i++) h = h * kPfBase + (uint32_t)(stage8[w0 + i] + 1);
-                for (int w = w0;;) {
-                    uint32_t slot = pf_slot(h, S.pf_log2);
-                    for (;;) {
-                        const uint32_t v = pf_vals_s[slot];
-                        if (v == kPfEmpty) break;
-                        const int len = (int)(v >> 16);
-                        if (pf_keys_s[slot] == h && w + len <= ncols) {
-                            const int b = (int)(v & 0xFFFFu);
-                            const uint8_t *qc = S.bc_cls + S.bc_off[b];
-                            bool same = true;
-                            for (int i = 0; i < len; i++)
-                                if (qc[i] != stage8[w + i]) { same = false; break; }
-                            if (same) found = min(found, b);
-                        }
-                        slot = (slot + 1) & (uint32_t)(pf_size - 1);
-                    }
-                    if (++w >= w1) break;
-                    h = (h - (uint32_t)(stage8[w - 1] + 1) * pw) * kPfBase + (uint32_t)(stage8[w - 1 + seed] + 1);
-                }
-            }
-            found = __reduce_min_sync(0xFFFFFFFFu, found);
-            if (found != 0x7FFFFFFF) {
-                if (lane == 0) out[read] = PassOut{found + 1, 0, -1, -1};
-                n_prefilter++;
-                continue;
-            }
-        }
         n_automaton++;
 
         for (int chunk = 0; chunk < n_pad; chunk += 32 * G) {
@@ -416,10 +361,189 @@ k_filter(const __grid_constant__ DevParams P, const int pass, const uint8_t *__r
             }
         }
     }
-    if (counters && lane == 0) {
-        if (n_prefilter) atomicAdd(counters + 0, (unsigned long long)n_prefilter);
-        if (n_automaton) atomicAdd(counters + 1, (unsigned long long)n_automaton);
+    if (counters && lane == 0 && n_automaton) atomicAdd(counters + 1, (unsigned long long)n_automaton);
+}
+
+// ---------------------------------------------------------------------------------------
+// k_prefilter: perfect-occurrence prefilter, one thread per read.
+//
+// In the exact regime without min_delta, a barcode that occurs verbatim inside the search
+// range scores 0, the running threshold drops to 0 and no later barcode can be accepted
+// (score < min_score is strict, classification.jl:658); an earlier barcode wins only with a
+// score of 0 itself, i.e. if IT occurs verbatim.  So the answer for such a read is the
+// lowest-index barcode with a verbatim occurrence: found with a rolling polynomial hash of
+// a seed-length window at every column, a table of barcode-prefix hashes in shared memory,
+// and byte-wise verification on a hit.  Resolved reads get their PassOut here; all other
+// reads are appended to the worklist the bit-parallel kernel then walks.
+// ---------------------------------------------------------------------------------------
+constexpr int kPfThreads = 256;
+constexpr int kPfStageBytes = 48 * 1024;   // raw bytes of one group of 256 reads (<= 192 bases each)
+constexpr int kPfMaxCand = 2;              // table hits remembered per read; more => leave it to the DP
+
+// Rolling-hash scan of one read's search range.  Table hits are only RECORDED in the loop
+// and verified byte by byte afterwards, when all lanes of the warp verify together (doing
+// it inside the loop serialises the lanes: each finds its hit at a different column).
+// Returns the lowest barcode index with a verified verbatim occurrence, 0x7FFFFFFF if none,
+// or -1 if there were more table hits than kPfMaxCand (the caller then leaves the read to
+// the bit-parallel kernel, which is always correct).
+template <typename BytePtr>
+__device__ __forceinline__ int pf_scan(BytePtr c0, int ncols, const DevSet &S, const uint32_t *keys_s,
+                                       const uint32_t *vals_s, const uint32_t *bitmap_s)
+{
+    const int seed = S.pf_seed;
+    const uint32_t pw = S.pf_pow;
+    const int bm_shift = 32 - S.pf_bm_log2;
+    const uint32_t size_mask = (1u << S.pf_log2) - 1u;
+    uint32_t h = 0;
+    for (int i = 0; i < seed; i++) h = h * kPfBase + (uint32_t)c0[i];
+    int cb[kPfMaxCand], cw[kPfMaxCand], nc = 0;
+    const int nwin = ncols - seed + 1;
+    for (int w = 0;;) {
+        const uint32_t bit = h >> bm_shift;
+        if ((bitmap_s[bit >> 5] >> (bit & 31)) & 1u) {       // rare: some barcode prefix hashes here
+            uint32_t slot = pf_slot(h, S.pf_log2);
+            for (;;) {
+                const uint32_t v = vals_s[slot];
+                if (v == kPfEmpty) break;
+                if (keys_s[slot] == h && w + (int)(v >> 16) <= ncols) {
+                    if (nc < kPfMaxCand) {
+                        cb[nc] = (int)(v & 0xFFFFu);
+                        cw[nc] = w;
+                    }
+                    nc++;
+                }
+                slot = (slot + 1) & size_mask;
+            }
+        }
+        if (++w >= nwin) break;
+        h = (h - (uint32_t)c0[w - 1] * pw) * kPfBase + (uint32_t)c0[w - 1 + seed];
     }
+    if (nc > kPfMaxCand) return -1;
+    int found = 0x7FFFFFFF;
+#pragma unroll
+    for (int k = 0; k < kPfMaxCand; k++) {
+        if (k < nc && cb[k] < found) {
+            const int b = cb[k];
+            const uint8_t *q = S.bc_bytes + S.bc_off[b];
+            const int len = S.bc_off[b + 1] - S.bc_off[b];
+            bool same = true;
+            for (int i = 0; i < len; i++)
+                if (q[i] != c0[cw[k] + i]) { same = false; break; }
+            if (same) found = b;
+        }
+    }
+    return found;
+}
+
+__global__ void __launch_bounds__(kPfThreads)
+k_prefilter(const __grid_constant__ DevParams P, const int pass, const uint8_t *__restrict__ seq,
+            const int *__restrict__ off, const int n_reads, PassOut *__restrict__ out,
+            const PassOut *__restrict__ prev_pass, int *__restrict__ worklist, int *__restrict__ n_work,
+            unsigned long long *__restrict__ counters)
+{
+    extern __shared__ __align__(16) uint32_t smem[];
+    const DevSet &S = P.set[pass];
+    const int pf_size = 1 << S.pf_log2;
+    const int bm_words = 1 << (S.pf_bm_log2 - 5);
+    uint8_t *stage = reinterpret_cast<uint8_t *>(smem);                     // kPfStageBytes + 16
+    uint32_t *keys_s = smem + (kPfStageBytes + 16) / 4;
+    uint32_t *vals_s = keys_s + pf_size;
+    uint32_t *bitmap_s = vals_s + pf_size;
+    for (int k = threadIdx.x; k < pf_size; k += blockDim.x) {
+        keys_s[k] = S.pf_keys[k];
+        vals_s[k] = S.pf_vals[k];
+    }
+    for (int k = threadIdx.x; k < bm_words; k += blockDim.x) bitmap_s[k] = S.pf_bitmap[k];
+
+    const int lane = threadIdx.x & 31;
+    const int seed = S.pf_seed;
+    const int n_groups = (n_reads + kPfThreads - 1) / kPfThreads;
+    unsigned int n_done = 0;
+
+    // persistent blocks: the tables are loaded once, then groups of 256 consecutive reads
+    for (int grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
+        const int r0 = grp * kPfThreads;
+        const int r1 = min(r0 + kPfThreads, n_reads);
+        // The group's reads are contiguous in the packed batch: copy them to shared memory with
+        // 128-bit coalesced loads (from the enclosing 16-byte aligned window), then every
+        // thread walks its own read from there.
+        const int blk_base = off[r0];
+        const int blk_end = off[r1];
+        const uintptr_t g0 = reinterpret_cast<uintptr_t>(seq + blk_base);
+        const int skew = (int)(g0 & 15);                       // stage[skew + k] = seq[blk_base + k]
+        const bool staged = blk_end - blk_base + skew <= kPfStageBytes;
+        __syncthreads();                                       // previous group done with `stage`
+        if (staged) {
+            const uint8_t *src = seq + blk_base - skew;        // 16-byte aligned
+            const int total = blk_end - blk_base + skew;
+            const int vecs = total >> 4;
+            const uint4 *src16 = reinterpret_cast<const uint4 *>(src);
+            uint4 *dst16 = reinterpret_cast<uint4 *>(stage);
+            for (int k = threadIdx.x; k < vecs; k += blockDim.x) dst16[k] = __ldg(src16 + k);
+            for (int k = (vecs << 4) + threadIdx.x; k < total; k += blockDim.x) stage[k] = src[k];
+        }
+        __syncthreads();
+
+        const int read = r0 + threadIdx.x;
+        bool resolved = false;
+        if (read < n_reads && !(pass == 1 && prev_pass[read].bc <= 0)) {
+            const int base = off[read];
+            const int n = off[read + 1] - base;
+            const Geometry g = pass_geometry(S, n);
+            const int ncols = g.end_j - g.start_j + 1;
+            // same regime test as k_filter's `fast` (score-only / unit costs are config-level and
+            // checked by the launcher)
+            if (g.valid && g.max_start_pos >= n && g.min_end_pos <= g.start_j && ncols >= seed) {
+                int found;
+                if (staged)
+                    found = pf_scan(stage + skew + (base - blk_base) + g.start_j - 1, ncols, S, keys_s, vals_s,
+                                    bitmap_s);
+                else
+                    found = pf_scan(seq + base + g.start_j - 1, ncols, S, keys_s, vals_s, bitmap_s);
+                if (found >= 0 && found != 0x7FFFFFFF) {
+                    out[read] = PassOut{found + 1, 0, -1, -1};
+                    resolved = true;
+                }
+            }
+        }
+        // warp-aggregated append of the unresolved reads
+        const bool todo = read < n_reads && !resolved;
+        const uint32_t mask = __ballot_sync(0xFFFFFFFFu, todo);
+        int base_slot = 0;
+        if (lane == 0 && mask) base_slot = atomicAdd(n_work, __popc(mask));
+        base_slot = __shfl_sync(0xFFFFFFFFu, base_slot, 0);
+        if (todo) worklist[base_slot + __popc(mask & ((1u << lane) - 1u))] = read;
+        n_done += __popc(__ballot_sync(0xFFFFFFFFu, resolved));
+    }
+    if (lane == 0 && n_done && counters) atomicAdd(counters + 0, (unsigned long long)n_done);
+}
+
+cudaError_t launch_prefilter(const DevParams &P, int pass, const uint8_t *seq, const int *off, int n,
+                             const Scratch &sc, int sm_count, unsigned long long *counters, cudaStream_t st)
+{
+    const DevSet &S = P.set[pass];
+    const size_t smem = kPfStageBytes + 16 + ((size_t)8 << S.pf_log2) + ((size_t)4 << (S.pf_bm_log2 - 5));
+    cudaError_t e = cudaFuncSetAttribute(k_prefilter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_prefilter, kPfThreads, smem);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) per_sm = 1;
+    const int groups = (n + kPfThreads - 1) / kPfThreads;
+    const int blocks = std::min(groups, sm_count * per_sm);
+    e = cudaMemsetAsync(sc.n_work, 0, sizeof(int), st);
+    if (e != cudaSuccess) return e;
+    k_prefilter<<<blocks, kPfThreads, smem, st>>>(P, pass, seq, off, n, sc.pass[pass], sc.pass[0], sc.worklist,
+                                                  sc.n_work, counters);
+    return cudaGetLastError();
+}
+
+// true when every read of this pass that is in the exact regime may be resolved by k_prefilter
+bool prefilter_applies(const DevParams &P, int pass)
+{
+    const DevSet &S = P.set[pass];
+    return P.algo == BDX_SEMIGLOBAL && S.words > 0 && S.pf_enabled && P.unit_costs && S.trim_side == 0 &&
+           !P.want_stats && P.min_delta == 0.0 && P.max_error_rate >= 0.0;
 }
 
 static size_t filter_smem_bytes(const DevSet &S)
@@ -428,14 +552,13 @@ static size_t filter_smem_bytes(const DevSet &S)
     size_t b = (size_t)S.words * S.n_classes * n_pad * 4;
     b += (size_t)kFilterWarps * kTile * 4;
     b += n_pad * 2 + n_pad + 256;
-    b += (size_t)kFilterWarps * kTile + 16;                   // stage8 + alignment slack
-    if (S.pf_enabled) b += (size_t)8 << S.pf_log2;            // prefilter keys + vals
     return (b + 15) & ~(size_t)15;
 }
 
 template <int W, int G, int CODING, bool PAIR>
 static cudaError_t launch_wgv(const DevParams &P, int pass, const uint8_t *seq, const int *off, int n,
-                              const Scratch &sc, int sm_count, unsigned long long *counters, cudaStream_t st)
+                              const Scratch &sc, int sm_count, unsigned long long *counters, bool use_worklist,
+                              cudaStream_t st)
 {
     const size_t smem = filter_smem_bytes(P.set[pass]);
     auto kern = k_filter<W, G, CODING, PAIR>;
@@ -451,7 +574,9 @@ static cudaError_t launch_wgv(const DevParams &P, int pass, const uint8_t *seq, 
     if (blocks > need) blocks = need;
     if (blocks < 1) blocks = 1;
     kern<<<(unsigned)blocks, kFilterWarps * 32, smem, st>>>(P, pass, seq, off, n, sc.pass[pass], sc.pass[0],
-                                                            sc.cand, sc.cand_cnt, counters);
+                                                            sc.cand, sc.cand_cnt, counters,
+                                                            use_worklist ? sc.worklist : nullptr,
+                                                            use_worklist ? sc.n_work : nullptr);
     return cudaGetLastError();
 }
 
@@ -470,34 +595,36 @@ static int filter_variant()
 
 template <int W, int G>
 static cudaError_t launch_wg(const DevParams &P, int pass, const uint8_t *seq, const int *off, int n,
-                             const Scratch &sc, int sm_count, unsigned long long *counters, cudaStream_t st)
+                             const Scratch &sc, int sm_count, unsigned long long *counters, bool use_worklist,
+                             cudaStream_t st)
 {
     if (P.algo == BDX_EXACT && !getenv("BDX_EXACT_VIA_MYERS"))
-        return launch_wgv<W, G, kShiftAnd, false>(P, pass, seq, off, n, sc, sm_count, counters, st);
+        return launch_wgv<W, G, kShiftAnd, false>(P, pass, seq, off, n, sc, sm_count, counters, use_worklist, st);
     if (W == 1) {
         switch (filter_variant()) {
-        case 0: return launch_wgv<W, G, kPlain, false>(P, pass, seq, off, n, sc, sm_count, counters, st);
-        case 2: return launch_wgv<W, G, kCarry, false>(P, pass, seq, off, n, sc, sm_count, counters, st);
-        case 3: return launch_wgv<W, G, kCarry, true>(P, pass, seq, off, n, sc, sm_count, counters, st);
-        case 4: return launch_wgv<W, G, kMadHi, false>(P, pass, seq, off, n, sc, sm_count, counters, st);
-        case 5: return launch_wgv<W, G, kMadHi, true>(P, pass, seq, off, n, sc, sm_count, counters, st);
-        case 6: return launch_wgv<W, G, kMadHiP, true>(P, pass, seq, off, n, sc, sm_count, counters, st);
-        case 7: return launch_wgv<W, G, kMadHiM, true>(P, pass, seq, off, n, sc, sm_count, counters, st);
+        case 0: return launch_wgv<W, G, kPlain, false>(P, pass, seq, off, n, sc, sm_count, counters, use_worklist, st);
+        case 2: return launch_wgv<W, G, kCarry, false>(P, pass, seq, off, n, sc, sm_count, counters, use_worklist, st);
+        case 3: return launch_wgv<W, G, kCarry, true>(P, pass, seq, off, n, sc, sm_count, counters, use_worklist, st);
+        case 4: return launch_wgv<W, G, kMadHi, false>(P, pass, seq, off, n, sc, sm_count, counters, use_worklist, st);
+        case 5: return launch_wgv<W, G, kMadHi, true>(P, pass, seq, off, n, sc, sm_count, counters, use_worklist, st);
+        case 6: return launch_wgv<W, G, kMadHiP, true>(P, pass, seq, off, n, sc, sm_count, counters, use_worklist, st);
+        case 7: return launch_wgv<W, G, kMadHiM, true>(P, pass, seq, off, n, sc, sm_count, counters, use_worklist, st);
         default: break;
         }
     }
-    return launch_wgv<W, G, kPlain, true>(P, pass, seq, off, n, sc, sm_count, counters, st);
+    return launch_wgv<W, G, kPlain, true>(P, pass, seq, off, n, sc, sm_count, counters, use_worklist, st);
 }
 
 cudaError_t launch_filter(const DevParams &P, int pass, const uint8_t *seq, const int *off, int n,
-                          const Scratch &sc, int sm_count, unsigned long long *counters, cudaStream_t st)
+                          const Scratch &sc, int sm_count, unsigned long long *counters, bool use_worklist,
+                          cudaStream_t st)
 {
     if (n <= 0) return cudaSuccess;
     const DevSet &S = P.set[pass];
     const int groups = S.n_bc_pad / 32;
     const int G = groups >= 4 && groups % 4 == 0 ? 4 : (groups % 3 == 0 ? 3 : (groups % 2 == 0 ? 2 : 1));
 #define BDX_CASE(W_, G_) \
-    if (S.words == W_ && G == G_) return launch_wg<W_, G_>(P, pass, seq, off, n, sc, sm_count, counters, st);
+    if (S.words == W_ && G == G_) return launch_wg<W_, G_>(P, pass, seq, off, n, sc, sm_count, counters, use_worklist, st);
     BDX_CASE(1, 1) BDX_CASE(1, 2) BDX_CASE(1, 3) BDX_CASE(1, 4)
     BDX_CASE(2, 1) BDX_CASE(2, 2) BDX_CASE(2, 3) BDX_CASE(2, 4)
 #undef BDX_CASE

@@ -200,7 +200,8 @@ static int build_set(const bdx_params &p, const bdx_barcode_set &in, HostSet &hs
     for (size_t k = 0; k < hs.bytes.size(); k++) hs.bc_cls[k] = hs.class_of[hs.bytes[k]];
     int min_m = hs.max_m;
     for (int b = 0; b < hs.n_bc; b++) min_m = std::min(min_m, hs.off[b + 1] - hs.off[b]);
-    if (hs.words && sg && !p.has_nindel && min_m >= kPfMinSeed && !getenv("BDX_DISABLE_PREFILTER")) {
+    const bool ex = p.algorithm == BDX_EXACT;   // :exact keeps duplicates (each index is a candidate)
+    if (hs.words && ((sg && !p.has_nindel) || ex) && min_m >= kPfMinSeed && !getenv("BDX_DISABLE_PREFILTER")) {
         const int seed = std::min(min_m, kPfMaxSeed);
         hs.pf_seed = seed;
         uint32_t pw = 1;
@@ -227,7 +228,8 @@ static int build_set(const bdx_params &p, const bdx_barcode_set &in, HostSet &hs
             while (hs.pf_vals[slot] != kPfEmpty) {
                 const uint32_t v = hs.pf_vals[slot];
                 const int ob = (int)(v & 0xFFFFu);
-                if ((int)(v >> 16) == m && memcmp(&hs.bytes[hs.off[ob]], &hs.bytes[hs.off[b]], (size_t)m) == 0) {
+                if (!ex && (int)(v >> 16) == m &&
+                    memcmp(&hs.bytes[hs.off[ob]], &hs.bytes[hs.off[b]], (size_t)m) == 0) {
                     dup = true;
                     break;
                 }
@@ -593,7 +595,13 @@ static int enqueue_classify(bdx_stream *s, const uint8_t *d_seq, const int32_t *
     const DevParams &P = s->tab->P;
     const int passes = P.is_dual ? 2 : 1;
     for (int pass = 0; pass < passes; pass++) {
-        if (P.set[pass].words > 0) {
+        if (exact_hash_applies(P, pass)) {
+            // :exact -- rolling-hash candidate generation, then the literal rules on the candidates
+            CU(launch_prefilter(P, pass, d_seq, d_off, n, s->sc, s->tab->sm_count, s->d_counters, s->st_comp));
+            s->launches++;
+            CU(launch_literal(P, pass, 1, d_seq, d_off, n, s->sc, s->st_comp));
+            s->launches++;
+        } else if (P.set[pass].words > 0) {
             const bool pre = prefilter_applies(P, pass);
             if (pre) {
                 CU(launch_prefilter(P, pass, d_seq, d_off, n, s->sc, s->tab->sm_count, s->d_counters, s->st_comp));

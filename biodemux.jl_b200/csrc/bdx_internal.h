@@ -107,6 +107,7 @@ cudaError_t launch_filter(const DevParams &P, int pass, const uint8_t *seq, cons
 cudaError_t launch_prefilter(const DevParams &P, int pass, const uint8_t *seq, const int *off, int n,
                              const Scratch &sc, int sm_count, unsigned long long *counters, cudaStream_t st);
 bool prefilter_applies(const DevParams &P, int pass);
+bool exact_hash_applies(const DevParams &P, int pass);
 cudaError_t launch_finalize(const DevParams &P, const int *off, int n, const Scratch &sc,
                             bdx_result *res, bdx_pass_detail *det, StatsDev stats, cudaStream_t st);
 cudaError_t launch_synth(const DevParams &P, const bdx_synth_spec &spec, int n, uint8_t *seq, int *off,

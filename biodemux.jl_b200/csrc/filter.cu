@@ -435,11 +435,62 @@ __device__ __forceinline__ int pf_scan(BytePtr c0, int ncols, const DevSet &S, c
     return found;
 }
 
+// :exact -- the same rolling-hash scan used as a CANDIDATE GENERATOR: every barcode whose
+// seed-length prefix occurs at a column where the whole barcode still fits in the read is
+// appended (distinct, ascending) to the read's candidate list; exact_literal then applies the
+// reference's start/end/trim rules to those few barcodes (classification.jl:485-548).  The
+// list is a superset of the barcodes with a valid occurrence, so the result is unchanged.
+// Returns the number of distinct candidates, or kCandOverflow.
+template <typename BytePtr>
+__device__ __forceinline__ int pf_scan_exact(BytePtr c0, int n_starts, int cols_left, const DevSet &S,
+                                             const uint32_t *keys_s, const uint32_t *vals_s,
+                                             const uint32_t *bitmap_s, uint16_t *list)
+{
+    // c0 = first allowed start column; n_starts start columns are scanned; cols_left = read
+    // columns available from c0 to the end of the read
+    const int seed = S.pf_seed;
+    const uint32_t pw = S.pf_pow;
+    const int bm_shift = 32 - S.pf_bm_log2;
+    const uint32_t size_mask = (1u << S.pf_log2) - 1u;
+    uint32_t h = 0;
+    for (int i = 0; i < seed; i++) h = h * kPfBase + (uint32_t)c0[i];
+    int nc = 0;
+    for (int w = 0;;) {
+        const uint32_t bit = h >> bm_shift;
+        if ((bitmap_s[bit >> 5] >> (bit & 31)) & 1u) {
+            uint32_t slot = pf_slot(h, S.pf_log2);
+            for (;;) {
+                const uint32_t v = vals_s[slot];
+                if (v == kPfEmpty) break;
+                if (keys_s[slot] == h && w + (int)(v >> 16) <= cols_left && nc != kCandOverflow) {
+                    const uint16_t b = (uint16_t)(v & 0xFFFFu);
+                    int pos = 0;                                   // sorted insert, skip duplicates
+                    while (pos < nc && list[pos] < b) pos++;
+                    if (pos == nc || list[pos] != b) {
+                        if (nc == kCandMax) {
+                            nc = kCandOverflow;
+                        } else {
+                            for (int k = nc; k > pos; k--) list[k] = list[k - 1];
+                            list[pos] = b;
+                            nc++;
+                        }
+                    }
+                }
+                slot = (slot + 1) & size_mask;
+            }
+        }
+        if (++w >= n_starts) break;
+        h = (h - (uint32_t)c0[w - 1] * pw) * kPfBase + (uint32_t)c0[w - 1 + seed];
+    }
+    return nc;
+}
+
+template <int MODE>   // 0: semiglobal perfect-occurrence resolve, 1: :exact candidate generation
 __global__ void __launch_bounds__(kPfThreads)
 k_prefilter(const __grid_constant__ DevParams P, const int pass, const uint8_t *__restrict__ seq,
             const int *__restrict__ off, const int n_reads, PassOut *__restrict__ out,
             const PassOut *__restrict__ prev_pass, int *__restrict__ worklist, int *__restrict__ n_work,
-            unsigned long long *__restrict__ counters)
+            unsigned long long *__restrict__ counters, uint16_t *__restrict__ cand, uint8_t *__restrict__ cand_cnt)
 {
     extern __shared__ __align__(16) uint32_t smem[];
     const DevSet &S = P.set[pass];
@@ -486,7 +537,39 @@ k_prefilter(const __grid_constant__ DevParams P, const int pass, const uint8_t *
 
         const int read = r0 + threadIdx.x;
         bool resolved = false;
-        if (read < n_reads && !(pass == 1 && prev_pass[read].bc <= 0)) {
+        if (MODE == 1) {
+            // every read is finished here: NotRun / Unknown directly, else a candidate list
+            if (read < n_reads) {
+                resolved = true;
+                if (pass == 1 && prev_pass[read].bc <= 0) {
+                    out[read] = PassOut{kBcNotRun, 0, -1, -1};
+                } else {
+                    const int base = off[read];
+                    const int n = off[read + 1] - base;
+                    const Geometry g = pass_geometry(S, n);
+                    // start columns: [start_j, min(end_j, n - seed + 1)] (classification.jl:490-491;
+                    // max_start_pos is left to exact_literal)
+                    const int n_starts = min(g.end_j, n - seed + 1) - g.start_j + 1;
+                    int nc = 0;
+                    uint16_t *list = cand + (size_t)read * kCandMax;
+                    if (g.valid && n_starts > 0) {
+                        const int cols_left = n - g.start_j + 1;
+                        if (staged)
+                            nc = pf_scan_exact(stage + skew + (base - blk_base) + g.start_j - 1, n_starts, cols_left, S,
+                                               keys_s, vals_s, bitmap_s, list);
+                        else
+                            nc = pf_scan_exact(seq + base + g.start_j - 1, n_starts, cols_left, S, keys_s, vals_s,
+                                               bitmap_s, list);
+                    }
+                    if (nc == 0) {
+                        out[read] = PassOut{kBcUnknown, 0, -1, -1};    // no barcode occurs (:820-821)
+                    } else {
+                        cand_cnt[read] = (uint8_t)nc;
+                        out[read] = PassOut{kBcPending, 0, -1, -1};
+                    }
+                }
+            }
+        } else if (read < n_reads && !(pass == 1 && prev_pass[read].bc <= 0)) {
             const int base = off[read];
             const int n = off[read + 1] - base;
             const Geometry g = pass_geometry(S, n);
@@ -506,6 +589,7 @@ k_prefilter(const __grid_constant__ DevParams P, const int pass, const uint8_t *
                 }
             }
         }
+        if (MODE == 1) continue;
         // warp-aggregated append of the unresolved reads
         const bool todo = read < n_reads && !resolved;
         const uint32_t mask = __ballot_sync(0xFFFFFFFFu, todo);
@@ -523,19 +607,27 @@ cudaError_t launch_prefilter(const DevParams &P, int pass, const uint8_t *seq, c
 {
     const DevSet &S = P.set[pass];
     const size_t smem = kPfStageBytes + 16 + ((size_t)8 << S.pf_log2) + ((size_t)4 << (S.pf_bm_log2 - 5));
-    cudaError_t e = cudaFuncSetAttribute(k_prefilter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    auto kern = P.algo == BDX_EXACT ? k_prefilter<1> : k_prefilter<0>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int per_sm = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_prefilter, kPfThreads, smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kPfThreads, smem);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
     const int groups = (n + kPfThreads - 1) / kPfThreads;
     const int blocks = std::min(groups, sm_count * per_sm);
     e = cudaMemsetAsync(sc.n_work, 0, sizeof(int), st);
     if (e != cudaSuccess) return e;
-    k_prefilter<<<blocks, kPfThreads, smem, st>>>(P, pass, seq, off, n, sc.pass[pass], sc.pass[0], sc.worklist,
-                                                  sc.n_work, counters);
+    kern<<<blocks, kPfThreads, smem, st>>>(P, pass, seq, off, n, sc.pass[pass], sc.pass[0], sc.worklist, sc.n_work,
+                                           counters, sc.cand, sc.cand_cnt);
     return cudaGetLastError();
+}
+
+// :exact with a hash table: k_prefilter<1> replaces the Shift-And filter kernel altogether
+bool exact_hash_applies(const DevParams &P, int pass)
+{
+    const DevSet &S = P.set[pass];
+    return P.algo == BDX_EXACT && S.words > 0 && S.pf_enabled && P.max_error_rate >= 0.0;
 }
 
 // true when every read of this pass that is in the exact regime may be resolved by k_prefilter

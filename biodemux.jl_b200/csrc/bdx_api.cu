@@ -68,6 +68,10 @@ struct HostSet {
     uint32_t pf_pow = 0;
     std::vector<uint32_t> pf_keys, pf_vals;
     std::vector<uint8_t> bc_cls;
+    // :hamming pigeonhole seeds
+    int hs_enabled = 0, hs_q = 0, hs_log2 = 0, hs_max_off = 0;
+    uint32_t hs_pow = 0;
+    std::vector<uint32_t> hs_bstart, hs_entries;
 };
 
 struct DeviceTables {
@@ -201,7 +205,10 @@ static int build_set(const bdx_params &p, const bdx_barcode_set &in, HostSet &hs
     int min_m = hs.max_m;
     for (int b = 0; b < hs.n_bc; b++) min_m = std::min(min_m, hs.off[b + 1] - hs.off[b]);
     const bool ex = p.algorithm == BDX_EXACT;   // :exact keeps duplicates (each index is a candidate)
-    if (hs.words && ((sg && !p.has_nindel) || ex) && min_m >= kPfMinSeed && !getenv("BDX_DISABLE_PREFILTER")) {
+    // :hamming treats every barcode N as a wildcard (classification.jl:597): no table then
+    const bool hm = p.algorithm == BDX_HAMMING &&
+                    std::find(hs.bytes.begin(), hs.bytes.end(), (uint8_t)'N') == hs.bytes.end();
+    if (hs.words && ((sg && !p.has_nindel) || ex || hm) && min_m >= kPfMinSeed && !getenv("BDX_DISABLE_PREFILTER")) {
         const int seed = std::min(min_m, kPfMaxSeed);
         hs.pf_seed = seed;
         uint32_t pw = 1;
@@ -241,6 +248,50 @@ static int build_set(const bdx_params &p, const bdx_barcode_set &in, HostSet &hs
             }
         }
         hs.pf_enabled = 1;
+    }
+    // ---- :hamming pigeonhole seeds: mismatches <= allowed_b leave one of allowed_b + 1 disjoint
+    // segments of the barcode intact, so every acceptable placement contains an exact seed ----
+    if (p.algorithm == BDX_HAMMING && hs.words && p.max_error_rate >= 0.0 && !getenv("BDX_DISABLE_PREFILTER") &&
+        std::find(hs.bytes.begin(), hs.bytes.end(), (uint8_t)'N') == hs.bytes.end()) {
+        int q = 8;
+        bool ok = true;
+        size_t n_entries = 0;
+        for (int b = 0; b < hs.n_bc && ok; b++) {
+            const int m = hs.off[b + 1] - hs.off[b];
+            const int a = hs.allowed0[b];
+            if (a < 0 || a > 254) { ok = false; break; }
+            q = std::min(q, m / (a + 1));
+            n_entries += (size_t)a + 1;
+        }
+        if (ok && q >= 4 && n_entries <= (1u << 20)) {
+            hs.hs_q = q;
+            uint32_t pw = 1;
+            for (int i = 1; i < q; i++) pw *= kPfBase;
+            hs.hs_pow = pw;
+            int lg = 8;
+            while (lg < 13 && (size_t)(1 << lg) < n_entries) lg++;
+            hs.hs_log2 = lg;
+            const uint32_t nb = 1u << lg;
+            std::vector<std::vector<uint32_t>> buckets(nb);
+            for (int b = 0; b < hs.n_bc; b++) {
+                const int m = hs.off[b + 1] - hs.off[b];
+                const int a = hs.allowed0[b];
+                const int seg = m / (a + 1);
+                for (int i = 0; i <= a; i++) {
+                    const int o = i * seg;
+                    uint32_t h = 0;
+                    for (int k = 0; k < q; k++) h = h * kPfBase + (uint32_t)hs.bytes[hs.off[b] + o + k];
+                    buckets[pf_slot(h, lg)].push_back(((uint32_t)b << 8) | (uint32_t)o);
+                    hs.hs_max_off = std::max(hs.hs_max_off, o);
+                }
+            }
+            hs.hs_bstart.assign(nb + 1, 0u);
+            for (uint32_t k = 0; k < nb; k++) {
+                hs.hs_bstart[k + 1] = hs.hs_bstart[k] + (uint32_t)buckets[k].size();
+                hs.hs_entries.insert(hs.hs_entries.end(), buckets[k].begin(), buckets[k].end());
+            }
+            hs.hs_enabled = hs.hs_max_off < 256;
+        }
     }
     return BDX_OK;
 }
@@ -391,6 +442,14 @@ static int get_tables(bdx_config *cfg, int device, DeviceTables **out)
         if (e == cudaSuccess) e = upload(t, hs.pf_keys, &D.pf_keys);
         if (e == cudaSuccess) e = upload(t, hs.pf_vals, &D.pf_vals);
         if (e == cudaSuccess) e = upload(t, hs.bc_cls, &D.bc_cls);
+        D.hs_enabled = hs.hs_enabled;
+        D.hs_q = hs.hs_q;
+        D.hs_pow = hs.hs_pow;
+        D.hs_log2 = hs.hs_log2;
+        D.hs_n_entries = (int)hs.hs_entries.size();
+        D.hs_max_off = hs.hs_max_off;
+        if (e == cudaSuccess) e = upload(t, hs.hs_bstart, &D.hs_bstart);
+        if (e == cudaSuccess) e = upload(t, hs.hs_entries, &D.hs_entries);
         if (e != cudaSuccess) {
             free_tables(t);
             return cuda_fail(e, "uploading barcode tables");
@@ -595,7 +654,13 @@ static int enqueue_classify(bdx_stream *s, const uint8_t *d_seq, const int32_t *
     const DevParams &P = s->tab->P;
     const int passes = P.is_dual ? 2 : 1;
     for (int pass = 0; pass < passes; pass++) {
-        if (exact_hash_applies(P, pass)) {
+        if (hamming_seed_applies(P, pass)) {
+            // :hamming -- pigeonhole seeds + in-place verification, then the literal rules on the candidates
+            CU(launch_seed_hamming(P, pass, d_seq, d_off, n, s->sc, s->tab->sm_count, s->st_comp));
+            s->launches++;
+            CU(launch_literal(P, pass, 1, d_seq, d_off, n, s->sc, s->st_comp));
+            s->launches++;
+        } else if (exact_hash_applies(P, pass)) {
             // :exact -- rolling-hash candidate generation, then the literal rules on the candidates
             CU(launch_prefilter(P, pass, d_seq, d_off, n, s->sc, s->tab->sm_count, s->d_counters, s->st_comp));
             s->launches++;

@@ -54,6 +54,16 @@ struct DevSet {
     const uint32_t *pf_keys;      // [size] hash of the first pf_seed class codes
     const uint32_t *pf_vals;      // [size] (len << 16) | barcode index (lowest of identical sequences); kPfEmpty
     const uint8_t *bc_cls;        // barcode bytes mapped through class_of (same offsets as bc_bytes)
+    // :hamming pigeonhole seeds (filter.cu, k_seed_hamming): allowed_b + 1 disjoint segments per
+    // barcode, the first hs_q bytes of each hashed into a CSR bucket table
+    int hs_enabled;
+    int hs_q;                     // seed length (4..8)
+    uint32_t hs_pow;              // kPfBase^(hs_q-1)
+    int hs_log2;                  // number of buckets = 1 << hs_log2
+    int hs_n_entries;
+    int hs_max_off;               // largest seed offset inside a barcode
+    const uint32_t *hs_bstart;    // [buckets + 1] CSR row starts
+    const uint32_t *hs_entries;   // [n_entries] (barcode index << 8) | seed offset
 };
 
 constexpr int kPfMaxSeed = 12;
@@ -108,6 +118,9 @@ cudaError_t launch_prefilter(const DevParams &P, int pass, const uint8_t *seq, c
                              const Scratch &sc, int sm_count, unsigned long long *counters, cudaStream_t st);
 bool prefilter_applies(const DevParams &P, int pass);
 bool exact_hash_applies(const DevParams &P, int pass);
+bool hamming_seed_applies(const DevParams &P, int pass);
+cudaError_t launch_seed_hamming(const DevParams &P, int pass, const uint8_t *seq, const int *off, int n,
+                                const Scratch &sc, int sm_count, cudaStream_t st);
 cudaError_t launch_finalize(const DevParams &P, const int *off, int n, const Scratch &sc,
                             bdx_result *res, bdx_pass_detail *det, StatsDev stats, cudaStream_t st);
 cudaError_t launch_synth(const DevParams &P, const bdx_synth_spec &spec, int n, uint8_t *seq, int *off,

@@ -388,7 +388,8 @@ constexpr int kPfMaxCand = 2;              // table hits remembered per read; mo
 // the bit-parallel kernel, which is always correct).
 template <typename BytePtr>
 __device__ __forceinline__ int pf_scan(BytePtr c0, int ncols, const DevSet &S, const uint32_t *keys_s,
-                                       const uint32_t *vals_s, const uint32_t *bitmap_s)
+                                       const uint32_t *vals_s, const uint32_t *bitmap_s, bool want_rightmost,
+                                       int &found_w)
 {
     const int seed = S.pf_seed;
     const uint32_t pw = S.pf_pow;
@@ -420,16 +421,22 @@ __device__ __forceinline__ int pf_scan(BytePtr c0, int ncols, const DevSet &S, c
     }
     if (nc > kPfMaxCand) return -1;
     int found = 0x7FFFFFFF;
+    found_w = -1;
 #pragma unroll
     for (int k = 0; k < kPfMaxCand; k++) {
-        if (k < nc && cb[k] < found) {
+        // candidates are in column order: a later occurrence of the SAME barcode replaces the
+        // position only when the rightmost one is wanted (trim_side == 3, classification.jl:613-619)
+        if (k < nc && (cb[k] < found || (cb[k] == found && want_rightmost))) {
             const int b = cb[k];
             const uint8_t *q = S.bc_bytes + S.bc_off[b];
             const int len = S.bc_off[b + 1] - S.bc_off[b];
             bool same = true;
             for (int i = 0; i < len; i++)
                 if (q[i] != c0[cw[k] + i]) { same = false; break; }
-            if (same) found = b;
+            if (same) {
+                found = b;
+                found_w = cw[k];
+            }
         }
     }
     return found;
@@ -485,7 +492,8 @@ __device__ __forceinline__ int pf_scan_exact(BytePtr c0, int n_starts, int cols_
     return nc;
 }
 
-template <int MODE>   // 0: semiglobal perfect-occurrence resolve, 1: :exact candidate generation
+template <int MODE>   // 0: semiglobal perfect-occurrence resolve, 1: :exact candidate generation,
+                      // 2: :hamming perfect-occurrence resolve (with positions)
 __global__ void __launch_bounds__(kPfThreads)
 k_prefilter(const __grid_constant__ DevParams P, const int pass, const uint8_t *__restrict__ seq,
             const int *__restrict__ off, const int n_reads, PassOut *__restrict__ out,
@@ -574,15 +582,41 @@ k_prefilter(const __grid_constant__ DevParams P, const int pass, const uint8_t *
             const int n = off[read + 1] - base;
             const Geometry g = pass_geometry(S, n);
             const int ncols = g.end_j - g.start_j + 1;
-            // same regime test as k_filter's `fast` (score-only / unit costs are config-level and
-            // checked by the launcher)
-            if (g.valid && g.max_start_pos >= n && g.min_end_pos <= g.start_j && ncols >= seed) {
-                int found;
+            if (MODE == 2) {
+                // :hamming -- a placement with 0 mismatches is a verbatim occurrence whose START lies
+                // in [start_j, min(end_j, max_start_pos, n - m + 1)] and whose end is >= min_end_pos
+                // (classification.jl:570-586).  The scan covers every column such a placement can touch.
+                const int last_start = min(g.end_j, g.max_start_pos);
+                const int cols = min(n, last_start + S.max_m - 1) - g.start_j + 1;   // columns a valid placement can touch
+                if (g.valid && cols >= seed) {
+                    int found, w = -1;
+                    const bool right = S.trim_side == 3;
+                    if (staged)
+                        found = pf_scan(stage + skew + (base - blk_base) + g.start_j - 1, cols, S, keys_s, vals_s,
+                                        bitmap_s, right, w);
+                    else
+                        found = pf_scan(seq + base + g.start_j - 1, cols, S, keys_s, vals_s, bitmap_s, right, w);
+                    if (found >= 0 && found != 0x7FFFFFFF) {
+                        const int m = S.bc_off[found + 1] - S.bc_off[found];
+                        const int s1 = g.start_j + w;                       // 1-based start
+                        // `found` is the lowest index among ALL occurrences seen; if its chosen
+                        // (leftmost / rightmost) occurrence is a valid placement it is also the
+                        // reference's answer, otherwise the DP path decides
+                        if (s1 <= min(last_start, n - m + 1) && s1 + m - 1 >= g.min_end_pos) {
+                            out[read] = PassOut{found + 1, 0, s1, s1 + m - 1};
+                            resolved = true;
+                        }
+                    }
+                }
+            } else if (g.valid && g.max_start_pos >= n && g.min_end_pos <= g.start_j && ncols >= seed) {
+                // same regime test as k_filter's `fast` (score-only / unit costs are config-level and
+                // checked by the launcher)
+                int found, w;
                 if (staged)
                     found = pf_scan(stage + skew + (base - blk_base) + g.start_j - 1, ncols, S, keys_s, vals_s,
-                                    bitmap_s);
+                                    bitmap_s, false, w);
                 else
-                    found = pf_scan(seq + base + g.start_j - 1, ncols, S, keys_s, vals_s, bitmap_s);
+                    found = pf_scan(seq + base + g.start_j - 1, ncols, S, keys_s, vals_s, bitmap_s, false, w);
                 if (found >= 0 && found != 0x7FFFFFFF) {
                     out[read] = PassOut{found + 1, 0, -1, -1};
                     resolved = true;
@@ -607,7 +641,7 @@ cudaError_t launch_prefilter(const DevParams &P, int pass, const uint8_t *seq, c
 {
     const DevSet &S = P.set[pass];
     const size_t smem = kPfStageBytes + 16 + ((size_t)8 << S.pf_log2) + ((size_t)4 << (S.pf_bm_log2 - 5));
-    auto kern = P.algo == BDX_EXACT ? k_prefilter<1> : k_prefilter<0>;
+    auto kern = P.algo == BDX_EXACT ? k_prefilter<1> : (P.algo == BDX_HAMMING ? k_prefilter<2> : k_prefilter<0>);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int per_sm = 0;
@@ -623,6 +657,164 @@ cudaError_t launch_prefilter(const DevParams &P, int pass, const uint8_t *seq, c
     return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------------------
+// k_seed_hamming: candidate generation for :hamming by pigeonhole seeds, one thread per read.
+// A placement of barcode b with at most allowed_b mismatches leaves at least one of its
+// allowed_b + 1 disjoint segments untouched, hence the first hs_q bytes of that segment occur
+// verbatim at the corresponding read column.  Every read column's q-mer is hashed (rolling)
+// into a CSR bucket table of (barcode, seed offset) entries; each entry fixes the placement
+// (Hamming distance has no shifts), which is checked against the start/end constraints of
+// hamming_align (classification.jl:570-586) and verified by counting mismatches with the
+// reference's early break (:592-604).  Barcodes with a verified placement form the read's
+// candidate list (distinct, ascending); hamming_literal then computes exactly what the
+// reference would for those barcodes, and all other barcodes return Inf in the reference.
+// ---------------------------------------------------------------------------------------
+template <typename BytePtr>
+__device__ __forceinline__ int seed_scan_hamming(BytePtr rd, int n, const Geometry &g, const DevSet &S,
+                                                 const uint32_t *bstart_s, const uint32_t *entries_s,
+                                                 uint16_t *list)
+{
+    const int q = S.hs_q;
+    const uint32_t pw = S.hs_pow;
+    const int p0 = g.start_j - 1;                                    // 0-based column of the first q-mer
+    const int p1 = min(n - q, g.end_j - 1 + S.hs_max_off);           // last q-mer that can belong to a valid start
+    if (p1 < p0) return 0;
+    uint32_t h = 0;
+    for (int i = 0; i < q; i++) h = h * kPfBase + (uint32_t)rd[p0 + i];
+    int nc = 0, last_b = -1;
+    for (int p = p0;;) {
+        const uint32_t bucket = pf_slot(h, S.hs_log2);
+        const uint32_t e1 = bstart_s[bucket + 1];
+        for (uint32_t e = bstart_s[bucket]; e < e1; e++) {
+            const uint32_t ent = entries_s[e];
+            const int b = (int)(ent >> 8);
+            const int s0 = p - (int)(ent & 0xFFu);                   // 0-based start of the barcode
+            if (b == last_b || s0 < p0) continue;
+            const int qo = S.bc_off[b];
+            const int m = S.bc_off[b + 1] - qo;
+            // start in [first, min(last(range), max_start_pos, n - m + 1)], end >= min_end_pos (:570-586)
+            if (s0 + 1 > min(g.end_j, min(g.max_start_pos, n - m + 1)) || s0 + m < g.min_end_pos) continue;
+            const int allowed = S.allowed0[b];
+            const uint8_t *bc = S.bc_bytes + qo;
+            int mm = 0;
+            for (int k = 0; k < m; k++) {
+                if (bc[k] != rd[s0 + k] && ++mm > allowed) break;
+            }
+            if (mm > allowed) continue;
+            last_b = b;
+            if (nc == kCandOverflow) continue;
+            int pos = 0;                                             // sorted insert, skip duplicates
+            while (pos < nc && list[pos] < b) pos++;
+            if (pos == nc || list[pos] != b) {
+                if (nc == kCandMax) {
+                    nc = kCandOverflow;
+                } else {
+                    for (int k = nc; k > pos; k--) list[k] = list[k - 1];
+                    list[pos] = (uint16_t)b;
+                    nc++;
+                }
+            }
+        }
+        if (++p > p1) break;
+        h = (h - (uint32_t)rd[p - 1] * pw) * kPfBase + (uint32_t)rd[p - 1 + q];
+    }
+    return nc;
+}
+
+__global__ void __launch_bounds__(kPfThreads)
+k_seed_hamming(const __grid_constant__ DevParams P, const int pass, const uint8_t *__restrict__ seq,
+               const int *__restrict__ off, const int n_reads, PassOut *__restrict__ out,
+               const PassOut *__restrict__ prev_pass, uint16_t *__restrict__ cand, uint8_t *__restrict__ cand_cnt)
+{
+    extern __shared__ __align__(16) uint32_t smem[];
+    const DevSet &S = P.set[pass];
+    const int n_buckets = 1 << S.hs_log2;
+    uint8_t *stage = reinterpret_cast<uint8_t *>(smem);                     // kPfStageBytes + 16
+    uint32_t *bstart_s = smem + (kPfStageBytes + 16) / 4;
+    uint32_t *entries_s = bstart_s + n_buckets + 1;
+    for (int k = threadIdx.x; k <= n_buckets; k += blockDim.x) bstart_s[k] = S.hs_bstart[k];
+    for (int k = threadIdx.x; k < S.hs_n_entries; k += blockDim.x) entries_s[k] = S.hs_entries[k];
+
+    const int n_groups = (n_reads + kPfThreads - 1) / kPfThreads;
+    for (int grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
+        const int r0 = grp * kPfThreads;
+        const int r1 = min(r0 + kPfThreads, n_reads);
+        const int blk_base = off[r0];
+        const int blk_end = off[r1];
+        const uintptr_t g0 = reinterpret_cast<uintptr_t>(seq + blk_base);
+        const int skew = (int)(g0 & 15);
+        const bool staged = blk_end - blk_base + skew <= kPfStageBytes;
+        __syncthreads();
+        if (staged) {
+            const uint8_t *src = seq + blk_base - skew;
+            const int total = blk_end - blk_base + skew;
+            const int vecs = total >> 4;
+            const uint4 *src16 = reinterpret_cast<const uint4 *>(src);
+            uint4 *dst16 = reinterpret_cast<uint4 *>(stage);
+            for (int k = threadIdx.x; k < vecs; k += blockDim.x) dst16[k] = __ldg(src16 + k);
+            for (int k = (vecs << 4) + threadIdx.x; k < total; k += blockDim.x) stage[k] = src[k];
+        }
+        __syncthreads();
+        const int read = r0 + threadIdx.x;
+        if (read >= n_reads) continue;
+        if (pass == 1 && prev_pass[read].bc <= 0) {
+            out[read] = PassOut{kBcNotRun, 0, -1, -1};
+            continue;
+        }
+        const int base = off[read];
+        const int n = off[read + 1] - base;
+        const Geometry g = pass_geometry(S, n);
+        int nc = 0;
+        uint16_t *list = cand + (size_t)read * kCandMax;
+        if (g.valid) {
+            if (staged)
+                nc = seed_scan_hamming(stage + skew + (base - blk_base), n, g, S, bstart_s, entries_s, list);
+            else
+                nc = seed_scan_hamming(seq + base, n, g, S, bstart_s, entries_s, list);
+        }
+        if (nc == 0) {
+            out[read] = PassOut{kBcUnknown, 0, -1, -1};
+        } else {
+            cand_cnt[read] = (uint8_t)nc;
+            out[read] = PassOut{kBcPending, 0, -1, -1};
+        }
+    }
+}
+
+static size_t seed_hamming_smem(const DevSet &S)
+{
+    return kPfStageBytes + 16 + ((size_t)(1 << S.hs_log2) + 1 + (size_t)S.hs_n_entries) * 4;
+}
+
+cudaError_t launch_seed_hamming(const DevParams &P, int pass, const uint8_t *seq, const int *off, int n,
+                                const Scratch &sc, int sm_count, cudaStream_t st)
+{
+    const DevSet &S = P.set[pass];
+    const size_t smem = seed_hamming_smem(S);
+    cudaError_t e = cudaFuncSetAttribute(k_seed_hamming, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_seed_hamming, kPfThreads, smem);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) per_sm = 1;
+    const int groups = (n + kPfThreads - 1) / kPfThreads;
+    const int blocks = std::min(groups, sm_count * per_sm);
+    k_seed_hamming<<<blocks, kPfThreads, smem, st>>>(P, pass, seq, off, n, sc.pass[pass], sc.pass[0], sc.cand,
+                                                     sc.cand_cnt);
+    return cudaGetLastError();
+}
+
+// Measured on B200 (config 5, 1 536 barcodes, q = 4): 4.7 M reads/s against 7.4 M reads/s for the
+// bit-parallel filter -- ~30 table entries per column make the per-thread byte-wise verification
+// diverge badly.  Kept for experiments (BDX_HAMMING_SEEDS=1) until the verification is rewritten
+// on 2-bit packed words; off by default.
+bool hamming_seed_applies(const DevParams &P, int pass)
+{
+    static const bool on = getenv("BDX_HAMMING_SEEDS") != nullptr;
+    const DevSet &S = P.set[pass];
+    return on && P.algo == BDX_HAMMING && S.hs_enabled && seed_hamming_smem(S) <= 200 * 1024;
+}
+
 // :exact with a hash table: k_prefilter<1> replaces the Shift-And filter kernel altogether
 bool exact_hash_applies(const DevParams &P, int pass)
 {
@@ -634,6 +826,8 @@ bool exact_hash_applies(const DevParams &P, int pass)
 bool prefilter_applies(const DevParams &P, int pass)
 {
     const DevSet &S = P.set[pass];
+    if (P.algo == BDX_HAMMING)   // positions are produced, so trim / stats are fine; needs no wildcard rows
+        return S.words > 0 && S.pf_enabled && P.min_delta == 0.0 && P.max_error_rate >= 0.0;
     return P.algo == BDX_SEMIGLOBAL && S.words > 0 && S.pf_enabled && P.unit_costs && S.trim_side == 0 &&
            !P.want_stats && P.min_delta == 0.0 && P.max_error_rate >= 0.0;
 }

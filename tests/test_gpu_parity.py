@@ -114,7 +114,14 @@ CONFIGS = {
     "hamming": dict(n_bc=96, m=(24, 24), matching_algorithm="hamming", n_frac=0.05),
     "hamming_trim3": dict(n_bc=40, m=(6, 12), matching_algorithm="hamming", trim_side=3, max_error_rate=0.34,
                           min_delta=0.1, barcode_start_range=R("1:40"), barcode_end_range=R("10:end")),
+    "hamming_pf": dict(n_bc=96, m=(24, 24), matching_algorithm="hamming", want_stats=True),
+    "hamming_pf_trim3": dict(n_bc=64, m=(10, 20), matching_algorithm="hamming", trim_side=3, max_error_rate=0.15,
+                             barcode_start_range=R("1:60"), barcode_end_range=R("15:end")),
+    "hamming_pf_trim5": dict(n_bc=64, m=(10, 20), matching_algorithm="hamming", trim_side=5,
+                             ref_search_range=R("3:90"), barcode_end_range=R("end-80:end")),
     "exact": dict(n_bc=96, m=(24, 24), matching_algorithm="exact"),
+    "exact_var": dict(n_bc=200, m=(8, 30), matching_algorithm="exact", trim_side=5, barcode_start_range=R("2:70"),
+                      barcode_end_range=R("20:end"), want_stats=True),
     "exact_trim3": dict(n_bc=30, m=(4, 8), matching_algorithm="exact", trim_side=3, min_delta=0.5,
                         barcode_start_range=R("1:60"), barcode_end_range=R("8:end")),
 }
@@ -244,3 +251,26 @@ def test_prefilter_counters():
         pre, auto = eng.stream.path_counters()
     assert (res["bc1"][:1000] == (np.arange(1000) % 96) + 1).all()
     assert pre >= 1000 and pre + auto == 2000
+
+
+def test_hash_paths_with_repeats_and_duplicates(monkeypatch):
+    """:hamming / :exact hash paths on adversarial inputs: duplicated barcodes, barcodes that are
+    prefixes of others, reads with the same barcode several times (rightmost / leftmost rules),
+    low-complexity reads with many table hits; hash paths off must agree."""
+    rng = np.random.default_rng(33)
+    base = synth.random_barcodes(rng, 30, 12, 12)
+    bcs = base + [base[2], base[5], base[5] + "ACGT", "A" * 12, "AC" * 6] + synth.random_barcodes(rng, 20, 13, 16)
+    reads = synth.random_reads(rng, 1500, bcs, min_len=40, max_len=130, max_edits=2)
+    for i in range(200):
+        b = bcs[int(rng.integers(0, len(bcs)))].encode()
+        reads.append(b"GT" * int(rng.integers(0, 5)) + b + b"TGCA" * int(rng.integers(0, 4)) + b + b"CC")
+    reads += [b"A" * 100, b"AC" * 60, b"ACGT" * 30, b"", b"ACGTACGTACG"]
+    for algo in ("hamming", "exact"):
+        for kw in (dict(), dict(trim_side=3), dict(trim_side=5, barcode_start_range=R("1:30")),
+                   dict(min_delta=0.2), dict(barcode_end_range=R("30:end"), trim_side=3)):
+            cfg = _cfg(bcs, matching_algorithm=algo, max_error_rate=0.1, **kw)
+            res, _ = compare(cfg, reads, label=f"{algo} {kw}")
+            monkeypatch.setenv("BDX_DISABLE_PREFILTER", "1")
+            off, _, _, _ = run_cuda(cfg, reads)
+            monkeypatch.delenv("BDX_DISABLE_PREFILTER")
+            assert (res == off).all(), (algo, kw)

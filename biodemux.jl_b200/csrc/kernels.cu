@@ -17,8 +17,12 @@ namespace bdx {
 //   from_filter = 1 : only reads the filter kernel left kBcPending; their
 //                     candidate list (or the whole set on overflow) is evaluated
 // ---------------------------------------------------------------------------
-template <int MAXM>
-__global__ void __launch_bounds__(128)
+constexpr int kLiteralThreads = 128;
+
+// SMEM_WS: the DP / origin columns live in shared memory as [row][thread] instead of in
+// thread-local (i.e. off-chip, L1-cached) arrays.
+template <int MAXM, bool SMEM_WS>
+__global__ void __launch_bounds__(kLiteralThreads)
 k_literal(const __grid_constant__ DevParams P, const int pass, const int from_filter,
           const uint8_t *__restrict__ seq, const int *__restrict__ off, const int n_reads,
           PassOut *__restrict__ out, const PassOut *__restrict__ prev_pass,
@@ -46,8 +50,12 @@ k_literal(const __grid_constant__ DevParams P, const int pass, const int from_fi
         out[i] = o;
         return;
     }
-    int DP[MAXM + 2];
-    int OR[MAXM + 2];
+    extern __shared__ int ws_smem[];
+    int dp_local[SMEM_WS ? 1 : MAXM + 2];
+    int or_local[SMEM_WS ? 1 : MAXM + 2];
+    const WsCol DP{SMEM_WS ? ws_smem + threadIdx.x : dp_local, SMEM_WS ? kLiteralThreads : 1};
+    const WsCol OR{SMEM_WS ? ws_smem + (MAXM + 2) * kLiteralThreads + threadIdx.x : or_local,
+                   SMEM_WS ? kLiteralThreads : 1};
     const Costs c{P.match, P.mismatch, P.indel, P.nindel, P.has_n};
     const bool with_delta = P.min_delta != 0.0;                   // :723
     const bool need_tb = S.trim_side != 0 || P.want_stats;         // :812
@@ -99,17 +107,30 @@ cudaError_t launch_literal(const DevParams &P, int pass, int from_filter, const 
                            const int *off, int n, const Scratch &sc, cudaStream_t st)
 {
     if (n <= 0) return cudaSuccess;
-    const int threads = 128;
+    const int threads = kLiteralThreads;
     const int blocks = (n + threads - 1) / threads;
     const int max_m = P.set[pass].max_m;
     PassOut *out = sc.pass[pass];
     const PassOut *prev = sc.pass[0];
-    if (max_m <= 32)
-        k_literal<32><<<blocks, threads, 0, st>>>(P, pass, from_filter, seq, off, n, out, prev, sc.cand, sc.cand_cnt);
-    else if (max_m <= 64)
-        k_literal<64><<<blocks, threads, 0, st>>>(P, pass, from_filter, seq, off, n, out, prev, sc.cand, sc.cand_cnt);
-    else
-        k_literal<kMaxBarcodeLen><<<blocks, threads, 0, st>>>(P, pass, from_filter, seq, off, n, out, prev, sc.cand, sc.cand_cnt);
+    if (max_m <= 32) {
+        const size_t smem = (size_t)2 * (32 + 2) * threads * sizeof(int);
+        k_literal<32, true><<<blocks, threads, smem, st>>>(P, pass, from_filter, seq, off, n, out, prev, sc.cand,
+                                                           sc.cand_cnt);
+    } else if (max_m <= 64) {
+        const size_t smem = (size_t)2 * (64 + 2) * threads * sizeof(int);
+        static bool attr_set = false;
+        if (!attr_set) {
+            cudaError_t e = cudaFuncSetAttribute(k_literal<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 (int)smem);
+            if (e != cudaSuccess) return e;
+            attr_set = true;
+        }
+        k_literal<64, true><<<blocks, threads, smem, st>>>(P, pass, from_filter, seq, off, n, out, prev, sc.cand,
+                                                           sc.cand_cnt);
+    } else {
+        k_literal<kMaxBarcodeLen, false><<<blocks, threads, 0, st>>>(P, pass, from_filter, seq, off, n, out, prev,
+                                                                     sc.cand, sc.cand_cnt);
+    }
     return cudaGetLastError();
 }
 

@@ -64,8 +64,17 @@ __device__ __forceinline__ Geometry pass_geometry(const DevSet &S, int n)
 // semiglobal_alignment_core (classification.jl:238-445).  q1 / r1 are 1-based
 // (pointer to the byte before the first).  Returns the integer score or kInf;
 // TB selects TracebackOutput(trim_side) vs ScoreOnly.
+// Workspace column (SemiGlobalWorkspace.DP / .origin, classification.jl:1-6): element i of this
+// thread lives at base[i * stride] -- stride 1 for thread-local arrays, stride = block size for
+// the shared-memory layout [row][thread] (conflict-free: a warp touches 32 consecutive words).
+struct WsCol {
+    int *base;
+    int stride;
+    __device__ __forceinline__ int &operator[](int i) const { return base[i * stride]; }
+};
+
 template <bool TB>
-__device__ int sg_literal(int *DP, int *OR, const uint8_t *q1, const uint8_t *r1, int m, int n,
+__device__ int sg_literal(const WsCol DP, const WsCol OR, const uint8_t *q1, const uint8_t *r1, int m, int n,
                           int allowed_error, const Costs &c, int trim_side, int range_first,
                           int range_last, int max_start_pos, int min_end_pos, int &out_s, int &out_e)
 {

@@ -274,3 +274,18 @@ def test_hash_paths_with_repeats_and_duplicates(monkeypatch):
             off, _, _, _ = run_cuda(cfg, reads)
             monkeypatch.delenv("BDX_DISABLE_PREFILTER")
             assert (res == off).all(), (algo, kw)
+
+
+@pytest.mark.parametrize("algo", ["semiglobal", "hamming", "exact"])
+def test_long_and_ragged_reads(algo):
+    """Reads longer than one staging tile (256 columns) and blocks of reads that exceed the
+    prefilter's shared-memory stage (48 KB per 256 reads) take the multi-tile / global-memory
+    paths; mixed with very short reads."""
+    rng = np.random.default_rng(41)
+    bcs = synth.random_barcodes(rng, 40, 20, 24)
+    reads = synth.random_reads(rng, 700, bcs, min_len=300, max_len=2000, max_edits=3)
+    reads += synth.random_reads(rng, 700, bcs, min_len=5, max_len=600, max_edits=3)
+    rng.shuffle(reads)
+    for kw in (dict(), dict(trim_side=3), dict(ref_search_range=R("end-400:end"), min_delta=0.05),
+               dict(barcode_start_range=R("200:end"), trim_side=5)):
+        compare(_cfg(bcs, matching_algorithm=algo, **kw), reads, label=f"long {algo} {kw}")

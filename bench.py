@@ -261,7 +261,7 @@ def run_ours(args):
     launches = stream.launch_count - l0
     filt_ms, filt_n = stream.profile_read()
     stream.profile(False)
-    pre_reads, auto_reads = stream.path_counters(reset=True)
+    pre_reads, seed_reads, auto_reads = stream.path_counters(reset=True)
     auto_per_launch = auto_reads / max(filt_n, 1)       # reads that actually ran the DP automaton
     clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([ms], dtype=torch.float64, device="cuda")
@@ -280,7 +280,8 @@ def run_ours(args):
             print(json.dumps({"value": value, "ms_per_step": ms_max / args.steps, "kernel_ms": filt_s * 1e3,
                               "matched_fraction": matched / n, "peak_Tops": peak_ops.value / 1e12,
                               "achieved_Tops": OPS_PER_READ * auto_per_launch / filt_s / 1e12,
-                              "prefilter_fraction": pre_reads / max(pre_reads + auto_reads, 1), "clocks": clocks,
+                              "prefilter_fraction": pre_reads / max(pre_reads + seed_reads + auto_reads, 1),
+                              "seed_fraction": seed_reads / max(pre_reads + seed_reads + auto_reads, 1), "clocks": clocks,
                               "variant": os.environ.get("BDX_FILTER_VARIANT")}))
         stream.close()
         return
@@ -382,6 +383,7 @@ def run_ours(args):
                          "kernel_share_of_step": filt_ms / ms if ms else None,
                          "ops_per_read": OPS_PER_READ, "reads_through_automaton_per_launch": auto_per_launch,
                          "reads_resolved_by_prefilter_per_launch": pre_reads / max(filt_n, 1),
+                         "reads_resolved_by_seed_kernel_per_launch": seed_reads / max(filt_n, 1),
                          "peak_source": "bdx_int_alu_peak: LOP3/IADD3 chains measured live on this GPU",
                          "hbm": {"achieved": hbm_gbs, "peak": hbm_peak, "unit": "GB/s",
                                  "frac": hbm_gbs / hbm_peak, "peak_source": hbm_src,

@@ -127,7 +127,7 @@ def load_library():
     L.bdx_stream_launch_count.restype = i64
     L.bdx_stream_profile.argtypes = [vp, C.c_int]
     L.bdx_stream_profile_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(i32)]
-    L.bdx_stream_path_counters.argtypes = [vp, C.POINTER(i64), C.POINTER(i64), C.c_int]
+    L.bdx_stream_path_counters.argtypes = [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64), C.c_int]
     L.bdx_stats_layout_get.argtypes = [vp, C.POINTER(StatsLayout)]
     L.bdx_stats_fetch.argtypes = [vp, vp, i64]
     L.bdx_stats_device_ptr.argtypes = [vp]
@@ -316,10 +316,11 @@ class Stream:
         return ms.value, n.value
 
     def path_counters(self, reset: bool = False):
-        """(reads resolved by the perfect-occurrence prefilter, reads that ran the automaton)."""
-        a, b = C.c_int64(), C.c_int64()
-        _check(self.lib.bdx_stream_path_counters(self.handle, C.byref(a), C.byref(b), int(reset)))
-        return a.value, b.value
+        """(reads resolved by the perfect-occurrence prefilter, by the seed-and-verify kernel,
+        reads that ran the full-range automaton)."""
+        a, b, c = C.c_int64(), C.c_int64(), C.c_int64()
+        _check(self.lib.bdx_stream_path_counters(self.handle, C.byref(a), C.byref(b), C.byref(c), int(reset)))
+        return a.value, b.value, c.value
 
     def stats(self) -> np.ndarray:
         out = np.zeros(self.config.layout.total_len, dtype=np.int64)

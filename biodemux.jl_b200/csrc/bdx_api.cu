@@ -72,6 +72,10 @@ struct HostSet {
     int hs_enabled = 0, hs_q = 0, hs_log2 = 0, hs_max_off = 0;
     uint32_t hs_pow = 0;
     std::vector<uint32_t> hs_bstart, hs_entries;
+    // :semiglobal depth-limited seeds
+    int sd_enabled = 0, sd_k = 0, sd_q = 0, sd_log2 = 0, sd_bm_log2 = 0, sd_m = 0;
+    uint32_t sd_pow = 0;
+    std::vector<uint32_t> sd_bstart, sd_entries, sd_ekeys, sd_bitmap;
 };
 
 struct DeviceTables {
@@ -228,7 +232,7 @@ static int build_set(const bdx_params &p, const bdx_barcode_set &in, HostSet &hs
             const int m = hs.off[b + 1] - hs.off[b];
             uint32_t h = 0;
             for (int i = 0; i < seed; i++) h = h * kPfBase + (uint32_t)hs.bytes[hs.off[b] + i];
-            const uint32_t bit = h >> (32 - bl);
+            const uint32_t bit = pf_bit(h, bl);
             hs.pf_bitmap[bit >> 5] |= 1u << (bit & 31);
             uint32_t slot = pf_slot(h, lg);
             bool dup = false;
@@ -248,6 +252,55 @@ static int build_set(const bdx_params &p, const bdx_barcode_set &in, HostSet &hs
             }
         }
         hs.pf_enabled = 1;
+    }
+    // ---- :semiglobal depth-limited seeds (seed.cu): uniform barcode length, no wildcard rows ----
+    if (hs.pf_enabled && sg && hs.words == 1 && min_m == hs.max_m && hs.allowed0[0] >= 1 &&
+        !getenv("BDX_DISABLE_SEED")) {
+        const int m = hs.max_m, allowed = hs.allowed0[0];
+        // deepest level whose seeds are long enough to be selective: q >= 6 and at most ~0.12
+        // chance hits per read column (entries / alphabet^q)
+        const double alpha = std::max(2, hs.n_classes - 1);
+        int K = 0;
+        for (int k = 1; k <= allowed; k++) {
+            const int qk = std::min(8, m / (k + 1));
+            if (qk >= 6 && (double)hs.n_bc * (k + 1) / std::pow(alpha, qk) <= 0.12) K = k;
+        }
+        if (K >= 1) {
+            const int seg = m / (K + 1), q = std::min(8, seg);
+            hs.sd_k = K;
+            hs.sd_q = q;
+            hs.sd_m = m;
+            uint32_t pw = 1;
+            for (int i = 1; i < q; i++) pw *= kPfBase;
+            hs.sd_pow = pw;
+            const size_t n_entries = (size_t)hs.n_bc * (K + 1);
+            int lg = 8;
+            while (lg < 14 && (size_t)(1 << lg) < n_entries) lg++;
+            hs.sd_log2 = lg;
+            int bl = 13;                                // ~64 bits per entry: 4 KB for 96 barcodes
+            while (bl < 18 && ((size_t)1 << bl) < 64 * n_entries) bl++;
+            hs.sd_bm_log2 = bl;
+            hs.sd_bitmap.assign((size_t)1 << (bl - 5), 0u);
+            std::vector<std::vector<std::pair<uint32_t, uint32_t>>> buckets((size_t)1 << lg);
+            for (int b = 0; b < hs.n_bc; b++)
+                for (int i = 0; i <= K; i++) {
+                    const int o = i * seg;
+                    uint32_t h = 0;
+                    for (int k = 0; k < q; k++) h = h * kPfBase + (uint32_t)hs.bc_cls[hs.off[b] + o + k];
+                    const uint32_t bit = pf_bit(h, bl);
+                    hs.sd_bitmap[bit >> 5] |= 1u << (bit & 31);
+                    buckets[pf_slot(h, lg)].emplace_back(((uint32_t)b << 8) | (uint32_t)o, h);
+                }
+            hs.sd_bstart.assign(((size_t)1 << lg) + 1, 0u);
+            for (size_t k = 0; k < buckets.size(); k++) {
+                hs.sd_bstart[k + 1] = hs.sd_bstart[k] + (uint32_t)buckets[k].size();
+                for (auto &pr : buckets[k]) {
+                    hs.sd_entries.push_back(pr.first);
+                    hs.sd_ekeys.push_back(pr.second);
+                }
+            }
+            hs.sd_enabled = 1;
+        }
     }
     // ---- :hamming pigeonhole seeds: mismatches <= allowed_b leave one of allowed_b + 1 disjoint
     // segments of the barcode intact, so every acceptable placement contains an exact seed ----
@@ -442,6 +495,18 @@ static int get_tables(bdx_config *cfg, int device, DeviceTables **out)
         if (e == cudaSuccess) e = upload(t, hs.pf_keys, &D.pf_keys);
         if (e == cudaSuccess) e = upload(t, hs.pf_vals, &D.pf_vals);
         if (e == cudaSuccess) e = upload(t, hs.bc_cls, &D.bc_cls);
+        D.sd_enabled = hs.sd_enabled;
+        D.sd_k = hs.sd_k;
+        D.sd_q = hs.sd_q;
+        D.sd_pow = hs.sd_pow;
+        D.sd_log2 = hs.sd_log2;
+        D.sd_bm_log2 = hs.sd_bm_log2;
+        D.sd_n_entries = (int)hs.sd_entries.size();
+        D.sd_m = hs.sd_m;
+        if (e == cudaSuccess) e = upload(t, hs.sd_bstart, &D.sd_bstart);
+        if (e == cudaSuccess) e = upload(t, hs.sd_entries, &D.sd_entries);
+        if (e == cudaSuccess) e = upload(t, hs.sd_ekeys, &D.sd_ekeys);
+        if (e == cudaSuccess) e = upload(t, hs.sd_bitmap, &D.sd_bitmap);
         D.hs_enabled = hs.hs_enabled;
         D.hs_q = hs.hs_q;
         D.hs_pow = hs.hs_pow;
@@ -519,6 +584,8 @@ static int ensure_scratch(bdx_stream *s, int64_t n)
     cudaFree(s->sc.cand_cnt);
     cudaFree(s->sc.worklist);
     cudaFree(s->sc.n_work);
+    cudaFree(s->sc.worklist2);
+    cudaFree(s->sc.n_work2);
     s->sc = Scratch{};
     s->sc_cap = 0;
     const int64_t cap = n + n / 8 + 1024;
@@ -528,6 +595,8 @@ static int ensure_scratch(bdx_stream *s, int64_t n)
     CU(cudaMalloc(&s->sc.cand_cnt, cap));
     CU(cudaMalloc(&s->sc.worklist, cap * sizeof(int)));
     CU(cudaMalloc(&s->sc.n_work, sizeof(int)));
+    CU(cudaMalloc(&s->sc.worklist2, cap * sizeof(int)));
+    CU(cudaMalloc(&s->sc.n_work2, sizeof(int)));
     s->sc_cap = cap;
     return BDX_OK;
 }
@@ -558,6 +627,8 @@ extern "C" void bdx_stream_destroy(bdx_stream *s)
     cudaFree(s->sc.cand_cnt);
     cudaFree(s->sc.worklist);
     cudaFree(s->sc.n_work);
+    cudaFree(s->sc.worklist2);
+    cudaFree(s->sc.n_work2);
     cudaFree(s->d_stats);
     cudaFree(s->d_counters);
     for (auto &pr : s->prof_events) {
@@ -672,13 +743,19 @@ static int enqueue_classify(bdx_stream *s, const uint8_t *d_seq, const int32_t *
                 CU(launch_prefilter(P, pass, d_seq, d_off, n, s->sc, s->tab->sm_count, s->d_counters, s->st_comp));
                 s->launches++;
             }
+            int wl = pre ? 1 : 0;
+            if (pre && seed_applies(P, pass)) {
+                CU(launch_seed(P, pass, d_seq, d_off, n, s->sc, s->tab->sm_count, s->d_counters, s->st_comp));
+                s->launches++;
+                wl = 2;
+            }
             cudaEvent_t e0 = nullptr, e1 = nullptr;
             if (s->profile) {
                 CU(cudaEventCreate(&e0));
                 CU(cudaEventCreate(&e1));
                 CU(cudaEventRecord(e0, s->st_comp));
             }
-            CU(launch_filter(P, pass, d_seq, d_off, n, s->sc, s->tab->sm_count, s->d_counters, pre, s->st_comp));
+            CU(launch_filter(P, pass, d_seq, d_off, n, s->sc, s->tab->sm_count, s->d_counters, wl, s->st_comp));
             s->launches++;
             if (s->profile) {
                 CU(cudaEventRecord(e1, s->st_comp));
@@ -907,8 +984,8 @@ extern "C" int bdx_stream_profile_read(bdx_stream *s, double *filter_ms, int32_t
     return BDX_OK;
 }
 
-extern "C" int bdx_stream_path_counters(bdx_stream *s, int64_t *prefilter_reads, int64_t *automaton_reads,
-                                        int reset)
+extern "C" int bdx_stream_path_counters(bdx_stream *s, int64_t *prefilter_reads, int64_t *seed_reads,
+                                        int64_t *automaton_reads, int reset)
 {
     if (!s) return fail(BDX_ERR_INVALID, "null stream");
     CU(cudaSetDevice(s->device));
@@ -916,6 +993,7 @@ extern "C" int bdx_stream_path_counters(bdx_stream *s, int64_t *prefilter_reads,
     unsigned long long h[4];
     CU(cudaMemcpy(h, s->d_counters, sizeof(h), cudaMemcpyDeviceToHost));
     if (prefilter_reads) *prefilter_reads = (int64_t)h[0];
+    if (seed_reads) *seed_reads = (int64_t)h[2];
     if (automaton_reads) *automaton_reads = (int64_t)h[1];
     if (reset) CU(cudaMemset(s->d_counters, 0, sizeof(h)));
     return BDX_OK;

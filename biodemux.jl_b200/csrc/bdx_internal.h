@@ -64,6 +64,20 @@ struct DevSet {
     int hs_max_off;               // largest seed offset inside a barcode
     const uint32_t *hs_bstart;    // [buckets + 1] CSR row starts
     const uint32_t *hs_entries;   // [n_entries] (barcode index << 8) | seed offset
+    // :semiglobal depth-limited seeds (seed.cu, k_seed): for uniform-length sets, every alignment
+    // with <= sd_k edits leaves one of sd_k + 1 disjoint barcode segments intact
+    int sd_enabled;
+    int sd_k;                     // edit depth the seeds are complete for (<= allowed)
+    int sd_q;                     // seed length (6..8)
+    uint32_t sd_pow;              // kPfBase^(sd_q-1)
+    int sd_log2;                  // buckets = 1 << sd_log2
+    int sd_bm_log2;               // first-level bitmap bits = 1 << sd_bm_log2
+    int sd_n_entries;
+    int sd_m;                     // the common barcode length
+    const uint32_t *sd_bstart;    // [buckets + 1]
+    const uint32_t *sd_entries;   // [n_entries] (barcode index << 8) | seed offset
+    const uint32_t *sd_ekeys;     // [n_entries] hash of the entry's q-mer
+    const uint32_t *sd_bitmap;
 };
 
 constexpr int kPfMaxSeed = 12;
@@ -75,6 +89,13 @@ constexpr uint32_t kPfEmpty = 0xFFFFFFFFu;
 __host__ __device__ inline uint32_t pf_slot(uint32_t h, int log2size)
 {
     return (h * kPfMix) >> (32 - log2size);
+}
+// first-level bitmap index.  The polynomial hash keeps its last bytes in the LOW bits, so the top
+// bits alone would alias all q-mers that differ only at the end; multiply first.
+constexpr uint32_t kPfMix2 = 0xC2B2AE35u;
+__host__ __device__ inline uint32_t pf_bit(uint32_t h, int log2bits)
+{
+    return (h * kPfMix2) >> (32 - log2bits);
 }
 
 struct DevParams {
@@ -104,16 +125,21 @@ struct Scratch {
     PassOut *pass[2];
     uint16_t *cand;       // [n][kCandMax]
     uint8_t *cand_cnt;    // [n]
-    int *worklist;        // [n] reads the prefilter left for the bit-parallel kernel
+    int *worklist;        // [n] reads the prefilter left for the next stage
     int *n_work;          // [1]
+    int *worklist2;       // [n] reads the seed kernel left for the bit-parallel kernel
+    int *n_work2;         // [1]
 };
 
 // ---- launch wrappers (kernels.cu / filter.cu) ----
 cudaError_t launch_literal(const DevParams &P, int pass, int from_filter, const uint8_t *seq,
                            const int *off, int n, const Scratch &sc, cudaStream_t st);
 cudaError_t launch_filter(const DevParams &P, int pass, const uint8_t *seq, const int *off, int n,
-                          const Scratch &sc, int sm_count, unsigned long long *counters, bool use_worklist,
-                          cudaStream_t st);
+                          const Scratch &sc, int sm_count, unsigned long long *counters, int use_worklist,
+                          cudaStream_t st);   // use_worklist: 0 = all reads, 1 = worklist, 2 = worklist2
+bool seed_applies(const DevParams &P, int pass);
+cudaError_t launch_seed(const DevParams &P, int pass, const uint8_t *seq, const int *off, int n, const Scratch &sc,
+                        int sm_count, unsigned long long *counters, cudaStream_t st);
 cudaError_t launch_prefilter(const DevParams &P, int pass, const uint8_t *seq, const int *off, int n,
                              const Scratch &sc, int sm_count, unsigned long long *counters, cudaStream_t st);
 bool prefilter_applies(const DevParams &P, int pass);

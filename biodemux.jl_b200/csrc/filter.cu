@@ -393,14 +393,14 @@ __device__ __forceinline__ int pf_scan(BytePtr c0, int ncols, const DevSet &S, c
 {
     const int seed = S.pf_seed;
     const uint32_t pw = S.pf_pow;
-    const int bm_shift = 32 - S.pf_bm_log2;
+    const int bm_log2 = S.pf_bm_log2;
     const uint32_t size_mask = (1u << S.pf_log2) - 1u;
     uint32_t h = 0;
     for (int i = 0; i < seed; i++) h = h * kPfBase + (uint32_t)c0[i];
     int cb[kPfMaxCand], cw[kPfMaxCand], nc = 0;
     const int nwin = ncols - seed + 1;
     for (int w = 0;;) {
-        const uint32_t bit = h >> bm_shift;
+        const uint32_t bit = pf_bit(h, bm_log2);
         if ((bitmap_s[bit >> 5] >> (bit & 31)) & 1u) {       // rare: some barcode prefix hashes here
             uint32_t slot = pf_slot(h, S.pf_log2);
             for (;;) {
@@ -457,13 +457,13 @@ __device__ __forceinline__ int pf_scan_exact(BytePtr c0, int n_starts, int cols_
     // columns available from c0 to the end of the read
     const int seed = S.pf_seed;
     const uint32_t pw = S.pf_pow;
-    const int bm_shift = 32 - S.pf_bm_log2;
+    const int bm_log2 = S.pf_bm_log2;
     const uint32_t size_mask = (1u << S.pf_log2) - 1u;
     uint32_t h = 0;
     for (int i = 0; i < seed; i++) h = h * kPfBase + (uint32_t)c0[i];
     int nc = 0;
     for (int w = 0;;) {
-        const uint32_t bit = h >> bm_shift;
+        const uint32_t bit = pf_bit(h, bm_log2);
         if ((bitmap_s[bit >> 5] >> (bit & 31)) & 1u) {
             uint32_t slot = pf_slot(h, S.pf_log2);
             for (;;) {
@@ -843,7 +843,7 @@ static size_t filter_smem_bytes(const DevSet &S)
 
 template <int W, int G, int CODING, bool PAIR>
 static cudaError_t launch_wgv(const DevParams &P, int pass, const uint8_t *seq, const int *off, int n,
-                              const Scratch &sc, int sm_count, unsigned long long *counters, bool use_worklist,
+                              const Scratch &sc, int sm_count, unsigned long long *counters, int use_worklist,
                               cudaStream_t st)
 {
     const size_t smem = filter_smem_bytes(P.set[pass]);
@@ -861,8 +861,8 @@ static cudaError_t launch_wgv(const DevParams &P, int pass, const uint8_t *seq, 
     if (blocks < 1) blocks = 1;
     kern<<<(unsigned)blocks, kFilterWarps * 32, smem, st>>>(P, pass, seq, off, n, sc.pass[pass], sc.pass[0],
                                                             sc.cand, sc.cand_cnt, counters,
-                                                            use_worklist ? sc.worklist : nullptr,
-                                                            use_worklist ? sc.n_work : nullptr);
+                                                            use_worklist == 2 ? sc.worklist2 : (use_worklist ? sc.worklist : nullptr),
+                                                            use_worklist == 2 ? sc.n_work2 : (use_worklist ? sc.n_work : nullptr));
     return cudaGetLastError();
 }
 
@@ -881,7 +881,7 @@ static int filter_variant()
 
 template <int W, int G>
 static cudaError_t launch_wg(const DevParams &P, int pass, const uint8_t *seq, const int *off, int n,
-                             const Scratch &sc, int sm_count, unsigned long long *counters, bool use_worklist,
+                             const Scratch &sc, int sm_count, unsigned long long *counters, int use_worklist,
                              cudaStream_t st)
 {
     if (P.algo == BDX_EXACT && !getenv("BDX_EXACT_VIA_MYERS"))
@@ -902,7 +902,7 @@ static cudaError_t launch_wg(const DevParams &P, int pass, const uint8_t *seq, c
 }
 
 cudaError_t launch_filter(const DevParams &P, int pass, const uint8_t *seq, const int *off, int n,
-                          const Scratch &sc, int sm_count, unsigned long long *counters, bool use_worklist,
+                          const Scratch &sc, int sm_count, unsigned long long *counters, int use_worklist,
                           cudaStream_t st)
 {
     if (n <= 0) return cudaSuccess;

@@ -191,9 +191,11 @@ void *bdx_stream_cuda_stream(bdx_stream *s);
  * since the last read, and clears the list. */
 int bdx_stream_profile(bdx_stream *s, int on);
 int bdx_stream_profile_read(bdx_stream *s, double *filter_ms, int32_t *n_launches);
-/* How many reads (summed over passes) were resolved by the perfect-occurrence prefilter and
- * how many ran the bit-parallel automaton since the last reset (syncs the stream). */
-int bdx_stream_path_counters(bdx_stream *s, int64_t *prefilter_reads, int64_t *automaton_reads, int reset);
+/* How many reads (summed over passes) were resolved by the perfect-occurrence prefilter, by the
+ * depth-limited seed-and-verify kernel, and how many ran the full-range bit-parallel automaton
+ * since the last reset (syncs the stream). */
+int bdx_stream_path_counters(bdx_stream *s, int64_t *prefilter_reads, int64_t *seed_reads,
+                             int64_t *automaton_reads, int reset);
 /* number of kernel launches this stream has issued so far */
 int64_t bdx_stream_launch_count(const bdx_stream *s);
 

@@ -248,9 +248,9 @@ def test_prefilter_counters():
     blob, off = bdx.pack_reads(reads)
     with capi.Engine(cfg, max_reads=len(reads), max_bytes=int(off[-1])) as eng:
         res = eng.classify_packed(blob, off)
-        pre, auto = eng.stream.path_counters()
+        pre, seed, auto = eng.stream.path_counters()
     assert (res["bc1"][:1000] == (np.arange(1000) % 96) + 1).all()
-    assert pre >= 1000 and pre + auto == 2000
+    assert pre >= 1000 and pre + seed + auto == 2000
 
 
 def test_hash_paths_with_repeats_and_duplicates(monkeypatch):

@@ -37,6 +37,11 @@ CU_PER_READ = N_BARCODES * BARCODE_LEN * READ_LEN          # full-matrix cell up
 OPS_PER_READ = 17 * N_BARCODES * ((BARCODE_LEN + 31) // 32) * READ_LEN   # algorithmic int-ops
 BYTES_PER_READ = READ_LEN + 4 + 20                         # sequence + offset in, bdx_result out
 CHUNK = 4000                                               # reference chunk_size (core.jl:521)
+# DRAM traffic of the dominant kernel from the committed `ncu --set full` capture
+# (profiles/r01b_kernels_ncu_summary.txt: k_filter<1,3,0,1>, 4 M-read step, 519 681 reads through the
+# automaton): dram__bytes_read.sum 164.43 MB + dram__bytes_write.sum 15.67 MB.  Per read that is 2x the
+# algorithmic 174 B: worklist-scattered 150-byte reads touch 6 32-byte sectors, offsets / PassOut one each.
+NCU_FILTER_DRAM_BYTES_PER_READ = (164.432640e6 + 15.673600e6) / 519681
 
 
 def make_config():
@@ -318,6 +323,18 @@ def run_ours(args):
 
     for _ in range(max(1, min(args.warmup, 2))):
         e2e_step()
+    # what the host link gives a plain pinned H2D copy of one batch (the e2e path's own bound)
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    d_probe = torch.empty(B * READ_LEN, dtype=torch.uint8, device="cuda")
+    d_probe.copy_(h_seq[:B * READ_LEN], non_blocking=True)
+    torch.cuda.synchronize()
+    p0.record()
+    for k in range(4):
+        d_probe.copy_(h_seq[k * B * READ_LEN:(k + 1) * B * READ_LEN], non_blocking=True)
+    p1.record()
+    torch.cuda.synchronize()
+    pcie_h2d_gbs = 4 * B * READ_LEN / (p0.elapsed_time(p1) * 1e-3) / 1e9
+    del d_probe
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
@@ -379,7 +396,10 @@ def run_ours(args):
                        "matched_fraction": matched / n, "e2e_batch_reads": B},
             "roofline": {"bound": "int_alu", "achieved": achieved_ops / 1e12, "peak": peak_ops.value / 1e12,
                          "unit": "Tint-op/s", "frac": achieved_ops / peak_ops.value if peak_ops.value else None,
-                         "traffic": None, "kernel": "k_filter<1,3>", "kernel_ms": filt_s * 1e3,
+                         "traffic": NCU_FILTER_DRAM_BYTES_PER_READ * auto_per_launch,
+                         "traffic_unit": "DRAM bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum per "
+                                         "automaton read, profiles/r01b_kernels_ncu_summary.txt, x reads per launch here)",
+                         "kernel": "k_filter<1,3>", "kernel_ms": filt_s * 1e3,
                          "kernel_share_of_step": filt_ms / ms if ms else None,
                          "ops_per_read": OPS_PER_READ, "reads_through_automaton_per_launch": auto_per_launch,
                          "reads_resolved_by_prefilter_per_launch": pre_reads / max(filt_n, 1),
@@ -390,7 +410,11 @@ def run_ours(args):
                                  "bytes_per_read": BYTES_PER_READ}},
             "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": nb * (B * READ_LEN + 4 * (B + 1)),
                     "d2h_bytes_per_step": nb * B * bdx.RESULT_DTYPE.itemsize,
-                    "api": "bdx_submit_pinned / bdx_fetch_view, 3 batches in flight"},
+                    "api": "bdx_submit_pinned / bdx_fetch_view, 3 batches in flight",
+                    "h2d_gbs_achieved": e2e_value / world * (READ_LEN + 4) / 1e9,
+                    "h2d_gbs_plain_memcpy": pcie_h2d_gbs,
+                    "bound": "host link: every read is 154 B of H2D; a bare pinned cudaMemcpyAsync of the same "
+                             "bytes runs at h2d_gbs_plain_memcpy on this box"},
             "gpu_launches": launches, "clocks": clocks,
         }
         if stats_ms is not None:

@@ -30,7 +30,7 @@ EXPORTS = [
     "bdx_fetch", "bdx_fetch_view", "bdx_classify", "bdx_classify_device", "bdx_stream_sync",
     "bdx_stream_cuda_stream", "bdx_stream_launch_count", "bdx_stream_profile", "bdx_stream_profile_read", "bdx_stream_path_counters", "bdx_stats_layout_get", "bdx_stats_fetch",
     "bdx_stats_device_ptr", "bdx_stats_reset", "bdx_synth_reads_device", "bdx_int_alu_peak",
-    "bdx_fastq_scan", "bdx_fastq_pack",
+    "bdx_fastq_scan", "bdx_fastq_pack", "bdx_demux_block", "bdx_demux_stage_ms",
 ]
 
 
@@ -73,6 +73,17 @@ class SynthSpec(C.Structure):
                 ("n_permille_x10", C.c_int32), ("set2_mode", C.c_int32), ("end_lo", C.c_int32),
                 ("end_hi", C.c_int32)]
 
+
+class DemuxOut(C.Structure):
+    _fields_ = [("n_records", C.c_int32), ("n_buckets", C.c_int32), ("consumed1", C.c_int64),
+                ("consumed2", C.c_int64), ("out1", C.c_void_p), ("out1_len", C.c_int64), ("out2", C.c_void_p),
+                ("out2_len", C.c_int64), ("buckets", C.c_void_p), ("results", C.c_void_p)]
+
+
+# bdx_demux_bucket (include/bdx.h)
+BUCKET_DTYPE = np.dtype([("status", "<i4"), ("bc1", "<i4"), ("bc2", "<i4"), ("n_records", "<i4"),
+                         ("offset1", "<i8"), ("length1", "<i8"), ("offset2", "<i8"), ("length2", "<i8")])
+DEMUX_SINGLE, DEMUX_MATES, DEMUX_BOTH, DEMUX_DEVICE_IO = 0, 1, 2, 16
 
 FASTQ_REC_DTYPE = np.dtype([("header_off", "<i8"), ("seq_off", "<i8"), ("plus_off", "<i8"), ("qual_off", "<i8"),
                             ("header_len", "<i4"), ("seq_len", "<i4"), ("plus_len", "<i4"), ("qual_len", "<i4")])
@@ -137,6 +148,8 @@ def load_library():
     L.bdx_int_alu_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]
     L.bdx_fastq_scan.argtypes = [vp, i64, C.c_int, i32, vp, C.POINTER(i32), C.POINTER(i64)]
     L.bdx_fastq_pack.argtypes = [vp, vp, i32, vp, i64, vp]
+    L.bdx_demux_block.argtypes = [vp, vp, i64, vp, i64, C.c_int, C.c_int, C.POINTER(DemuxOut)]
+    L.bdx_demux_stage_ms.argtypes = [vp, C.POINTER(C.c_float * 8)]
     _LIB = L
     return L
 
@@ -321,6 +334,39 @@ class Stream:
         a, b, c = C.c_int64(), C.c_int64(), C.c_int64()
         _check(self.lib.bdx_stream_path_counters(self.handle, C.byref(a), C.byref(b), C.byref(c), int(reset)))
         return a.value, b.value, c.value
+
+    def demux_block(self, fastq1, fastq2=None, final_block: int = 1, mode: int = DEMUX_SINGLE):
+        """bdx_demux_block over host uint8 arrays (or ``(device_ptr, length)`` pairs with
+        DEMUX_DEVICE_IO).  Returns the raw ``DemuxOut``; host-mode helpers: ``demux_views``."""
+        def ptr_len(x):
+            if x is None:
+                return None, 0
+            if isinstance(x, tuple):
+                return x[0], int(x[1])
+            return (x.ctypes.data if x.size else None), int(x.size)
+        p1, l1 = ptr_len(fastq1)
+        p2, l2 = ptr_len(fastq2)
+        out = DemuxOut()
+        _check(self.lib.bdx_demux_block(self.handle, p1, l1, p2, l2, int(final_block), int(mode), C.byref(out)))
+        return out
+
+    @staticmethod
+    def demux_views(out: "DemuxOut"):
+        """numpy views (no copy; valid until the next demux_block) of a host-mode DemuxOut:
+        (buckets, out1 bytes, out2 bytes, per-record results)."""
+        def view(ptr, nbytes, dtype=np.uint8):
+            if not ptr or nbytes == 0:
+                return np.zeros(0, dtype)
+            buf = (C.c_char * nbytes).from_address(ptr)
+            return np.frombuffer(buf, dtype=dtype)
+        buckets = view(out.buckets, out.n_buckets * BUCKET_DTYPE.itemsize, BUCKET_DTYPE)
+        res = view(out.results, out.n_records * RESULT_DTYPE.itemsize, RESULT_DTYPE)
+        return buckets, view(out.out1, out.out1_len), view(out.out2, out.out2_len), res
+
+    def demux_stage_ms(self):
+        ms = (C.c_float * 8)()
+        _check(self.lib.bdx_demux_stage_ms(self.handle, C.byref(ms)))
+        return list(ms)
 
     def stats(self) -> np.ndarray:
         out = np.zeros(self.config.layout.total_len, dtype=np.int64)

@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "bdx_internal.h"
+#include "demux.h"
 
 using namespace bdx;
 
@@ -571,6 +572,7 @@ struct bdx_stream {
     // optional per-kernel timing of the dominant (filter) kernel, for roofline reporting
     bool profile = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
+    DemuxState *demux = nullptr;               // device FASTQ block demultiplexer (demux.cu), created on first use
 };
 
 static int ensure_scratch(bdx_stream *s, int64_t n)
@@ -631,6 +633,7 @@ extern "C" void bdx_stream_destroy(bdx_stream *s)
     cudaFree(s->sc.n_work2);
     cudaFree(s->d_stats);
     cudaFree(s->d_counters);
+    demux_state_destroy(s->demux);
     for (auto &pr : s->prof_events) {
         cudaEventDestroy(pr.first);
         cudaEventDestroy(pr.second);
@@ -1001,6 +1004,36 @@ extern "C" int bdx_stream_path_counters(bdx_stream *s, int64_t *prefilter_reads,
 
 extern "C" void *bdx_stream_cuda_stream(bdx_stream *s) { return s ? (void *)s->st_comp : nullptr; }
 extern "C" int64_t bdx_stream_launch_count(const bdx_stream *s) { return s ? s->launches : 0; }
+
+// ---------------------------------------------------------------------------
+// device FASTQ block demultiplexer (demux.cu)
+// ---------------------------------------------------------------------------
+extern "C" int bdx_demux_block(bdx_stream *s, const uint8_t *fq1, int64_t len1, const uint8_t *fq2, int64_t len2,
+                               int final_block, int mode, bdx_demux_out *out)
+{
+    if (!s || !out) return fail(BDX_ERR_INVALID, "null argument");
+    if ((mode & 3) > BDX_DEMUX_BOTH || (mode & ~(3 | BDX_DEMUX_DEVICE_IO))) return fail(BDX_ERR_INVALID, "unknown demux mode");
+    if (s->in_flight) return fail(BDX_ERR_STATE, "batches in flight");
+    CU(cudaSetDevice(s->device));
+    if (!s->demux && !(s->demux = demux_state_create())) return fail(BDX_ERR_NOMEM, "out of memory");
+    std::string err;
+    const int rc = demux_run(
+        s->demux, s->tab->P, s->st_comp,
+        [s](const uint8_t *d_seq, const int *d_off, int n, bdx_result *d_res) {
+            return enqueue_classify(s, d_seq, d_off, n, d_res, nullptr);
+        },
+        fq1, len1, fq2, len2, final_block, mode, &s->launches, out, err);
+    if (rc && !err.empty()) g_err = err;
+    return rc;
+}
+
+extern "C" int bdx_demux_stage_ms(const bdx_stream *s, float ms[8])
+{
+    if (!s || !ms) return fail(BDX_ERR_INVALID, "null argument");
+    if (!s->demux) return fail(BDX_ERR_STATE, "no bdx_demux_block call yet");
+    memcpy(ms, demux_stage_ms(s->demux), 8 * sizeof(float));
+    return BDX_OK;
+}
 
 // ---------------------------------------------------------------------------
 // stats

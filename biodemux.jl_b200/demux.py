@@ -155,6 +155,86 @@ def run_pipeline(cfg: DemuxConfig, classify_chunk: Callable[[Sequence[bytes]], n
         w.close()
 
 
+class _BlockReader:
+    """Blocks of (inflated) FASTQ text with the unconsumed tail carried over to the next block."""
+
+    def __init__(self, path: Optional[str], block_bytes: int):
+        from .fileio import smart_open
+        self.fh = smart_open(path, "r") if path is not None else None
+        self.block_bytes = block_bytes
+        self.tail = b""
+        self.eof = self.fh is None
+
+    def next_block(self) -> np.ndarray:
+        data = b""
+        if not self.eof and len(self.tail) < self.block_bytes:
+            data = self.fh.read(self.block_bytes)
+            if not self.fh.peek(1):
+                self.eof = True
+        buf = self.tail + data
+        self.tail = b""
+        return np.frombuffer(buf, dtype=np.uint8)
+
+    def keep_tail(self, buf: np.ndarray, consumed: int):
+        self.tail = buf[consumed:].tobytes()
+
+    def close(self):
+        if self.fh is not None:
+            self.fh.close()
+
+
+def run_pipeline_device(cfg: DemuxConfig, stream, fastq1: str, fastq2: Optional[str], output_dir: str,
+                        prefix1: str, prefix2: str, block_bytes: int = 32 << 20):
+    """The host side of the device FASTQ path (``bdx_demux_block``): read blocks of text, hand them to the
+    GPU, append every returned bucket to its file.  Replaces reader_task's record splitting
+    (core.jl:43-110) and writer_task's per-record trimming and routing (core.jl:118-224); file naming and
+    append semantics are the reference's."""
+    from .capi import DEMUX_BOTH, DEMUX_MATES, DEMUX_SINGLE
+
+    os.makedirs(output_dir, exist_ok=True)
+    paired = fastq2 is not None
+    mode = DEMUX_SINGLE if not paired else (DEMUX_BOTH if cfg.classify_both else DEMUX_MATES)
+    r1, r2 = _BlockReader(fastq1, block_bytes), _BlockReader(fastq2, block_bytes)
+    handles: Dict[str, object] = {}
+
+    def handle(filename: str):
+        h = handles.get(filename)
+        if h is None:
+            path = os.path.join(output_dir, filename)
+            h = gzip.open(path, "ab") if (cfg.gzip_output or path.lower().endswith(".gz")) else open(path, "ab")
+            handles[filename] = h
+        return h
+
+    try:
+        while True:
+            b1 = r1.next_block()
+            b2 = r2.next_block() if paired else None
+            if b1.size == 0 or (paired and b2.size == 0):
+                break       # `while !eof(io1) && !eof(io2)` (core.jl:48): an exhausted input ends the run
+            final = (1 if r1.eof else 0) | (2 if paired and r2.eof else 0)
+            out = stream.demux_block(b1, b2, final_block=final, mode=mode)
+            buckets, o1, o2, _ = stream.demux_views(out)
+            for bk in buckets:
+                name = output_filename(cfg, int(bk["status"]), int(bk["bc1"]), int(bk["bc2"]))
+                if mode != DEMUX_MATES:
+                    handle(prefix1 + "." + name).write(o1[bk["offset1"]:bk["offset1"] + bk["length1"]].tobytes())
+                if mode != DEMUX_SINGLE:
+                    handle(prefix2 + "." + name).write(o2[bk["offset2"]:bk["offset2"] + bk["length2"]].tobytes())
+            r1.keep_tail(b1, out.consumed1)
+            if paired:
+                r2.keep_tail(b2, out.consumed2)
+            if out.n_records == 0:
+                if r1.eof and r2.eof:
+                    break
+                r1.block_bytes *= 2     # a record longer than the block: take more text next time
+                r2.block_bytes *= 2
+    finally:
+        r1.close()
+        r2.close()
+        for h in handles.values():
+            h.close()
+
+
 def _strip_fastq_ext(path: str) -> str:
     return re.sub(r"\.fastq(\.gz)?$", "", os.path.basename(path))
 
@@ -173,7 +253,7 @@ def execute_demultiplexing(fastq1: str, a: str, b: str, c: Optional[str] = None,
                            trim_side: Optional[int] = None, trim_side2: Optional[int] = None,
                            summary: bool = False, summary_format: str = "html",
                            matching_algorithm: str = "semiglobal", log: bool = False,
-                           device: int = 0):
+                           device: int = 0, device_io: bool = False, block_bytes: int = 32 << 20):
     """Both reference methods (core.jl:360-392 paired, :500-529 single):
 
         execute_demultiplexing(FASTQ_file, barcode_file, output_directory; ...)
@@ -200,7 +280,11 @@ def execute_demultiplexing(fastq1: str, a: str, b: str, c: Optional[str] = None,
                        ref_search_range2, barcode_start_range2, barcode_end_range2,
                        trim_side, trim_side2, summary, summary_format, matching_algorithm)
     with Engine(cfg, device=device, max_reads=chunk_size) as eng:
-        run_pipeline(cfg, eng.classify_reads, fastq1, fastq2, output_directory, prefix1, prefix2, chunk_size)
+        if device_io:
+            # FASTQ text in, per-file record runs out, all on the device (bdx_demux_block)
+            run_pipeline_device(cfg, eng.stream, fastq1, fastq2, output_directory, prefix1, prefix2, block_bytes)
+        else:
+            run_pipeline(cfg, eng.classify_reads, fastq1, fastq2, output_directory, prefix1, prefix2, chunk_size)
         if cfg.summary:
             return eng.demux_stats()
     return None

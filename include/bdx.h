@@ -246,6 +246,58 @@ int bdx_fastq_scan(const uint8_t *buf, int64_t len, int final_block, int32_t max
 int bdx_fastq_pack(const uint8_t *buf, const bdx_fastq_record *recs, int32_t n, uint8_t *seq_out,
                    int64_t seq_cap, int32_t *offsets_out);
 
+/* ---- device FASTQ block demultiplexer (SURVEY.md section 8f-1 + 8f-3) --------------------------
+ * The data formats either side of the hot path, on the device: raw FASTQ text in (the bytes
+ * reader_task would split with four readlines per record, core.jl:96-101), and per output file one
+ * contiguous run of finished records out -- header, sequence[keep], plus, quality[keep], each
+ * followed by "\n" (write_entry, core.jl:135-137; keep range applied as in core.jl:155-173) -- in
+ * input order (core.jl:146-148).  The host appends every bucket to its file
+ * (prefix "." ids[bc1] ["." ids2[bc2]] ".fastq[.gz]", "unknown...", "ambiguous_classification...",
+ * classification.jl:877-900): one write per file and block instead of one per record. */
+typedef struct bdx_demux_bucket {
+    int32_t status;     /* bdx_read_status: which output file */
+    int32_t bc1, bc2;   /* 1-based, 0 = none (as in bdx_result) */
+    int32_t n_records;
+    int64_t offset1, length1;   /* byte range in out1: the read-1 records (trimmed) */
+    int64_t offset2, length2;   /* byte range in out2: the mate records (never trimmed) */
+} bdx_demux_bucket;
+
+typedef struct bdx_demux_out {
+    int32_t n_records;          /* complete records taken from the block(s) */
+    int32_t n_buckets;
+    int64_t consumed1, consumed2;   /* bytes of each input covered by those records; re-present the
+                                       rest in front of the next block */
+    const uint8_t *out1;        /* file-1 records grouped by bucket (NULL in BDX_DEMUX_MATES mode) */
+    int64_t out1_len;
+    const uint8_t *out2;        /* mate records grouped by bucket (NULL in BDX_DEMUX_SINGLE mode) */
+    int64_t out2_len;
+    const bdx_demux_bucket *buckets;   /* ascending (status-or-barcode) key order */
+    const bdx_result *results;  /* per record, input order */
+} bdx_demux_out;
+
+enum {
+    BDX_DEMUX_SINGLE = 0,       /* single-end (core.jl:191-196) */
+    BDX_DEMUX_MATES = 1,        /* paired, classify_both = false: only file 2 is written, routed by read 1 (:185-190) */
+    BDX_DEMUX_BOTH = 2,         /* paired, classify_both = true (:174-184) */
+    BDX_DEMUX_DEVICE_IO = 16    /* OR-ed in: fastq1 / fastq2 are device pointers (16-byte aligned) and the
+                                   out pointers stay on the device */
+};
+
+/* One block of FASTQ text per input file (fastq2 / len2 ignored in BDX_DEMUX_SINGLE mode).  Records
+ * are complete when all four lines are terminated inside the block; when the block is the last of
+ * its file (single-end: final_block != 0; paired: bit 0 of final_block for file 1, bit 1 for file 2)
+ * a truncated last record is completed with empty lines, as `readline` at EOF does.  In the paired
+ * modes min(records of file 1, records of file 2) records are taken (`while !eof(io1) && !eof(io2)`,
+ * core.jl:48): stop once a final block has been consumed completely.  Blocks must stay below 2^31 bytes.  Synchronous; the pointers in *out
+ * belong to the stream and stay valid until its next bdx_demux_block call.  When the config was
+ * created with want_stats the DemuxStats counters are updated as by any other classification. */
+int bdx_demux_block(bdx_stream *s, const uint8_t *fastq1, int64_t len1, const uint8_t *fastq2, int64_t len2,
+                    int final_block, int mode, bdx_demux_out *out);
+/* CUDA-event milliseconds of the last bdx_demux_block call: [0] H2D, [1] newline index + records,
+ * [2] sequence packing, [3] classification, [4] keys + stable radix sort, [5] offsets + bucket
+ * table, [6] record copy, [7] D2H. */
+int bdx_demux_stage_ms(const bdx_stream *s, float ms[8]);
+
 /* ---- bench / test utilities (not part of the reference boundary) ----------
  * Synthetic reads of SURVEY.md section 8(d): fixed-length reads over ACGT with a
  * barcode of set 1 (and set 2 when dual) planted after k random edits.  Philox-style

@@ -31,6 +31,9 @@ EXPORTS = [
     "bdx_stream_cuda_stream", "bdx_stream_launch_count", "bdx_stream_profile", "bdx_stream_profile_read", "bdx_stream_path_counters", "bdx_stats_layout_get", "bdx_stats_fetch",
     "bdx_stats_device_ptr", "bdx_stats_reset", "bdx_synth_reads_device", "bdx_int_alu_peak",
     "bdx_fastq_scan", "bdx_fastq_pack", "bdx_demux_block", "bdx_demux_stage_ms",
+    "bdx_barcode_table_load", "bdx_barcode_table_destroy", "bdx_barcode_table_count", "bdx_barcode_table_id_count",
+    "bdx_barcode_table_bytes", "bdx_barcode_table_offsets", "bdx_barcode_table_lengths_no_n", "bdx_barcode_table_id",
+    "bdx_barcode_table_error",
 ]
 
 
@@ -148,6 +151,18 @@ def load_library():
     L.bdx_int_alu_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]
     L.bdx_fastq_scan.argtypes = [vp, i64, C.c_int, i32, vp, C.POINTER(i32), C.POINTER(i64)]
     L.bdx_fastq_pack.argtypes = [vp, vp, i32, vp, i64, vp]
+    L.bdx_barcode_table_load.argtypes = [C.c_char_p, C.c_int, C.c_int, C.POINTER(vp)]
+    L.bdx_barcode_table_destroy.argtypes = [vp]
+    L.bdx_barcode_table_destroy.restype = None
+    for name in ("count", "id_count"):
+        getattr(L, "bdx_barcode_table_" + name).argtypes = [vp]
+        getattr(L, "bdx_barcode_table_" + name).restype = i32
+    for name in ("bytes", "offsets", "lengths_no_n"):
+        getattr(L, "bdx_barcode_table_" + name).argtypes = [vp]
+        getattr(L, "bdx_barcode_table_" + name).restype = vp
+    L.bdx_barcode_table_id.argtypes = [vp, i32]
+    L.bdx_barcode_table_id.restype = C.c_char_p
+    L.bdx_barcode_table_error.restype = C.c_char_p
     L.bdx_demux_block.argtypes = [vp, vp, i64, vp, i64, C.c_int, C.c_int, C.POINTER(DemuxOut)]
     L.bdx_demux_stage_ms.argtypes = [vp, C.POINTER(C.c_float * 8)]
     _LIB = L
@@ -182,6 +197,26 @@ def fastq_pack(buf: np.ndarray, recs: np.ndarray, seq_out: Optional[np.ndarray] 
     _check(load_library().bdx_fastq_pack(buf.ctypes.data if buf.size else None, recs.ctypes.data, len(recs),
                                          seq_out.ctypes.data, seq_out.size, off.ctypes.data))
     return seq_out[:total], off
+
+
+def load_barcode_table(path: str, complement: bool = False, rev: bool = False):
+    """bdx_barcode_table_load -> ``(sequences, lengths_no_N, ids)`` like preprocess_bc_file (fileio.jl:7-72)."""
+    L = load_library()
+    h = C.c_void_p()
+    rc = L.bdx_barcode_table_load(os.fsencode(path), int(complement), int(rev), C.byref(h))
+    if rc != BDX_OK:
+        raise BdxError(rc, L.bdx_barcode_table_error().decode("utf-8", "replace"))
+    try:
+        n, n_ids = L.bdx_barcode_table_count(h), L.bdx_barcode_table_id_count(h)
+        off = np.ctypeslib.as_array(C.cast(L.bdx_barcode_table_offsets(h), C.POINTER(C.c_int32)), (n + 1,)).copy()
+        blob = C.string_at(L.bdx_barcode_table_bytes(h), int(off[-1]))
+        lens = (np.ctypeslib.as_array(C.cast(L.bdx_barcode_table_lengths_no_n(h), C.POINTER(C.c_int32)), (n,)).tolist()
+                if n else [])
+        seqs = [blob[off[i]:off[i + 1]].decode("utf-8", "replace") for i in range(n)]
+        ids = [L.bdx_barcode_table_id(h, i).decode("utf-8", "replace") for i in range(n_ids)]
+    finally:
+        L.bdx_barcode_table_destroy(h)
+    return seqs, lens, ids
 
 
 class Config:

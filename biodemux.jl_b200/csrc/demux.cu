@@ -231,16 +231,67 @@ k_fq_records(const uint8_t *__restrict__ text, const int len, const int *__restr
     if (seq_len) seq_len[i] = r.len[1];
 }
 
+// Warp-wide byte copy with 32-bit stores: the destination is brought to 4-byte alignment, then every lane
+// moves one word per step, assembled from the two aligned source words that hold its bytes (funnel shift).
+// The aligned source words read never reach past the word that holds the last source byte.
+__device__ __forceinline__ void warp_copy(uint8_t *__restrict__ dst, const uint8_t *__restrict__ src, int len, int lane)
+{
+    const int head = min(len, (int)((4u - (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 3u)) & 3u));
+    if (lane < head) dst[lane] = src[lane];
+    dst += head;
+    src += head;
+    len -= head;
+    const int words = len >> 2;
+    const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(src) & 3u);
+    const uint32_t *sw = reinterpret_cast<const uint32_t *>(src - mis);
+    uint32_t *dw = reinterpret_cast<uint32_t *>(dst);
+    // four words per lane are loaded before the first store, so a whole 512-byte stretch is in flight
+    if (mis == 0) {
+        for (int w0 = lane; w0 < words; w0 += 128) {
+            uint32_t v[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+                if (w0 + 32 * u < words) v[u] = sw[w0 + 32 * u];
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+                if (w0 + 32 * u < words) dw[w0 + 32 * u] = v[u];
+        }
+    } else {
+        const uint32_t sh = mis * 8u;
+        for (int w0 = lane; w0 < words; w0 += 128) {
+            uint32_t v[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+                if (w0 + 32 * u < words) v[u] = __funnelshift_r(sw[w0 + 32 * u], sw[w0 + 32 * u + 1], sh);
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+                if (w0 + 32 * u < words) dw[w0 + 32 * u] = v[u];
+        }
+    }
+    const int done = words << 2;
+    if (lane < len - done) dst[done + lane] = src[done + lane];
+}
+
+// One warp per 32 records: the lanes fetch the 32 records' metadata together, then the warp copies the
+// records one after the other (a warp per record would pay the metadata latency once per record).
 __global__ void __launch_bounds__(256)
 k_fq_pack(const uint8_t *__restrict__ text, const FqRec *__restrict__ recs, const int *__restrict__ off,
           const int n_rec, uint8_t *__restrict__ seq)
 {
     const int lane = threadIdx.x & 31;
-    const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (i >= n_rec) return;
-    const int s = recs[i].start[1], l = recs[i].len[1];
-    uint8_t *dst = seq + off[i];
-    for (int t = lane; t < l; t += 32) dst[t] = text[s + t];
+    const int i0 = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32;
+    if (i0 >= n_rec) return;
+    const int i = i0 + lane;
+    int src = 0, len = 0, dst = 0;
+    if (i < n_rec) {
+        src = recs[i].start[1];
+        len = recs[i].len[1];
+        dst = off[i];
+    }
+    const int cnt = min(32, n_rec - i0);
+    for (int r = 0; r < cnt; r++)
+        warp_copy(seq + __shfl_sync(0xFFFFFFFFu, dst, r), text + __shfl_sync(0xFFFFFFFFu, src, r),
+                  __shfl_sync(0xFFFFFFFFu, len, r), lane);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -420,30 +471,67 @@ k_part_buckets(const int *__restrict__ bstart, const int *__restrict__ bkey, con
 // ---------------------------------------------------------------------------------------
 // 8: write_entry (core.jl:135-137) for every record, at its final place
 // ---------------------------------------------------------------------------------------
-__device__ __forceinline__ uint8_t *emit_line(uint8_t *dst, const uint8_t *__restrict__ src, int len, int lane)
-{
-    for (int t = lane; t < len; t += 32) dst[t] = src[t];
-    if (lane == 0) dst[len] = '\n';
-    return dst + len + 1;
-}
-
+// One warp per 32 consecutive output records: every lane prepares one record (its source runs), then the
+// warp copies the records one after the other.
 __global__ void __launch_bounds__(256)
-k_part_copy(const uint8_t *__restrict__ text, const FqRec *__restrict__ recs, const bdx_result *__restrict__ res,
-            const int do_trim, const int *__restrict__ sidx, const long long *__restrict__ ooff, const int n,
-            uint8_t *__restrict__ out)
+k_part_copy(const uint8_t *__restrict__ text, const int text_len, const FqRec *__restrict__ recs,
+            const bdx_result *__restrict__ res, const int do_trim, const int *__restrict__ sidx,
+            const long long *__restrict__ ooff, const int n, uint8_t *__restrict__ out)
 {
     const int lane = threadIdx.x & 31;
-    const int p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (p >= n) return;
-    const int i = sidx[p];
-    const FqRec r = recs[i];
-    int ns = r.len[1], nq = r.len[3], first = 0;
-    if (res) first = keep_of(res[i], do_trim, r.len[1], r.len[3], ns, nq);
-    uint8_t *dst = out + ooff[p];
-    dst = emit_line(dst, text + r.start[0], r.len[0], lane);
-    dst = emit_line(dst, text + r.start[1] + first, ns, lane);
-    dst = emit_line(dst, text + r.start[2], r.len[2], lane);
-    emit_line(dst, text + r.start[3] + first, nq, lane);
+    const int p0 = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32;
+    if (p0 >= n) return;
+    const int p = p0 + lane;
+    // the four output lines as source runs; a run whose "\n" sits right behind it in the text takes it along,
+    // and runs that are adjacent in the text merge: an untrimmed "\n"-terminated record is ONE copy.
+    // run_len: bytes to copy (incl. a trailing "\n" taken from the text); run_nl: 1 = write the "\n" separately
+    int run_src[4] = {0, 0, 0, 0}, run_len[4] = {0, 0, 0, 0}, run_nl[4] = {0, 0, 0, 0}, n_runs = 0;
+    long long dst0 = 0;
+    if (p < n) {
+        const int i = sidx[p];
+        const FqRec r = recs[i];
+        int ns = r.len[1], nq = r.len[3], first = 0;
+        if (res) first = keep_of(res[i], do_trim, r.len[1], r.len[3], ns, nq);
+        const int src[4] = {r.start[0], r.start[1] + first, r.start[2], r.start[3] + first};
+        const int len[4] = {r.len[0], ns, r.len[2], nq};
+        bool nl[4];      // the text has the line's own "\n" directly behind the run
+        nl[0] = r.start[1] == r.start[0] + r.len[0] + 1;
+        nl[1] = first + ns == r.len[1] && r.start[2] == r.start[1] + r.len[1] + 1;
+        nl[2] = r.start[3] == r.start[2] + r.len[2] + 1;
+        const int e = r.start[3] + r.len[3];
+        nl[3] = first + nq == r.len[3] && e < text_len && text[e] == '\n';
+        dst0 = ooff[p];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            // line k extends the current run when it starts right after that run's "\n"
+            const bool joins = k > 0 && run_nl[n_runs - 1] == 0 && src[k] == run_src[n_runs - 1] + run_len[n_runs - 1];
+            if (joins) {
+                run_len[n_runs - 1] += len[k] + (nl[k] ? 1 : 0);
+                run_nl[n_runs - 1] = nl[k] ? 0 : 1;
+            } else {
+                run_src[n_runs] = src[k];
+                run_len[n_runs] = len[k] + (nl[k] ? 1 : 0);
+                run_nl[n_runs] = nl[k] ? 0 : 1;
+                n_runs++;
+            }
+        }
+    }
+    const int cnt = min(32, n - p0);
+    for (int r = 0; r < cnt; r++) {
+        uint8_t *dst = out + __shfl_sync(0xFFFFFFFFu, dst0, r);
+        const int nr = __shfl_sync(0xFFFFFFFFu, n_runs, r);
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int rs = __shfl_sync(0xFFFFFFFFu, run_src[k], r);
+            const int rl = __shfl_sync(0xFFFFFFFFu, run_len[k], r);
+            const int rn = __shfl_sync(0xFFFFFFFFu, run_nl[k], r);
+            if (k < nr) {
+                warp_copy(dst, text + rs, rl, lane);
+                if (rn && lane == 0) dst[rl] = '\n';
+                dst += rl + rn;
+            }
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -625,7 +713,7 @@ int demux_run(DemuxState *d, const DevParams &P, cudaStream_t st, const DemuxCla
     int *off = d->seq_len.as<int>();
     DM(scan_exclusive<int>(off, off, n, (long long)n + 1, d->scan_ws.p, st));
     DM(d->seq.reserve((size_t)len[0] + 16, st));
-    k_fq_pack<<<(n + 7) / 8, 256, 0, st>>>(text[0], d->side[0].recs.as<FqRec>(), off, n, d->seq.as<uint8_t>());
+    k_fq_pack<<<(n + 255) / 256, 256, 0, st>>>(text[0], d->side[0].recs.as<FqRec>(), off, n, d->seq.as<uint8_t>());
     DM(cudaGetLastError());
     *launches += 2;
     DM(cudaEventRecord(d->ev[3], st));
@@ -704,7 +792,7 @@ int demux_run(DemuxState *d, const DevParams &P, cudaStream_t st, const DemuxCla
         if (!(s == 0 ? emit1 : emit2)) continue;
         DemuxSide &S = d->side[s];
         DM(S.out.reserve((size_t)len[s] + 16, st));
-        k_part_copy<<<(n + 7) / 8, 256, 0, st>>>(text[s], S.recs.as<FqRec>(), s == 0 ? d->res.as<bdx_result>() : nullptr, do_trim,
+        k_part_copy<<<(n + 255) / 256, 256, 0, st>>>(text[s], (int)len[s], S.recs.as<FqRec>(), s == 0 ? d->res.as<bdx_result>() : nullptr, do_trim,
                                                  sidx, s == 0 ? ss1 : ss2, n, S.out.as<uint8_t>());
         DM(cudaGetLastError());
         *launches += 1;

@@ -246,6 +246,26 @@ int bdx_fastq_scan(const uint8_t *buf, int64_t len, int final_block, int32_t max
 int bdx_fastq_pack(const uint8_t *buf, const bdx_fastq_record *recs, int32_t n, uint8_t *seq_out,
                    int64_t seq_cap, int32_t *offsets_out);
 
+/* ---- host-side barcode-table loader -----------------------------------
+ * preprocess_bc_file (fileio.jl:7-72): FASTA when the path ends in .fasta / .fa, otherwise a table
+ * (',' for .csv, tab otherwise) with the columns Full_seq, ID, Full_annotation.  Keeps the bases
+ * annotated 'B', upper-cases, U -> T, optional complement (ATGCN only) and reversal.  bytes / offsets /
+ * lengths_no_n are laid out as bdx_barcode_set wants them and stay valid until the table is destroyed.
+ * As in the reference, a FASTA record without sequence lines yields an ID but no sequence, so
+ * id_count can exceed count.  Errors (missing file / columns, "Length mismatch between sequence and
+ * annotation for ID: ...", fileio.jl:46) return BDX_ERR_INVALID with the text in
+ * bdx_barcode_table_error().  Thread-safe; needs no CUDA device. */
+typedef struct bdx_barcode_table bdx_barcode_table;
+int bdx_barcode_table_load(const char *path, int complement, int rev, bdx_barcode_table **out);
+void bdx_barcode_table_destroy(bdx_barcode_table *t);
+int32_t bdx_barcode_table_count(const bdx_barcode_table *t);
+int32_t bdx_barcode_table_id_count(const bdx_barcode_table *t);
+const uint8_t *bdx_barcode_table_bytes(const bdx_barcode_table *t);
+const int32_t *bdx_barcode_table_offsets(const bdx_barcode_table *t);       /* count + 1 */
+const int32_t *bdx_barcode_table_lengths_no_n(const bdx_barcode_table *t);  /* bc_lengths_no_N */
+const char *bdx_barcode_table_id(const bdx_barcode_table *t, int32_t i);
+const char *bdx_barcode_table_error(void);
+
 /* ---- device FASTQ block demultiplexer (SURVEY.md section 8f-1 + 8f-3) --------------------------
  * The data formats either side of the hot path, on the device: raw FASTQ text in (the bytes
  * reader_task would split with four readlines per record, core.jl:96-101), and per output file one

@@ -33,7 +33,7 @@ EXPORTS = [
     "bdx_fastq_scan", "bdx_fastq_pack", "bdx_demux_block", "bdx_demux_stage_ms",
     "bdx_barcode_table_load", "bdx_barcode_table_destroy", "bdx_barcode_table_count", "bdx_barcode_table_id_count",
     "bdx_barcode_table_bytes", "bdx_barcode_table_offsets", "bdx_barcode_table_lengths_no_n", "bdx_barcode_table_id",
-    "bdx_barcode_table_error",
+    "bdx_barcode_table_error", "bdx_stats_entries",
 ]
 
 
@@ -144,6 +144,8 @@ def load_library():
     L.bdx_stream_path_counters.argtypes = [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64), C.c_int]
     L.bdx_stats_layout_get.argtypes = [vp, C.POINTER(StatsLayout)]
     L.bdx_stats_fetch.argtypes = [vp, vp, i64]
+    L.bdx_stats_entries.argtypes = [vp, vp, vp, i64]
+    L.bdx_stats_entries.restype = i64
     L.bdx_stats_device_ptr.argtypes = [vp]
     L.bdx_stats_device_ptr.restype = vp
     L.bdx_stats_reset.argtypes = [vp]
@@ -197,6 +199,22 @@ def fastq_pack(buf: np.ndarray, recs: np.ndarray, seq_out: Optional[np.ndarray] 
     _check(load_library().bdx_fastq_pack(buf.ctypes.data if buf.size else None, recs.ctypes.data, len(recs),
                                          seq_out.ctypes.data, seq_out.size, off.ctypes.data))
     return seq_out[:total], off
+
+
+STATS_ENTRY_DTYPE = np.dtype([("pass", "<i4"), ("kind", "<i4"), ("bc", "<i4"), ("reserved", "<i4"),
+                              ("key", "<i8"), ("score", "<f8"), ("count", "<i8")])
+
+
+def stats_entries(config: "Config", counters: np.ndarray) -> np.ndarray:
+    """bdx_stats_entries: the DemuxStats Dict entries of a (summed) counter buffer."""
+    L = load_library()
+    counters = np.ascontiguousarray(counters, dtype=np.int64)
+    n = L.bdx_stats_entries(config.handle, counters.ctypes.data, None, 0)
+    if n < 0:
+        _check(int(n))
+    out = np.zeros(int(n), dtype=STATS_ENTRY_DTYPE)
+    L.bdx_stats_entries(config.handle, counters.ctypes.data, out.ctypes.data, int(n))
+    return out
 
 
 def load_barcode_table(path: str, complement: bool = False, rev: bool = False):

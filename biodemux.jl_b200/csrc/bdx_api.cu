@@ -1056,6 +1056,50 @@ extern "C" int bdx_stats_fetch(bdx_stream *s, int64_t *out, int64_t out_len)
     return BDX_OK;
 }
 
+// DemuxStats dictionaries from a (summed) counter buffer: what match_barcode_pass stores per matched pass
+// (classification.jl:827-865) -- keys are alignment start, alignment length and round(score, digits=2).
+extern "C" int64_t bdx_stats_entries(const bdx_config *cfg, const int64_t *counters, bdx_stats_entry *out, int64_t cap)
+{
+    if (!cfg || !counters) return fail(BDX_ERR_INVALID, "null argument");
+    const bdx_stats_layout &L = cfg->lay;
+    int64_t n = 0;
+    auto emit = [&](int pass, int kind, int bc, int64_t key, double score, int64_t count) {
+        if (out && n < cap) out[n] = bdx_stats_entry{pass, kind, bc, 0, key, score, count};
+        n++;
+    };
+    const int passes = cfg->base.is_dual ? 2 : 1;
+    for (int p = 0; p < passes; p++) {
+        const HostSet &hs = cfg->set[p];
+        const int nb = p == 0 ? L.b1 : L.b2;
+        std::map<double, int64_t> global_score;   // the global score Dict is keyed by the rounded score, so it
+                                                  // has to be re-binned from the per-barcode distances
+        for (int b = 0; b <= nb; b++) {
+            const int64_t *pos = counters + L.pos_off[p] + (int64_t)b * L.pos_bins;
+            const int64_t *len = counters + L.len_off[p] + (int64_t)b * L.len_bins;
+            const int64_t *dst = counters + L.dist_off[p] + (int64_t)b * L.dist_bins;
+            for (int k = 0; k < L.pos_bins; k++)
+                if (pos[k]) emit(p + 1, BDX_STATS_POS, b, k - L.pos_bias, 0.0, pos[k]);
+            for (int k = 0; k < L.len_bins; k++)
+                if (len[k]) emit(p + 1, BDX_STATS_LEN, b, k, 0.0, len[k]);
+            if (b == 0) continue;
+            // normalisation as in the kernels: bc_lengths_no_N under NScoring, else the barcode length
+            const int norm = cfg->base.algo == BDX_SEMIGLOBAL ? hs.norm[b - 1] : hs.off[b] - hs.off[b - 1];
+            for (int k = 0; k < L.dist_bins; k++) {
+                if (!dst[k]) continue;
+                const double score = (double)(k - L.dist_bias) / (double)norm;
+                // Base.round(x, digits=2): round-half-even of x * 100, divided by 100; x itself if that is not finite
+                volatile double scaled = score * 100.0;
+                double r = std::nearbyint(scaled) / 100.0;
+                if (!std::isfinite(r)) r = score;
+                emit(p + 1, BDX_STATS_SCORE, b, 0, r, dst[k]);
+                global_score[r] += dst[k];
+            }
+        }
+        for (auto &kv : global_score) emit(p + 1, BDX_STATS_SCORE, 0, 0, kv.first, kv.second);
+    }
+    return n;
+}
+
 extern "C" void *bdx_stats_device_ptr(bdx_stream *s) { return s ? (void *)s->d_stats : nullptr; }
 
 extern "C" int bdx_stats_reset(bdx_stream *s)

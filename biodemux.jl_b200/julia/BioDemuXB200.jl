@@ -237,4 +237,78 @@ function fetch_stats(s::Ptr{Cvoid}, g::GpuConfig)
     st
 end
 
+# ---- device FASTQ path (bdx_demux_block): replaces reader_task's record splitting and writer_task's
+# per-record trimming / routing (core.jl:43-224).  The Julia host keeps file I/O and (de)compression.
+struct BdxDemuxBucket      # bdx_demux_bucket
+    status::Int32
+    bc1::Int32
+    bc2::Int32
+    n_records::Int32
+    offset1::Int64
+    length1::Int64
+    offset2::Int64
+    length2::Int64
+end
+
+struct BdxDemuxOut         # bdx_demux_out
+    n_records::Int32
+    n_buckets::Int32
+    consumed1::Int64
+    consumed2::Int64
+    out1::Ptr{UInt8}
+    out1_len::Int64
+    out2::Ptr{UInt8}
+    out2_len::Int64
+    buckets::Ptr{BdxDemuxBucket}
+    results::Ptr{BdxResult}
+end
+
+const BDX_DEMUX_SINGLE, BDX_DEMUX_MATES, BDX_DEMUX_BOTH = Cint(0), Cint(1), Cint(2)
+
+"""
+    demux_block!(handles, s, c, block1, block2, final, mode, prefix1, prefix2)
+
+One block of FASTQ text per input through `bdx_demux_block`; every returned bucket is appended to its
+output file (`handles(filename)::IO` is writer_task's `get_handle`, core.jl:122-132).  Returns
+`(n_records, consumed1, consumed2)`; the caller re-presents `block[consumed+1:end]` in front of the next block
+and stops once a final block has been consumed completely (`while !eof(io1) && !eof(io2)`, core.jl:48).
+"""
+function demux_block!(handles, s::Ptr{Cvoid}, c::DemuxConfig, block1::Vector{UInt8}, block2::Union{Vector{UInt8},Nothing},
+                      final::Integer, mode::Cint, prefix1::String, prefix2::String)
+    out = Ref{BdxDemuxOut}()
+    b2 = isnothing(block2) ? UInt8[] : block2
+    GC.@preserve block1 b2 check(ccall((:bdx_demux_block, libbdx), Cint,
+        (Ptr{Cvoid}, Ptr{UInt8}, Int64, Ptr{UInt8}, Int64, Cint, Cint, Ref{BdxDemuxOut}),
+        s, block1, length(block1), b2, length(b2), final, mode, out))
+    o = out[]
+    for k in 1:o.n_buckets
+        b = unsafe_load(o.buckets, k)
+        name = filename_of(c, BdxResult(b.status, b.bc1, b.bc2, -1, -1))
+        if mode != BDX_DEMUX_MATES
+            unsafe_write(handles(prefix1 * "." * name), o.out1 + b.offset1, b.length1)
+        end
+        if mode != BDX_DEMUX_SINGLE
+            unsafe_write(handles(prefix2 * "." * name), o.out2 + b.offset2, b.length2)
+        end
+    end
+    (o.n_records, o.consumed1, o.consumed2)
+end
+
+# ---- barcode tables through the C++ loader (preprocess_bc_file twin, fileio.jl:7-72) ------------------
+function load_barcode_table(path::String, complement::Bool, rev::Bool)
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    rc = ccall((:bdx_barcode_table_load, libbdx), Cint, (Cstring, Cint, Cint, Ref{Ptr{Cvoid}}), path, complement, rev, h)
+    rc == 0 || error(unsafe_string(ccall((:bdx_barcode_table_error, libbdx), Cstring, ())))
+    t = h[]
+    n = ccall((:bdx_barcode_table_count, libbdx), Int32, (Ptr{Cvoid},), t)
+    nid = ccall((:bdx_barcode_table_id_count, libbdx), Int32, (Ptr{Cvoid},), t)
+    off = unsafe_wrap(Array, ccall((:bdx_barcode_table_offsets, libbdx), Ptr{Int32}, (Ptr{Cvoid},), t), n + 1)
+    bytes = ccall((:bdx_barcode_table_bytes, libbdx), Ptr{UInt8}, (Ptr{Cvoid},), t)
+    lens = n == 0 ? Int[] : Int.(unsafe_wrap(Array, ccall((:bdx_barcode_table_lengths_no_n, libbdx), Ptr{Int32}, (Ptr{Cvoid},), t), n))
+    seqs = [unsafe_string(bytes + off[i], off[i+1] - off[i]) for i in 1:n]
+    ids = [unsafe_string(ccall((:bdx_barcode_table_id, libbdx), Cstring, (Ptr{Cvoid}, Int32), t, i - 1)) for i in 1:nid]
+    ccall((:bdx_barcode_table_destroy, libbdx), Cvoid, (Ptr{Cvoid},), t)
+    seqs, lens, ids
+end
+
 end # module

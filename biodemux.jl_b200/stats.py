@@ -115,3 +115,19 @@ def stats_from_passes(status, bc1, bc2, passes, cfg) -> DemuxStats:
         else:
             st.ambiguous_reads += 1
     return st
+
+
+def stats_from_entries(buf: np.ndarray, lay, entries: np.ndarray) -> DemuxStats:
+    """DemuxStats from the counter header + the entry list of ``bdx_stats_entries`` (the C report bridge)."""
+    st = DemuxStats()
+    st.total_reads, st.matched_reads, st.unmatched_reads, st.ambiguous_reads = (int(x) for x in buf[:4])
+    samp = buf[lay.sample_off: lay.sample_off + (lay.b1 + 1) * (lay.b2 + 1)].reshape(lay.b1 + 1, lay.b2 + 1)
+    for i, j in zip(*np.nonzero(samp)):
+        st.sample_counts[(int(i), int(j))] = int(samp[i, j])
+    names = {0: "pos", 1: "len", 2: "score"}
+    for e in entries:
+        pre, kind, b = f"bc{int(e['pass'])}", names[int(e["kind"])], int(e["bc"])
+        key = float(e["score"]) if kind == "score" else int(e["key"])
+        d = getattr(st, f"{pre}_{kind}_counts") if b == 0 else getattr(st, f"{pre}_per_bc_{kind}_counts").setdefault(b, {})
+        _bump(d, key, int(e["count"]))
+    return st

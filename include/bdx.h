@@ -221,6 +221,23 @@ typedef struct bdx_stats_layout {
 } bdx_stats_layout;
 
 int bdx_stats_layout_get(const bdx_config *cfg, bdx_stats_layout *out);
+
+/* Report bridge: the Dict entries of DemuxStats (classification.jl:736-758) from a
+ * counter buffer that has been summed over streams / GPUs.  One entry per non-zero key: pass 1 or 2;
+ * kind = position / length / score; bc = 0 for the global Dict (bcN_pos_counts, ...), b >= 1 for
+ * bcN_per_bc_*_counts[b]; key for positions and lengths, score = round(dist / norm, digits = 2) for
+ * scores (classification.jl:835, :853; equal rounded scores of different distances are merged in the global
+ * Dict, exactly as the reference's Dict does).  total / matched / unmatched / ambiguous are counters[0..3],
+ * sample_counts is counters[sample_off + bc1 * (b2 + 1) + bc2].  Returns the number of entries (call with
+ * out = NULL to size the array), or a negative bdx_status. */
+enum { BDX_STATS_POS = 0, BDX_STATS_LEN = 1, BDX_STATS_SCORE = 2 };
+typedef struct bdx_stats_entry {
+    int32_t pass, kind, bc, reserved;
+    int64_t key;
+    double score;
+    int64_t count;
+} bdx_stats_entry;
+int64_t bdx_stats_entries(const bdx_config *cfg, const int64_t *counters, bdx_stats_entry *out, int64_t cap);
 /* copies the stream's device counters to host (after syncing the stream) */
 int bdx_stats_fetch(bdx_stream *s, int64_t *out, int64_t out_len);
 /* device pointer of the counters (for an in-place NCCL all-reduce by the host) */

@@ -127,3 +127,59 @@ def test_build_config_validation(refdata):
 def test_stats_roundtrip_helpers():
     from bdx_b200.stats import julia_round2
     assert julia_round2(1 / 3) == 0.33 and julia_round2(0.125) == 0.12 and julia_round2(1 / 6) == 0.17
+
+
+@pytest.mark.parametrize("dual,nindel", [(False, None), (True, None), (False, 2)])
+def test_stats_entries_bridge(dual, nindel):
+    """bdx_stats_entries (C report bridge) == the Python conversion of the same counter buffer,
+    == DemuxStats built from per-pass records the way determine_filename_and_stats does."""
+    from bdx_b200.stats import stats_from_counters, stats_from_entries, stats_from_passes
+    rng = np.random.default_rng(11 + dual)
+    bcs = ["ACGTNCGTAC", "TTGGCCAATTGG", "ANNNNNNNNT", "GATTACAGATTACAGA"]
+    lens = [sum(1 for c in s if c != "N") for s in bcs]
+    kw = dict(bc_seqs=bcs, bc_lengths_no_N=lens, ids=list("abcd"), summary=True, nindel=nindel, max_error_rate=0.5)
+    if dual:
+        kw.update(is_dual=True, bc_seqs2=bcs[:3], bc_lengths_no_N2=lens[:3], ids2=list("xyz"))
+    cfg = bdx.DemuxConfig(**kw)
+    config = capi.Config(cfg)
+    lay = config.layout
+    from bdx_b200.stats import pass_norms
+    norms = [pass_norms(cfg, False), pass_norms(cfg, True) if dual else []]
+    n = 4000
+    buf = np.zeros(lay.total_len, dtype=np.int64)
+    status, bc1, bc2, passes = [], [], [], []
+    for _ in range(n):
+        rec = []
+        ok = True
+        for p in range(2 if dual else 1):
+            if not ok or rng.random() < 0.2:
+                rec.append((1, 0, -1, -1, float("inf")))
+                ok = False
+                continue
+            nb = len(norms[p])
+            b = int(rng.integers(1, nb + 1))
+            dist = int(rng.integers(0, int(0.5 * norms[p][b - 1]) + 1))
+            s = int(rng.integers(-3, 60))
+            e = s + int(rng.integers(0, 20))
+            rec.append((0, b, s, e, dist / norms[p][b - 1]))
+            bsz = (lay.pos_bins, lay.len_bins, lay.dist_bins)
+            for row in (0, b):
+                buf[lay.pos_off[p] + row * bsz[0] + s + lay.pos_bias] += 1
+                buf[lay.len_off[p] + row * bsz[1] + (e - s + 1)] += 1
+                buf[lay.dist_off[p] + row * bsz[2] + dist + lay.dist_bias] += 1
+        while len(rec) < 2:
+            rec.append((-1, 0, -1, -1, float("inf")))
+        passes.append(rec)
+        buf[0] += 1
+        if ok:
+            status.append(0); bc1.append(rec[0][1]); bc2.append(rec[1][1] if dual else 0)
+            buf[1] += 1
+            buf[lay.sample_off + bc1[-1] * (lay.b2 + 1) + bc2[-1]] += 1
+        else:
+            status.append(1); bc1.append(0); bc2.append(0)
+            buf[2] += 1
+    ent = capi.stats_entries(config, buf)
+    got = stats_from_entries(buf, lay, ent)
+    assert got == stats_from_counters(buf, lay, cfg)
+    assert got == stats_from_passes(status, bc1, bc2, passes, cfg)
+    config.close()

@@ -74,9 +74,13 @@ struct HostSet {
     uint32_t hs_pow = 0;
     std::vector<uint32_t> hs_bstart, hs_entries;
     // :semiglobal depth-limited seeds
-    int sd_enabled = 0, sd_k = 0, sd_q = 0, sd_log2 = 0, sd_bm_log2 = 0, sd_m = 0;
-    uint32_t sd_pow = 0;
-    std::vector<uint32_t> sd_bstart, sd_entries, sd_ekeys, sd_bitmap;
+    struct HostSeedLevel {
+        int k = 0, q = 0, log2 = 0, bm_log2 = 0;
+        uint32_t pow = 0;
+        std::vector<uint32_t> bstart, entries, ekeys, bitmap;
+    };
+    int sd_levels = 0, sd_m = 0;
+    HostSeedLevel sd[2];
 };
 
 struct DeviceTables {
@@ -255,52 +259,58 @@ static int build_set(const bdx_params &p, const bdx_barcode_set &in, HostSet &hs
         hs.pf_enabled = 1;
     }
     // ---- :semiglobal depth-limited seeds (seed.cu): uniform barcode length, no wildcard rows ----
-    if (hs.pf_enabled && sg && hs.words == 1 && min_m == hs.max_m && hs.allowed0[0] >= 1 &&
+    if (hs.pf_enabled && sg && hs.words == 1 && min_m == hs.max_m && hs.allowed0[0] >= 1 && hs.n_bc < (1 << 14) &&
         !getenv("BDX_DISABLE_SEED")) {
         const int m = hs.max_m, allowed = hs.allowed0[0];
-        // deepest level whose seeds are long enough to be selective: q >= 6 and at most ~0.12
-        // chance hits per read column (entries / alphabet^q)
         const double alpha = std::max(2, hs.n_classes - 1);
+        // chance hits per read column of level k: entries / alphabet^q with q = min(12, m / (k + 1))
+        auto q_of = [&](int k) { return std::min(12, m / (k + 1)); };
+        auto rate_of = [&](int k) { return (double)hs.n_bc * (k + 1) / std::pow(alpha, q_of(k)); };
+        // deepest level whose seeds are long enough to be selective (q >= 6, <= 0.12 chance hits per column)
         int K = 0;
-        for (int k = 1; k <= allowed; k++) {
-            const int qk = std::min(8, m / (k + 1));
-            if (qk >= 6 && (double)hs.n_bc * (k + 1) / std::pow(alpha, qk) <= 0.12) K = k;
-        }
-        if (K >= 1) {
-            const int seg = m / (K + 1), q = std::min(8, seg);
-            hs.sd_k = K;
-            hs.sd_q = q;
-            hs.sd_m = m;
+        for (int k = 1; k <= std::min(allowed, 7); k++)   // hit records keep the diagonal span in 3 bits
+            if (q_of(k) >= 6 && rate_of(k) <= 0.12) K = k;
+        // a shallower level with far fewer chance hits in front of it pays when the deep one has many
+        int K0 = 0;
+        if (K >= 2 && rate_of(K) > 0.02 && !getenv("BDX_SEED_ONE_LEVEL"))
+            for (int k = 1; k < K; k++)
+                if (rate_of(k) <= 0.01) K0 = k;
+        hs.sd_m = m;
+        for (int K_l : {K0, K}) {
+            if (K_l < 1) continue;
+            HostSet::HostSeedLevel &L = hs.sd[hs.sd_levels++];
+            const int seg = m / (K_l + 1), q = std::min(12, seg);
+            L.k = K_l;
+            L.q = q;
             uint32_t pw = 1;
             for (int i = 1; i < q; i++) pw *= kPfBase;
-            hs.sd_pow = pw;
-            const size_t n_entries = (size_t)hs.n_bc * (K + 1);
+            L.pow = pw;
+            const size_t n_entries = (size_t)hs.n_bc * (K_l + 1);
             int lg = 8;
             while (lg < 14 && (size_t)(1 << lg) < n_entries) lg++;
-            hs.sd_log2 = lg;
+            L.log2 = lg;
             int bl = 13;                                // ~64 bits per entry: 4 KB for 96 barcodes
             while (bl < 18 && ((size_t)1 << bl) < 64 * n_entries) bl++;
-            hs.sd_bm_log2 = bl;
-            hs.sd_bitmap.assign((size_t)1 << (bl - 5), 0u);
+            L.bm_log2 = bl;
+            L.bitmap.assign((size_t)1 << (bl - 5), 0u);
             std::vector<std::vector<std::pair<uint32_t, uint32_t>>> buckets((size_t)1 << lg);
             for (int b = 0; b < hs.n_bc; b++)
-                for (int i = 0; i <= K; i++) {
+                for (int i = 0; i <= K_l; i++) {
                     const int o = i * seg;
                     uint32_t h = 0;
                     for (int k = 0; k < q; k++) h = h * kPfBase + (uint32_t)hs.bc_cls[hs.off[b] + o + k];
                     const uint32_t bit = pf_bit(h, bl);
-                    hs.sd_bitmap[bit >> 5] |= 1u << (bit & 31);
+                    L.bitmap[bit >> 5] |= 1u << (bit & 31);
                     buckets[pf_slot(h, lg)].emplace_back(((uint32_t)b << 8) | (uint32_t)o, h);
                 }
-            hs.sd_bstart.assign(((size_t)1 << lg) + 1, 0u);
+            L.bstart.assign(((size_t)1 << lg) + 1, 0u);
             for (size_t k = 0; k < buckets.size(); k++) {
-                hs.sd_bstart[k + 1] = hs.sd_bstart[k] + (uint32_t)buckets[k].size();
+                L.bstart[k + 1] = L.bstart[k] + (uint32_t)buckets[k].size();
                 for (auto &pr : buckets[k]) {
-                    hs.sd_entries.push_back(pr.first);
-                    hs.sd_ekeys.push_back(pr.second);
+                    L.entries.push_back(pr.first);
+                    L.ekeys.push_back(pr.second);
                 }
             }
-            hs.sd_enabled = 1;
         }
     }
     // ---- :hamming pigeonhole seeds: mismatches <= allowed_b leave one of allowed_b + 1 disjoint
@@ -496,18 +506,22 @@ static int get_tables(bdx_config *cfg, int device, DeviceTables **out)
         if (e == cudaSuccess) e = upload(t, hs.pf_keys, &D.pf_keys);
         if (e == cudaSuccess) e = upload(t, hs.pf_vals, &D.pf_vals);
         if (e == cudaSuccess) e = upload(t, hs.bc_cls, &D.bc_cls);
-        D.sd_enabled = hs.sd_enabled;
-        D.sd_k = hs.sd_k;
-        D.sd_q = hs.sd_q;
-        D.sd_pow = hs.sd_pow;
-        D.sd_log2 = hs.sd_log2;
-        D.sd_bm_log2 = hs.sd_bm_log2;
-        D.sd_n_entries = (int)hs.sd_entries.size();
+        D.sd_levels = hs.sd_levels;
         D.sd_m = hs.sd_m;
-        if (e == cudaSuccess) e = upload(t, hs.sd_bstart, &D.sd_bstart);
-        if (e == cudaSuccess) e = upload(t, hs.sd_entries, &D.sd_entries);
-        if (e == cudaSuccess) e = upload(t, hs.sd_ekeys, &D.sd_ekeys);
-        if (e == cudaSuccess) e = upload(t, hs.sd_bitmap, &D.sd_bitmap);
+        for (int l = 0; l < hs.sd_levels; l++) {
+            const HostSet::HostSeedLevel &H = hs.sd[l];
+            SeedLevel &L = D.sd[l];
+            L.k = H.k;
+            L.q = H.q;
+            L.pow = H.pow;
+            L.log2 = H.log2;
+            L.bm_log2 = H.bm_log2;
+            L.n_entries = (int)H.entries.size();
+            if (e == cudaSuccess) e = upload(t, H.bstart, &L.bstart);
+            if (e == cudaSuccess) e = upload(t, H.entries, &L.entries);
+            if (e == cudaSuccess) e = upload(t, H.ekeys, &L.ekeys);
+            if (e == cudaSuccess) e = upload(t, H.bitmap, &L.bitmap);
+        }
         D.hs_enabled = hs.hs_enabled;
         D.hs_q = hs.hs_q;
         D.hs_pow = hs.hs_pow;
@@ -747,10 +761,17 @@ static int enqueue_classify(bdx_stream *s, const uint8_t *d_seq, const int32_t *
                 s->launches++;
             }
             int wl = pre ? 1 : 0;
-            if (pre && seed_applies(P, pass)) {
-                CU(launch_seed(P, pass, d_seq, d_off, n, s->sc, s->tab->sm_count, s->d_counters, s->st_comp));
-                s->launches++;
-                wl = 2;
+            if (pre) {
+                // seed levels hand the reads they cannot finish from one worklist to the other
+                const int levels = seed_levels(P, pass);
+                for (int l = 0; l < levels; l++) {
+                    const bool from1 = wl == 1;
+                    CU(launch_seed(P, pass, l, d_seq, d_off, n, s->sc, from1 ? s->sc.worklist : s->sc.worklist2,
+                                   from1 ? s->sc.n_work : s->sc.n_work2, from1 ? s->sc.worklist2 : s->sc.worklist,
+                                   from1 ? s->sc.n_work2 : s->sc.n_work, s->tab->sm_count, s->d_counters, s->st_comp));
+                    s->launches++;
+                    wl = from1 ? 2 : 1;
+                }
             }
             cudaEvent_t e0 = nullptr, e1 = nullptr;
             if (s->profile) {

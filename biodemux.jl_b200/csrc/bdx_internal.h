@@ -27,6 +27,19 @@ struct DevRange {
     int start_off, start_from_end, end_off, end_from_end;
 };
 
+struct SeedLevel {
+    int k;                        // edit depth the seeds are complete for (<= allowed)
+    int q;                        // seed length (6..12)
+    uint32_t pow;                 // kPfBase^(q-1)
+    int log2;                     // buckets = 1 << log2
+    int bm_log2;                  // first-level bitmap bits = 1 << bm_log2
+    int n_entries;
+    const uint32_t *bstart;       // [buckets + 1]
+    const uint32_t *entries;      // [n_entries] (barcode index << 8) | seed offset
+    const uint32_t *ekeys;        // [n_entries] hash of the entry's q-mer
+    const uint32_t *bitmap;
+};
+
 struct DevSet {
     int n_bc;
     int n_bc_pad;     // n_bc rounded up to a multiple of 32
@@ -65,19 +78,11 @@ struct DevSet {
     const uint32_t *hs_bstart;    // [buckets + 1] CSR row starts
     const uint32_t *hs_entries;   // [n_entries] (barcode index << 8) | seed offset
     // :semiglobal depth-limited seeds (seed.cu, k_seed): for uniform-length sets, every alignment
-    // with <= sd_k edits leaves one of sd_k + 1 disjoint barcode segments intact
-    int sd_enabled;
-    int sd_k;                     // edit depth the seeds are complete for (<= allowed)
-    int sd_q;                     // seed length (6..8)
-    uint32_t sd_pow;              // kPfBase^(sd_q-1)
-    int sd_log2;                  // buckets = 1 << sd_log2
-    int sd_bm_log2;               // first-level bitmap bits = 1 << sd_bm_log2
-    int sd_n_entries;
+    // with <= k edits leaves one of k + 1 disjoint barcode segments intact.  Up to two levels: a
+    // shallow one with long, very selective seeds, then the deepest level that is still selective.
+    int sd_levels;                // 0 = off
     int sd_m;                     // the common barcode length
-    const uint32_t *sd_bstart;    // [buckets + 1]
-    const uint32_t *sd_entries;   // [n_entries] (barcode index << 8) | seed offset
-    const uint32_t *sd_ekeys;     // [n_entries] hash of the entry's q-mer
-    const uint32_t *sd_bitmap;
+    SeedLevel sd[2];
 };
 
 constexpr int kPfMaxSeed = 12;
@@ -137,9 +142,11 @@ cudaError_t launch_literal(const DevParams &P, int pass, int from_filter, const 
 cudaError_t launch_filter(const DevParams &P, int pass, const uint8_t *seq, const int *off, int n,
                           const Scratch &sc, int sm_count, unsigned long long *counters, int use_worklist,
                           cudaStream_t st);   // use_worklist: 0 = all reads, 1 = worklist, 2 = worklist2
-bool seed_applies(const DevParams &P, int pass);
-cudaError_t launch_seed(const DevParams &P, int pass, const uint8_t *seq, const int *off, int n, const Scratch &sc,
-                        int sm_count, unsigned long long *counters, cudaStream_t st);
+int seed_levels(const DevParams &P, int pass);   // number of k_seed levels that apply (0 = none)
+// level `level` over the reads of wl_in; the reads it cannot finish are appended to wl_out
+cudaError_t launch_seed(const DevParams &P, int pass, int level, const uint8_t *seq, const int *off, int n,
+                        const Scratch &sc, const int *wl_in, const int *n_in, int *wl_out, int *n_out, int sm_count,
+                        unsigned long long *counters, cudaStream_t st);
 cudaError_t launch_prefilter(const DevParams &P, int pass, const uint8_t *seq, const int *off, int n,
                              const Scratch &sc, int sm_count, unsigned long long *counters, cudaStream_t st);
 bool prefilter_applies(const DevParams &P, int pass);

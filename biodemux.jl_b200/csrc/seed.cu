@@ -35,47 +35,140 @@
 namespace bdx {
 
 constexpr int kSeedThreads = 128;
-constexpr int kSeedSlot = 176;      // staged class codes per read (longer reads take the full path)
-constexpr int kSeedMaxHits = 28;    // hits remembered per read (more => full path)
+constexpr int kSeedSlot = 180;      // staged class codes per read (longer reads take the full path); 45 words:
+                                    // an odd word stride keeps the lock-step scan free of bank conflicts
+constexpr int kSeedMaxHits = 28;    // distinct (barcode, diagonal group) hits remembered per read (more => next stage)
 constexpr int kSeedMaxWins = 32;    // bitmap-passing columns remembered per read (more => full path)
 constexpr int kSeedIlp = 4;         // hits verified concurrently per thread
 
+// Hit record: barcode << 13 | diagonal span << 10 | lowest diagonal + 256   (barcode < 2^14, span <= K <= 7)
+__device__ __forceinline__ uint32_t hit_pack(uint32_t b, int span, int dmin)
+{
+    return (b << 13) | ((uint32_t)span << 10) | (uint32_t)(dmin + 256);
+}
+
+struct SeedVerifyCtx {
+    const uint32_t *hits;           // [kSeedMaxHits][kSeedThreads], column warp * 32 + lane belongs to a lane
+    const uint32_t *peq_s;
+    const uint8_t *warp_slots;      // slot of lane 0 of this warp
+    uint32_t *res;                  // [32] per-read minimum of (distance << 14 | barcode) of this warp
+    int n_pad, m, K, win, total;
+    uint32_t row_mask;
+};
+
+// Verifies pooled hits [i0, i0 + 32 * ILP) of the warp, one per lane and chain: windowed Myers/Hyyro automaton
+// over the columns the hit's alignment can occupy.  The hits of the warp's 32 reads form one pool (lane L owns
+// the indices [excl(L), incl(L)) of the inclusive prefix sum `incl` of the per-lane hit counts), so every lane
+// has work whatever its own read found.  Branch-free so that the ILP chains of a lane interleave: past the
+// end of its window a chain keeps stepping on class 0 and its minimum is not updated.
+template <int ILP>
+__device__ __forceinline__ void seed_verify(const SeedVerifyCtx &v, int i0, int lane, int incl, int start_j, int end_j)
+{
+    int hb[ILP], c0[ILP], c1[ILP], score[ILP], best[ILP], owner[ILP];
+    uint32_t pv[ILP], mv[ILP];
+    const uint8_t *slot[ILP];
+#pragma unroll
+    for (int u = 0; u < ILP; u++) {
+        const int i = i0 + 32 * u + lane;
+        const bool live = i < v.total;
+        // owner = first lane whose inclusive prefix exceeds i (binary search over the lanes by shuffles)
+        int lo = 0;
+#pragma unroll
+        for (int step = 16; step >= 1; step >>= 1) {
+            const int probe = __shfl_sync(0xFFFFFFFFu, incl, lo + step - 1);
+            if (probe <= i) lo += step;
+        }
+        owner[u] = live ? lo : 0;
+        const int prev_incl = __shfl_sync(0xFFFFFFFFu, incl, max(owner[u] - 1, 0));   // all lanes shuffle
+        const int o_excl = owner[u] ? prev_incl : 0;
+        const uint32_t rec = live ? v.hits[(i - o_excl) * kSeedThreads + owner[u]] : 0u;
+        hb[u] = (int)(rec >> 13);
+        const int dmin = (int)(rec & 0x3FFu) - 256, span = (int)((rec >> 10) & 0x7u);
+        const int sj = __shfl_sync(0xFFFFFFFFu, start_j, owner[u]);
+        const int ej = __shfl_sync(0xFFFFFFFFu, end_j, owner[u]);
+        // 1-based columns an alignment with <= K edits on these diagonals can occupy
+        c0[u] = live ? max(sj, dmin + 1 - v.K) : 1;
+        c1[u] = live ? min(ej, dmin + span + v.m + 2 * v.K) : 0;
+        slot[u] = v.warp_slots + (size_t)owner[u] * kSeedSlot;
+        pv[u] = v.row_mask;
+        mv[u] = 0u;
+        score[u] = v.m;
+        best[u] = kInf;
+    }
+    for (int t = 0; t < v.win; t++) {
+        uint32_t eq[ILP];
+        bool in[ILP];
+#pragma unroll
+        for (int u = 0; u < ILP; u++) {
+            const int c = c0[u] + t;
+            in[u] = c <= c1[u];
+            // outside the window nothing staged may be read: class 0 then
+            const uint32_t cls = in[u] ? (uint32_t)slot[u][c - 1] : 0u;
+            eq[u] = v.peq_s[cls * v.n_pad + hb[u]];
+        }
+#pragma unroll
+        for (int u = 0; u < ILP; u++) {
+            const uint32_t xv = eq[u] | mv[u];
+            const uint32_t xh = ((((eq[u] & pv[u]) + pv[u]) ^ pv[u]) | eq[u]);
+            const uint32_t ph = mv[u] | ~(xh | pv[u]);
+            const uint32_t mh = pv[u] & xh;
+            score[u] += (int)(ph >> 31) - (int)(mh >> 31);
+            const uint32_t phs = ph << 1, mhs = mh << 1;
+            pv[u] = mhs | ~(xv | phs);
+            mv[u] = phs & xv;
+            best[u] = in[u] ? min(best[u], score[u]) : best[u];
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < ILP; u++)
+        if (best[u] <= v.K) atomicMin(v.res + owner[u], ((uint32_t)best[u] << 14) | (uint32_t)hb[u]);
+}
+
+// TAB_SMEM: the CSR bucket table (bstart / entries / ekeys) is copied to shared memory; large sets read it
+// from global memory instead (it is touched only on first-level bitmap hits).
+template <bool TAB_SMEM>
 __global__ void __launch_bounds__(kSeedThreads)
-k_seed(const __grid_constant__ DevParams P, const int pass, const uint8_t *__restrict__ seq,
+k_seed(const __grid_constant__ DevParams P, const int pass, const int level, const uint8_t *__restrict__ seq,
        const int *__restrict__ off, PassOut *__restrict__ out, const int *__restrict__ worklist,
        const int *__restrict__ n_work, int *__restrict__ worklist2, int *__restrict__ n_work2,
        unsigned long long *__restrict__ counters)
 {
     extern __shared__ __align__(16) uint32_t smem[];
     const DevSet &S = P.set[pass];
+    const SeedLevel &SL = S.sd[level];
     const int n_pad = S.n_bc_pad;
-    const int n_buckets = 1 << S.sd_log2;
-    const int bm_words = 1 << (S.sd_bm_log2 - 5);
+    const int n_buckets = 1 << SL.log2;
+    const int bm_words = 1 << (SL.bm_log2 - 5);
     uint32_t *peq_s = smem;                                     // [n_classes][n_pad]
     uint32_t *bitmap_s = peq_s + S.n_classes * n_pad;
-    uint32_t *bstart_s = bitmap_s + bm_words;                   // [n_buckets + 1]
-    uint32_t *entries_s = bstart_s + n_buckets + 1;             // [sd_n_entries]
-    uint32_t *ekeys_s = entries_s + S.sd_n_entries;             // [sd_n_entries] full hash of each entry
-    uint32_t *hits_s = ekeys_s + S.sd_n_entries;                // [kSeedMaxHits][kSeedThreads]
-    uint8_t *wins_s = reinterpret_cast<uint8_t *>(hits_s + kSeedMaxHits * kSeedThreads);   // [kSeedMaxWins][threads]
+    uint32_t *tab_s = bitmap_s + bm_words;
+    const uint32_t *bstart_s = TAB_SMEM ? tab_s : SL.bstart;    // [n_buckets + 1]
+    const uint32_t *entries_s = TAB_SMEM ? tab_s + n_buckets + 1 : SL.entries;             // [n_entries]
+    const uint32_t *ekeys_s = TAB_SMEM ? tab_s + n_buckets + 1 + SL.n_entries : SL.ekeys;  // [n_entries] full hashes
+    uint32_t *hits_s = TAB_SMEM ? tab_s + n_buckets + 1 + 2 * SL.n_entries : tab_s;        // [kSeedMaxHits][kSeedThreads]
+    uint32_t *res_s = hits_s + kSeedMaxHits * kSeedThreads;     // [kSeedThreads]
+    uint8_t *wins_s = reinterpret_cast<uint8_t *>(res_s + kSeedThreads);   // [kSeedMaxWins][threads]
     uint8_t *class_s = wins_s + kSeedMaxWins * kSeedThreads;
     uint8_t *slot_s = class_s + 256;                            // [kSeedThreads][kSeedSlot] class codes
 
     for (int k = threadIdx.x; k < S.n_classes * n_pad; k += blockDim.x) peq_s[k] = S.peq[k];
-    for (int k = threadIdx.x; k < bm_words; k += blockDim.x) bitmap_s[k] = S.sd_bitmap[k];
-    for (int k = threadIdx.x; k <= n_buckets; k += blockDim.x) bstart_s[k] = S.sd_bstart[k];
-    for (int k = threadIdx.x; k < S.sd_n_entries; k += blockDim.x) {
-        entries_s[k] = S.sd_entries[k];
-        ekeys_s[k] = S.sd_ekeys[k];
+    for (int k = threadIdx.x; k < bm_words; k += blockDim.x) bitmap_s[k] = SL.bitmap[k];
+    if (TAB_SMEM) {
+        for (int k = threadIdx.x; k <= n_buckets; k += blockDim.x) tab_s[k] = SL.bstart[k];
+        for (int k = threadIdx.x; k < SL.n_entries; k += blockDim.x) {
+            tab_s[n_buckets + 1 + k] = SL.entries[k];
+            tab_s[n_buckets + 1 + SL.n_entries + k] = SL.ekeys[k];
+        }
     }
     for (int k = threadIdx.x; k < 256; k += blockDim.x) class_s[k] = S.class_of[k];
     __syncthreads();
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    const int m = S.sd_m, K = S.sd_k, q = S.sd_q;
-    const uint32_t pw = S.sd_pow;
-    const int bm_log2 = S.sd_bm_log2;
+    const int m = S.sd_m, K = SL.k, q = SL.q;
+    const bool last_level = level == S.sd_levels - 1;
+    const uint32_t pw = SL.pow;
+    const int bm_log2 = SL.bm_log2;
     const int n_items = *n_work;
     const int n_groups = (n_items + kSeedThreads - 1) / kSeedThreads;
     const uint32_t row_mask = m >= 32 ? 0xFFFFFFFFu : (0xFFFFFFFFu << (32 - m));
@@ -88,16 +181,30 @@ k_seed(const __grid_constant__ DevParams P, const int pass, const uint8_t *__res
         const int base = have ? off[read] : 0;
         const int n = have ? off[read + 1] - base : 0;
 
-        // ---- stage the warp's 32 reads as class codes, one read at a time, coalesced ----
+        // ---- stage the warp's 32 reads as class codes, coalesced: four reads at a time, all their
+        // global loads issued before the first table lookup / store ----
         uint8_t *my_slot = slot_s + (size_t)threadIdx.x * kSeedSlot;
         __syncwarp();
-        for (int r = 0; r < 32; r++) {
-            const int rb = __shfl_sync(0xFFFFFFFFu, base, r);
-            const int rn = __shfl_sync(0xFFFFFFFFu, n, r);
-            if (rn > kSeedSlot) continue;
-            uint8_t *dst = slot_s + (size_t)(warp * 32 + r) * kSeedSlot;
-            const uint8_t *src = seq + rb;
-            for (int t = lane; t < rn; t += 32) dst[t] = class_s[src[t]];
+        constexpr int kIt = (kSeedSlot + 31) / 32;
+        for (int r0 = 0; r0 < 32; r0 += 4) {
+            uint8_t v[4][kIt];
+            int rn4[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int rb = __shfl_sync(0xFFFFFFFFu, base, r0 + j);
+                const int rn = __shfl_sync(0xFFFFFFFFu, n, r0 + j);
+                rn4[j] = rn > kSeedSlot ? 0 : rn;
+                const uint8_t *src = seq + rb;
+#pragma unroll
+                for (int it = 0; it < kIt; it++) v[j][it] = lane + 32 * it < rn4[j] ? src[lane + 32 * it] : (uint8_t)0;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                uint8_t *dst = slot_s + (size_t)(warp * 32 + r0 + j) * kSeedSlot;
+#pragma unroll
+                for (int it = 0; it < kIt; it++)
+                    if (lane + 32 * it < rn4[j]) dst[lane + 32 * it] = class_s[v[j][it]];
+            }
         }
         __syncwarp();
 
@@ -105,7 +212,7 @@ k_seed(const __grid_constant__ DevParams P, const int pass, const uint8_t *__res
         // (Doing the bucket walk right here would serialise the lanes of a warp: every lane hits
         // at different columns.  The divergent part is kept to one shared-memory store.) ----
         int n_wins = 0;
-        bool punt = !have;       // true => this read goes to worklist2 (or is not a read at all)
+        bool punt = !have;       // true => this read goes to the next stage (or is not a read at all)
         Geometry g{};
         if (have) {
             g = pass_geometry(S, n);
@@ -142,77 +249,67 @@ k_seed(const __grid_constant__ DevParams P, const int pass, const uint8_t *__res
                 const int p = wins_s[k * kSeedThreads + threadIdx.x];
                 uint32_t h = 0;
                 for (int i = 0; i < q; i++) h = h * kPfBase + (uint32_t)my_slot[p + i];
-                const uint32_t bucket = pf_slot(h, S.sd_log2);
+                const uint32_t bucket = pf_slot(h, SL.log2);
                 const uint32_t e1 = bstart_s[bucket + 1];
                 for (uint32_t e = bstart_s[bucket]; e < e1; e++) {
                     if (ekeys_s[e] != h) continue;                      // bucket-mate with another q-mer
                     const uint32_t ent = entries_s[e];
                     // 32-bit hash collisions are harmless: a false hit only costs a verification
                     const int delta = p - (int)(ent & 0xFFu);           // 0-based diagonal
-                    const uint32_t rec = ((ent >> 8) << 16) | (uint32_t)(delta + 256);
-                    // (several intact segments of one alignment give the same record several times;
-                    // searching the list for duplicates costs more than verifying them again)
-                    if (n_hits < kSeedMaxHits) hits_s[n_hits * kSeedThreads + threadIdx.x] = rec;
+                    const uint32_t b = ent >> 8;
+                    // Several intact segments of one alignment hit the same barcode on diagonals at most K
+                    // apart: they join one record whose window is the union of theirs (still a sub-range
+                    // with free ends, and it contains every alignment either window contained).
+                    bool merged = false;
+                    const int have_hits = min(n_hits, kSeedMaxHits);
+                    for (int j = 0; j < have_hits && !merged; j++) {
+                        const uint32_t old = hits_s[j * kSeedThreads + threadIdx.x];
+                        if ((old >> 13) != b) continue;
+                        const int dmin = (int)(old & 0x3FFu) - 256, span = (int)((old >> 10) & 0x7u);
+                        const int lo = min(dmin, delta), hi = max(dmin + span, delta);
+                        if (hi - lo <= K) {
+                            hits_s[j * kSeedThreads + threadIdx.x] = hit_pack(b, hi - lo, lo);
+                            merged = true;
+                        }
+                    }
+                    if (merged) continue;
+                    if (n_hits < kSeedMaxHits) hits_s[n_hits * kSeedThreads + threadIdx.x] = hit_pack(b, 0, delta);
                     n_hits++;
                 }
             }
             if (n_hits > kSeedMaxHits) punt = true;
         }
 
-        // ---- verify the hits in lock step: windowed bit-parallel automaton, kSeedIlp hits at a
-        // time per thread (independent dependency chains hide the latency of the serial column
-        // recurrence at the low occupancy the shared-memory tables allow) ----
-        int best_d = kInf, best_b = 0x7FFFFFFF;
+        // ---- verify: the warp pools the hits of its 32 reads and spreads them evenly over the lanes
+        // (a lane's own read has 0..kSeedMaxHits hits; verifying per lane would leave most lanes idle) ----
         const int my_hits = punt ? 0 : n_hits;
-        const int max_hits = __reduce_max_sync(0xFFFFFFFFu, my_hits);
-        const int win = m + 3 * K + 1;                       // columns [delta + 1 - K, delta + m + 2K]
-        for (int k0 = 0; k0 < max_hits; k0 += kSeedIlp) {
-            int hb[kSeedIlp], c0[kSeedIlp], c1[kSeedIlp], score[kSeedIlp], best[kSeedIlp];
-            uint32_t pv[kSeedIlp], mv[kSeedIlp];
+        int incl = my_hits;                                      // inclusive prefix sum over the lanes
 #pragma unroll
-            for (int u = 0; u < kSeedIlp; u++) {
-                const bool live = k0 + u < my_hits;
-                const uint32_t rec = live ? hits_s[(k0 + u) * kSeedThreads + threadIdx.x] : 0u;
-                hb[u] = (int)(rec >> 16);
-                const int delta = (int)(rec & 0xFFFFu) - 256;
-                // 1-based columns an alignment with <= K edits on this diagonal can occupy
-                c0[u] = live ? max(g.start_j, delta + 1 - K) : 1;
-                c1[u] = live ? min(g.end_j, delta + m + 2 * K) : 0;
-                pv[u] = row_mask;
-                mv[u] = 0u;
-                score[u] = m;
-                best[u] = kInf;
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        const int total_hits = __shfl_sync(0xFFFFFFFFu, incl, 31);
+        res_s[threadIdx.x] = 0xFFFFFFFFu;
+        __syncwarp();
+        {
+            const int win = m + 4 * K + 1;                   // columns [dmin + 1 - K, dmin + span + m + 2K], span <= K
+            const SeedVerifyCtx vc{hits_s + warp * 32, peq_s, slot_s + (size_t)warp * 32 * kSeedSlot, res_s + warp * 32,
+                                   n_pad, m, K, win, total_hits, row_mask};
+            int i0 = 0;
+            for (; i0 + 32 < total_hits; i0 += 64) seed_verify<2>(vc, i0, lane, incl, g.start_j, g.end_j);
+            if (i0 < total_hits) seed_verify<1>(vc, i0, lane, incl, g.start_j, g.end_j);
+        }
+        __syncwarp();
+        int best_d = kInf, best_b = 0x7FFFFFFF;
+        {
+            const uint32_t r = res_s[threadIdx.x];
+            if (r != 0xFFFFFFFFu) {
+                best_d = (int)(r >> 14);
+                best_b = (int)(r & 0x3FFFu);
             }
-            for (int t = 0; t < win; t++) {
-#pragma unroll
-                for (int u = 0; u < kSeedIlp; u++) {
-                    const int c = c0[u] + t;
-                    if (c <= c1[u]) {
-                        const uint32_t eq = peq_s[(int)my_slot[c - 1] * n_pad + hb[u]];
-                        const uint32_t xv = eq | mv[u];
-                        const uint32_t xh = ((((eq & pv[u]) + pv[u]) ^ pv[u]) | eq);
-                        const uint32_t ph = mv[u] | ~(xh | pv[u]);
-                        const uint32_t mh = pv[u] & xh;
-                        score[u] += (int)(ph >> 31) - (int)(mh >> 31);
-                        const uint32_t phs = ph << 1, mhs = mh << 1;
-                        pv[u] = mhs | ~(xv | phs);
-                        mv[u] = phs & xv;
-                        best[u] = min(best[u], score[u]);
-                    }
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < kSeedIlp; u++)
-                if (best[u] <= K && (best[u] < best_d || (best[u] == best_d && hb[u] < best_b))) {
-                    best_d = best[u];
-                    best_b = hb[u];
-                }
         }
 
-#ifdef BDX_SEED_DEBUG
-        if (item < 3) printf("item %d read %d n %d punt %d wins %d hits %d best_d %d best_b %d\n", item, read, n, (int)punt,
-                             n_wins, n_hits, best_d, best_b);
-#endif
         // ---- decide ----
         bool resolved = false;
         if (!punt) {
@@ -226,7 +323,7 @@ k_seed(const __grid_constant__ DevParams P, const int pass, const uint8_t *__res
                     out[read] = PassOut{best_b + 1, best_d, -1, -1};
                     resolved = true;
                 }
-            } else if (K >= S.allowed0[0]) {
+            } else if (last_level && K >= S.allowed0[0]) {
                 out[read] = PassOut{kBcUnknown, 0, -1, -1};    // nothing within the allowed distance
                 resolved = true;
             }
@@ -242,38 +339,48 @@ k_seed(const __grid_constant__ DevParams P, const int pass, const uint8_t *__res
     if (lane == 0 && n_done && counters) atomicAdd(counters + 2, (unsigned long long)n_done);
 }
 
-static size_t seed_smem(const DevSet &S)
+static size_t seed_tab_words(const SeedLevel &L) { return ((size_t)1 << L.log2) + 1 + 2 * (size_t)L.n_entries; }
+
+static size_t seed_smem(const DevSet &S, const SeedLevel &L, bool tab_smem)
 {
-    size_t words = (size_t)S.n_classes * S.n_bc_pad + ((size_t)1 << (S.sd_bm_log2 - 5)) + ((size_t)1 << S.sd_log2) + 1 +
-                   2 * (size_t)S.sd_n_entries + (size_t)kSeedMaxHits * kSeedThreads;
+    size_t words = (size_t)S.n_classes * S.n_bc_pad + ((size_t)1 << (L.bm_log2 - 5)) + (tab_smem ? seed_tab_words(L) : 0) +
+                   (size_t)kSeedMaxHits * kSeedThreads + kSeedThreads;
     return words * 4 + (size_t)kSeedMaxWins * kSeedThreads + 256 + (size_t)kSeedThreads * kSeedSlot + 16;
 }
 
-bool seed_applies(const DevParams &P, int pass)
+// the CSR table goes to shared memory while the whole carve-up stays small enough for >= 3 blocks per SM
+static bool seed_tab_in_smem(const DevSet &S, const SeedLevel &L) { return seed_smem(S, L, true) <= 72 * 1024; }
+
+int seed_levels(const DevParams &P, int pass)
 {
     static const bool off = getenv("BDX_DISABLE_SEED") != nullptr;
     const DevSet &S = P.set[pass];
-    return !off && prefilter_applies(P, pass) && P.algo == BDX_SEMIGLOBAL && S.sd_enabled && S.words == 1 &&
-           seed_smem(S) <= 100 * 1024;
+    if (off || !prefilter_applies(P, pass) || P.algo != BDX_SEMIGLOBAL || S.words != 1) return 0;
+    for (int l = 0; l < S.sd_levels; l++)
+        if (seed_smem(S, S.sd[l], seed_tab_in_smem(S, S.sd[l])) > 110 * 1024) return 0;
+    return S.sd_levels;
 }
 
-cudaError_t launch_seed(const DevParams &P, int pass, const uint8_t *seq, const int *off, int n, const Scratch &sc,
-                        int sm_count, unsigned long long *counters, cudaStream_t st)
+cudaError_t launch_seed(const DevParams &P, int pass, int level, const uint8_t *seq, const int *off, int n,
+                        const Scratch &sc, const int *wl_in, const int *n_in, int *wl_out, int *n_out, int sm_count,
+                        unsigned long long *counters, cudaStream_t st)
 {
     const DevSet &S = P.set[pass];
-    const size_t smem = seed_smem(S);
-    cudaError_t e = cudaFuncSetAttribute(k_seed, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const SeedLevel &L = S.sd[level];
+    const bool tab = seed_tab_in_smem(S, L);
+    const size_t smem = seed_smem(S, L, tab);
+    auto kern = tab ? k_seed<true> : k_seed<false>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int per_sm = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_seed, kSeedThreads, smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kSeedThreads, smem);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
     const int groups = (n + kSeedThreads - 1) / kSeedThreads;     // upper bound: the worklist is <= n
     const int blocks = std::max(1, std::min(groups, sm_count * per_sm));
-    e = cudaMemsetAsync(sc.n_work2, 0, sizeof(int), st);
+    e = cudaMemsetAsync(n_out, 0, sizeof(int), st);
     if (e != cudaSuccess) return e;
-    k_seed<<<blocks, kSeedThreads, smem, st>>>(P, pass, seq, off, sc.pass[pass], sc.worklist, sc.n_work,
-                                               sc.worklist2, sc.n_work2, counters);
+    kern<<<blocks, kSeedThreads, smem, st>>>(P, pass, level, seq, off, sc.pass[pass], wl_in, n_in, wl_out, n_out, counters);
     return cudaGetLastError();
 }
 

@@ -302,27 +302,30 @@ def run_ours(args):
     seq_np, off_np = h_seq.numpy(), h_off.numpy()
     e2e_matched = 0
 
-    DEPTH = 3  # batches kept in flight (BDX_MAX_IN_FLIGHT = 4)
+    DEPTH = int(os.environ.get("BDX_E2E_DEPTH", "4"))  # batches kept in flight (BDX_MAX_IN_FLIGHT = 4)
 
-    def e2e_step():
+    def e2e_steps(n_steps):
+        """n_steps passes over the workload as ONE pipeline of batches: every batch is copied H2D from pinned
+        host memory, classified, its results copied D2H and read by the host; DEPTH batches are in flight,
+        the pipeline is drained at the end (inside the timed region), not between steps."""
         nonlocal e2e_matched
         m = 0
         queued = 0
-        for k in range(nb):
-            stream.submit(seq_np[k * B * READ_LEN:(k + 1) * B * READ_LEN], off_np, tag=k, pinned=True)
-            queued += 1
-            if queued == DEPTH:
-                _, r = stream.fetch(copy=False)
-                m += int(np.count_nonzero(r["bc1"]))      # the host reads every result record
-                queued -= 1
+        for _ in range(n_steps):
+            for k in range(nb):
+                stream.submit(seq_np[k * B * READ_LEN:(k + 1) * B * READ_LEN], off_np, tag=k, pinned=True)
+                queued += 1
+                if queued == DEPTH:
+                    _, r = stream.fetch(copy=False)
+                    m += int(np.count_nonzero(r["bc1"]))      # the host reads every result record
+                    queued -= 1
         while queued:
             _, r = stream.fetch(copy=False)
             m += int(np.count_nonzero(r["bc1"]))
             queued -= 1
         e2e_matched = m
 
-    for _ in range(max(1, min(args.warmup, 2))):
-        e2e_step()
+    e2e_steps(max(1, min(args.warmup, 2)))
     # what the host link gives a plain pinned H2D copy of one batch (the e2e path's own bound)
     p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     d_probe = torch.empty(B * READ_LEN, dtype=torch.uint8, device="cuda")
@@ -330,22 +333,21 @@ def run_ours(args):
     torch.cuda.synchronize()
     p0.record()
     for k in range(4):
-        d_probe.copy_(h_seq[k * B * READ_LEN:(k + 1) * B * READ_LEN], non_blocking=True)
+        d_probe.copy_(h_seq[(k % nb) * B * READ_LEN:(k % nb + 1) * B * READ_LEN], non_blocking=True)
     p1.record()
     torch.cuda.synchronize()
     pcie_h2d_gbs = 4 * B * READ_LEN / (p0.elapsed_time(p1) * 1e-3) / 1e9
     del d_probe
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        e2e_step()
+    e2e_steps(args.steps)
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     t = torch.tensor([dt], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = world * nb * B * args.steps / float(t.item())
-    assert e2e_matched == int((res["status"][:nb * B] == 0).sum()), "e2e and device-resident results disagree"
+    assert e2e_matched == args.steps * int((res["status"][:nb * B] == 0).sum()), "e2e and device-resident results disagree"
 
     # ---- N > 1: the one collective of the path -- DemuxStats counters summed over GPUs ------
     stats_ms = None
@@ -410,7 +412,7 @@ def run_ours(args):
                                  "bytes_per_read": BYTES_PER_READ}},
             "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": nb * (B * READ_LEN + 4 * (B + 1)),
                     "d2h_bytes_per_step": nb * B * bdx.RESULT_DTYPE.itemsize,
-                    "api": "bdx_submit_pinned / bdx_fetch_view, 3 batches in flight",
+                    "api": f"bdx_submit_pinned / bdx_fetch_view, {DEPTH} batches in flight",
                     "h2d_gbs_achieved": e2e_value / world * (READ_LEN + 4) / 1e9,
                     "h2d_gbs_plain_memcpy": pcie_h2d_gbs,
                     "bound": "host link: every read is 154 B of H2D; a bare pinned cudaMemcpyAsync of the same "
@@ -443,7 +445,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--reads", type=int, default=10_000_000, help="reads per GPU (config 2: 10 M)")
-    ap.add_argument("--e2e-batch", type=int, default=1_000_000)
+    ap.add_argument("--e2e-batch", type=int, default=500_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="device-resident timing only (kernel experiments)")
     args = ap.parse_args()

@@ -34,6 +34,8 @@ EXPORTS = [
     "bdx_barcode_table_load", "bdx_barcode_table_destroy", "bdx_barcode_table_count", "bdx_barcode_table_id_count",
     "bdx_barcode_table_bytes", "bdx_barcode_table_offsets", "bdx_barcode_table_lengths_no_n", "bdx_barcode_table_id",
     "bdx_barcode_table_error", "bdx_stats_entries",
+    "bdx_pool_create", "bdx_pool_destroy", "bdx_pool_submit", "bdx_pool_submit_pinned", "bdx_pool_fetch",
+    "bdx_pool_fetch_view", "bdx_pool_in_flight", "bdx_pool_stats_fetch",
 ]
 
 
@@ -153,6 +155,15 @@ def load_library():
     L.bdx_int_alu_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]
     L.bdx_fastq_scan.argtypes = [vp, i64, C.c_int, i32, vp, C.POINTER(i32), C.POINTER(i64)]
     L.bdx_fastq_pack.argtypes = [vp, vp, i32, vp, i64, vp]
+    L.bdx_pool_create.argtypes = [vp, C.POINTER(C.c_int), C.c_int, C.c_int, i32, i64, C.POINTER(vp)]
+    L.bdx_pool_destroy.argtypes = [vp]
+    L.bdx_pool_destroy.restype = None
+    L.bdx_pool_submit.argtypes = [vp, vp, vp, i32, u64]
+    L.bdx_pool_submit_pinned.argtypes = [vp, vp, vp, i32, u64]
+    L.bdx_pool_fetch.argtypes = [vp, C.POINTER(u64), C.POINTER(i32), vp, vp]
+    L.bdx_pool_fetch_view.argtypes = [vp, C.POINTER(u64), C.POINTER(i32), C.POINTER(vp), C.POINTER(vp)]
+    L.bdx_pool_in_flight.argtypes = [vp]
+    L.bdx_pool_stats_fetch.argtypes = [vp, vp, i64]
     L.bdx_barcode_table_load.argtypes = [C.c_char_p, C.c_int, C.c_int, C.POINTER(vp)]
     L.bdx_barcode_table_destroy.argtypes = [vp]
     L.bdx_barcode_table_destroy.restype = None
@@ -443,6 +454,63 @@ class Stream:
             self.close()
         except Exception:
             pass
+
+
+class Pool:
+    """``bdx_pool``: batches dealt round-robin to streams on several GPUs, results in submission order."""
+
+    def __init__(self, config: Config, devices: Sequence[int], streams_per_device: int = 2, max_reads: int = 4000,
+                 max_bytes: Optional[int] = None):
+        self.lib, self.config = config.lib, config
+        devs = (C.c_int * len(devices))(*devices)
+        mb = int(max_bytes if max_bytes is not None else max(max_reads, 1) * 1024)
+        self.handle = C.c_void_p()
+        _check(self.lib.bdx_pool_create(config.handle, devs, len(devices), streams_per_device, max_reads, mb,
+                                        C.byref(self.handle)))
+
+    def submit(self, seq: np.ndarray, off: np.ndarray, tag: int = 0, pinned: bool = False):
+        fn = self.lib.bdx_pool_submit_pinned if pinned else self.lib.bdx_pool_submit
+        _check(fn(self.handle, seq.ctypes.data, off.ctypes.data, len(off) - 1, tag))
+
+    def try_submit(self, seq, off, tag=0, pinned=False) -> bool:
+        """False when the stream whose turn it is is full (fetch first)."""
+        try:
+            self.submit(seq, off, tag, pinned)
+            return True
+        except BdxError as e:
+            if e.code == BDX_ERR_STATE:
+                return False
+            raise
+
+    def fetch(self):
+        tag, n = C.c_uint64(), C.c_int32()
+        res_p, det_p = C.c_void_p(), C.c_void_p()
+        _check(self.lib.bdx_pool_fetch_view(self.handle, C.byref(tag), C.byref(n), C.byref(res_p), C.byref(det_p)))
+        if n.value == 0:
+            return tag.value, np.zeros(0, RESULT_DTYPE)
+        buf = (C.c_char * (n.value * RESULT_DTYPE.itemsize)).from_address(res_p.value)
+        return tag.value, np.frombuffer(buf, dtype=RESULT_DTYPE, count=n.value).copy()
+
+    @property
+    def in_flight(self) -> int:
+        return int(self.lib.bdx_pool_in_flight(self.handle))
+
+    def stats(self) -> np.ndarray:
+        out = np.zeros(self.config.layout.total_len, dtype=np.int64)
+        _check(self.lib.bdx_pool_stats_fetch(self.handle, out.ctypes.data, out.size))
+        return out
+
+    def close(self):
+        if self.handle:
+            self.lib.bdx_pool_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+        return False
 
 
 class Engine:

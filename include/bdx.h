@@ -263,6 +263,27 @@ int bdx_fastq_scan(const uint8_t *buf, int64_t len, int final_block, int32_t max
 int bdx_fastq_pack(const uint8_t *buf, const bdx_fastq_record *recs, int32_t n, uint8_t *seq_out,
                    int64_t seq_cap, int32_t *offsets_out);
 
+/* ---- dispatcher over several GPUs ------------------------------------------
+ * Reads are independent, so batches are dealt round-robin to streams on the given devices (barcode tables
+ * replicated per device, no data-path collective) and come back in submission order -- what a host that
+ * owns the writers needs (core.jl:139-148).  A pool belongs to one thread at a time, like a stream.
+ * bdx_pool_submit returns BDX_ERR_STATE when the stream whose turn it is already has BDX_MAX_IN_FLIGHT
+ * batches in flight: fetch first.  At most n_devices * streams_per_device * BDX_MAX_IN_FLIGHT batches can
+ * be in flight.  bdx_pool_stats_fetch sums the DemuxStats counters of all streams (across processes the
+ * host sums the buffers with one all-reduce, see bdx_stats_device_ptr). */
+typedef struct bdx_pool bdx_pool;
+int bdx_pool_create(const bdx_config *cfg, const int *devices, int n_devices, int streams_per_device,
+                    int32_t max_reads, int64_t max_bytes, bdx_pool **out);
+void bdx_pool_destroy(bdx_pool *p);
+int bdx_pool_submit(bdx_pool *p, const uint8_t *seq_bytes, const int32_t *offsets, int32_t n_reads, uint64_t tag);
+int bdx_pool_submit_pinned(bdx_pool *p, const uint8_t *seq_bytes, const int32_t *offsets, int32_t n_reads,
+                           uint64_t tag);
+int bdx_pool_fetch(bdx_pool *p, uint64_t *tag, int32_t *n_reads, bdx_result *results, bdx_pass_detail *details);
+int bdx_pool_fetch_view(bdx_pool *p, uint64_t *tag, int32_t *n_reads, const bdx_result **results,
+                        const bdx_pass_detail **details);
+int bdx_pool_in_flight(const bdx_pool *p);
+int bdx_pool_stats_fetch(bdx_pool *p, int64_t *out, int64_t out_len);
+
 /* ---- host-side barcode-table loader -----------------------------------
  * preprocess_bc_file (fileio.jl:7-72): FASTA when the path ends in .fasta / .fa, otherwise a table
  * (',' for .csv, tab otherwise) with the columns Full_seq, ID, Full_annotation.  Keeps the bases

@@ -289,3 +289,36 @@ def test_long_and_ragged_reads(algo):
     for kw in (dict(), dict(trim_side=3), dict(ref_search_range=R("end-400:end"), min_delta=0.05),
                dict(barcode_start_range=R("200:end"), trim_side=5)):
         compare(_cfg(bcs, matching_algorithm=algo, **kw), reads, label=f"long {algo} {kw}")
+
+
+@pytest.mark.parametrize("streams_per_device", [1, 3])
+def test_pool_dispatcher_order_and_stats(streams_per_device):
+    """bdx_pool: batches dealt round-robin over streams (and GPUs when there are several) come back in
+    submission order with the results of a single stream; the summed counters equal one stream's."""
+    rng = np.random.default_rng(31)
+    bcs = synth.random_barcodes(rng, 48, 20)
+    cfg = _cfg(bcs, trim_side=5, summary=True)
+    batches = [synth.random_reads(rng, 300 + 41 * i, bcs, min_len=100) for i in range(11)]
+    packed = [bdx.pack_reads(b) for b in batches]
+    config = capi.Config(cfg)
+    n_dev = capi.load_library().bdx_device_count()
+    with capi.Engine(cfg, max_reads=1000, max_bytes=1000 * 110) as eng:
+        want = [eng.classify_packed(*p) for p in packed]
+        want_stats = eng.stream.stats()
+    with capi.Pool(config, list(range(n_dev)), streams_per_device, max_reads=1000, max_bytes=1000 * 110) as pool:
+        got, nxt = [], 0
+        while len(got) < len(packed):
+            while nxt < len(packed) and pool.try_submit(packed[nxt][0], packed[nxt][1], tag=1000 + nxt):
+                nxt += 1
+            tag, res = pool.fetch()
+            assert tag == 1000 + len(got)
+            got.append(res)
+        assert pool.in_flight == 0
+        for g, w in zip(got, want):
+            for f in ("status", "bc1", "bc2", "keep_start", "keep_end"):
+                assert (g[f] == w[f]).all()
+        assert (pool.stats() == want_stats).all()
+        with pytest.raises(capi.BdxError) as ei:
+            pool.fetch()
+        assert ei.value.code == capi.BDX_ERR_STATE
+    config.close()

@@ -74,6 +74,11 @@ struct HostSet {
     uint32_t hs_pow = 0;
     std::vector<uint32_t> hs_bstart, hs_entries;
     // :semiglobal depth-limited seeds
+    // :hamming packed scan (hamming.cu)
+    int hp_enabled = 0, hp_m = 0, hp_allowed = 0, hp_n_seg = 0;
+    int hp_off[8] = {}, hp_q[8] = {}, hp_base[8] = {};
+    std::vector<uint16_t> hp_bstart, hp_entries;
+    std::vector<uint2> hp_bcw;
     struct HostSeedLevel {
         int k = 0, q = 0, log2 = 0, bm_log2 = 0;
         uint32_t pow = 0;
@@ -313,6 +318,61 @@ static int build_set(const bdx_params &p, const bdx_barcode_set &in, HostSet &hs
             }
         }
     }
+    // ---- :hamming on packed words (hamming.cu): uniform length <= 32, <= 4 distinct barcode bytes, no 'N' ----
+    if (p.algorithm == BDX_HAMMING && min_m == hs.max_m && hs.max_m <= 32 && hs.n_classes - 1 <= 4 && hs.n_bc <= 65535 &&
+        hs.allowed0[0] >= 0 && hs.allowed0[0] <= 7 && p.max_error_rate >= 0.0 &&
+        std::find(hs.bytes.begin(), hs.bytes.end(), (uint8_t)'N') == hs.bytes.end()) {
+        const int m = hs.max_m, n_seg = hs.allowed0[0] + 1;
+        const int seg_len = m / n_seg, extra = m % n_seg;      // the first `extra` segments are one base longer
+        if (seg_len >= 2) {
+            hs.hp_m = m;
+            hs.hp_allowed = hs.allowed0[0];
+            hs.hp_n_seg = n_seg;
+            int o = 0, base = 0;
+            for (int i = 0; i < n_seg; i++) {
+                const int len = seg_len + (i < extra ? 1 : 0);
+                hs.hp_off[i] = o;
+                hs.hp_q[i] = std::min(len, 6);                  // direct-address table of 4^q buckets
+                hs.hp_base[i] = base;
+                base += (1 << (2 * hs.hp_q[i])) + 1;
+                o += len;
+            }
+            auto code_of = [&](int b, int pos) { return (uint32_t)(hs.bc_cls[hs.off[b] + pos] - 1) & 3u; };
+            hs.hp_bstart.assign((size_t)base, 0);
+            hs.hp_entries.assign((size_t)n_seg * hs.n_bc, 0);
+            for (int i = 0; i < n_seg; i++) {
+                const int nb = 1 << (2 * hs.hp_q[i]);
+                std::vector<std::vector<uint16_t>> buckets((size_t)nb);
+                for (int b = 0; b < hs.n_bc; b++) {
+                    uint32_t gram = 0;           // bit plane 0 of the q bases, then bit plane 1
+                    for (int k = 0; k < hs.hp_q[i]; k++) {
+                        const uint32_t c = code_of(b, hs.hp_off[i] + k);
+                        gram |= (c & 1u) << k;
+                        gram |= (c >> 1) << (hs.hp_q[i] + k);
+                    }
+                    buckets[gram].push_back((uint16_t)b);
+                }
+                uint16_t run = 0;
+                size_t w = (size_t)i * hs.n_bc;
+                for (int gidx = 0; gidx < nb; gidx++) {
+                    hs.hp_bstart[(size_t)hs.hp_base[i] + gidx] = run;
+                    for (uint16_t b : buckets[(size_t)gidx]) hs.hp_entries[w++] = b;
+                    run = (uint16_t)(run + buckets[(size_t)gidx].size());
+                }
+                hs.hp_bstart[(size_t)hs.hp_base[i] + nb] = run;
+            }
+            hs.hp_bcw.resize((size_t)hs.n_bc);
+            for (int b = 0; b < hs.n_bc; b++) {
+                uint32_t w0 = 0, w1 = 0;         // the two bit planes, base k in bit k
+                for (int k = 0; k < m; k++) {
+                    w0 |= (code_of(b, k) & 1u) << k;
+                    w1 |= (code_of(b, k) >> 1) << k;
+                }
+                hs.hp_bcw[(size_t)b] = make_uint2(w0, w1);
+            }
+            hs.hp_enabled = 1;
+        }
+    }
     // ---- :hamming pigeonhole seeds: mismatches <= allowed_b leave one of allowed_b + 1 disjoint
     // segments of the barcode intact, so every acceptable placement contains an exact seed ----
     if (p.algorithm == BDX_HAMMING && hs.words && p.max_error_rate >= 0.0 && !getenv("BDX_DISABLE_PREFILTER") &&
@@ -522,6 +582,19 @@ static int get_tables(bdx_config *cfg, int device, DeviceTables **out)
             if (e == cudaSuccess) e = upload(t, H.ekeys, &L.ekeys);
             if (e == cudaSuccess) e = upload(t, H.bitmap, &L.bitmap);
         }
+        D.hp.enabled = hs.hp_enabled;
+        D.hp.m = hs.hp_m;
+        D.hp.allowed = hs.hp_allowed;
+        D.hp.n_seg = hs.hp_n_seg;
+        D.hp.n_bstart = (int)hs.hp_bstart.size();
+        for (int k = 0; k < 8; k++) {
+            D.hp.seg_off[k] = hs.hp_off[k];
+            D.hp.seg_q[k] = hs.hp_q[k];
+            D.hp.seg_base[k] = hs.hp_base[k];
+        }
+        if (e == cudaSuccess) e = upload(t, hs.hp_bstart, &D.hp.bstart);
+        if (e == cudaSuccess) e = upload(t, hs.hp_entries, &D.hp.entries);
+        if (e == cudaSuccess) e = upload(t, hs.hp_bcw, &D.hp.bcw);
         D.hs_enabled = hs.hs_enabled;
         D.hs_q = hs.hs_q;
         D.hs_pow = hs.hs_pow;
@@ -742,7 +815,13 @@ static int enqueue_classify(bdx_stream *s, const uint8_t *d_seq, const int32_t *
     const DevParams &P = s->tab->P;
     const int passes = P.is_dual ? 2 : 1;
     for (int pass = 0; pass < passes; pass++) {
-        if (hamming_seed_applies(P, pass)) {
+        if (hamming_packed_applies(P, pass)) {
+            // :hamming -- packed pigeonhole scan over every start position, then the literal rules on the candidates
+            CU(launch_hamming_scan(P, pass, d_seq, d_off, n, s->sc, s->tab->sm_count, s->st_comp));
+            s->launches++;
+            CU(launch_literal(P, pass, 1, d_seq, d_off, n, s->sc, s->st_comp));
+            s->launches++;
+        } else if (hamming_seed_applies(P, pass)) {
             // :hamming -- pigeonhole seeds + in-place verification, then the literal rules on the candidates
             CU(launch_seed_hamming(P, pass, d_seq, d_off, n, s->sc, s->tab->sm_count, s->st_comp));
             s->launches++;

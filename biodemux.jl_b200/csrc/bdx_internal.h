@@ -40,6 +40,19 @@ struct SeedLevel {
     const uint32_t *bitmap;
 };
 
+// :hamming on 2-bit packed words (hamming.cu): uniform barcode length, <= 4 distinct barcode bytes, no 'N'
+struct HammingPacked {
+    int enabled;
+    int m;                        // the common barcode length (<= 32)
+    int allowed;                  // floor(max_error_rate * m)
+    int n_seg;                    // allowed + 1 disjoint segments
+    int n_bstart;                 // entries of bstart (sum of the segments' buckets + 1 each)
+    int seg_off[8], seg_q[8], seg_base[8];   // first base / seed length / first bstart entry of every segment
+    const uint16_t *bstart;       // per segment: [4^q + 1] CSR row starts into that segment's entry row
+    const uint16_t *entries;      // [n_seg][n_bc] barcode indices grouped by seed code
+    const uint2 *bcw;             // [n_bc] the two bit planes of the barcode's 2-bit base codes, base k in bit k
+};
+
 struct DevSet {
     int n_bc;
     int n_bc_pad;     // n_bc rounded up to a multiple of 32
@@ -80,6 +93,7 @@ struct DevSet {
     // :semiglobal depth-limited seeds (seed.cu, k_seed): for uniform-length sets, every alignment
     // with <= k edits leaves one of k + 1 disjoint barcode segments intact.  Up to two levels: a
     // shallow one with long, very selective seeds, then the deepest level that is still selective.
+    HammingPacked hp;
     int sd_levels;                // 0 = off
     int sd_m;                     // the common barcode length
     SeedLevel sd[2];
@@ -152,6 +166,9 @@ cudaError_t launch_prefilter(const DevParams &P, int pass, const uint8_t *seq, c
 bool prefilter_applies(const DevParams &P, int pass);
 bool exact_hash_applies(const DevParams &P, int pass);
 bool hamming_seed_applies(const DevParams &P, int pass);
+bool hamming_packed_applies(const DevParams &P, int pass);
+cudaError_t launch_hamming_scan(const DevParams &P, int pass, const uint8_t *seq, const int *off, int n,
+                                const Scratch &sc, int sm_count, cudaStream_t st);
 cudaError_t launch_seed_hamming(const DevParams &P, int pass, const uint8_t *seq, const int *off, int n,
                                 const Scratch &sc, int sm_count, cudaStream_t st);
 cudaError_t launch_finalize(const DevParams &P, const int *off, int n, const Scratch &sc,

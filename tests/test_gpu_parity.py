@@ -119,6 +119,15 @@ CONFIGS = {
                              barcode_start_range=R("1:60"), barcode_end_range=R("15:end")),
     "hamming_pf_trim5": dict(n_bc=64, m=(10, 20), matching_algorithm="hamming", trim_side=5,
                              ref_search_range=R("3:90"), barcode_end_range=R("end-80:end")),
+    # uniform length, no N in the barcodes: the bit-plane packed scan (hamming.cu)
+    "hamming_packed_delta": dict(n_bc=200, m=(24, 24), matching_algorithm="hamming", min_delta=0.1, trim_side=5,
+                                 want_stats=True),
+    "hamming_packed_m32": dict(n_bc=64, m=(32, 32), matching_algorithm="hamming", max_error_rate=0.22, trim_side=3,
+                               barcode_start_range=R("1:100"), barcode_end_range=R("40:end")),
+    "hamming_packed_zero": dict(n_bc=96, m=(16, 16), matching_algorithm="hamming", max_error_rate=0.05),
+    "hamming_packed_short": dict(n_bc=300, m=(8, 8), matching_algorithm="hamming", max_error_rate=0.4,
+                                 ref_search_range=R("2:end-3")),
+    "hamming_packed_many": dict(n_bc=1536, m=(24, 24), matching_algorithm="hamming", n_reads=1500),
     "exact": dict(n_bc=96, m=(24, 24), matching_algorithm="exact"),
     "exact_var": dict(n_bc=200, m=(8, 30), matching_algorithm="exact", trim_side=5, barcode_start_range=R("2:70"),
                       barcode_end_range=R("20:end"), want_stats=True),

@@ -11,11 +11,13 @@
 //   * One thread per read then walks the start positions hamming_align allows (:570-571, :583-586): the m-base
 //     window of each plane is one funnel shift, each segment's q-gram is looked up, and every listed barcode
 //     is verified with xor / or / popcount on 32-bit words: no byte loop, no early-exit divergence.
-//   * Barcodes with a placement within `allowed` form the read's candidate list (distinct, ascending).
+//   * Barcodes with a placement within `allowed` form the read's list (ascending), each with its best placement
+//     (fewest mismatches; ties leftmost, rightmost when trimming 3', :609-620).
 // The list is exactly {b : hamming_align(b) is finite at the initial threshold}; every other barcode returns Inf
-// in the reference under any running threshold, so k_literal's replay over the list (hamming_literal, in file
-// order, with the running threshold and the leftmost / rightmost rule) gives the reference's result.  Reads
-// longer than the packed capacity are handed to k_literal with "scan every barcode".
+// in the reference under any running threshold, and for a listed barcode hamming_align returns that best
+// placement whenever it is within the threshold of its turn.  So the reference's sequential selection is
+// replayed over the list right here (file order, running threshold, doubles).  Reads longer than the packed
+// capacity, or with more than kCandMax acceptable barcodes, are handed to k_literal ("scan every barcode").
 #include <algorithm>
 #include <cstdlib>
 #include <math_constants.h>
@@ -43,7 +45,8 @@ k_hamming_scan(const __grid_constant__ DevParams P, const int pass, const uint8_
     uint2 *bcw_s = reinterpret_cast<uint2 *>(pi_s + kHpPlane * kHpThreads);   // [n_bc] barcode planes
     uint16_t *bstart_s = reinterpret_cast<uint16_t *>(bcw_s + S.n_bc);        // [n_bstart]
     uint16_t *entries_s = bstart_s + ((H.n_bstart + 1) & ~1);                 // [n_seg][n_bc]
-    uint16_t *list_s = entries_s + ((H.n_seg * S.n_bc + 1) & ~1);             // [kCandMax][threads]
+    // [kCandMax][threads] barcode << 12 | mismatches << 8 | start of its best placement, ascending barcode
+    uint32_t *list_s = reinterpret_cast<uint32_t *>(entries_s + ((H.n_seg * S.n_bc + 1) & ~1));
     uint8_t *class_s = reinterpret_cast<uint8_t *>(list_s + kCandMax * kHpThreads);
 
     for (int k = threadIdx.x; k < S.n_bc; k += blockDim.x) bcw_s[k] = H.bcw[k];
@@ -55,6 +58,8 @@ k_hamming_scan(const __grid_constant__ DevParams P, const int pass, const uint8_
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int m = H.m, allowed = H.allowed, n_seg = H.n_seg;
     const uint32_t len_mask = m >= 32 ? 0xFFFFFFFFu : ((1u << m) - 1u);
+    const bool rightmost = S.trim_side == 3;       // ties between placements: leftmost, rightmost when trimming 3' (:613-619)
+    const bool with_delta = P.min_delta != 0.0;
     const int n_groups = (n_reads + kHpThreads - 1) / kHpThreads;
 
     for (int grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
@@ -131,27 +136,46 @@ k_hamming_scan(const __grid_constant__ DevParams P, const int pass, const uint8_
                     const uint2 bw = bcw_s[b];
                     const int mm = __popc(((W0 ^ bw.x) | (W1 ^ bw.y) | WI) & len_mask);
                     if (mm > allowed || nc == kCandOverflow) continue;
-                    int pos = 0;                                         // sorted insert, skip duplicates
-                    while (pos < nc && list_s[pos * kHpThreads + threadIdx.x] < b) pos++;
-                    if (pos < nc && list_s[pos * kHpThreads + threadIdx.x] == b) continue;
+                    const uint32_t item = ((uint32_t)b << 12) | ((uint32_t)mm << 8) | (uint32_t)s;
+                    int pos = 0;                                         // sorted by barcode
+                    while (pos < nc && (int)(list_s[pos * kHpThreads + threadIdx.x] >> 12) < b) pos++;
+                    if (pos < nc && (int)(list_s[pos * kHpThreads + threadIdx.x] >> 12) == b) {
+                        // the barcode's best placement so far: fewer mismatches win, ties by the start rule
+                        const uint32_t old = list_s[pos * kHpThreads + threadIdx.x];
+                        const int old_mm = (int)((old >> 8) & 0xFu);
+                        if (mm < old_mm || (mm == old_mm && rightmost && s > (int)(old & 0xFFu)))
+                            list_s[pos * kHpThreads + threadIdx.x] = item;
+                        continue;
+                    }
                     if (nc == kCandMax) {
                         nc = kCandOverflow;
                         continue;
                     }
                     for (int k = nc; k > pos; k--) list_s[k * kHpThreads + threadIdx.x] = list_s[(k - 1) * kHpThreads + threadIdx.x];
-                    list_s[pos * kHpThreads + threadIdx.x] = (uint16_t)b;
+                    list_s[pos * kHpThreads + threadIdx.x] = item;
                     nc++;
                 }
             }
         }
-        if (nc == 0) {
-            out[read] = PassOut{kBcUnknown, 0, -1, -1};                  // every barcode returns Inf (:820-821)
-        } else {
-            if (nc != kCandOverflow)
-                for (int k = 0; k < nc; k++) cand[(size_t)read * kCandMax + k] = list_s[k * kHpThreads + threadIdx.x];
-            cand_cnt[read] = (uint8_t)nc;
+        if (nc == kCandOverflow) {                     // too many acceptable barcodes to list: k_literal scans them all
+            cand_cnt[read] = (uint8_t)kCandOverflow;
             out[read] = PassOut{kBcPending, 0, -1, -1};
+            continue;
         }
+        // ---- the reference's sequential selection over the listed barcodes, in file order, with the running
+        // threshold (find_best_matching_bc_*, :632-713).  For a barcode on the list hamming_align returns its
+        // best placement when that is within floor(thr * m) at its turn, else Inf; unlisted barcodes return Inf
+        // under every threshold. ----
+        BestState bs;
+        best_init(bs, P.max_error_rate);
+        for (int k = 0; k < nc; k++) {
+            const uint32_t item = list_s[k * kHpThreads + threadIdx.x];
+            const int b = (int)(item >> 12), mm = (int)((item >> 8) & 0xFu), st = (int)(item & 0xFFu);
+            const bool ok = mm <= allowed_from(bs.thr, m);                                   // :567
+            const double score = ok ? __ddiv_rn((double)mm, (double)m) : CUDART_INF;        // :607
+            best_consider(bs, with_delta, score, ok ? mm : kInf, b + 1, ok ? st : -1, ok ? st + m - 1 : -1);
+        }
+        out[read] = best_finish(bs, with_delta, P.min_delta);
     }
 }
 
@@ -161,7 +185,7 @@ static size_t hamming_scan_smem(const DevSet &S)
     size_t b = 3 * (size_t)kHpPlane * kHpThreads * 4;
     b += (size_t)S.n_bc * 8;
     b += (size_t)((H.n_bstart + 1) & ~1) * 2 + (size_t)((H.n_seg * S.n_bc + 1) & ~1) * 2;
-    b += (size_t)kCandMax * kHpThreads * 2 + 256;
+    b += (size_t)kCandMax * kHpThreads * 4 + 256;
     return (b + 15) & ~(size_t)15;
 }
 

@@ -63,3 +63,41 @@ def _random_case(seed):
 def test_fuzz_random_config(seed):
     cfg, reads, want_stats = _random_case(1000 + seed)
     compare(cfg, reads, want_stats=want_stats, label=f"seed{seed}: {cfg.matching_algorithm}")
+
+
+def _fast_case(seed, algo):
+    """The regimes the shortcut kernels own: uniform barcode length, ACGT barcodes, unit costs; for :semiglobal
+    score-only with default start / end ranges and no min_delta (k_prefilter -> k_seed levels -> k_filter), for
+    :hamming anything (k_hamming_scan).  Random set sizes, lengths, thresholds, search ranges, read lengths
+    (beyond the kernels' staging capacity too), duplicated barcodes, N / lower-case bases in the reads."""
+    rng = np.random.default_rng(seed)
+    m = int(rng.choice([8, 12, 16, 20, 24, 24, 28, 32]))
+    n_bc = int(rng.choice([8, 24, 96, 96, 200, 384, 700]))
+    bcs = synth.random_barcodes(rng, n_bc, m, m)
+    if rng.random() < 0.3:                      # identical sequences: the lowest index has to win
+        for _ in range(3):
+            bcs[int(rng.integers(0, n_bc))] = bcs[int(rng.integers(0, n_bc))]
+    kw = dict(matching_algorithm=algo, max_error_rate=float(rng.choice([0.0, 0.05, 0.1, 0.13, 0.2, 0.2, 0.25, 0.3])))
+    if rng.random() < 0.5:
+        kw["ref_search_range"] = R(_range(rng, "any"))
+    if algo == "hamming":
+        kw["min_delta"] = float(rng.choice([0.0, 0.0, 0.05, 0.1]))
+        kw["trim_side"] = [None, 3, 5][int(rng.integers(0, 3))]
+        if rng.random() < 0.4:
+            kw["barcode_start_range"] = R(_range(rng, "any"))
+        if rng.random() < 0.4:
+            kw["barcode_end_range"] = R(_range(rng, "any"))
+    cfg = bdx.DemuxConfig(bc_seqs=bcs, bc_lengths_no_N=[m] * n_bc, ids=[f"a{i}" for i in range(n_bc)], **kw)
+    lo = int(rng.choice([m, 40, 100, 150]))
+    hi = int(rng.choice([150, 150, 185, 200, 400]))
+    reads = synth.random_reads(rng, 1500, bcs, min_len=min(lo, hi), max_len=hi, max_edits=int(rng.choice([3, 5, 6])),
+                               lower_prob=0.02, n_prob=0.03)
+    reads += [b"", b"A", bcs[0].encode(), bcs[-1].encode() * 3, b"N" * 60]
+    return cfg, reads, bool(algo == "hamming" and rng.random() < 0.3)
+
+
+@pytest.mark.parametrize("seed", range(40))
+@pytest.mark.parametrize("algo", ["semiglobal", "hamming"])
+def test_fuzz_shortcut_regimes(seed, algo):
+    cfg, reads, want_stats = _fast_case(5000 + seed, algo)
+    compare(cfg, reads, want_stats=want_stats, label=f"fast seed{seed}: {algo}")

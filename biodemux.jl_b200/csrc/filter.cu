@@ -611,14 +611,20 @@ k_prefilter(const __grid_constant__ DevParams P, const int pass, const uint8_t *
             } else if (g.valid && g.max_start_pos >= n && g.min_end_pos <= g.start_j && ncols >= seed) {
                 // same regime test as k_filter's `fast` (score-only / unit costs are config-level and
                 // checked by the launcher)
+                // Positions (trimming / stats): every hit of the winning barcode scores 0, so the reference keeps
+                // the first one it meets (early exit for trim 5, no later hit is strictly better otherwise,
+                // classification.jl:419-436, :141-153) -- the leftmost occurrence -- or, trimming 3', the one
+                // with the largest start: the rightmost occurrence.  A verbatim hit is one diagonal: start = end - m + 1.
+                const bool need_tb = S.trim_side != 0 || P.want_stats;
                 int found, w;
                 if (staged)
                     found = pf_scan(stage + skew + (base - blk_base) + g.start_j - 1, ncols, S, keys_s, vals_s,
-                                    bitmap_s, false, w);
+                                    bitmap_s, S.trim_side == 3, w);
                 else
-                    found = pf_scan(seq + base + g.start_j - 1, ncols, S, keys_s, vals_s, bitmap_s, false, w);
+                    found = pf_scan(seq + base + g.start_j - 1, ncols, S, keys_s, vals_s, bitmap_s, S.trim_side == 3, w);
                 if (found >= 0 && found != 0x7FFFFFFF) {
-                    out[read] = PassOut{found + 1, 0, -1, -1};
+                    const int s1 = g.start_j + w, len = S.bc_off[found + 1] - S.bc_off[found];
+                    out[read] = PassOut{found + 1, 0, need_tb ? s1 : -1, need_tb ? s1 + len - 1 : -1};
                     resolved = true;
                 }
             }
@@ -828,8 +834,10 @@ bool prefilter_applies(const DevParams &P, int pass)
     const DevSet &S = P.set[pass];
     if (P.algo == BDX_HAMMING)   // positions are produced, so trim / stats are fine; needs no wildcard rows
         return S.words > 0 && S.pf_enabled && P.min_delta == 0.0 && P.max_error_rate >= 0.0;
-    return P.algo == BDX_SEMIGLOBAL && S.words > 0 && S.pf_enabled && P.unit_costs && S.trim_side == 0 &&
-           !P.want_stats && P.min_delta == 0.0 && P.max_error_rate >= 0.0;
+    // :semiglobal -- with trimming / stats the resolved reads also need positions: a verbatim occurrence has
+    // them (k_prefilter), a seed-resolved read gets them from k_literal run on its single winning barcode
+    return P.algo == BDX_SEMIGLOBAL && S.words > 0 && S.pf_enabled && P.unit_costs && P.min_delta == 0.0 &&
+           P.max_error_rate >= 0.0;
 }
 
 static size_t filter_smem_bytes(const DevSet &S)

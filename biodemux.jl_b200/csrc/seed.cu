@@ -131,11 +131,15 @@ __global__ void __launch_bounds__(kSeedThreads)
 k_seed(const __grid_constant__ DevParams P, const int pass, const int level, const uint8_t *__restrict__ seq,
        const int *__restrict__ off, PassOut *__restrict__ out, const int *__restrict__ worklist,
        const int *__restrict__ n_work, int *__restrict__ worklist2, int *__restrict__ n_work2,
-       unsigned long long *__restrict__ counters)
+       unsigned long long *__restrict__ counters, uint16_t *__restrict__ cand, uint8_t *__restrict__ cand_cnt)
 {
     extern __shared__ __align__(16) uint32_t smem[];
     const DevSet &S = P.set[pass];
     const SeedLevel &SL = S.sd[level];
+    // with trimming / stats the winner's alignment positions are needed too: the read is handed to k_literal
+    // with the winner as its only candidate (in this regime a barcode's result does not depend on the running
+    // threshold, so evaluating it alone gives the reference's positions)
+    const bool need_tb = S.trim_side != 0 || P.want_stats;
     const int n_pad = S.n_bc_pad;
     const int n_buckets = 1 << SL.log2;
     const int bm_words = 1 << (SL.bm_log2 - 5);
@@ -320,7 +324,13 @@ k_seed(const __grid_constant__ DevParams P, const int pass, const int level, con
                 const int norm = S.norm[best_b];
                 const double sc = __ddiv_rn((double)best_d, (double)norm);
                 if (best_d <= allowed_from(P.max_error_rate, norm) && sc <= P.max_error_rate) {
-                    out[read] = PassOut{best_b + 1, best_d, -1, -1};
+                    if (need_tb) {
+                        cand[(size_t)read * kCandMax] = (uint16_t)best_b;
+                        cand_cnt[read] = 1;
+                        out[read] = PassOut{kBcPending, 0, -1, -1};
+                    } else {
+                        out[read] = PassOut{best_b + 1, best_d, -1, -1};
+                    }
                     resolved = true;
                 }
             } else if (last_level && K >= S.allowed0[0]) {
@@ -380,7 +390,8 @@ cudaError_t launch_seed(const DevParams &P, int pass, int level, const uint8_t *
     const int blocks = std::max(1, std::min(groups, sm_count * per_sm));
     e = cudaMemsetAsync(n_out, 0, sizeof(int), st);
     if (e != cudaSuccess) return e;
-    kern<<<blocks, kSeedThreads, smem, st>>>(P, pass, level, seq, off, sc.pass[pass], wl_in, n_in, wl_out, n_out, counters);
+    kern<<<blocks, kSeedThreads, smem, st>>>(P, pass, level, seq, off, sc.pass[pass], wl_in, n_in, wl_out, n_out, counters,
+                                             sc.cand, sc.cand_cnt);
     return cudaGetLastError();
 }
 

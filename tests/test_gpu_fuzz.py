@@ -80,9 +80,9 @@ def _fast_case(seed, algo):
     kw = dict(matching_algorithm=algo, max_error_rate=float(rng.choice([0.0, 0.05, 0.1, 0.13, 0.2, 0.2, 0.25, 0.3])))
     if rng.random() < 0.5:
         kw["ref_search_range"] = R(_range(rng, "any"))
+    kw["trim_side"] = [None, 3, 5][int(rng.integers(0, 3))]       # positions: verbatim hits / winner re-aligned
     if algo == "hamming":
         kw["min_delta"] = float(rng.choice([0.0, 0.0, 0.05, 0.1]))
-        kw["trim_side"] = [None, 3, 5][int(rng.integers(0, 3))]
         if rng.random() < 0.4:
             kw["barcode_start_range"] = R(_range(rng, "any"))
         if rng.random() < 0.4:
@@ -92,8 +92,10 @@ def _fast_case(seed, algo):
     hi = int(rng.choice([150, 150, 185, 200, 400]))
     reads = synth.random_reads(rng, 1500, bcs, min_len=min(lo, hi), max_len=hi, max_edits=int(rng.choice([3, 5, 6])),
                                lower_prob=0.02, n_prob=0.03)
-    reads += [b"", b"A", bcs[0].encode(), bcs[-1].encode() * 3, b"N" * 60]
-    return cfg, reads, bool(algo == "hamming" and rng.random() < 0.3)
+    reads += [b"", b"A", bcs[0].encode(), bcs[-1].encode() * 3, b"N" * 60,
+              b"ACGT" * 5 + bcs[1].encode() + b"TTG" + bcs[1].encode() + b"CA",          # two verbatim occurrences
+              bcs[2].encode() + b"GATTACA" + bcs[2].encode() + b"C" + bcs[2].encode()]   # three of them
+    return cfg, reads, bool(rng.random() < 0.3)
 
 
 @pytest.mark.parametrize("seed", range(40))

@@ -840,16 +840,18 @@ static int enqueue_classify(bdx_stream *s, const uint8_t *d_seq, const int32_t *
                 s->launches++;
             }
             int wl = pre ? 1 : 0;
-            if (pre) {
-                // seed levels hand the reads they cannot finish from one worklist to the other
+            {
+                // seed levels hand the reads they cannot finish from one worklist to the other; without a
+                // prefilter in front (min_delta != 0) the first level takes every read of the batch
                 const int levels = seed_levels(P, pass);
                 for (int l = 0; l < levels; l++) {
-                    const bool from1 = wl == 1;
-                    CU(launch_seed(P, pass, l, d_seq, d_off, n, s->sc, from1 ? s->sc.worklist : s->sc.worklist2,
-                                   from1 ? s->sc.n_work : s->sc.n_work2, from1 ? s->sc.worklist2 : s->sc.worklist,
-                                   from1 ? s->sc.n_work2 : s->sc.n_work, s->tab->sm_count, s->d_counters, s->st_comp));
+                    const int *wl_in = wl == 0 ? nullptr : (wl == 1 ? s->sc.worklist : s->sc.worklist2);
+                    const int *n_in = wl == 0 ? nullptr : (wl == 1 ? s->sc.n_work : s->sc.n_work2);
+                    const bool to2 = wl != 2;
+                    CU(launch_seed(P, pass, l, d_seq, d_off, n, s->sc, wl_in, n_in, to2 ? s->sc.worklist2 : s->sc.worklist,
+                                   to2 ? s->sc.n_work2 : s->sc.n_work, s->tab->sm_count, s->d_counters, s->st_comp));
                     s->launches++;
-                    wl = from1 ? 2 : 1;
+                    wl = to2 ? 2 : 1;
                 }
             }
             cudaEvent_t e0 = nullptr, e1 = nullptr;

@@ -48,10 +48,10 @@ __device__ __forceinline__ uint32_t hit_pack(uint32_t b, int span, int dmin)
 }
 
 struct SeedVerifyCtx {
-    const uint32_t *hits;           // [kSeedMaxHits][kSeedThreads], column warp * 32 + lane belongs to a lane
+    uint32_t *hits;                 // [kSeedMaxHits][kSeedThreads], column warp * 32 + lane belongs to a lane;
+                                    // bits 27..30 of a record receive the verified distance (15 = more than K)
     const uint32_t *peq_s;
     const uint8_t *warp_slots;      // slot of lane 0 of this warp
-    uint32_t *res;                  // [32] per-read minimum of (distance << 14 | barcode) of this warp
     int n_pad, m, K, win, total;
     uint32_t row_mask;
 };
@@ -59,13 +59,13 @@ struct SeedVerifyCtx {
 // Verifies pooled hits [i0, i0 + 32 * ILP) of the warp, one per lane and chain: windowed Myers/Hyyro automaton
 // over the columns the hit's alignment can occupy.  The hits of the warp's 32 reads form one pool (lane L owns
 // the indices [excl(L), incl(L)) of the inclusive prefix sum `incl` of the per-lane hit counts), so every lane
-// has work whatever its own read found.  Branch-free so that the ILP chains of a lane interleave: past the
+// has work whatever its own read found; the distance goes back into the hit record for its owner.  Branch-free so that the ILP chains of a lane interleave: past the
 // end of its window a chain keeps stepping on class 0 and its minimum is not updated.
 template <int ILP>
 __device__ __forceinline__ void seed_verify(const SeedVerifyCtx &v, int i0, int lane, int incl, int start_j, int end_j)
 {
-    int hb[ILP], c0[ILP], c1[ILP], score[ILP], best[ILP], owner[ILP];
-    uint32_t pv[ILP], mv[ILP];
+    int hb[ILP], c0[ILP], c1[ILP], score[ILP], best[ILP], owner[ILP], at[ILP];
+    uint32_t pv[ILP], mv[ILP], recs[ILP];
     const uint8_t *slot[ILP];
 #pragma unroll
     for (int u = 0; u < ILP; u++) {
@@ -81,7 +81,9 @@ __device__ __forceinline__ void seed_verify(const SeedVerifyCtx &v, int i0, int 
         owner[u] = live ? lo : 0;
         const int prev_incl = __shfl_sync(0xFFFFFFFFu, incl, max(owner[u] - 1, 0));   // all lanes shuffle
         const int o_excl = owner[u] ? prev_incl : 0;
-        const uint32_t rec = live ? v.hits[(i - o_excl) * kSeedThreads + owner[u]] : 0u;
+        at[u] = live ? (i - o_excl) * kSeedThreads + owner[u] : -1;
+        const uint32_t rec = live ? v.hits[at[u]] : 0u;
+        recs[u] = rec;
         hb[u] = (int)(rec >> 13);
         const int dmin = (int)(rec & 0x3FFu) - 256, span = (int)((rec >> 10) & 0x7u);
         const int sj = __shfl_sync(0xFFFFFFFFu, start_j, owner[u]);
@@ -121,7 +123,7 @@ __device__ __forceinline__ void seed_verify(const SeedVerifyCtx &v, int i0, int 
     }
 #pragma unroll
     for (int u = 0; u < ILP; u++)
-        if (best[u] <= v.K) atomicMin(v.res + owner[u], ((uint32_t)best[u] << 14) | (uint32_t)hb[u]);
+        if (at[u] >= 0) v.hits[at[u]] = recs[u] | ((uint32_t)(best[u] <= v.K ? best[u] : 15) << 27);
 }
 
 // TAB_SMEM: the CSR bucket table (bstart / entries / ekeys) is copied to shared memory; large sets read it
@@ -129,7 +131,8 @@ __device__ __forceinline__ void seed_verify(const SeedVerifyCtx &v, int i0, int 
 template <bool TAB_SMEM>
 __global__ void __launch_bounds__(kSeedThreads)
 k_seed(const __grid_constant__ DevParams P, const int pass, const int level, const uint8_t *__restrict__ seq,
-       const int *__restrict__ off, PassOut *__restrict__ out, const int *__restrict__ worklist,
+       const int *__restrict__ off, const int n_reads, PassOut *__restrict__ out,
+       const PassOut *__restrict__ prev_pass, const int *__restrict__ worklist,
        const int *__restrict__ n_work, int *__restrict__ worklist2, int *__restrict__ n_work2,
        unsigned long long *__restrict__ counters, uint16_t *__restrict__ cand, uint8_t *__restrict__ cand_cnt)
 {
@@ -150,8 +153,7 @@ k_seed(const __grid_constant__ DevParams P, const int pass, const int level, con
     const uint32_t *entries_s = TAB_SMEM ? tab_s + n_buckets + 1 : SL.entries;             // [n_entries]
     const uint32_t *ekeys_s = TAB_SMEM ? tab_s + n_buckets + 1 + SL.n_entries : SL.ekeys;  // [n_entries] full hashes
     uint32_t *hits_s = TAB_SMEM ? tab_s + n_buckets + 1 + 2 * SL.n_entries : tab_s;        // [kSeedMaxHits][kSeedThreads]
-    uint32_t *res_s = hits_s + kSeedMaxHits * kSeedThreads;     // [kSeedThreads]
-    uint8_t *wins_s = reinterpret_cast<uint8_t *>(res_s + kSeedThreads);   // [kSeedMaxWins][threads]
+    uint8_t *wins_s = reinterpret_cast<uint8_t *>(hits_s + kSeedMaxHits * kSeedThreads);   // [kSeedMaxWins][threads]
     uint8_t *class_s = wins_s + kSeedMaxWins * kSeedThreads;
     uint8_t *slot_s = class_s + 256;                            // [kSeedThreads][kSeedSlot] class codes
 
@@ -173,7 +175,8 @@ k_seed(const __grid_constant__ DevParams P, const int pass, const int level, con
     const bool last_level = level == S.sd_levels - 1;
     const uint32_t pw = SL.pow;
     const int bm_log2 = SL.bm_log2;
-    const int n_items = *n_work;
+    const int n_items = worklist ? *n_work : n_reads;         // no worklist: every read of the batch
+    const bool with_delta = P.min_delta != 0.0;
     const int n_groups = (n_items + kSeedThreads - 1) / kSeedThreads;
     const uint32_t row_mask = m >= 32 ? 0xFFFFFFFFu : (0xFFFFFFFFu << (32 - m));
     unsigned int n_done = 0;
@@ -181,7 +184,7 @@ k_seed(const __grid_constant__ DevParams P, const int pass, const int level, con
     for (int grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
         const int item = grp * kSeedThreads + threadIdx.x;
         const bool have = item < n_items;
-        const int read = have ? worklist[item] : 0;
+        const int read = have ? (worklist ? worklist[item] : item) : 0;
         const int base = have ? off[read] : 0;
         const int n = have ? off[read + 1] - base : 0;
 
@@ -217,8 +220,14 @@ k_seed(const __grid_constant__ DevParams P, const int pass, const int level, con
         // at different columns.  The divergent part is kept to one shared-memory store.) ----
         int n_wins = 0;
         bool punt = !have;       // true => this read goes to the next stage (or is not a read at all)
+        bool skip = false;       // pass 2 of a read whose pass 1 did not match: nothing to do
         Geometry g{};
-        if (have) {
+        if (have && pass == 1 && prev_pass[read].bc <= 0) {      // classification.jl:879-888
+            out[read] = PassOut{kBcNotRun, 0, -1, -1};
+            skip = true;
+            punt = true;
+        }
+        if (have && !skip) {
             g = pass_geometry(S, n);
             // the regime test of k_filter's `fast` / k_prefilter<0>
             if (!(g.valid && g.max_start_pos >= n && g.min_end_pos <= g.start_j) || n > kSeedSlot) punt = true;
@@ -294,51 +303,77 @@ k_seed(const __grid_constant__ DevParams P, const int pass, const int level, con
             if (lane >= o) incl += t;
         }
         const int total_hits = __shfl_sync(0xFFFFFFFFu, incl, 31);
-        res_s[threadIdx.x] = 0xFFFFFFFFu;
         __syncwarp();
         {
             const int win = m + 4 * K + 1;                   // columns [dmin + 1 - K, dmin + span + m + 2K], span <= K
-            const SeedVerifyCtx vc{hits_s + warp * 32, peq_s, slot_s + (size_t)warp * 32 * kSeedSlot, res_s + warp * 32,
-                                   n_pad, m, K, win, total_hits, row_mask};
+            const SeedVerifyCtx vc{hits_s + warp * 32, peq_s, slot_s + (size_t)warp * 32 * kSeedSlot, n_pad, m, K, win,
+                                   total_hits, row_mask};
             int i0 = 0;
             for (; i0 + 32 < total_hits; i0 += 64) seed_verify<2>(vc, i0, lane, incl, g.start_j, g.end_j);
             if (i0 < total_hits) seed_verify<1>(vc, i0, lane, incl, g.start_j, g.end_j);
         }
         __syncwarp();
-        int best_d = kInf, best_b = 0x7FFFFFFF;
-        {
-            const uint32_t r = res_s[threadIdx.x];
-            if (r != 0xFFFFFFFFu) {
-                best_d = (int)(r >> 14);
-                best_b = (int)(r & 0x3FFFu);
+        // ---- the read's own hits, now with distances: d_b = min over the hit groups of barcode b.
+        // best = smallest distance, lowest index among equals; second = smallest d_b of any OTHER barcode ----
+        int best_d = kInf, best_b = 0x7FFFFFFF, second_d = kInf;
+        for (int k = 0; k < my_hits; k++) {
+            const uint32_t rec = hits_s[k * kSeedThreads + threadIdx.x];
+            const int d = (int)((rec >> 27) & 0xFu), b = (int)((rec >> 13) & 0x3FFFu);
+            if (d > K) continue;
+            if (d < best_d || (d == best_d && b < best_b)) {
+                best_d = d;
+                best_b = b;
             }
         }
+        if (with_delta)
+            for (int k = 0; k < my_hits; k++) {
+                const uint32_t rec = hits_s[k * kSeedThreads + threadIdx.x];
+                const int d = (int)((rec >> 27) & 0xFu), b = (int)((rec >> 13) & 0x3FFFu);
+                if (d <= K && b != best_b) second_d = min(second_d, d);
+            }
 
         // ---- decide ----
         bool resolved = false;
         if (!punt) {
             if (best_d <= K) {
-                // acceptance exactly as find_best_matching_bc_no_delta does it for this barcode
-                // (classification.jl:254, :658); with one common length the earlier, worse
-                // barcodes the reference may accept first cannot change the final winner
+                // acceptance exactly as find_best_matching_bc_* does it for this barcode (classification.jl:254,
+                // :658, :696); with one common length the earlier, worse barcodes the reference may accept first
+                // cannot change the final winner
                 const int norm = S.norm[best_b];
                 const double sc = __ddiv_rn((double)best_d, (double)norm);
                 if (best_d <= allowed_from(P.max_error_rate, norm) && sc <= P.max_error_rate) {
-                    if (need_tb) {
-                        cand[(size_t)read * kCandMax] = (uint16_t)best_b;
-                        cand_cnt[read] = 1;
-                        out[read] = PassOut{kBcPending, 0, -1, -1};
-                    } else {
-                        out[read] = PassOut{best_b + 1, best_d, -1, -1};
+                    bool decided = true, ambiguous = false;
+                    if (with_delta) {
+                        // delta = second-best score - best score (:711).  Every barcode within K edits is known
+                        // exactly; an unseen runner-up is more than K edits away (or not acceptable at all)
+                        const int allowed0 = S.allowed0[0];
+                        if (second_d <= K) {
+                            const double sc2 = __ddiv_rn((double)second_d, (double)norm);
+                            ambiguous = __dsub_rn(sc2, sc) < P.min_delta;
+                        } else if (K + 1 <= allowed0) {
+                            const double sc2 = __ddiv_rn((double)(K + 1), (double)norm);
+                            decided = !(__dsub_rn(sc2, sc) < P.min_delta);      // safe whatever the runner-up is
+                        }
                     }
-                    resolved = true;
+                    if (decided) {
+                        if (ambiguous) {
+                            out[read] = PassOut{kBcAmbiguous, 0, -1, -1};
+                        } else if (need_tb) {
+                            cand[(size_t)read * kCandMax] = (uint16_t)best_b;
+                            cand_cnt[read] = 1;
+                            out[read] = PassOut{kBcPending, 0, -1, -1};
+                        } else {
+                            out[read] = PassOut{best_b + 1, best_d, -1, -1};
+                        }
+                        resolved = true;
+                    }
                 }
             } else if (last_level && K >= S.allowed0[0]) {
                 out[read] = PassOut{kBcUnknown, 0, -1, -1};    // nothing within the allowed distance
                 resolved = true;
             }
         }
-        const bool todo = have && !resolved;
+        const bool todo = have && !resolved && !skip;
         const uint32_t mask = __ballot_sync(0xFFFFFFFFu, todo);
         int base_slot = 0;
         if (lane == 0 && mask) base_slot = atomicAdd(n_work2, __popc(mask));
@@ -354,7 +389,7 @@ static size_t seed_tab_words(const SeedLevel &L) { return ((size_t)1 << L.log2) 
 static size_t seed_smem(const DevSet &S, const SeedLevel &L, bool tab_smem)
 {
     size_t words = (size_t)S.n_classes * S.n_bc_pad + ((size_t)1 << (L.bm_log2 - 5)) + (tab_smem ? seed_tab_words(L) : 0) +
-                   (size_t)kSeedMaxHits * kSeedThreads + kSeedThreads;
+                   (size_t)kSeedMaxHits * kSeedThreads;
     return words * 4 + (size_t)kSeedMaxWins * kSeedThreads + 256 + (size_t)kSeedThreads * kSeedSlot + 16;
 }
 
@@ -365,7 +400,9 @@ int seed_levels(const DevParams &P, int pass)
 {
     static const bool off = getenv("BDX_DISABLE_SEED") != nullptr;
     const DevSet &S = P.set[pass];
-    if (off || !prefilter_applies(P, pass) || P.algo != BDX_SEMIGLOBAL || S.words != 1) return 0;
+    // the exact regime of k_filter (unit costs, uniform length, no wildcard rows: the tables exist only then);
+    // min_delta is handled, trimming / stats go through k_literal for the positions
+    if (off || P.algo != BDX_SEMIGLOBAL || !P.unit_costs || !S.pf_enabled || S.words != 1 || P.max_error_rate < 0.0) return 0;
     for (int l = 0; l < S.sd_levels; l++)
         if (seed_smem(S, S.sd[l], seed_tab_in_smem(S, S.sd[l])) > 110 * 1024) return 0;
     return S.sd_levels;
@@ -390,8 +427,8 @@ cudaError_t launch_seed(const DevParams &P, int pass, int level, const uint8_t *
     const int blocks = std::max(1, std::min(groups, sm_count * per_sm));
     e = cudaMemsetAsync(n_out, 0, sizeof(int), st);
     if (e != cudaSuccess) return e;
-    kern<<<blocks, kSeedThreads, smem, st>>>(P, pass, level, seq, off, sc.pass[pass], wl_in, n_in, wl_out, n_out, counters,
-                                             sc.cand, sc.cand_cnt);
+    kern<<<blocks, kSeedThreads, smem, st>>>(P, pass, level, seq, off, n, sc.pass[pass], sc.pass[0], wl_in, n_in, wl_out, n_out,
+                                             counters, sc.cand, sc.cand_cnt);
     return cudaGetLastError();
 }
 

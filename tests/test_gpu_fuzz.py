@@ -67,7 +67,7 @@ def test_fuzz_random_config(seed):
 
 def _fast_case(seed, algo):
     """The regimes the shortcut kernels own: uniform barcode length, ACGT barcodes, unit costs; for :semiglobal
-    score-only with default start / end ranges and no min_delta (k_prefilter -> k_seed levels -> k_filter), for
+    default start / end ranges (k_prefilter -> k_seed levels -> k_filter; min_delta, trimming and stats included), for
     :hamming anything (k_hamming_scan).  Random set sizes, lengths, thresholds, search ranges, read lengths
     (beyond the kernels' staging capacity too), duplicated barcodes, N / lower-case bases in the reads."""
     rng = np.random.default_rng(seed)
@@ -81,8 +81,8 @@ def _fast_case(seed, algo):
     if rng.random() < 0.5:
         kw["ref_search_range"] = R(_range(rng, "any"))
     kw["trim_side"] = [None, 3, 5][int(rng.integers(0, 3))]       # positions: verbatim hits / winner re-aligned
+    kw["min_delta"] = float(rng.choice([0.0, 0.0, 0.05, 0.1, 0.13]))   # semiglobal: decided from the seeds' exact distances
     if algo == "hamming":
-        kw["min_delta"] = float(rng.choice([0.0, 0.0, 0.05, 0.1]))
         if rng.random() < 0.4:
             kw["barcode_start_range"] = R(_range(rng, "any"))
         if rng.random() < 0.4:

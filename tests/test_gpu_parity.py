@@ -90,6 +90,8 @@ def test_edge_cases():
 CONFIGS = {
     "default96": dict(n_bc=96, m=(24, 24)),
     "delta": dict(n_bc=96, m=(24, 24), min_delta=0.1),
+    "delta_trim_stats": dict(n_bc=96, m=(24, 24), min_delta=0.08, trim_side=3, want_stats=True),
+    "delta_close_pairs": dict(n_bc=96, m=(24, 24), min_delta=0.13, close_pairs=True),
     "weighted": dict(n_bc=48, m=(24, 24), max_error_rate=0.25, min_delta=0.15, mismatch=1, indel=2),
     "mismatch3": dict(n_bc=40, m=(16, 28), max_error_rate=0.3, mismatch=3, indel=1),
     "match1": dict(n_bc=20, m=(12, 20), max_error_rate=0.4, match=1, mismatch=2, indel=2),
@@ -146,6 +148,9 @@ def test_random_parity(name):
     start_hi = spec.pop("start_hi", None)
     bcs = synth.random_barcodes(rng, n_bc, m_lo, m_hi, alphabet=spec.pop("alphabet", b"ACGT"),
                                 n_frac=spec.pop("n_frac", 0.0))
+    if spec.pop("close_pairs", False):          # barcodes one or two edits apart: runner-ups that make reads ambiguous
+        for k in range(0, n_bc - 1, 4):
+            bcs[k + 1] = synth.mutate(rng, bcs[k].encode(), int(rng.integers(1, 3))).decode()[:m_lo].ljust(m_lo, "A")
     cfg = _cfg(bcs, **spec)
     reads = synth.random_reads(rng, n_reads, bcs, min_len=60, max_len=160, start_hi=start_hi, lower_prob=0.02)
     reads += [b"", b"ACG"]

@@ -39,7 +39,6 @@ constexpr int kSeedSlot = 180;      // staged class codes per read (longer reads
                                     // an odd word stride keeps the lock-step scan free of bank conflicts
 constexpr int kSeedMaxHits = 28;    // distinct (barcode, diagonal group) hits remembered per read (more => next stage)
 constexpr int kSeedMaxWins = 32;    // bitmap-passing columns remembered per read (more => full path)
-constexpr int kSeedIlp = 4;         // hits verified concurrently per thread
 
 // Hit record: barcode << 13 | diagonal span << 10 | lowest diagonal + 256   (barcode < 2^14, span <= K <= 7)
 __device__ __forceinline__ uint32_t hit_pack(uint32_t b, int span, int dmin)

@@ -13,6 +13,7 @@ constexpr int kMaxBarcodeLen = 256;   // literal kernel DP workspace bound
 constexpr int kMaxFilterWords = 2;    // bit-parallel filter: barcodes up to 64 nt
 constexpr int kCandMax = 16;          // candidate slots per read and pass
 constexpr int kCandOverflow = 255;    // cand_cnt value: scan every barcode
+constexpr int kCandWindow = 254;      // cand_cnt value: one candidate, cand[1..2] = read columns that hold all its best alignments
 constexpr int kInf = 1 << 29;         // INF_INT stand-in for int32 cells (classification.jl:7)
 constexpr int kMaxCost = 1 << 20;
 

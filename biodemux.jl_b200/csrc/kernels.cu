@@ -64,9 +64,15 @@ k_literal(const __grid_constant__ DevParams P, const int pass, const int from_fi
 
     int n_iter = S.n_bc;
     bool use_list = false;
+    int win_first = 0, win_last = 0x7FFFFFFF;
     if (from_filter) {
         const int cnt = cand_cnt[i];
-        if (cnt != kCandOverflow) {
+        if (cnt == kCandWindow) {            // k_seed's winner with the columns that hold all its best alignments
+            n_iter = 1;
+            use_list = true;
+            win_first = cand[(size_t)i * kCandMax + 1];
+            win_last = cand[(size_t)i * kCandMax + 2];
+        } else if (cnt != kCandOverflow) {
             n_iter = cnt;
             use_list = true;
         }
@@ -92,7 +98,7 @@ k_literal(const __grid_constant__ DevParams P, const int pass, const int from_fi
             const int allowed = allowed_from(bs.thr, norm);        // :254
             if (need_tb)
                 dist = sg_literal<true>(DP, OR, q - 1, r - 1, m, n, allowed, c, S.trim_side, g.start_j,
-                                        g.end_j, g.max_start_pos, g.min_end_pos, s, e);
+                                        g.end_j, g.max_start_pos, g.min_end_pos, s, e, win_first, win_last);
             else
                 dist = sg_literal<false>(DP, OR, q - 1, r - 1, m, n, allowed, c, S.trim_side, g.start_j,
                                          g.end_j, g.max_start_pos, g.min_end_pos, s, e);

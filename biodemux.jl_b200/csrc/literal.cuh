@@ -73,10 +73,20 @@ struct WsCol {
     __device__ __forceinline__ int &operator[](int i) const { return base[i * stride]; }
 };
 
+// win_first / win_last (optional): a column window that is known to hold EVERY minimum-score alignment of this
+// barcode, start to end (k_seed derives it from the verified seed hits).  The DP then runs over the window
+// only.  Nothing outside can change the result: update_result keeps minimum-score hits only (:141-153), all of
+// which end inside the window; a cell on a minimum-score path has the same value as in the full DP (a cheaper
+// path into it from outside would give a cheaper alignment), and a tie at such a cell against a path from
+// outside would make that path a minimum-score alignment itself -- which the window contains by construction.
+// The column before an inner window start stands for "free start here": cost indel * i like the true first
+// column, labelled with its own column number, which is the label the reference gives an alignment that
+// opens with skipped barcode bases there (previous_score_origin = j, :287, :305).
 template <bool TB>
 __device__ int sg_literal(const WsCol DP, const WsCol OR, const uint8_t *q1, const uint8_t *r1, int m, int n,
                           int allowed_error, const Costs &c, int trim_side, int range_first,
-                          int range_last, int max_start_pos, int min_end_pos, int &out_s, int &out_e)
+                          int range_last, int max_start_pos, int min_end_pos, int &out_s, int &out_e,
+                          int win_first = 0, int win_last = 0x7FFFFFFF)
 {
     out_s = -1;
     out_e = -1;
@@ -89,9 +99,12 @@ __device__ int sg_literal(const WsCol DP, const WsCol OR, const uint8_t *q1, con
     if (min_valid_start > range_first) range_first = max(range_first, min_valid_start);  // :266-268
     const int band_offset = max(m - n - steps, -max_start_pos - steps);                  // :270
 
+    const bool inner_start = win_first > range_first;
+    if (inner_start) range_first = win_first;
+    range_last = min(range_last, win_last);
     for (int i = 1; i <= m; i++) {                                    // :278-283
         DP[i] = c.indel * i;
-        if (TB) OR[i] = 1 - i;
+        if (TB) OR[i] = inner_start ? range_first - 1 : 1 - i;
     }
     int lact = min(allowed_error + 1, m);                             // :286
     for (int j = range_first; j <= range_last; j++) {

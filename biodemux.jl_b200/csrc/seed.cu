@@ -358,8 +358,21 @@ k_seed(const __grid_constant__ DevParams P, const int pass, const int level, con
                         if (ambiguous) {
                             out[read] = PassOut{kBcAmbiguous, 0, -1, -1};
                         } else if (need_tb) {
+                            // columns that hold every best alignment of the winner: the union of the windows
+                            // of its hit groups that verified at the best distance (any column where it
+                            // scores best_d ends an alignment with an intact segment, i.e. lies in one of them)
+                            int lo = 0x7FFFFFFF, hi = 0;
+                            for (int k = 0; k < my_hits; k++) {
+                                const uint32_t rec = hits_s[k * kSeedThreads + threadIdx.x];
+                                if ((int)((rec >> 27) & 0xFu) != best_d || (int)((rec >> 13) & 0x3FFFu) != best_b) continue;
+                                const int dmin = (int)(rec & 0x3FFu) - 256, span = (int)((rec >> 10) & 0x7u);
+                                lo = min(lo, dmin + 1 - K);
+                                hi = max(hi, dmin + span + m + 2 * K);
+                            }
                             cand[(size_t)read * kCandMax] = (uint16_t)best_b;
-                            cand_cnt[read] = 1;
+                            cand[(size_t)read * kCandMax + 1] = (uint16_t)max(lo - 2, 1);
+                            cand[(size_t)read * kCandMax + 2] = (uint16_t)min(hi + 2, n);
+                            cand_cnt[read] = (uint8_t)kCandWindow;
                             out[read] = PassOut{kBcPending, 0, -1, -1};
                         } else {
                             out[read] = PassOut{best_b + 1, best_d, -1, -1};

@@ -57,7 +57,7 @@ extern "C" int bdx_device_count(void)
 // configuration
 // ---------------------------------------------------------------------------
 struct HostSet {
-    int n_bc = 0, n_bc_pad = 0, max_m = 0, trim_side = 0, words = 0, n_classes = 1;
+    int n_bc = 0, n_bc_pad = 0, max_m = 0, trim_side = 0, words = 0, n_classes = 1, use_filter = 0;
     DevRange rs{}, bs{}, be{};
     std::vector<uint8_t> bytes;
     std::vector<int> off, norm, filt_allowed, allowed0;
@@ -175,9 +175,11 @@ static int build_set(const bdx_params &p, const bdx_barcode_set &in, HostSet &hs
     const bool benign = p.match >= 0 && p.mismatch >= 1 && p.indel >= 1 && (!p.has_nindel || p.nindel >= p.indel);
     // The unit-cost filter is also a superset filter for :hamming (Hamming distance >= edit
     // distance; a barcode N is a wildcard there, classification.jl:597) and :exact (distance 0).
-    // Tiny sets are cheaper to scan with the literal kernel than to spread over 32 lanes.
+    // Tiny sets are cheaper to scan with the literal kernel than to spread over 32 lanes: they get the tables
+    // (for the thread-per-read prefilter / seed kernels) but not the filter kernel.
     const bool sg = p.algorithm == BDX_SEMIGLOBAL;
-    if ((sg && !benign) || disable_filter || hs.n_classes > 64 || hs.n_bc < 8) hs.words = 0;
+    if ((sg && !benign) || disable_filter || hs.n_classes > 64) hs.words = 0;
+    hs.use_filter = hs.words > 0 && hs.n_bc >= 8;
 
     hs.allowed0.assign(hs.n_bc_pad, -1);
     hs.filt_allowed.assign(hs.n_bc_pad, -1);
@@ -264,7 +266,7 @@ static int build_set(const bdx_params &p, const bdx_barcode_set &in, HostSet &hs
         hs.pf_enabled = 1;
     }
     // ---- :semiglobal depth-limited seeds (seed.cu): uniform barcode length, no wildcard rows ----
-    if (hs.pf_enabled && sg && hs.words == 1 && min_m == hs.max_m && hs.allowed0[0] >= 1 && hs.n_bc < (1 << 14) &&
+    if (hs.pf_enabled && sg && hs.words >= 1 && min_m == hs.max_m && hs.allowed0[0] >= 1 && hs.n_bc < (1 << 14) &&
         !getenv("BDX_DISABLE_SEED")) {
         const int m = hs.max_m, allowed = hs.allowed0[0];
         const double alpha = std::max(2, hs.n_classes - 1);
@@ -375,7 +377,7 @@ static int build_set(const bdx_params &p, const bdx_barcode_set &in, HostSet &hs
     }
     // ---- :hamming pigeonhole seeds: mismatches <= allowed_b leave one of allowed_b + 1 disjoint
     // segments of the barcode intact, so every acceptable placement contains an exact seed ----
-    if (p.algorithm == BDX_HAMMING && hs.words && p.max_error_rate >= 0.0 && !getenv("BDX_DISABLE_PREFILTER") &&
+    if (p.algorithm == BDX_HAMMING && hs.use_filter && p.max_error_rate >= 0.0 && !getenv("BDX_DISABLE_PREFILTER") &&
         std::find(hs.bytes.begin(), hs.bytes.end(), (uint8_t)'N') == hs.bytes.end()) {
         int q = 8;
         bool ok = true;
@@ -455,7 +457,7 @@ extern "C" int bdx_config_create(const bdx_params *p, bdx_config **out)
     P.algo = p->algorithm;
     P.is_dual = p->is_dual ? 1 : 0;
     P.want_stats = p->want_stats ? 1 : 0;
-    P.filter_ok = cfg->set[0].words > 0 && (!p->is_dual || cfg->set[1].words > 0);
+    P.filter_ok = cfg->set[0].use_filter && (!p->is_dual || cfg->set[1].use_filter);
     P.two = 2;
     P.unit_costs = p->match == 0 && p->mismatch == 1 && p->indel == 1 && (!p->has_nindel || p->nindel == 1);
 
@@ -545,6 +547,7 @@ static int get_tables(bdx_config *cfg, int device, DeviceTables **out)
         D.max_m = hs.max_m;
         D.trim_side = hs.trim_side;
         D.words = hs.words;
+        D.use_filter = hs.use_filter;
         D.n_classes = hs.n_classes;
         D.rs = hs.rs;
         D.bs = hs.bs;
@@ -609,10 +612,13 @@ static int get_tables(bdx_config *cfg, int device, DeviceTables **out)
         }
         if (D.words && filter_smem_bytes_for(D) > (size_t)prop.sharedMemPerBlockOptin) {
             D.pf_enabled = 0;   // drop the prefilter table first, then the filter itself
-            if (filter_smem_bytes_for(D) > (size_t)prop.sharedMemPerBlockOptin) D.words = 0;
+            if (filter_smem_bytes_for(D) > (size_t)prop.sharedMemPerBlockOptin) {
+                D.words = 0;
+                D.use_filter = 0;
+            }
         }
     }
-    t->P.filter_ok = t->P.set[0].words > 0 && (!t->P.is_dual || t->P.set[1].words > 0);
+    t->P.filter_ok = t->P.set[0].use_filter && (!t->P.is_dual || t->P.set[1].use_filter);
     cfg->per_device[device] = t;
     *out = t;
     return BDX_OK;
@@ -853,6 +859,19 @@ static int enqueue_classify(bdx_stream *s, const uint8_t *d_seq, const int32_t *
                     s->launches++;
                     wl = to2 ? 2 : 1;
                 }
+            }
+            if (!P.set[pass].use_filter) {
+                // tiny set: no filter kernel.  What the shortcut stages left goes to k_literal over every barcode.
+                if (wl == 0) {
+                    CU(launch_literal(P, pass, 0, d_seq, d_off, n, s->sc, s->st_comp));
+                } else {
+                    CU(launch_mark_pending(P, pass, n, s->sc, wl == 1 ? s->sc.worklist : s->sc.worklist2,
+                                           wl == 1 ? s->sc.n_work : s->sc.n_work2, s->st_comp));
+                    s->launches++;
+                    CU(launch_literal(P, pass, 1, d_seq, d_off, n, s->sc, s->st_comp));
+                }
+                s->launches++;
+                continue;
             }
             cudaEvent_t e0 = nullptr, e1 = nullptr;
             if (s->profile) {

@@ -61,7 +61,8 @@ struct DevSet {
     int trim_side;    // 0, 3, 5
     int words;        // 32-bit words per barcode in the filter tables; 0 = no filter for this set
     int n_classes;    // byte classes incl. class 0 = "byte absent from every barcode"
-    int pad0, pad1;
+    int use_filter;   // the bit-parallel filter kernel runs for this set (tables exist and the set is not tiny)
+    int pad1;
     DevRange rs, bs, be;          // ref_search_range, barcode_start_range, barcode_end_range
     const uint8_t *bc_bytes;      // concatenated barcodes
     const int *bc_off;            // n_bc + 1
@@ -162,6 +163,9 @@ int seed_levels(const DevParams &P, int pass);   // number of k_seed levels that
 cudaError_t launch_seed(const DevParams &P, int pass, int level, const uint8_t *seq, const int *off, int n,
                         const Scratch &sc, const int *wl_in, const int *n_in, int *wl_out, int *n_out, int sm_count,
                         unsigned long long *counters, cudaStream_t st);
+// reads of a worklist that no kernel resolved: queue them for k_literal over every barcode
+cudaError_t launch_mark_pending(const DevParams &P, int pass, int n, const Scratch &sc, const int *wl, const int *n_wl,
+                                cudaStream_t st);
 cudaError_t launch_prefilter(const DevParams &P, int pass, const uint8_t *seq, const int *off, int n,
                              const Scratch &sc, int sm_count, unsigned long long *counters, cudaStream_t st);
 bool prefilter_applies(const DevParams &P, int pass);

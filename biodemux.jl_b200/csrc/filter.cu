@@ -825,7 +825,7 @@ bool hamming_seed_applies(const DevParams &P, int pass)
 bool exact_hash_applies(const DevParams &P, int pass)
 {
     const DevSet &S = P.set[pass];
-    return P.algo == BDX_EXACT && S.words > 0 && S.pf_enabled && P.max_error_rate >= 0.0;
+    return P.algo == BDX_EXACT && S.use_filter && S.pf_enabled && P.max_error_rate >= 0.0;
 }
 
 // true when every read of this pass that is in the exact regime may be resolved by k_prefilter
@@ -833,7 +833,7 @@ bool prefilter_applies(const DevParams &P, int pass)
 {
     const DevSet &S = P.set[pass];
     if (P.algo == BDX_HAMMING)   // positions are produced, so trim / stats are fine; needs no wildcard rows
-        return S.words > 0 && S.pf_enabled && P.min_delta == 0.0 && P.max_error_rate >= 0.0;
+        return S.use_filter && S.pf_enabled && P.min_delta == 0.0 && P.max_error_rate >= 0.0;
     // :semiglobal -- with trimming / stats the resolved reads also need positions: a verbatim occurrence has
     // them (k_prefilter), a seed-resolved read gets them from k_literal run on its single winning barcode
     return P.algo == BDX_SEMIGLOBAL && S.words > 0 && S.pf_enabled && P.unit_costs && P.min_delta == 0.0 &&

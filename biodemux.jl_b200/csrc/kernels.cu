@@ -1,6 +1,7 @@
 // kernels.cu -- literal (reference-order) classification kernel, result
 // finalisation + DemuxStats counters, synthetic read generator, integer-ALU peak
 // microbenchmark.  sm_100a only.
+#include <algorithm>
 #include <cstdio>
 #include <math_constants.h>
 
@@ -137,6 +138,36 @@ cudaError_t launch_literal(const DevParams &P, int pass, int from_filter, const 
         k_literal<kMaxBarcodeLen, false><<<blocks, threads, 0, st>>>(P, pass, from_filter, seq, off, n, out, prev,
                                                                      sc.cand, sc.cand_cnt);
     }
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
+// k_mark_pending: the reads a worklist still holds after the shortcut stages of a set without filter
+// kernel are queued for k_literal with "scan every barcode".
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_mark_pending(const int pass, const int *__restrict__ wl, const int *__restrict__ n_wl, PassOut *__restrict__ out,
+               const PassOut *__restrict__ prev_pass, uint8_t *__restrict__ cand_cnt)
+{
+    const int n = *n_wl;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        const int read = wl[k];
+        if (pass == 1 && prev_pass[read].bc <= 0) {                  // classification.jl:879-888
+            out[read] = PassOut{kBcNotRun, 0, -1, -1};
+        } else {
+            cand_cnt[read] = (uint8_t)kCandOverflow;
+            out[read] = PassOut{kBcPending, 0, -1, -1};
+        }
+    }
+}
+
+cudaError_t launch_mark_pending(const DevParams &P, int pass, int n, const Scratch &sc, const int *wl, const int *n_wl,
+                                cudaStream_t st)
+{
+    (void)P;
+    if (n <= 0) return cudaSuccess;
+    const int blocks = std::max(1, std::min((n + 255) / 256, 2048));
+    k_mark_pending<<<blocks, 256, 0, st>>>(pass, wl, n_wl, sc.pass[pass], sc.pass[0], sc.cand_cnt);
     return cudaGetLastError();
 }
 

@@ -28,6 +28,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <math_constants.h>
+#include <type_traits>
 
 #include "bdx_internal.h"
 #include "literal.cuh"
@@ -51,8 +52,7 @@ struct SeedVerifyCtx {
                                     // bits 27..30 of a record receive the verified distance (15 = more than K)
     const uint32_t *peq_s;
     const uint8_t *warp_slots;      // slot of lane 0 of this warp
-    int n_pad, m, K, win, total;
-    uint32_t row_mask;
+    int n_pad, plane, m, K, win, total;      // plane: words per 32-bit plane of the Peq table (barcodes > 32 nt use two)
 };
 
 // Verifies pooled hits [i0, i0 + 32 * ILP) of the warp, one per lane and chain: windowed Myers/Hyyro automaton
@@ -60,11 +60,14 @@ struct SeedVerifyCtx {
 // the indices [excl(L), incl(L)) of the inclusive prefix sum `incl` of the per-lane hit counts), so every lane
 // has work whatever its own read found; the distance goes back into the hit record for its owner.  Branch-free so that the ILP chains of a lane interleave: past the
 // end of its window a chain keeps stepping on class 0 and its minimum is not updated.
-template <int ILP>
+template <int ILP, typename WT>      // WT: uint32_t for barcodes up to 32 nt, unsigned long long up to 64
 __device__ __forceinline__ void seed_verify(const SeedVerifyCtx &v, int i0, int lane, int incl, int start_j, int end_j)
 {
+    constexpr int kMsb = (int)sizeof(WT) * 8 - 1;
+    const WT row_mask = v.m > kMsb ? ~(WT)0 : (~(WT)0 << (kMsb + 1 - v.m));     // barcode rows top-aligned
     int hb[ILP], c0[ILP], c1[ILP], score[ILP], best[ILP], owner[ILP], at[ILP];
-    uint32_t pv[ILP], mv[ILP], recs[ILP];
+    WT pv[ILP], mv[ILP];
+    uint32_t recs[ILP];
     const uint8_t *slot[ILP];
 #pragma unroll
     for (int u = 0; u < ILP; u++) {
@@ -91,13 +94,13 @@ __device__ __forceinline__ void seed_verify(const SeedVerifyCtx &v, int i0, int 
         c0[u] = live ? max(sj, dmin + 1 - v.K) : 1;
         c1[u] = live ? min(ej, dmin + span + v.m + 2 * v.K) : 0;
         slot[u] = v.warp_slots + (size_t)owner[u] * kSeedSlot;
-        pv[u] = v.row_mask;
-        mv[u] = 0u;
+        pv[u] = row_mask;
+        mv[u] = 0;
         score[u] = v.m;
         best[u] = kInf;
     }
     for (int t = 0; t < v.win; t++) {
-        uint32_t eq[ILP];
+        WT eq[ILP];
         bool in[ILP];
 #pragma unroll
         for (int u = 0; u < ILP; u++) {
@@ -106,15 +109,16 @@ __device__ __forceinline__ void seed_verify(const SeedVerifyCtx &v, int i0, int 
             // outside the window nothing staged may be read: class 0 then
             const uint32_t cls = in[u] ? (uint32_t)slot[u][c - 1] : 0u;
             eq[u] = v.peq_s[cls * v.n_pad + hb[u]];
+            if (sizeof(WT) == 8) eq[u] |= (WT)v.peq_s[v.plane + cls * v.n_pad + hb[u]] << (kMsb - 31);
         }
 #pragma unroll
         for (int u = 0; u < ILP; u++) {
-            const uint32_t xv = eq[u] | mv[u];
-            const uint32_t xh = ((((eq[u] & pv[u]) + pv[u]) ^ pv[u]) | eq[u]);
-            const uint32_t ph = mv[u] | ~(xh | pv[u]);
-            const uint32_t mh = pv[u] & xh;
-            score[u] += (int)(ph >> 31) - (int)(mh >> 31);
-            const uint32_t phs = ph << 1, mhs = mh << 1;
+            const WT xv = eq[u] | mv[u];
+            const WT xh = ((((eq[u] & pv[u]) + pv[u]) ^ pv[u]) | eq[u]);
+            const WT ph = mv[u] | ~(xh | pv[u]);
+            const WT mh = pv[u] & xh;
+            score[u] += (int)(ph >> kMsb) - (int)(mh >> kMsb);
+            const WT phs = ph << 1, mhs = mh << 1;
             pv[u] = mhs | ~(xv | phs);
             mv[u] = phs & xv;
             best[u] = in[u] ? min(best[u], score[u]) : best[u];
@@ -127,7 +131,7 @@ __device__ __forceinline__ void seed_verify(const SeedVerifyCtx &v, int i0, int 
 
 // TAB_SMEM: the CSR bucket table (bstart / entries / ekeys) is copied to shared memory; large sets read it
 // from global memory instead (it is touched only on first-level bitmap hits).
-template <bool TAB_SMEM>
+template <bool TAB_SMEM, int W>      // W: 32-bit words per barcode row vector (1: up to 32 nt, 2: up to 64)
 __global__ void __launch_bounds__(kSeedThreads)
 k_seed(const __grid_constant__ DevParams P, const int pass, const int level, const uint8_t *__restrict__ seq,
        const int *__restrict__ off, const int n_reads, PassOut *__restrict__ out,
@@ -145,8 +149,9 @@ k_seed(const __grid_constant__ DevParams P, const int pass, const int level, con
     const int n_pad = S.n_bc_pad;
     const int n_buckets = 1 << SL.log2;
     const int bm_words = 1 << (SL.bm_log2 - 5);
-    uint32_t *peq_s = smem;                                     // [n_classes][n_pad]
-    uint32_t *bitmap_s = peq_s + S.n_classes * n_pad;
+    const int plane = S.n_classes * n_pad;
+    uint32_t *peq_s = smem;                                     // [W][n_classes][n_pad]
+    uint32_t *bitmap_s = peq_s + W * plane;
     uint32_t *tab_s = bitmap_s + bm_words;
     const uint32_t *bstart_s = TAB_SMEM ? tab_s : SL.bstart;    // [n_buckets + 1]
     const uint32_t *entries_s = TAB_SMEM ? tab_s + n_buckets + 1 : SL.entries;             // [n_entries]
@@ -156,7 +161,7 @@ k_seed(const __grid_constant__ DevParams P, const int pass, const int level, con
     uint8_t *class_s = wins_s + kSeedMaxWins * kSeedThreads;
     uint8_t *slot_s = class_s + 256;                            // [kSeedThreads][kSeedSlot] class codes
 
-    for (int k = threadIdx.x; k < S.n_classes * n_pad; k += blockDim.x) peq_s[k] = S.peq[k];
+    for (int k = threadIdx.x; k < W * plane; k += blockDim.x) peq_s[k] = S.peq[k];
     for (int k = threadIdx.x; k < bm_words; k += blockDim.x) bitmap_s[k] = SL.bitmap[k];
     if (TAB_SMEM) {
         for (int k = threadIdx.x; k <= n_buckets; k += blockDim.x) tab_s[k] = SL.bstart[k];
@@ -177,7 +182,6 @@ k_seed(const __grid_constant__ DevParams P, const int pass, const int level, con
     const int n_items = worklist ? *n_work : n_reads;         // no worklist: every read of the batch
     const bool with_delta = P.min_delta != 0.0;
     const int n_groups = (n_items + kSeedThreads - 1) / kSeedThreads;
-    const uint32_t row_mask = m >= 32 ? 0xFFFFFFFFu : (0xFFFFFFFFu << (32 - m));
     unsigned int n_done = 0;
 
     for (int grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
@@ -305,11 +309,12 @@ k_seed(const __grid_constant__ DevParams P, const int pass, const int level, con
         __syncwarp();
         {
             const int win = m + 4 * K + 1;                   // columns [dmin + 1 - K, dmin + span + m + 2K], span <= K
-            const SeedVerifyCtx vc{hits_s + warp * 32, peq_s, slot_s + (size_t)warp * 32 * kSeedSlot, n_pad, m, K, win,
-                                   total_hits, row_mask};
+            using WT = typename std::conditional<W == 1, uint32_t, unsigned long long>::type;
+            const SeedVerifyCtx vc{hits_s + warp * 32, peq_s, slot_s + (size_t)warp * 32 * kSeedSlot, n_pad, plane, m, K, win,
+                                   total_hits};
             int i0 = 0;
-            for (; i0 + 32 < total_hits; i0 += 64) seed_verify<2>(vc, i0, lane, incl, g.start_j, g.end_j);
-            if (i0 < total_hits) seed_verify<1>(vc, i0, lane, incl, g.start_j, g.end_j);
+            for (; i0 + 32 < total_hits; i0 += 64) seed_verify<2, WT>(vc, i0, lane, incl, g.start_j, g.end_j);
+            if (i0 < total_hits) seed_verify<1, WT>(vc, i0, lane, incl, g.start_j, g.end_j);
         }
         __syncwarp();
         // ---- the read's own hits, now with distances: d_b = min over the hit groups of barcode b.
@@ -400,7 +405,7 @@ static size_t seed_tab_words(const SeedLevel &L) { return ((size_t)1 << L.log2) 
 
 static size_t seed_smem(const DevSet &S, const SeedLevel &L, bool tab_smem)
 {
-    size_t words = (size_t)S.n_classes * S.n_bc_pad + ((size_t)1 << (L.bm_log2 - 5)) + (tab_smem ? seed_tab_words(L) : 0) +
+    size_t words = (size_t)S.words * S.n_classes * S.n_bc_pad + ((size_t)1 << (L.bm_log2 - 5)) + (tab_smem ? seed_tab_words(L) : 0) +
                    (size_t)kSeedMaxHits * kSeedThreads;
     return words * 4 + (size_t)kSeedMaxWins * kSeedThreads + 256 + (size_t)kSeedThreads * kSeedSlot + 16;
 }
@@ -414,7 +419,7 @@ int seed_levels(const DevParams &P, int pass)
     const DevSet &S = P.set[pass];
     // the exact regime of k_filter (unit costs, uniform length, no wildcard rows: the tables exist only then);
     // min_delta is handled, trimming / stats go through k_literal for the positions
-    if (off || P.algo != BDX_SEMIGLOBAL || !P.unit_costs || !S.pf_enabled || S.words != 1 || P.max_error_rate < 0.0) return 0;
+    if (off || P.algo != BDX_SEMIGLOBAL || !P.unit_costs || !S.pf_enabled || S.words < 1 || P.max_error_rate < 0.0) return 0;
     for (int l = 0; l < S.sd_levels; l++)
         if (seed_smem(S, S.sd[l], seed_tab_in_smem(S, S.sd[l])) > 110 * 1024) return 0;
     return S.sd_levels;
@@ -428,7 +433,7 @@ cudaError_t launch_seed(const DevParams &P, int pass, int level, const uint8_t *
     const SeedLevel &L = S.sd[level];
     const bool tab = seed_tab_in_smem(S, L);
     const size_t smem = seed_smem(S, L, tab);
-    auto kern = tab ? k_seed<true> : k_seed<false>;
+    auto kern = S.words == 1 ? (tab ? k_seed<true, 1> : k_seed<false, 1>) : (tab ? k_seed<true, 2> : k_seed<false, 2>);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int per_sm = 0;

@@ -102,6 +102,12 @@ CONFIGS = {
     "nindel": dict(n_bc=64, m=(20, 26), nindel=1, n_frac=0.15, max_error_rate=0.3),
     "nindel2": dict(n_bc=30, m=(20, 26), nindel=2, indel=1, n_frac=0.15, max_error_rate=0.3),
     "nindel_lt": dict(n_bc=30, m=(10, 16), nindel=1, indel=2, n_frac=0.2, max_error_rate=0.5),
+    # tiny sets (no filter kernel) and barcodes of 33..64 nt through the shortcut stages
+    "tiny_adapter": dict(n_bc=1, m=(33, 33), trim_side=3),
+    "tiny_set5": dict(n_bc=5, m=(20, 20), trim_side=5, want_stats=True),
+    "tiny_set3_plain": dict(n_bc=3, m=(12, 18)),
+    "uniform40_delta": dict(n_bc=50, m=(40, 40), min_delta=0.06),
+    "uniform64_trim": dict(n_bc=12, m=(64, 64), trim_side=3, max_error_rate=0.12),
     "trim3": dict(n_bc=96, m=(24, 24), trim_side=3),
     "trim5": dict(n_bc=96, m=(24, 24), trim_side=5, min_delta=0.05),
     "stats": dict(n_bc=50, m=(18, 24), want_stats=True),
@@ -164,6 +170,7 @@ DUAL = {
                         ref_search_range2=R("end-39:end"), barcode_end_range2=R("end-5:end"), min_delta=0.1,
                         max_error_rate=0.25),
     "dual_stats": dict(want_stats=True, trim_side2=5),
+    "dual_adapter_uniform": dict(ref_search_range=R("1:32"), trim_side=5, trim_side2=3, adapter=True, uniform1=True),
     "dual_hamming": dict(matching_algorithm="hamming", trim_side=5),
     "dual_adapter": dict(ref_search_range=R("1:32"), trim_side=5, trim_side2=3, adapter=True),
 }
@@ -175,7 +182,8 @@ def test_random_parity_dual(name):
     rng = np.random.default_rng(sum(map(ord, name)))
     want_stats = spec.pop("want_stats", False)
     adapter = spec.pop("adapter", False)
-    b1 = synth.random_barcodes(rng, 96 if adapter else 60, 16, 28)
+    uniform1 = spec.pop("uniform1", False)
+    b1 = synth.random_barcodes(rng, 96 if adapter else 60, 24 if uniform1 else 16, 24 if uniform1 else 28)
     b2 = ["AGATCGGAAGAGCACACGTCTGAACTCCAGTCA"] if adapter else synth.random_barcodes(rng, 70, 16, 28)
     cfg = _dual(b1, b2, **spec)
     reads = synth.random_reads(rng, 3000, b1, barcodes2=b2, min_len=100, max_len=150, start_hi=4,

@@ -681,6 +681,9 @@ static int ensure_scratch(bdx_stream *s, int64_t n)
     cudaFree(s->sc.n_work);
     cudaFree(s->sc.worklist2);
     cudaFree(s->sc.n_work2);
+    cudaFree(s->sc.wl_win);
+    cudaFree(s->sc.wl_full);
+    cudaFree(s->sc.n_lit);
     s->sc = Scratch{};
     s->sc_cap = 0;
     const int64_t cap = n + n / 8 + 1024;
@@ -692,6 +695,9 @@ static int ensure_scratch(bdx_stream *s, int64_t n)
     CU(cudaMalloc(&s->sc.n_work, sizeof(int)));
     CU(cudaMalloc(&s->sc.worklist2, cap * sizeof(int)));
     CU(cudaMalloc(&s->sc.n_work2, sizeof(int)));
+    CU(cudaMalloc(&s->sc.wl_win, cap * sizeof(int)));
+    CU(cudaMalloc(&s->sc.wl_full, cap * sizeof(int)));
+    CU(cudaMalloc(&s->sc.n_lit, 2 * sizeof(int)));
     s->sc_cap = cap;
     return BDX_OK;
 }
@@ -724,6 +730,9 @@ extern "C" void bdx_stream_destroy(bdx_stream *s)
     cudaFree(s->sc.n_work);
     cudaFree(s->sc.worklist2);
     cudaFree(s->sc.n_work2);
+    cudaFree(s->sc.wl_win);
+    cudaFree(s->sc.wl_full);
+    cudaFree(s->sc.n_lit);
     cudaFree(s->d_stats);
     cudaFree(s->d_counters);
     demux_state_destroy(s->demux);
@@ -841,6 +850,7 @@ static int enqueue_classify(bdx_stream *s, const uint8_t *d_seq, const int32_t *
             s->launches++;
         } else if (P.set[pass].words > 0) {
             const bool pre = prefilter_applies(P, pass);
+            CU(cudaMemsetAsync(s->sc.n_lit, 0, 2 * sizeof(int), s->st_comp));   // k_literal's two read lists
             if (pre) {
                 CU(launch_prefilter(P, pass, d_seq, d_off, n, s->sc, s->tab->sm_count, s->d_counters, s->st_comp));
                 s->launches++;
@@ -865,10 +875,14 @@ static int enqueue_classify(bdx_stream *s, const uint8_t *d_seq, const int32_t *
                 if (wl == 0) {
                     CU(launch_literal(P, pass, 0, d_seq, d_off, n, s->sc, s->st_comp));
                 } else {
-                    CU(launch_mark_pending(P, pass, n, s->sc, wl == 1 ? s->sc.worklist : s->sc.worklist2,
-                                           wl == 1 ? s->sc.n_work : s->sc.n_work2, s->st_comp));
+                    const int *rest = wl == 1 ? s->sc.worklist : s->sc.worklist2;
+                    const int *n_rest = wl == 1 ? s->sc.n_work : s->sc.n_work2;
+                    CU(launch_mark_pending(P, pass, n, s->sc, rest, n_rest, s->st_comp));
                     s->launches++;
-                    CU(launch_literal(P, pass, 1, d_seq, d_off, n, s->sc, s->st_comp));
+                    // seed winners (windowed) and the scan-everything rest as separate, compacted launches
+                    CU(launch_literal(P, pass, 1, d_seq, d_off, n, s->sc, s->st_comp, s->sc.wl_win, s->sc.n_lit));
+                    s->launches++;
+                    CU(launch_literal(P, pass, 1, d_seq, d_off, n, s->sc, s->st_comp, rest, n_rest));
                 }
                 s->launches++;
                 continue;
@@ -893,7 +907,13 @@ static int enqueue_classify(bdx_stream *s, const uint8_t *d_seq, const int32_t *
             const bool default_geometry = bs.start_off <= 1 && !bs.start_from_end && bs.end_from_end &&
                                           bs.end_off >= 0 && be.start_off <= 1 && !be.start_from_end;
             if (!(may_finish && default_geometry)) {
-                CU(launch_literal(P, pass, 1, d_seq, d_off, n, s->sc, s->st_comp));
+                // seed winners (windowed DP) and k_filter's candidate reads as separate, compacted launches:
+                // a warp costs as much as its most expensive lane
+                if (wl != 0 && seed_levels(P, pass) > 0) {
+                    CU(launch_literal(P, pass, 1, d_seq, d_off, n, s->sc, s->st_comp, s->sc.wl_win, s->sc.n_lit));
+                    s->launches++;
+                }
+                CU(launch_literal(P, pass, 1, d_seq, d_off, n, s->sc, s->st_comp, s->sc.wl_full, s->sc.n_lit + 1));
                 s->launches++;
             }
         } else {

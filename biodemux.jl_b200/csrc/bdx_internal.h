@@ -150,11 +150,15 @@ struct Scratch {
     int *n_work;          // [1]
     int *worklist2;       // [n] reads the seed kernel left for the bit-parallel kernel
     int *n_work2;         // [1]
+    int *wl_win;          // [n] seed winners queued for k_literal with a column window
+    int *wl_full;         // [n] reads k_filter queued for k_literal with candidate lists
+    int *n_lit;           // [2] lengths of wl_win, wl_full
 };
 
 // ---- launch wrappers (kernels.cu / filter.cu) ----
 cudaError_t launch_literal(const DevParams &P, int pass, int from_filter, const uint8_t *seq,
-                           const int *off, int n, const Scratch &sc, cudaStream_t st);
+                           const int *off, int n, const Scratch &sc, cudaStream_t st, const int *list = nullptr,
+                           const int *n_list = nullptr);   // list: compacted read indices (length on the device)
 cudaError_t launch_filter(const DevParams &P, int pass, const uint8_t *seq, const int *off, int n,
                           const Scratch &sc, int sm_count, unsigned long long *counters, int use_worklist,
                           cudaStream_t st);   // use_worklist: 0 = all reads, 1 = worklist, 2 = worklist2

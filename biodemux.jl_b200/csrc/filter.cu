@@ -204,7 +204,8 @@ k_filter(const __grid_constant__ DevParams P, const int pass, const uint8_t *__r
          const int *__restrict__ off, const int n_reads, PassOut *__restrict__ out,
          const PassOut *__restrict__ prev_pass, uint16_t *__restrict__ cand,
          uint8_t *__restrict__ cand_cnt, unsigned long long *__restrict__ counters,
-         const int *__restrict__ worklist, const int *__restrict__ n_work)
+         const int *__restrict__ worklist, const int *__restrict__ n_work, int *__restrict__ wl_full,
+         int *__restrict__ n_full)
 {
     extern __shared__ __align__(16) uint32_t smem[];
     const DevSet &S = P.set[pass];
@@ -358,6 +359,7 @@ k_filter(const __grid_constant__ DevParams P, const int pass, const uint8_t *__r
             } else {
                 cand_cnt[read] = (uint8_t)(n_cand > kCandMax ? kCandOverflow : n_cand);
                 out[read] = PassOut{kBcPending, 0, -1, -1};
+                wl_full[atomicAdd(n_full, 1)] = read;     // k_literal walks this compacted list
             }
         }
     }
@@ -870,7 +872,8 @@ static cudaError_t launch_wgv(const DevParams &P, int pass, const uint8_t *seq, 
     kern<<<(unsigned)blocks, kFilterWarps * 32, smem, st>>>(P, pass, seq, off, n, sc.pass[pass], sc.pass[0],
                                                             sc.cand, sc.cand_cnt, counters,
                                                             use_worklist == 2 ? sc.worklist2 : (use_worklist ? sc.worklist : nullptr),
-                                                            use_worklist == 2 ? sc.n_work2 : (use_worklist ? sc.n_work : nullptr));
+                                                            use_worklist == 2 ? sc.n_work2 : (use_worklist ? sc.n_work : nullptr),
+                                                            sc.wl_full, sc.n_lit + 1);
     return cudaGetLastError();
 }
 

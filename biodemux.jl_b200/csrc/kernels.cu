@@ -22,15 +22,15 @@ constexpr int kLiteralThreads = 128;
 
 // SMEM_WS: the DP / origin columns live in shared memory as [row][thread] instead of in
 // thread-local (i.e. off-chip, L1-cached) arrays.
+// list / n_list (optional): the reads to evaluate, compacted by the kernels that queued them -- the lanes of a
+// warp then all have work of the same kind (a warp costs as much as its most expensive lane).
 template <int MAXM, bool SMEM_WS>
-__global__ void __launch_bounds__(kLiteralThreads)
-k_literal(const __grid_constant__ DevParams P, const int pass, const int from_filter,
-          const uint8_t *__restrict__ seq, const int *__restrict__ off, const int n_reads,
-          PassOut *__restrict__ out, const PassOut *__restrict__ prev_pass,
-          const uint16_t *__restrict__ cand, const uint8_t *__restrict__ cand_cnt)
+__device__ __forceinline__ void literal_one(const DevParams &P, const int pass, const int from_filter,
+                                            const uint8_t *__restrict__ seq, const int *__restrict__ off, const int i,
+                                            PassOut *__restrict__ out, const PassOut *__restrict__ prev_pass,
+                                            const uint16_t *__restrict__ cand, const uint8_t *__restrict__ cand_cnt,
+                                            int *ws_smem)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_reads) return;
     if (from_filter) {
         if (out[i].bc != kBcPending) return;
     } else if (pass == 1) {
@@ -51,7 +51,6 @@ k_literal(const __grid_constant__ DevParams P, const int pass, const int from_fi
         out[i] = o;
         return;
     }
-    extern __shared__ int ws_smem[];
     int dp_local[SMEM_WS ? 1 : MAXM + 2];
     int or_local[SMEM_WS ? 1 : MAXM + 2];
     const WsCol DP{SMEM_WS ? ws_smem + threadIdx.x : dp_local, SMEM_WS ? kLiteralThreads : 1};
@@ -110,19 +109,36 @@ k_literal(const __grid_constant__ DevParams P, const int pass, const int from_fi
     out[i] = best_finish(bs, with_delta, P.min_delta);
 }
 
+template <int MAXM, bool SMEM_WS>
+__global__ void __launch_bounds__(kLiteralThreads)
+k_literal(const __grid_constant__ DevParams P, const int pass, const int from_filter,
+          const uint8_t *__restrict__ seq, const int *__restrict__ off, const int n_reads,
+          PassOut *__restrict__ out, const PassOut *__restrict__ prev_pass,
+          const uint16_t *__restrict__ cand, const uint8_t *__restrict__ cand_cnt,
+          const int *__restrict__ list, const int *__restrict__ n_list)
+{
+    extern __shared__ int ws_smem[];
+    const int n_items = list ? *n_list : n_reads;
+    for (int item = blockIdx.x * blockDim.x + threadIdx.x; item < n_items; item += gridDim.x * blockDim.x)
+        literal_one<MAXM, SMEM_WS>(P, pass, from_filter, seq, off, list ? list[item] : item, out, prev_pass, cand,
+                                   cand_cnt, ws_smem);
+}
+
 cudaError_t launch_literal(const DevParams &P, int pass, int from_filter, const uint8_t *seq,
-                           const int *off, int n, const Scratch &sc, cudaStream_t st)
+                           const int *off, int n, const Scratch &sc, cudaStream_t st, const int *list,
+                           const int *n_list)
 {
     if (n <= 0) return cudaSuccess;
     const int threads = kLiteralThreads;
-    const int blocks = (n + threads - 1) / threads;
+    // a list's length is known on the device only: a capped grid strides over it
+    const int blocks = list ? std::max(1, std::min((n + threads - 1) / threads, 148 * 16)) : (n + threads - 1) / threads;
     const int max_m = P.set[pass].max_m;
     PassOut *out = sc.pass[pass];
     const PassOut *prev = sc.pass[0];
     if (max_m <= 32) {
         const size_t smem = (size_t)2 * (32 + 2) * threads * sizeof(int);
         k_literal<32, true><<<blocks, threads, smem, st>>>(P, pass, from_filter, seq, off, n, out, prev, sc.cand,
-                                                           sc.cand_cnt);
+                                                           sc.cand_cnt, list, n_list);
     } else if (max_m <= 64) {
         const size_t smem = (size_t)2 * (64 + 2) * threads * sizeof(int);
         static bool attr_set = false;
@@ -133,10 +149,10 @@ cudaError_t launch_literal(const DevParams &P, int pass, int from_filter, const 
             attr_set = true;
         }
         k_literal<64, true><<<blocks, threads, smem, st>>>(P, pass, from_filter, seq, off, n, out, prev, sc.cand,
-                                                           sc.cand_cnt);
+                                                           sc.cand_cnt, list, n_list);
     } else {
         k_literal<kMaxBarcodeLen, false><<<blocks, threads, 0, st>>>(P, pass, from_filter, seq, off, n, out, prev,
-                                                                     sc.cand, sc.cand_cnt);
+                                                                     sc.cand, sc.cand_cnt, list, n_list);
     }
     return cudaGetLastError();
 }

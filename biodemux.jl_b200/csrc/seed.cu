@@ -137,7 +137,8 @@ k_seed(const __grid_constant__ DevParams P, const int pass, const int level, con
        const int *__restrict__ off, const int n_reads, PassOut *__restrict__ out,
        const PassOut *__restrict__ prev_pass, const int *__restrict__ worklist,
        const int *__restrict__ n_work, int *__restrict__ worklist2, int *__restrict__ n_work2,
-       unsigned long long *__restrict__ counters, uint16_t *__restrict__ cand, uint8_t *__restrict__ cand_cnt)
+       unsigned long long *__restrict__ counters, uint16_t *__restrict__ cand, uint8_t *__restrict__ cand_cnt,
+       int *__restrict__ wl_win, int *__restrict__ n_win)
 {
     extern __shared__ __align__(16) uint32_t smem[];
     const DevSet &S = P.set[pass];
@@ -337,7 +338,7 @@ k_seed(const __grid_constant__ DevParams P, const int pass, const int level, con
             }
 
         // ---- decide ----
-        bool resolved = false;
+        bool resolved = false, queued = false;      // queued: winner handed to k_literal for its positions
         if (!punt) {
             if (best_d <= K) {
                 // acceptance exactly as find_best_matching_bc_* does it for this barcode (classification.jl:254,
@@ -379,6 +380,7 @@ k_seed(const __grid_constant__ DevParams P, const int pass, const int level, con
                             cand[(size_t)read * kCandMax + 2] = (uint16_t)min(hi + 2, n);
                             cand_cnt[read] = (uint8_t)kCandWindow;
                             out[read] = PassOut{kBcPending, 0, -1, -1};
+                            queued = true;
                         } else {
                             out[read] = PassOut{best_b + 1, best_d, -1, -1};
                         }
@@ -389,6 +391,13 @@ k_seed(const __grid_constant__ DevParams P, const int pass, const int level, con
                 out[read] = PassOut{kBcUnknown, 0, -1, -1};    // nothing within the allowed distance
                 resolved = true;
             }
+        }
+        {   // warp-aggregated append of the queued winners to k_literal's list
+            const uint32_t qm = __ballot_sync(0xFFFFFFFFu, queued);
+            int qb = 0;
+            if (lane == 0 && qm) qb = atomicAdd(n_win, __popc(qm));
+            qb = __shfl_sync(0xFFFFFFFFu, qb, 0);
+            if (queued) wl_win[qb + __popc(qm & ((1u << lane) - 1u))] = read;
         }
         const bool todo = have && !resolved && !skip;
         const uint32_t mask = __ballot_sync(0xFFFFFFFFu, todo);
@@ -445,7 +454,7 @@ cudaError_t launch_seed(const DevParams &P, int pass, int level, const uint8_t *
     e = cudaMemsetAsync(n_out, 0, sizeof(int), st);
     if (e != cudaSuccess) return e;
     kern<<<blocks, kSeedThreads, smem, st>>>(P, pass, level, seq, off, n, sc.pass[pass], sc.pass[0], wl_in, n_in, wl_out, n_out,
-                                             counters, sc.cand, sc.cand_cnt);
+                                             counters, sc.cand, sc.cand_cnt, sc.wl_win, sc.n_lit);
     return cudaGetLastError();
 }
 

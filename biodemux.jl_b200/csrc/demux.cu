@@ -419,11 +419,12 @@ k_rs_scatter(const int *__restrict__ keys_in, const int *__restrict__ vals_in, i
 __global__ void __launch_bounds__(256)
 k_part_gather(const int *__restrict__ sidx, const int *__restrict__ skey, const int n, const int *__restrict__ size1,
               const int *__restrict__ size2, long long *__restrict__ ss1, long long *__restrict__ ss2,
-              int *__restrict__ flag)
+              int *__restrict__ flag, int *__restrict__ rank)
 {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n) return;
     const int i = sidx[p];
+    rank[i] = p;                  // where record i stands in the output order
     if (ss1) ss1[p] = size1[i];
     if (ss2) ss2[p] = size2[i];
     flag[p] = p == 0 || skey[p] != skey[p - 1];
@@ -471,24 +472,25 @@ k_part_buckets(const int *__restrict__ bstart, const int *__restrict__ bkey, con
 // ---------------------------------------------------------------------------------------
 // 8: write_entry (core.jl:135-137) for every record, at its final place
 // ---------------------------------------------------------------------------------------
-// One warp per 32 consecutive output records: every lane prepares one record (its source runs), then the
-// warp copies the records one after the other.
+// One warp per 32 consecutive INPUT records: every lane prepares one record (its source runs and where it goes),
+// then the warp copies the records one after the other.  Input order keeps the reads of the text and of the
+// per-record tables sequential; the writes advance one frontier per output file, which the L2 absorbs.
 __global__ void __launch_bounds__(256)
 k_part_copy(const uint8_t *__restrict__ text, const int text_len, const FqRec *__restrict__ recs,
-            const bdx_result *__restrict__ res, const int do_trim, const int *__restrict__ sidx,
+            const bdx_result *__restrict__ res, const int do_trim, const int *__restrict__ rank,
             const long long *__restrict__ ooff, const int n, uint8_t *__restrict__ out)
 {
     const int lane = threadIdx.x & 31;
     const int p0 = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32;
     if (p0 >= n) return;
-    const int p = p0 + lane;
+    const int p = p0 + lane;      // input record of this lane
     // the four output lines as source runs; a run whose "\n" sits right behind it in the text takes it along,
     // and runs that are adjacent in the text merge: an untrimmed "\n"-terminated record is ONE copy.
     // run_len: bytes to copy (incl. a trailing "\n" taken from the text); run_nl: 1 = write the "\n" separately
     int run_src[4] = {0, 0, 0, 0}, run_len[4] = {0, 0, 0, 0}, run_nl[4] = {0, 0, 0, 0}, n_runs = 0;
     long long dst0 = 0;
     if (p < n) {
-        const int i = sidx[p];
+        const int i = p;
         const FqRec r = recs[i];
         int ns = r.len[1], nq = r.len[3], first = 0;
         if (res) first = keep_of(res[i], do_trim, r.len[1], r.len[3], ns, nq);
@@ -500,7 +502,7 @@ k_part_copy(const uint8_t *__restrict__ text, const int text_len, const FqRec *_
         nl[2] = r.start[3] == r.start[2] + r.len[2] + 1;
         const int e = r.start[3] + r.len[3];
         nl[3] = first + nq == r.len[3] && e < text_len && text[e] == '\n';
-        dst0 = ooff[p];
+        dst0 = ooff[rank[i]];
 #pragma unroll
         for (int k = 0; k < 4; k++) {
             // line k extends the current run when it starts right after that run's "\n"
@@ -770,8 +772,9 @@ int demux_run(DemuxState *d, const DevParams &P, cudaStream_t st, const DemuxCla
     DM(d->buckets.reserve((size_t)max_buckets * sizeof(bdx_demux_bucket), st));
     long long *ss1 = emit1 ? d->side[0].ssize.as<long long>() : nullptr;
     long long *ss2 = emit2 ? d->side[1].ssize.as<long long>() : nullptr;
+    int *rank = d->idx[cur ^ 1].as<int>();        // the sort's spare buffer
     k_part_gather<<<(n + 255) / 256, 256, 0, st>>>(sidx, skey, n, d->side[0].size.as<int>(), d->side[1].size.as<int>(), ss1,
-                                                   ss2, d->flag.as<int>());
+                                                   ss2, d->flag.as<int>(), rank);
     DM(cudaGetLastError());
     if (ss1) DM(scan_exclusive<long long>(ss1, ss1, n, (long long)n + 1, d->scan_ws.p, st));
     if (ss2) DM(scan_exclusive<long long>(ss2, ss2, n, (long long)n + 1, d->scan_ws.p, st));
@@ -793,7 +796,7 @@ int demux_run(DemuxState *d, const DevParams &P, cudaStream_t st, const DemuxCla
         DemuxSide &S = d->side[s];
         DM(S.out.reserve((size_t)len[s] + 16, st));
         k_part_copy<<<(n + 255) / 256, 256, 0, st>>>(text[s], (int)len[s], S.recs.as<FqRec>(), s == 0 ? d->res.as<bdx_result>() : nullptr, do_trim,
-                                                 sidx, s == 0 ? ss1 : ss2, n, S.out.as<uint8_t>());
+                                                 rank, s == 0 ? ss1 : ss2, n, S.out.as<uint8_t>());
         DM(cudaGetLastError());
         *launches += 1;
     }

@@ -35,7 +35,7 @@ EXPORTS = [
     "bdx_barcode_table_bytes", "bdx_barcode_table_offsets", "bdx_barcode_table_lengths_no_n", "bdx_barcode_table_id",
     "bdx_barcode_table_error", "bdx_stats_entries",
     "bdx_pool_create", "bdx_pool_destroy", "bdx_pool_submit", "bdx_pool_submit_pinned", "bdx_pool_fetch",
-    "bdx_pool_fetch_view", "bdx_pool_in_flight", "bdx_pool_stats_fetch",
+    "bdx_pool_fetch_view", "bdx_pool_in_flight", "bdx_pool_stats_fetch", "bdx_stats_overflow_fetch",
 ]
 
 
@@ -146,6 +146,7 @@ def load_library():
     L.bdx_stream_path_counters.argtypes = [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64), C.c_int]
     L.bdx_stats_layout_get.argtypes = [vp, C.POINTER(StatsLayout)]
     L.bdx_stats_fetch.argtypes = [vp, vp, i64]
+    L.bdx_stats_overflow_fetch.argtypes = [vp, vp, i64, C.POINTER(i64), C.POINTER(i64)]
     L.bdx_stats_entries.argtypes = [vp, vp, vp, i64]
     L.bdx_stats_entries.restype = i64
     L.bdx_stats_device_ptr.argtypes = [vp]
@@ -212,6 +213,7 @@ def fastq_pack(buf: np.ndarray, recs: np.ndarray, seq_out: Optional[np.ndarray] 
     return seq_out[:total], off
 
 
+STATS_OVERFLOW_DTYPE = np.dtype([("pass", "<i4"), ("bc", "<i4"), ("start", "<i4"), ("length", "<i4")])
 STATS_ENTRY_DTYPE = np.dtype([("pass", "<i4"), ("kind", "<i4"), ("bc", "<i4"), ("reserved", "<i4"),
                               ("key", "<i8"), ("score", "<f8"), ("count", "<i8")])
 
@@ -437,6 +439,17 @@ class Stream:
         _check(self.lib.bdx_stats_fetch(self.handle, out.ctypes.data, out.size))
         return out
 
+    def stats_overflow(self) -> np.ndarray:
+        """Exact records of the matched passes that did not fit the pos / len histograms."""
+        n, lost = C.c_int64(), C.c_int64()
+        _check(self.lib.bdx_stats_overflow_fetch(self.handle, None, 0, C.byref(n), C.byref(lost)))
+        if lost.value:
+            raise BdxError(BDX_ERR_TOO_LARGE, f"{lost.value} stats overflow records were lost")
+        out = np.zeros(n.value, dtype=STATS_OVERFLOW_DTYPE)
+        if n.value:
+            _check(self.lib.bdx_stats_overflow_fetch(self.handle, out.ctypes.data, n.value, C.byref(n), C.byref(lost)))
+        return out
+
     @property
     def stats_device_ptr(self) -> int:
         return int(self.lib.bdx_stats_device_ptr(self.handle) or 0)
@@ -531,7 +544,7 @@ class Engine:
 
     def demux_stats(self):
         from .stats import stats_from_counters
-        return stats_from_counters(self.stream.stats(), self.config.layout, self.cfg)
+        return stats_from_counters(self.stream.stats(), self.config.layout, self.cfg, self.stream.stats_overflow())
 
     def close(self):
         self.stream.close()

@@ -659,6 +659,8 @@ struct bdx_stream {
     Scratch sc{};
     int64_t sc_cap = 0;
     unsigned long long *d_stats = nullptr;
+    bdx_stats_overflow *d_ovf = nullptr;       // exact records of passes outside the pos / len histograms
+    unsigned int *d_n_ovf = nullptr;           // [2] appended, lost
     unsigned long long *d_counters = nullptr;  // [0] reads resolved by the perfect-occurrence prefilter,
                                                // [1] reads that ran the bit-parallel automaton
     int64_t launches = 0;
@@ -734,6 +736,8 @@ extern "C" void bdx_stream_destroy(bdx_stream *s)
     cudaFree(s->sc.wl_full);
     cudaFree(s->sc.n_lit);
     cudaFree(s->d_stats);
+    cudaFree(s->d_ovf);
+    cudaFree(s->d_n_ovf);
     cudaFree(s->d_counters);
     demux_state_destroy(s->demux);
     for (auto &pr : s->prof_events) {
@@ -772,6 +776,9 @@ static int stream_create_impl(bdx_stream *s)
     if (s->cfg->base.want_stats) {
         CU(cudaMalloc(&s->d_stats, (size_t)s->cfg->lay.total_len * 8));
         CU(cudaMemset(s->d_stats, 0, (size_t)s->cfg->lay.total_len * 8));
+        CU(cudaMalloc(&s->d_ovf, (size_t)kStatsOvfCap * sizeof(bdx_stats_overflow)));
+        CU(cudaMalloc(&s->d_n_ovf, 2 * sizeof(unsigned int)));
+        CU(cudaMemset(s->d_n_ovf, 0, 2 * sizeof(unsigned int)));
     }
     return BDX_OK;
 }
@@ -921,7 +928,7 @@ static int enqueue_classify(bdx_stream *s, const uint8_t *d_seq, const int32_t *
             s->launches++;
         }
     }
-    StatsDev sd{s->d_stats, s->cfg->lay};
+    StatsDev sd{s->d_stats, s->cfg->lay, s->d_ovf, s->d_n_ovf};
     CU(launch_finalize(P, d_off, n, s->sc, d_res, d_det, sd, s->st_comp));
     s->launches++;
     return BDX_OK;
@@ -1340,6 +1347,24 @@ extern "C" int64_t bdx_stats_entries(const bdx_config *cfg, const int64_t *count
     return n;
 }
 
+extern "C" int bdx_stats_overflow_fetch(bdx_stream *s, bdx_stats_overflow *out, int64_t cap, int64_t *n, int64_t *lost)
+{
+    if (!s || !n || cap < 0 || (cap > 0 && !out)) return fail(BDX_ERR_INVALID, "bad argument");
+    *n = 0;
+    if (lost) *lost = 0;
+    if (!s->d_stats) return fail(BDX_ERR_STATE, "config was created without want_stats");
+    CU(cudaSetDevice(s->device));
+    CU(cudaStreamSynchronize(s->st_comp));
+    unsigned int h[2];
+    CU(cudaMemcpy(h, s->d_n_ovf, sizeof(h), cudaMemcpyDeviceToHost));
+    const int64_t kept = std::min<int64_t>(h[0], kStatsOvfCap);
+    *n = kept;
+    if (lost) *lost = h[1];
+    const int64_t take = std::min(kept, cap);
+    if (take > 0) CU(cudaMemcpy(out, s->d_ovf, (size_t)take * sizeof(bdx_stats_overflow), cudaMemcpyDeviceToHost));
+    return BDX_OK;
+}
+
 extern "C" void *bdx_stats_device_ptr(bdx_stream *s) { return s ? (void *)s->d_stats : nullptr; }
 
 extern "C" int bdx_stats_reset(bdx_stream *s)
@@ -1348,6 +1373,7 @@ extern "C" int bdx_stats_reset(bdx_stream *s)
     if (!s->d_stats) return BDX_OK;
     CU(cudaSetDevice(s->device));
     CU(cudaMemsetAsync(s->d_stats, 0, (size_t)s->cfg->lay.total_len * 8, s->st_comp));
+    CU(cudaMemsetAsync(s->d_n_ovf, 0, 2 * sizeof(unsigned int), s->st_comp));
     return BDX_OK;
 }
 

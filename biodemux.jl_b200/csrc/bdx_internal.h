@@ -137,9 +137,12 @@ struct PassOut {
     int start, end;
 };
 
+constexpr int kStatsOvfCap = 1 << 20;   // overflow records kept per stream
 struct StatsDev {
     unsigned long long *buf;  // layout: bdx_stats_layout
     bdx_stats_layout lay;
+    bdx_stats_overflow *ovf;  // [kStatsOvfCap] passes whose start / length do not fit the histograms
+    unsigned int *n_ovf;      // [2] records appended (may exceed the capacity), records lost
 };
 
 struct Scratch {

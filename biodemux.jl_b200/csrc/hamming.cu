@@ -68,11 +68,31 @@ k_hamming_scan(const __grid_constant__ DevParams P, const int pass, const uint8_
         const int base = have ? off[read] : 0;
         const int n = have ? off[read + 1] - base : 0;
 
+        // which start positions hamming_align visits (:570-571) and the end constraint (:583-586); only the
+        // columns those placements touch are packed, so a long read with a short search range fits as well
+        bool skip = !have, notrun = false, none = false, toolong = false;
+        int s_first = 1, s_last = 0;
+        if (have) {
+            if (pass == 1 && prev_pass[read].bc <= 0) {
+                notrun = true;
+            } else {
+                const Geometry g = pass_geometry(S, n);
+                s_first = max(g.start_j, max(1, g.min_end_pos - m + 1));
+                s_last = min(min(g.end_j, g.max_start_pos), n - m + 1);
+                if (!g.valid || s_last < s_first) none = true;
+                else if (s_last - s_first + m > kHpWords * 32) toolong = true;
+            }
+            skip = notrun || none || toolong;
+        }
+        const int pbase = skip ? 0 : s_first - 1;                // packed base k = absolute column pbase + k + 1
+        const int plen = skip ? 0 : s_last - s_first + m;
+
         // ---- pack the warp's 32 reads, one after the other: coalesced byte loads, three ballots per 32 bases ----
         __syncwarp();
         for (int r = 0; r < 32; r++) {
-            const int rb = __shfl_sync(0xFFFFFFFFu, base, r);
-            const int rn = min(__shfl_sync(0xFFFFFFFFu, n, r), kHpWords * 32);
+            const int rb = __shfl_sync(0xFFFFFFFFu, base + pbase, r);
+            const int rn = __shfl_sync(0xFFFFFFFFu, plen, r);
+            if (rn == 0) continue;                                // warp-uniform
             const int col = warp * 32 + r;
             uint8_t v[kHpWords];
 #pragma unroll
@@ -98,19 +118,15 @@ k_hamming_scan(const __grid_constant__ DevParams P, const int pass, const uint8_
         __syncwarp();
 
         if (!have) continue;
-        if (pass == 1 && prev_pass[read].bc <= 0) {
+        if (notrun) {
             out[read] = PassOut{kBcNotRun, 0, -1, -1};
             continue;
         }
-        const Geometry g = pass_geometry(S, n);
-        // start positions hamming_align visits (:570-571), and the end constraint (:583-586)
-        const int s_first = max(g.start_j, max(1, g.min_end_pos - m + 1));
-        const int s_last = min(min(g.end_j, g.max_start_pos), n - m + 1);
-        if (!g.valid || s_last < s_first) {
+        if (none) {
             out[read] = PassOut{kBcUnknown, 0, -1, -1};
             continue;
         }
-        if (n > kHpWords * 32) {                       // beyond the packed capacity: k_literal scans every barcode
+        if (toolong) {                                 // beyond the packed capacity: k_literal scans every barcode
             cand_cnt[read] = (uint8_t)kCandOverflow;
             out[read] = PassOut{kBcPending, 0, -1, -1};
             continue;
@@ -118,7 +134,8 @@ k_hamming_scan(const __grid_constant__ DevParams P, const int pass, const uint8_
 
         // ---- every start position: window, per-segment table lookup, popcount verification ----
         int nc = 0;
-        for (int s = s_first; s <= s_last; s++) {
+        const int n_starts = s_last - s_first + 1;
+        for (int s = 1; s <= n_starts; s++) {                 // relative start: absolute start = s + pbase
             const int wi = (s - 1) >> 5;
             const uint32_t sh = (uint32_t)(s - 1) & 31u;
             const int i0 = wi * kHpThreads + threadIdx.x, i1 = i0 + kHpThreads;
@@ -170,7 +187,7 @@ k_hamming_scan(const __grid_constant__ DevParams P, const int pass, const uint8_
         best_init(bs, P.max_error_rate);
         for (int k = 0; k < nc; k++) {
             const uint32_t item = list_s[k * kHpThreads + threadIdx.x];
-            const int b = (int)(item >> 12), mm = (int)((item >> 8) & 0xFu), st = (int)(item & 0xFFu);
+            const int b = (int)(item >> 12), mm = (int)((item >> 8) & 0xFu), st = (int)(item & 0xFFu) + pbase;
             const bool ok = mm <= allowed_from(bs.thr, m);                                   // :567
             const double score = ok ? __ddiv_rn((double)mm, (double)m) : CUDART_INF;        // :607
             best_consider(bs, with_delta, score, ok ? mm : kInf, b + 1, ok ? st : -1, ok ? st + m - 1 : -1);

@@ -203,17 +203,26 @@ __device__ __forceinline__ int pass_norm(const DevParams &P, const DevSet &S, in
 __device__ void stats_pass(const DevParams &P, const StatsDev &st, int pass, const PassOut &o)
 {
     const bdx_stats_layout &L = st.lay;
-    const int pos = min(max(o.start + L.pos_bias, 0), L.pos_bins - 1);
-    const int len = min(max(o.end - o.start + 1, 0), L.len_bins - 1);
+    const int pos = o.start + L.pos_bias;
+    const int len = o.end - o.start + 1;
     const int d = min(max(o.dist + L.dist_bias, 0), L.dist_bins - 1);
     unsigned long long *bp = st.buf + L.pos_off[pass], *bl = st.buf + L.len_off[pass],
                        *bd = st.buf + L.dist_off[pass];
+    stat_add(bd + d);
+    stat_add(bd + (size_t)o.bc * L.dist_bins + d);
+    if (pos < 0 || pos >= L.pos_bins || len < 0 || len >= L.len_bins) {
+        // outside the histograms (a long read searched near its end): keep the exact record instead
+        const unsigned int k = atomicAdd(st.n_ovf, 1u);
+        if (k < (unsigned int)kStatsOvfCap)
+            st.ovf[k] = bdx_stats_overflow{pass + 1, o.bc, o.start, len};
+        else
+            atomicAdd(st.n_ovf + 1, 1u);
+        return;
+    }
     stat_add(bp + pos);
     stat_add(bl + len);
-    stat_add(bd + d);
     stat_add(bp + (size_t)o.bc * L.pos_bins + pos);
     stat_add(bl + (size_t)o.bc * L.len_bins + len);
-    stat_add(bd + (size_t)o.bc * L.dist_bins + d);
 }
 
 __global__ void __launch_bounds__(256)

@@ -36,7 +36,8 @@
 namespace bdx {
 
 constexpr int kSeedThreads = 128;
-constexpr int kSeedSlot = 180;      // staged class codes per read (longer reads take the full path); 45 words:
+constexpr int kSeedSlot = 180;      // staged class codes per read = columns of its search range (longer ranges take the
+                                    // full path); 45 words:
                                     // an odd word stride keeps the lock-step scan free of bank conflicts
 constexpr int kSeedMaxHits = 28;    // distinct (barcode, diagonal group) hits remembered per read (more => next stage)
 constexpr int kSeedMaxWins = 32;    // bitmap-passing columns remembered per read (more => full path)
@@ -192,8 +193,28 @@ k_seed(const __grid_constant__ DevParams P, const int pass, const int level, con
         const int base = have ? off[read] : 0;
         const int n = have ? off[read + 1] - base : 0;
 
-        // ---- stage the warp's 32 reads as class codes, coalesced: four reads at a time, all their
-        // global loads issued before the first table lookup / store ----
+        bool punt = !have;       // true => this read goes to the next stage (or is not a read at all)
+        bool skip = false;       // pass 2 of a read whose pass 1 did not match: nothing to do
+        Geometry g{};
+        if (have && pass == 1 && prev_pass[read].bc <= 0) {      // classification.jl:879-888
+            out[read] = PassOut{kBcNotRun, 0, -1, -1};
+            skip = true;
+            punt = true;
+        }
+        if (have && !skip) {
+            g = pass_geometry(S, n);
+            // the regime test of k_filter's `fast` / k_prefilter<0>; the search range has to fit the slot
+            // (the read itself may be much longer: only the columns of its search range are staged)
+            if (!(g.valid && g.max_start_pos >= n && g.min_end_pos <= g.start_j) || g.end_j - g.start_j + 1 > kSeedSlot)
+                punt = true;
+        }
+        // From here on columns are RELATIVE to the search range: column c of the range (1-based, 1 = start_j)
+        // is absolute column c + sbase and lives in my_slot[c - 1].
+        const int sbase = punt ? 0 : g.start_j - 1;
+        const int L = punt ? 0 : g.end_j - g.start_j + 1;
+
+        // ---- stage the search ranges of the warp's 32 reads as class codes, coalesced: four reads at a time,
+        // all their global loads issued before the first table lookup / store ----
         uint8_t *my_slot = slot_s + (size_t)threadIdx.x * kSeedSlot;
         __syncwarp();
         constexpr int kIt = (kSeedSlot + 31) / 32;
@@ -202,9 +223,8 @@ k_seed(const __grid_constant__ DevParams P, const int pass, const int level, con
             int rn4[4];
 #pragma unroll
             for (int j = 0; j < 4; j++) {
-                const int rb = __shfl_sync(0xFFFFFFFFu, base, r0 + j);
-                const int rn = __shfl_sync(0xFFFFFFFFu, n, r0 + j);
-                rn4[j] = rn > kSeedSlot ? 0 : rn;
+                const int rb = __shfl_sync(0xFFFFFFFFu, base + sbase, r0 + j);
+                rn4[j] = __shfl_sync(0xFFFFFFFFu, L, r0 + j);
                 const uint8_t *src = seq + rb;
 #pragma unroll
                 for (int it = 0; it < kIt; it++) v[j][it] = lane + 32 * it < rn4[j] ? src[lane + 32 * it] : (uint8_t)0;
@@ -223,22 +243,9 @@ k_seed(const __grid_constant__ DevParams P, const int pass, const int level, con
         // (Doing the bucket walk right here would serialise the lanes of a warp: every lane hits
         // at different columns.  The divergent part is kept to one shared-memory store.) ----
         int n_wins = 0;
-        bool punt = !have;       // true => this read goes to the next stage (or is not a read at all)
-        bool skip = false;       // pass 2 of a read whose pass 1 did not match: nothing to do
-        Geometry g{};
-        if (have && pass == 1 && prev_pass[read].bc <= 0) {      // classification.jl:879-888
-            out[read] = PassOut{kBcNotRun, 0, -1, -1};
-            skip = true;
-            punt = true;
-        }
-        if (have && !skip) {
-            g = pass_geometry(S, n);
-            // the regime test of k_filter's `fast` / k_prefilter<0>
-            if (!(g.valid && g.max_start_pos >= n && g.min_end_pos <= g.start_j) || n > kSeedSlot) punt = true;
-        }
         if (!punt) {
-            const int p0 = g.start_j - 1;              // 0-based column of the first q-mer
-            const int p1 = g.end_j - q;                // last one that lies inside the search range
+            const int p0 = 0;                          // 0-based (relative) column of the first q-mer
+            const int p1 = L - q;                      // last one that lies inside the search range
             if (p1 >= p0) {
                 uint32_t h = 0;
                 for (int i = 0; i < q; i++) h = h * kPfBase + (uint32_t)my_slot[p0 + i];
@@ -314,8 +321,8 @@ k_seed(const __grid_constant__ DevParams P, const int pass, const int level, con
             const SeedVerifyCtx vc{hits_s + warp * 32, peq_s, slot_s + (size_t)warp * 32 * kSeedSlot, n_pad, plane, m, K, win,
                                    total_hits};
             int i0 = 0;
-            for (; i0 + 32 < total_hits; i0 += 64) seed_verify<2, WT>(vc, i0, lane, incl, g.start_j, g.end_j);
-            if (i0 < total_hits) seed_verify<1, WT>(vc, i0, lane, incl, g.start_j, g.end_j);
+            for (; i0 + 32 < total_hits; i0 += 64) seed_verify<2, WT>(vc, i0, lane, incl, 1, L);
+            if (i0 < total_hits) seed_verify<1, WT>(vc, i0, lane, incl, 1, L);
         }
         __syncwarp();
         // ---- the read's own hits, now with distances: d_b = min over the hit groups of barcode b.
@@ -376,9 +383,11 @@ k_seed(const __grid_constant__ DevParams P, const int pass, const int level, con
                                 hi = max(hi, dmin + span + m + 2 * K);
                             }
                             cand[(size_t)read * kCandMax] = (uint16_t)best_b;
-                            cand[(size_t)read * kCandMax + 1] = (uint16_t)max(lo - 2, 1);
-                            cand[(size_t)read * kCandMax + 2] = (uint16_t)min(hi + 2, n);
-                            cand_cnt[read] = (uint8_t)kCandWindow;
+                            const int w_lo = max(lo - 2 + sbase, 1), w_hi = min(hi + 2 + sbase, n);   // absolute columns
+                            cand[(size_t)read * kCandMax + 1] = (uint16_t)w_lo;
+                            cand[(size_t)read * kCandMax + 2] = (uint16_t)w_hi;
+                            // (columns beyond the uint16 slots: k_literal aligns the winner over the whole range)
+                            cand_cnt[read] = (uint8_t)(w_hi <= 65535 ? kCandWindow : 1);
                             out[read] = PassOut{kBcPending, 0, -1, -1};
                             queued = true;
                         } else {

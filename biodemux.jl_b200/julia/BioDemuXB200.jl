@@ -62,6 +62,13 @@ struct BdxResult           # bdx_result
     keep_end::Int32
 end
 
+struct BdxStatsOverflow    # bdx_stats_overflow
+    pass::Int32
+    bc::Int32
+    start::Int32
+    length::Int32
+end
+
 struct BdxStatsLayout      # bdx_stats_layout
     total_len::Int64
     sample_off::Int64
@@ -233,6 +240,24 @@ function fetch_stats(s::Ptr{Cvoid}, g::GpuConfig)
                 gsc[key] = get(gsc, key, 0) + v
             end
         end
+    end
+    # matched passes whose start / length lies outside the device histograms (long reads searched near
+    # their end) come back as exact records
+    n, lost = Ref{Int64}(0), Ref{Int64}(0)
+    check(ccall((:bdx_stats_overflow_fetch, libbdx), Cint, (Ptr{Cvoid}, Ptr{BdxStatsOverflow}, Int64, Ref{Int64}, Ref{Int64}),
+                s, C_NULL, 0, n, lost))
+    lost[] == 0 || error("libbdx: $(lost[]) stats overflow records were lost")
+    ovf = Vector{BdxStatsOverflow}(undef, n[])
+    n[] > 0 && check(ccall((:bdx_stats_overflow_fetch, libbdx), Cint,
+                           (Ptr{Cvoid}, Ptr{BdxStatsOverflow}, Int64, Ref{Int64}, Ref{Int64}), s, ovf, length(ovf), n, lost))
+    for e in ovf
+        gpos, glen, pbp, pbl = e.pass == 1 ?
+            (st.bc1_pos_counts, st.bc1_len_counts, st.bc1_per_bc_pos_counts, st.bc1_per_bc_len_counts) :
+            (st.bc2_pos_counts, st.bc2_len_counts, st.bc2_per_bc_pos_counts, st.bc2_per_bc_len_counts)
+        gpos[e.start] = get(gpos, e.start, 0) + 1
+        glen[e.length] = get(glen, e.length, 0) + 1
+        dp = get!(() -> Dict{Int,Int}(), pbp, Int(e.bc)); dp[e.start] = get(dp, e.start, 0) + 1
+        dl = get!(() -> Dict{Int,Int}(), pbl, Int(e.bc)); dl[e.length] = get(dl, e.length, 0) + 1
     end
     st
 end

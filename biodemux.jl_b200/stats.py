@@ -54,7 +54,19 @@ def pass_norms(cfg, pass2: bool):
     return [len(s.encode("latin-1")) if isinstance(s, str) else len(s) for s in seqs]
 
 
-def stats_from_counters(buf: np.ndarray, lay, cfg) -> DemuxStats:
+def merge_overflow(st: DemuxStats, overflow) -> DemuxStats:
+    """Adds the exact (pass, barcode, start, length) records of ``bdx_stats_overflow_fetch`` -- matched passes whose
+    position or length lies outside the device histograms -- to the position / length Dicts."""
+    for e in overflow if overflow is not None else ():
+        pre, b = f"bc{int(e['pass'])}", int(e["bc"])
+        _bump(getattr(st, pre + "_pos_counts"), int(e["start"]))
+        _bump(getattr(st, pre + "_len_counts"), int(e["length"]))
+        _bump(getattr(st, pre + "_per_bc_pos_counts").setdefault(b, {}), int(e["start"]))
+        _bump(getattr(st, pre + "_per_bc_len_counts").setdefault(b, {}), int(e["length"]))
+    return st
+
+
+def stats_from_counters(buf: np.ndarray, lay, cfg, overflow=None) -> DemuxStats:
     st = DemuxStats()
     st.total_reads, st.matched_reads, st.unmatched_reads, st.ambiguous_reads = (int(x) for x in buf[:4])
     b1, b2 = lay.b1, lay.b2
@@ -86,7 +98,7 @@ def stats_from_counters(buf: np.ndarray, lay, cfg) -> DemuxStats:
                 key = julia_round2(float(dist) / float(norms[b - 1])) if norms[b - 1] else float("nan")
                 _bump(pb_sc.setdefault(b, {}), key, int(ds[b, d]))
                 _bump(g_sc, key, int(ds[b, d]))
-    return st
+    return merge_overflow(st, overflow)
 
 
 def stats_from_passes(status, bc1, bc2, passes, cfg) -> DemuxStats:

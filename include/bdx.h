@@ -207,7 +207,9 @@ int64_t bdx_stream_launch_count(const bdx_stream *s);
  *     row 0 of each is the global histogram, row b the per-barcode one;
  *     pos bin = start + pos_bias (start can be <= 0), len bin = end - start + 1 (up to n + m),
  *     dist bin = integer distance + dist_bias (host converts to round(dist / norm_b, digits=2) keys).
- *     pos/len histograms cover reads up to 1024 bases; longer reads land in the last bin.
+ *     pos/len histograms cover positions up to 1024 bases; a matched pass whose start or length falls
+ *     outside goes, exactly, to the stream's overflow list instead (bdx_stats_overflow_fetch) -- long reads
+ *     searched near their end.  Its distance is still counted in dist[].
  * bdx_stats_layout describes the offsets; sum the buffers of all streams / GPUs
  * (e.g. one ncclAllReduce(sum, int64)) before converting to DemuxStats. */
 typedef struct bdx_stats_layout {
@@ -240,6 +242,16 @@ typedef struct bdx_stats_entry {
 int64_t bdx_stats_entries(const bdx_config *cfg, const int64_t *counters, bdx_stats_entry *out, int64_t cap);
 /* copies the stream's device counters to host (after syncing the stream) */
 int bdx_stats_fetch(bdx_stream *s, int64_t *out, int64_t out_len);
+/* Matched passes whose start / length did not fit the pos / len histograms: one exact record each.  Returns
+ * up to cap records, their total number in *n, and in *lost how many could not be kept (the list holds
+ * 2^20 records per stream; lost != 0 means the pos / len Dicts are incomplete).  Concatenate over streams / GPUs. */
+typedef struct bdx_stats_overflow {
+    int32_t pass;     /* 1 or 2 */
+    int32_t bc;       /* 1-based barcode index of that pass */
+    int32_t start;    /* alignment start (Dict key of bcN_pos_counts) */
+    int32_t length;   /* end - start + 1 (Dict key of bcN_len_counts) */
+} bdx_stats_overflow;
+int bdx_stats_overflow_fetch(bdx_stream *s, bdx_stats_overflow *out, int64_t cap, int64_t *n, int64_t *lost);
 /* device pointer of the counters (for an in-place NCCL all-reduce by the host) */
 void *bdx_stats_device_ptr(bdx_stream *s);
 int bdx_stats_reset(bdx_stream *s);

@@ -23,7 +23,7 @@ def run_cuda(cfg, reads, want_stats=False, details=True):
         if details:
             eng.stream.enable_details(True)
         out = eng.classify_packed(blob, off, want_details=details)
-        counters = eng.stream.stats() if want_stats else None
+        counters = (eng.stream.stats(), eng.stream.stats_overflow()) if want_stats else None
         layout = eng.config.layout
     if details:
         return out[0], out[1], counters, layout
@@ -54,7 +54,7 @@ def compare(cfg, reads, want_stats=False, label=""):
         assert bad.size == 0, f"{label}: pass {p} score differs at {bad[0]}: {score[bad[0]]} vs {rp['score'][bad[0]]}"
     if want_stats:
         from bdx_b200.stats import stats_from_counters, stats_from_passes
-        got = stats_from_counters(counters, layout, cfg)
+        got = stats_from_counters(counters[0], layout, cfg, counters[1])
         passes = [[tuple(ref["passes"][i, p][k] for k in ("status", "bc", "start", "end", "score")) for p in (0, 1)]
                   for i in range(n)]
         want = stats_from_passes(ref["status"], ref["bc1"], ref["bc2"], passes, cfg)

@@ -344,3 +344,27 @@ def test_pool_dispatcher_order_and_stats(streams_per_device):
             pool.fetch()
         assert ei.value.code == capi.BDX_ERR_STATE
     config.close()
+
+
+@pytest.mark.parametrize("algo", ["semiglobal", "hamming"])
+@pytest.mark.parametrize("rng_expr,at_end", [("1:120", False), ("end-119:end", True), ("30:180", False)])
+def test_long_reads_short_search_ranges(algo, rng_expr, at_end):
+    """Nanopore-style input: reads of thousands of bases, barcode searched in a short range near one end.  The
+    shortcut kernels stage only the columns of the search range, so these reads take them too."""
+    rng = np.random.default_rng(len(rng_expr) * 31 + len(algo))
+    bcs = synth.random_barcodes(rng, 96, 24)
+    reads = []
+    for r in synth.random_reads(rng, 1200, bcs, min_len=100, max_len=118, start_hi=60):
+        pad = bytes(synth.BASES[rng.integers(0, 4, int(rng.integers(500, 4000)))])
+        reads.append(pad + r if at_end else r + pad)
+    for kw in (dict(), dict(trim_side=3 if at_end else 5, summary=True), dict(min_delta=0.09)):
+        cfg = _cfg(bcs, matching_algorithm=algo, ref_search_range=R(rng_expr), **kw)
+        compare(cfg, reads, want_stats=bool(kw.get("summary")), label=f"{algo} {rng_expr} {kw}")
+    # the reads really went through the shortcut stages
+    cfg = _cfg(bcs, matching_algorithm=algo, ref_search_range=R(rng_expr))
+    blob, off = bdx.pack_reads(reads)
+    with capi.Engine(cfg, max_reads=len(reads), max_bytes=int(off[-1])) as eng:
+        eng.classify_packed(blob, off)
+        pre, seed, auto = eng.stream.path_counters()
+        if algo == "semiglobal":
+            assert pre + seed > 0.4 * len(reads), (pre, seed, auto)   # ("30:180" cuts half of the planted barcodes)

@@ -1,5 +1,7 @@
 """Randomised differential fuzz: random option combinations (costs, thresholds, ranges,
 trims, algorithms, dual sets, N wildcards, odd alphabets) -- CUDA path vs oracle, bit-exact."""
+import os
+
 import numpy as np
 import pytest
 
@@ -9,6 +11,10 @@ from gpu_common import compare
 
 pytestmark = pytest.mark.gpu
 R = bdx.parse_dynamic_range
+
+
+# BDX_FUZZ_EXTRA=<n> adds n more seeds per algorithm (soak runs on the GPU box; the default stays short)
+_EXTRA = int(os.environ.get("BDX_FUZZ_EXTRA", "0"))
 
 
 def _range(rng, kind):
@@ -59,7 +65,7 @@ def _random_case(seed):
     return cfg, reads, want_stats
 
 
-@pytest.mark.parametrize("seed", range(80))
+@pytest.mark.parametrize("seed", list(range(80)) + list(range(3000, 3000 + _EXTRA)))
 def test_fuzz_random_config(seed):
     cfg, reads, want_stats = _random_case(1000 + seed)
     compare(cfg, reads, want_stats=want_stats, label=f"seed{seed}: {cfg.matching_algorithm}")
@@ -98,7 +104,7 @@ def _fast_case(seed, algo):
     return cfg, reads, bool(rng.random() < 0.3)
 
 
-@pytest.mark.parametrize("seed", range(40))
+@pytest.mark.parametrize("seed", list(range(40)) + list(range(1000, 1000 + _EXTRA)))
 @pytest.mark.parametrize("algo", ["semiglobal", "hamming"])
 def test_fuzz_shortcut_regimes(seed, algo):
     cfg, reads, want_stats = _fast_case(5000 + seed, algo)

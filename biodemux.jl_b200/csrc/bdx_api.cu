@@ -86,6 +86,8 @@ struct HostSet {
     };
     int sd_levels = 0, sd_m = 0;
     HostSeedLevel sd[2];
+    int sdd_n = 0, sdd_k = 0;      // deepest level (seed_deep.cu): one table per seed length
+    HostSeedLevel sdd[2];
 };
 
 struct DeviceTables {
@@ -316,6 +318,72 @@ static int build_set(const bdx_params &p, const bdx_barcode_set &in, HostSet &hs
                 for (auto &pr : buckets[k]) {
                     L.entries.push_back(pr.first);
                     L.ekeys.push_back(pr.second);
+                }
+            }
+        }
+    }
+    // ---- deepest seed level (seed_deep.cu): depth beyond the regular levels, each segment hashed with its own
+    // length.  Measured on B200: with 0.75 chance hits per column (96 x 24 nt at depth 4) it is slower than the
+    // bit-parallel kernel it would replace (17 vs 11.5 ms per 10 M-read step), so it is used while the hits
+    // stay rare (<= 0.25 per column) -- small sets, e.g. one adapter, whose alternative is k_literal ----
+    if (hs.sd_levels > 0 && !getenv("BDX_DISABLE_SEED_DEEP")) {
+        const int m = hs.max_m, allowed = hs.allowed0[0];
+        const double alpha = std::max(2, hs.n_classes - 1);
+        int KD = 0;
+        for (int k = hs.sd[hs.sd_levels - 1].k + 1; k <= std::min(allowed, 7); k++) {
+            const int n_seg = k + 1, base_len = m / n_seg, extra = m % n_seg;
+            if (base_len < 4) break;
+            double rate = 0.0;
+            for (int i = 0; i < n_seg; i++) rate += hs.n_bc / std::pow(alpha, std::min(base_len + (i < extra ? 1 : 0), 8));
+            if (rate <= 0.25) KD = k;
+        }
+        if (KD > 0) {
+            const int n_seg = KD + 1, base_len = m / n_seg, extra = m % n_seg;
+            const int q_long = std::min(base_len + 1, 8), q_short = std::min(base_len, 8);
+            hs.sdd_k = KD;
+            // table 0: the longer seeds (if any segment is longer and that changes the seed length), table 1 / 0: the rest
+            struct Seg { int off, q; };
+            std::vector<Seg> segs[2];
+            int o = 0;
+            for (int i = 0; i < n_seg; i++) {
+                const int len = base_len + (i < extra ? 1 : 0);
+                const int q = std::min(len, 8);
+                segs[(q == q_long && q_long != q_short) ? 0 : 1].push_back(Seg{o, q});
+                o += len;
+            }
+            for (int t = 0; t < 2; t++) {
+                if (segs[t].empty()) continue;
+                HostSet::HostSeedLevel &L = hs.sdd[hs.sdd_n++];
+                const int q = segs[t][0].q;
+                L.k = KD;
+                L.q = q;
+                uint32_t pw = 1;
+                for (int i = 1; i < q; i++) pw *= kPfBase;
+                L.pow = pw;
+                const size_t n_entries = (size_t)hs.n_bc * segs[t].size();
+                int lg = 8;
+                while (lg < 14 && (size_t)(1 << lg) < n_entries) lg++;
+                L.log2 = lg;
+                int bl = 13;
+                while (bl < 18 && ((size_t)1 << bl) < 64 * n_entries) bl++;
+                L.bm_log2 = bl;
+                L.bitmap.assign((size_t)1 << (bl - 5), 0u);
+                std::vector<std::vector<std::pair<uint32_t, uint32_t>>> buckets((size_t)1 << lg);
+                for (int b = 0; b < hs.n_bc; b++)
+                    for (const Seg &sg2 : segs[t]) {
+                        uint32_t h = 0;
+                        for (int k = 0; k < q; k++) h = h * kPfBase + (uint32_t)hs.bc_cls[hs.off[b] + sg2.off + k];
+                        const uint32_t bit = pf_bit(h, bl);
+                        L.bitmap[bit >> 5] |= 1u << (bit & 31);
+                        buckets[pf_slot(h, lg)].emplace_back(((uint32_t)b << 8) | (uint32_t)sg2.off, h);
+                    }
+                L.bstart.assign(((size_t)1 << lg) + 1, 0u);
+                for (size_t k = 0; k < buckets.size(); k++) {
+                    L.bstart[k + 1] = L.bstart[k] + (uint32_t)buckets[k].size();
+                    for (auto &pr : buckets[k]) {
+                        L.entries.push_back(pr.first);
+                        L.ekeys.push_back(pr.second);
+                    }
                 }
             }
         }
@@ -574,6 +642,22 @@ static int get_tables(bdx_config *cfg, int device, DeviceTables **out)
         for (int l = 0; l < hs.sd_levels; l++) {
             const HostSet::HostSeedLevel &H = hs.sd[l];
             SeedLevel &L = D.sd[l];
+            L.k = H.k;
+            L.q = H.q;
+            L.pow = H.pow;
+            L.log2 = H.log2;
+            L.bm_log2 = H.bm_log2;
+            L.n_entries = (int)H.entries.size();
+            if (e == cudaSuccess) e = upload(t, H.bstart, &L.bstart);
+            if (e == cudaSuccess) e = upload(t, H.entries, &L.entries);
+            if (e == cudaSuccess) e = upload(t, H.ekeys, &L.ekeys);
+            if (e == cudaSuccess) e = upload(t, H.bitmap, &L.bitmap);
+        }
+        D.sdd_n = hs.sdd_n;
+        D.sdd_k = hs.sdd_k;
+        for (int l = 0; l < hs.sdd_n; l++) {
+            const HostSet::HostSeedLevel &H = hs.sdd[l];
+            SeedLevel &L = D.sdd[l];
             L.k = H.k;
             L.q = H.q;
             L.pow = H.pow;
@@ -873,6 +957,14 @@ static int enqueue_classify(bdx_stream *s, const uint8_t *d_seq, const int32_t *
                     const bool to2 = wl != 2;
                     CU(launch_seed(P, pass, l, d_seq, d_off, n, s->sc, wl_in, n_in, to2 ? s->sc.worklist2 : s->sc.worklist,
                                    to2 ? s->sc.n_work2 : s->sc.n_work, s->tab->sm_count, s->d_counters, s->st_comp));
+                    s->launches++;
+                    wl = to2 ? 2 : 1;
+                }
+                if (levels > 0 && seed_deep_applies(P, pass)) {
+                    const bool to2 = wl != 2;
+                    CU(launch_seed_deep(P, pass, d_seq, d_off, n, s->sc, wl == 1 ? s->sc.worklist : s->sc.worklist2,
+                                        wl == 1 ? s->sc.n_work : s->sc.n_work2, to2 ? s->sc.worklist2 : s->sc.worklist,
+                                        to2 ? s->sc.n_work2 : s->sc.n_work, s->tab->sm_count, s->d_counters, s->st_comp));
                     s->launches++;
                     wl = to2 ? 2 : 1;
                 }

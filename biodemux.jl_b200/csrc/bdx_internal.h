@@ -99,6 +99,11 @@ struct DevSet {
     int sd_levels;                // 0 = off
     int sd_m;                     // the common barcode length
     SeedLevel sd[2];
+    // the deepest level (seed_deep.cu, k_seed_deep): depth sdd_k, segments hashed with their own length --
+    // one table per seed length (at most two)
+    int sdd_n;                    // 0 = off
+    int sdd_k;
+    SeedLevel sdd[2];
 };
 
 constexpr int kPfMaxSeed = 12;
@@ -173,6 +178,10 @@ cudaError_t launch_seed(const DevParams &P, int pass, int level, const uint8_t *
 // reads of a worklist that no kernel resolved: queue them for k_literal over every barcode
 cudaError_t launch_mark_pending(const DevParams &P, int pass, int n, const Scratch &sc, const int *wl, const int *n_wl,
                                 cudaStream_t st);
+bool seed_deep_applies(const DevParams &P, int pass);
+cudaError_t launch_seed_deep(const DevParams &P, int pass, const uint8_t *seq, const int *off, int n, const Scratch &sc,
+                             const int *wl_in, const int *n_in, int *wl_out, int *n_out, int sm_count,
+                             unsigned long long *counters, cudaStream_t st);
 cudaError_t launch_prefilter(const DevParams &P, int pass, const uint8_t *seq, const int *off, int n,
                              const Scratch &sc, int sm_count, unsigned long long *counters, cudaStream_t st);
 bool prefilter_applies(const DevParams &P, int pass);

@@ -141,13 +141,9 @@ cudaError_t launch_literal(const DevParams &P, int pass, int from_filter, const 
                                                            sc.cand_cnt, list, n_list);
     } else if (max_m <= 64) {
         const size_t smem = (size_t)2 * (64 + 2) * threads * sizeof(int);
-        static bool attr_set = false;
-        if (!attr_set) {
-            cudaError_t e = cudaFuncSetAttribute(k_literal<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                 (int)smem);
-            if (e != cudaSuccess) return e;
-            attr_set = true;
-        }
+        // per device (and cheap): a process-wide "done" flag would leave other GPUs of a bdx_pool without it
+        cudaError_t e = cudaFuncSetAttribute(k_literal<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
         k_literal<64, true><<<blocks, threads, smem, st>>>(P, pass, from_filter, seq, off, n, out, prev, sc.cand,
                                                            sc.cand_cnt, list, n_list);
     } else {

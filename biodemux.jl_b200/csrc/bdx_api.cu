@@ -329,13 +329,15 @@ static int build_set(const bdx_params &p, const bdx_barcode_set &in, HostSet &hs
     if (hs.sd_levels > 0 && !getenv("BDX_DISABLE_SEED_DEEP")) {
         const int m = hs.max_m, allowed = hs.allowed0[0];
         const double alpha = std::max(2, hs.n_classes - 1);
+        const char *dr = getenv("BDX_SEED_DEEP_RATE");      // experiments: chance hits per column the deep level accepts
+        const double deep_rate = dr ? atof(dr) : 0.25;
         int KD = 0;
         for (int k = hs.sd[hs.sd_levels - 1].k + 1; k <= std::min(allowed, 7); k++) {
             const int n_seg = k + 1, base_len = m / n_seg, extra = m % n_seg;
             if (base_len < 4) break;
             double rate = 0.0;
             for (int i = 0; i < n_seg; i++) rate += hs.n_bc / std::pow(alpha, std::min(base_len + (i < extra ? 1 : 0), 8));
-            if (rate <= 0.25) KD = k;
+            if (rate <= deep_rate) KD = k;
         }
         if (KD > 0) {
             const int n_seg = KD + 1, base_len = m / n_seg, extra = m % n_seg;

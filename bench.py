@@ -70,19 +70,21 @@ def numpy_reads(cfg, n, seed):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    """nvidia-smi clocks / throttle reasons during the timed regions (B200_PROFILING.md).  One nvidia-smi process
+    runs from before the warm-up (its start-up takes longer than a short timed region); only the samples that
+    arrive inside a marked window [begin(), end()] are kept."""
 
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
-        self.index, self.proc, self.lines = index, None, []
+        self.index, self.proc, self.lines, self.windows, self._t0 = index, None, [], [], None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._pump, daemon=True)
             self.t.start()
@@ -91,7 +93,15 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.perf_counter(), line.strip()))
+
+    def begin(self):
+        self._t0 = time.perf_counter()
+
+    def end(self):
+        if self._t0 is not None:
+            self.windows.append((self._t0, time.perf_counter()))
+            self._t0 = None
 
     def stop(self):
         if not self.proc:
@@ -103,7 +113,9 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons, power = [], [], set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        for ts, ln in self.lines:
+            if not any(a <= ts <= b for a, b in self.windows):
+                continue
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 7:
                 continue
@@ -115,7 +127,8 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(nm)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons),
+                "windows": "device-resident timed region + e2e timed region"}
 
 
 def oracle_rate(cfg, blob, off64, threads):
@@ -242,6 +255,9 @@ def run_ours(args):
     def step():
         stream.classify_device(d_seq.data_ptr(), d_off.data_ptr(), n, d_res.data_ptr())
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     # ---- device-resident: value + roofline of the dominant kernel -------------------------
     for _ in range(args.warmup):
         step()
@@ -249,9 +265,7 @@ def run_ours(args):
     peak_ops = capi.C.c_double()
     capi._check(stream.lib.bdx_int_alu_peak(local, capi.C.byref(peak_ops)))
     barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
+    sampler.begin()
     stream.profile(True)
     stream.path_counters(reset=True)
     l0 = stream.launch_count
@@ -262,13 +276,16 @@ def run_ours(args):
     e1.record(ext)
     stream.sync()
     barrier()
+    sampler.end()
     ms = e0.elapsed_time(e1)
     launches = stream.launch_count - l0
     filt_ms, filt_n = stream.profile_read()
     stream.profile(False)
     pre_reads, seed_reads, auto_reads = stream.path_counters(reset=True)
     auto_per_launch = auto_reads / max(filt_n, 1)       # reads that actually ran the DP automaton
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = None
+    if args.no_e2e and rank == 0:
+        clocks = sampler.stop()
     t = torch.tensor([ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -339,10 +356,14 @@ def run_ours(args):
     pcie_h2d_gbs = 4 * B * READ_LEN / (p0.elapsed_time(p1) * 1e-3) / 1e9
     del d_probe
     barrier()
+    sampler.begin()                           # second sampling window: the e2e timed region
     t0 = time.perf_counter()
     e2e_steps(args.steps)
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
+    sampler.end()
+    if rank == 0:
+        clocks = sampler.stop()
     t = torch.tensor([dt], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -279,7 +279,8 @@ def run_ours(args):
     sampler.end()
     ms = e0.elapsed_time(e1)
     launches = stream.launch_count - l0
-    filt_ms, filt_n = stream.profile_read()
+    stages = stream.profile_read_stages()
+    filt_ms, filt_n = stages["k_filter"]
     stream.profile(False)
     pre_reads, seed_reads, auto_reads = stream.path_counters(reset=True)
     auto_per_launch = auto_reads / max(filt_n, 1)       # reads that actually ran the DP automaton
@@ -424,6 +425,7 @@ def run_ours(args):
                                          "automaton read, profiles/r01d_kernels_ncu_summary.txt, x reads per launch here)",
                          "kernel": "k_filter<1,3>", "kernel_ms": filt_s * 1e3,
                          "kernel_share_of_step": filt_ms / ms if ms else None,
+                         "stage_ms_per_step": {k: v[0] / args.steps for k, v in stages.items() if v[1]},
                          "ops_per_read": OPS_PER_READ, "reads_through_automaton_per_launch": auto_per_launch,
                          "reads_resolved_by_prefilter_per_launch": pre_reads / max(filt_n, 1),
                          "reads_resolved_by_seed_kernel_per_launch": seed_reads / max(filt_n, 1),

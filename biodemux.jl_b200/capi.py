@@ -28,7 +28,7 @@ EXPORTS = [
     "bdx_stream_create", "bdx_stream_destroy", "bdx_submit", "bdx_acquire", "bdx_commit",
     "bdx_submit_pinned", "bdx_host_alloc", "bdx_host_free", "bdx_stream_enable_details",
     "bdx_fetch", "bdx_fetch_view", "bdx_classify", "bdx_classify_device", "bdx_stream_sync",
-    "bdx_stream_cuda_stream", "bdx_stream_launch_count", "bdx_stream_profile", "bdx_stream_profile_read", "bdx_stream_path_counters", "bdx_stats_layout_get", "bdx_stats_fetch",
+    "bdx_stream_cuda_stream", "bdx_stream_launch_count", "bdx_stream_profile", "bdx_stream_profile_read", "bdx_stream_profile_read_stages", "bdx_stream_path_counters", "bdx_stats_layout_get", "bdx_stats_fetch",
     "bdx_stats_device_ptr", "bdx_stats_reset", "bdx_synth_reads_device", "bdx_int_alu_peak",
     "bdx_fastq_scan", "bdx_fastq_pack", "bdx_demux_block", "bdx_demux_stage_ms",
     "bdx_barcode_table_load", "bdx_barcode_table_destroy", "bdx_barcode_table_count", "bdx_barcode_table_id_count",
@@ -143,6 +143,7 @@ def load_library():
     L.bdx_stream_launch_count.restype = i64
     L.bdx_stream_profile.argtypes = [vp, C.c_int]
     L.bdx_stream_profile_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(i32)]
+    L.bdx_stream_profile_read_stages.argtypes = [vp, C.POINTER(C.c_double * 8), C.POINTER(i32 * 8)]
     L.bdx_stream_path_counters.argtypes = [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64), C.c_int]
     L.bdx_stats_layout_get.argtypes = [vp, C.POINTER(StatsLayout)]
     L.bdx_stats_fetch.argtypes = [vp, vp, i64]
@@ -393,6 +394,14 @@ class Stream:
         ms, n = C.c_double(), C.c_int32()
         _check(self.lib.bdx_stream_profile_read(self.handle, C.byref(ms), C.byref(n)))
         return ms.value, n.value
+
+    STAGES = ("k_prefilter", "k_seed", "k_seed_deep", "k_filter", "k_literal", "k_hamming_scan", "k_finalize", "other")
+
+    def profile_read_stages(self):
+        """{stage: (summed ms, launches)} of the launches profiled since the last read."""
+        ms, n = (C.c_double * 8)(), (C.c_int32 * 8)()
+        _check(self.lib.bdx_stream_profile_read_stages(self.handle, C.byref(ms), C.byref(n)))
+        return {name: (ms[k], n[k]) for k, name in enumerate(self.STAGES)}
 
     def path_counters(self, reset: bool = False):
         """(reads resolved by the perfect-occurrence prefilter, by the seed-and-verify kernel,

@@ -728,6 +728,14 @@ struct Slot {
     bool busy = false;
 };
 
+// stage of a profiled kernel launch (bdx_stream_profile_read_stages)
+enum { kStPrefilter = 0, kStSeed = 1, kStSeedDeep = 2, kStFilter = 3, kStLiteral = 4, kStHamming = 5, kStFinalize = 6,
+       kStOther = 7 };
+struct ProfEvent {
+    int kind;
+    cudaEvent_t e0, e1;
+};
+
 struct bdx_stream {
     bdx_config *cfg = nullptr;
     DeviceTables *tab = nullptr;
@@ -752,7 +760,7 @@ struct bdx_stream {
     int64_t launches = 0;
     // optional per-kernel timing of the dominant (filter) kernel, for roofline reporting
     bool profile = false;
-    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
+    std::vector<ProfEvent> prof_events;
     DemuxState *demux = nullptr;               // device FASTQ block demultiplexer (demux.cu), created on first use
 };
 
@@ -827,8 +835,8 @@ extern "C" void bdx_stream_destroy(bdx_stream *s)
     cudaFree(s->d_counters);
     demux_state_destroy(s->demux);
     for (auto &pr : s->prof_events) {
-        cudaEventDestroy(pr.first);
-        cudaEventDestroy(pr.second);
+        cudaEventDestroy(pr.e0);
+        cudaEventDestroy(pr.e1);
     }
     if (s->st_copy) cudaStreamDestroy(s->st_copy);
     if (s->st_comp) cudaStreamDestroy(s->st_comp);
@@ -920,33 +928,43 @@ static int enqueue_classify(bdx_stream *s, const uint8_t *d_seq, const int32_t *
     if (n == 0) return BDX_OK;
     int rc = ensure_scratch(s, n);
     if (rc) return rc;
+    // every kernel launch goes through here: counted, and bracketed by CUDA events while profiling is on
+    auto staged = [s](int kind, auto &&launch) -> int {
+        cudaEvent_t e0 = nullptr, e1 = nullptr;
+        if (s->profile) {
+            CU(cudaEventCreate(&e0));
+            CU(cudaEventCreate(&e1));
+            CU(cudaEventRecord(e0, s->st_comp));
+        }
+        const cudaError_t e = launch();
+        if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
+        s->launches++;
+        if (s->profile) {
+            CU(cudaEventRecord(e1, s->st_comp));
+            s->prof_events.push_back(ProfEvent{kind, e0, e1});
+        }
+        return BDX_OK;
+    };
     const DevParams &P = s->tab->P;
     const int passes = P.is_dual ? 2 : 1;
     for (int pass = 0; pass < passes; pass++) {
         if (hamming_packed_applies(P, pass)) {
             // :hamming -- packed pigeonhole scan over every start position, then the literal rules on the candidates
-            CU(launch_hamming_scan(P, pass, d_seq, d_off, n, s->sc, s->tab->sm_count, s->st_comp));
-            s->launches++;
-            CU(launch_literal(P, pass, 1, d_seq, d_off, n, s->sc, s->st_comp));
-            s->launches++;
+            if ((rc = staged(kStHamming, [&] { return launch_hamming_scan(P, pass, d_seq, d_off, n, s->sc, s->tab->sm_count, s->st_comp); }))) return rc;
+            if ((rc = staged(kStLiteral, [&] { return launch_literal(P, pass, 1, d_seq, d_off, n, s->sc, s->st_comp); }))) return rc;
         } else if (hamming_seed_applies(P, pass)) {
             // :hamming -- pigeonhole seeds + in-place verification, then the literal rules on the candidates
-            CU(launch_seed_hamming(P, pass, d_seq, d_off, n, s->sc, s->tab->sm_count, s->st_comp));
-            s->launches++;
-            CU(launch_literal(P, pass, 1, d_seq, d_off, n, s->sc, s->st_comp));
-            s->launches++;
+            if ((rc = staged(kStHamming, [&] { return launch_seed_hamming(P, pass, d_seq, d_off, n, s->sc, s->tab->sm_count, s->st_comp); }))) return rc;
+            if ((rc = staged(kStLiteral, [&] { return launch_literal(P, pass, 1, d_seq, d_off, n, s->sc, s->st_comp); }))) return rc;
         } else if (exact_hash_applies(P, pass)) {
             // :exact -- rolling-hash candidate generation, then the literal rules on the candidates
-            CU(launch_prefilter(P, pass, d_seq, d_off, n, s->sc, s->tab->sm_count, s->d_counters, s->st_comp));
-            s->launches++;
-            CU(launch_literal(P, pass, 1, d_seq, d_off, n, s->sc, s->st_comp));
-            s->launches++;
+            if ((rc = staged(kStPrefilter, [&] { return launch_prefilter(P, pass, d_seq, d_off, n, s->sc, s->tab->sm_count, s->d_counters, s->st_comp); }))) return rc;
+            if ((rc = staged(kStLiteral, [&] { return launch_literal(P, pass, 1, d_seq, d_off, n, s->sc, s->st_comp); }))) return rc;
         } else if (P.set[pass].words > 0) {
             const bool pre = prefilter_applies(P, pass);
             CU(cudaMemsetAsync(s->sc.n_lit, 0, 2 * sizeof(int), s->st_comp));   // k_literal's two read lists
             if (pre) {
-                CU(launch_prefilter(P, pass, d_seq, d_off, n, s->sc, s->tab->sm_count, s->d_counters, s->st_comp));
-                s->launches++;
+                if ((rc = staged(kStPrefilter, [&] { return launch_prefilter(P, pass, d_seq, d_off, n, s->sc, s->tab->sm_count, s->d_counters, s->st_comp); }))) return rc;
             }
             int wl = pre ? 1 : 0;
             {
@@ -957,49 +975,33 @@ static int enqueue_classify(bdx_stream *s, const uint8_t *d_seq, const int32_t *
                     const int *wl_in = wl == 0 ? nullptr : (wl == 1 ? s->sc.worklist : s->sc.worklist2);
                     const int *n_in = wl == 0 ? nullptr : (wl == 1 ? s->sc.n_work : s->sc.n_work2);
                     const bool to2 = wl != 2;
-                    CU(launch_seed(P, pass, l, d_seq, d_off, n, s->sc, wl_in, n_in, to2 ? s->sc.worklist2 : s->sc.worklist,
-                                   to2 ? s->sc.n_work2 : s->sc.n_work, s->tab->sm_count, s->d_counters, s->st_comp));
-                    s->launches++;
+                    if ((rc = staged(kStSeed, [&] { return launch_seed(P, pass, l, d_seq, d_off, n, s->sc, wl_in, n_in, to2 ? s->sc.worklist2 : s->sc.worklist,
+                                   to2 ? s->sc.n_work2 : s->sc.n_work, s->tab->sm_count, s->d_counters, s->st_comp); }))) return rc;
                     wl = to2 ? 2 : 1;
                 }
                 if (levels > 0 && seed_deep_applies(P, pass)) {
                     const bool to2 = wl != 2;
-                    CU(launch_seed_deep(P, pass, d_seq, d_off, n, s->sc, wl == 1 ? s->sc.worklist : s->sc.worklist2,
+                    if ((rc = staged(kStSeedDeep, [&] { return launch_seed_deep(P, pass, d_seq, d_off, n, s->sc, wl == 1 ? s->sc.worklist : s->sc.worklist2,
                                         wl == 1 ? s->sc.n_work : s->sc.n_work2, to2 ? s->sc.worklist2 : s->sc.worklist,
-                                        to2 ? s->sc.n_work2 : s->sc.n_work, s->tab->sm_count, s->d_counters, s->st_comp));
-                    s->launches++;
+                                        to2 ? s->sc.n_work2 : s->sc.n_work, s->tab->sm_count, s->d_counters, s->st_comp); }))) return rc;
                     wl = to2 ? 2 : 1;
                 }
             }
             if (!P.set[pass].use_filter) {
                 // tiny set: no filter kernel.  What the shortcut stages left goes to k_literal over every barcode.
                 if (wl == 0) {
-                    CU(launch_literal(P, pass, 0, d_seq, d_off, n, s->sc, s->st_comp));
+                    if ((rc = staged(kStLiteral, [&] { return launch_literal(P, pass, 0, d_seq, d_off, n, s->sc, s->st_comp); }))) return rc;
                 } else {
                     const int *rest = wl == 1 ? s->sc.worklist : s->sc.worklist2;
                     const int *n_rest = wl == 1 ? s->sc.n_work : s->sc.n_work2;
-                    CU(launch_mark_pending(P, pass, n, s->sc, rest, n_rest, s->st_comp));
-                    s->launches++;
+                    if ((rc = staged(kStOther, [&] { return launch_mark_pending(P, pass, n, s->sc, rest, n_rest, s->st_comp); }))) return rc;
                     // seed winners (windowed) and the scan-everything rest as separate, compacted launches
-                    CU(launch_literal(P, pass, 1, d_seq, d_off, n, s->sc, s->st_comp, s->sc.wl_win, s->sc.n_lit));
-                    s->launches++;
-                    CU(launch_literal(P, pass, 1, d_seq, d_off, n, s->sc, s->st_comp, rest, n_rest));
+                    if ((rc = staged(kStLiteral, [&] { return launch_literal(P, pass, 1, d_seq, d_off, n, s->sc, s->st_comp, s->sc.wl_win, s->sc.n_lit); }))) return rc;
+                    if ((rc = staged(kStLiteral, [&] { return launch_literal(P, pass, 1, d_seq, d_off, n, s->sc, s->st_comp, rest, n_rest); }))) return rc;
                 }
-                s->launches++;
                 continue;
             }
-            cudaEvent_t e0 = nullptr, e1 = nullptr;
-            if (s->profile) {
-                CU(cudaEventCreate(&e0));
-                CU(cudaEventCreate(&e1));
-                CU(cudaEventRecord(e0, s->st_comp));
-            }
-            CU(launch_filter(P, pass, d_seq, d_off, n, s->sc, s->tab->sm_count, s->d_counters, wl, s->st_comp));
-            s->launches++;
-            if (s->profile) {
-                CU(cudaEventRecord(e1, s->st_comp));
-                s->prof_events.emplace_back(e0, e1);
-            }
+            if ((rc = staged(kStFilter, [&] { return launch_filter(P, pass, d_seq, d_off, n, s->sc, s->tab->sm_count, s->d_counters, wl, s->st_comp); }))) return rc;
             // the exact regime finishes inside the filter kernel; anything else leaves
             // kBcPending reads with candidate lists for the literal kernel
             const bool may_finish = P.algo == BDX_SEMIGLOBAL && P.unit_costs && P.set[pass].trim_side == 0 &&
@@ -1011,20 +1013,16 @@ static int enqueue_classify(bdx_stream *s, const uint8_t *d_seq, const int32_t *
                 // seed winners (windowed DP) and k_filter's candidate reads as separate, compacted launches:
                 // a warp costs as much as its most expensive lane
                 if (wl != 0 && seed_levels(P, pass) > 0) {
-                    CU(launch_literal(P, pass, 1, d_seq, d_off, n, s->sc, s->st_comp, s->sc.wl_win, s->sc.n_lit));
-                    s->launches++;
+                    if ((rc = staged(kStLiteral, [&] { return launch_literal(P, pass, 1, d_seq, d_off, n, s->sc, s->st_comp, s->sc.wl_win, s->sc.n_lit); }))) return rc;
                 }
-                CU(launch_literal(P, pass, 1, d_seq, d_off, n, s->sc, s->st_comp, s->sc.wl_full, s->sc.n_lit + 1));
-                s->launches++;
+                if ((rc = staged(kStLiteral, [&] { return launch_literal(P, pass, 1, d_seq, d_off, n, s->sc, s->st_comp, s->sc.wl_full, s->sc.n_lit + 1); }))) return rc;
             }
         } else {
-            CU(launch_literal(P, pass, 0, d_seq, d_off, n, s->sc, s->st_comp));
-            s->launches++;
+            if ((rc = staged(kStLiteral, [&] { return launch_literal(P, pass, 0, d_seq, d_off, n, s->sc, s->st_comp); }))) return rc;
         }
     }
     StatsDev sd{s->d_stats, s->cfg->lay, s->d_ovf, s->d_n_ovf};
-    CU(launch_finalize(P, d_off, n, s->sc, d_res, d_det, sd, s->st_comp));
-    s->launches++;
+    if ((rc = staged(kStFinalize, [&] { return launch_finalize(P, d_off, n, s->sc, d_res, d_det, sd, s->st_comp); }))) return rc;
     return BDX_OK;
 }
 
@@ -1210,22 +1208,36 @@ extern "C" int bdx_stream_profile(bdx_stream *s, int on)
     return BDX_OK;
 }
 
+extern "C" int bdx_stream_profile_read_stages(bdx_stream *s, double ms[BDX_PROFILE_STAGES], int32_t n_launches[BDX_PROFILE_STAGES])
+{
+    if (!s || !ms || !n_launches) return fail(BDX_ERR_INVALID, "null argument");
+    CU(cudaSetDevice(s->device));
+    CU(cudaStreamSynchronize(s->st_comp));
+    for (int k = 0; k < BDX_PROFILE_STAGES; k++) {
+        ms[k] = 0.0;
+        n_launches[k] = 0;
+    }
+    for (auto &pr : s->prof_events) {
+        float t = 0.f;
+        CU(cudaEventElapsedTime(&t, pr.e0, pr.e1));
+        ms[pr.kind] += t;
+        n_launches[pr.kind]++;
+        cudaEventDestroy(pr.e0);
+        cudaEventDestroy(pr.e1);
+    }
+    s->prof_events.clear();
+    return BDX_OK;
+}
+
 extern "C" int bdx_stream_profile_read(bdx_stream *s, double *filter_ms, int32_t *n_launches)
 {
     if (!s || !filter_ms || !n_launches) return fail(BDX_ERR_INVALID, "null argument");
-    CU(cudaSetDevice(s->device));
-    CU(cudaStreamSynchronize(s->st_comp));
-    double total = 0.0;
-    for (auto &pr : s->prof_events) {
-        float ms = 0.f;
-        CU(cudaEventElapsedTime(&ms, pr.first, pr.second));
-        total += ms;
-        cudaEventDestroy(pr.first);
-        cudaEventDestroy(pr.second);
-    }
-    *filter_ms = total;
-    *n_launches = (int32_t)s->prof_events.size();
-    s->prof_events.clear();
+    double ms[BDX_PROFILE_STAGES];
+    int32_t nl[BDX_PROFILE_STAGES];
+    const int rc = bdx_stream_profile_read_stages(s, ms, nl);
+    if (rc) return rc;
+    *filter_ms = ms[kStFilter];
+    *n_launches = nl[kStFilter];
     return BDX_OK;
 }
 

@@ -191,6 +191,11 @@ void *bdx_stream_cuda_stream(bdx_stream *s);
  * since the last read, and clears the list. */
 int bdx_stream_profile(bdx_stream *s, int on);
 int bdx_stream_profile_read(bdx_stream *s, double *filter_ms, int32_t *n_launches);
+/* The same for every stage: summed milliseconds and launch counts since the last read, indexed
+ * [0] k_prefilter [1] k_seed [2] k_seed_deep [3] k_filter [4] k_literal [5] k_hamming_scan / k_seed_hamming
+ * [6] k_finalize [7] other.  Clears the list like bdx_stream_profile_read (use one or the other). */
+#define BDX_PROFILE_STAGES 8
+int bdx_stream_profile_read_stages(bdx_stream *s, double ms[BDX_PROFILE_STAGES], int32_t n_launches[BDX_PROFILE_STAGES]);
 /* How many reads (summed over passes) were resolved by the perfect-occurrence prefilter, by the
  * depth-limited seed-and-verify kernel, and how many ran the full-range bit-parallel automaton
  * since the last reset (syncs the stream). */

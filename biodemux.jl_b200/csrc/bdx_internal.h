@@ -163,6 +163,11 @@ struct Scratch {
     int *n_lit;           // [2] lengths of wl_win, wl_full
 };
 
+// Resident blocks per SM of `kern` with `threads` threads and `smem` bytes of dynamic shared memory on the
+// current device; raises the kernel's dynamic shared-memory limit on first use.  Cached per (device, kernel,
+// threads, smem): the two runtime queries cost microseconds each, which adds up for 4000-read batches.
+cudaError_t blocks_per_sm_cached(const void *kern, int threads, size_t smem, int *per_sm);
+
 // ---- launch wrappers (kernels.cu / filter.cu) ----
 cudaError_t launch_literal(const DevParams &P, int pass, int from_filter, const uint8_t *seq,
                            const int *off, int n, const Scratch &sc, cudaStream_t st, const int *list = nullptr,

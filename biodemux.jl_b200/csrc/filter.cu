@@ -650,12 +650,9 @@ cudaError_t launch_prefilter(const DevParams &P, int pass, const uint8_t *seq, c
     const DevSet &S = P.set[pass];
     const size_t smem = kPfStageBytes + 16 + ((size_t)8 << S.pf_log2) + ((size_t)4 << (S.pf_bm_log2 - 5));
     auto kern = P.algo == BDX_EXACT ? k_prefilter<1> : (P.algo == BDX_HAMMING ? k_prefilter<2> : k_prefilter<0>);
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
     int per_sm = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kPfThreads, smem);
+    cudaError_t e = blocks_per_sm_cached((const void *)kern, kPfThreads, smem, &per_sm);
     if (e != cudaSuccess) return e;
-    if (per_sm < 1) per_sm = 1;
     const int groups = (n + kPfThreads - 1) / kPfThreads;
     const int blocks = std::min(groups, sm_count * per_sm);
     e = cudaMemsetAsync(sc.n_work, 0, sizeof(int), st);
@@ -799,12 +796,9 @@ cudaError_t launch_seed_hamming(const DevParams &P, int pass, const uint8_t *seq
 {
     const DevSet &S = P.set[pass];
     const size_t smem = seed_hamming_smem(S);
-    cudaError_t e = cudaFuncSetAttribute(k_seed_hamming, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
     int per_sm = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_seed_hamming, kPfThreads, smem);
+    cudaError_t e = blocks_per_sm_cached((const void *)k_seed_hamming, kPfThreads, smem, &per_sm);
     if (e != cudaSuccess) return e;
-    if (per_sm < 1) per_sm = 1;
     const int groups = (n + kPfThreads - 1) / kPfThreads;
     const int blocks = std::min(groups, sm_count * per_sm);
     k_seed_hamming<<<blocks, kPfThreads, smem, st>>>(P, pass, seq, off, n, sc.pass[pass], sc.pass[0], sc.cand,
@@ -858,12 +852,9 @@ static cudaError_t launch_wgv(const DevParams &P, int pass, const uint8_t *seq, 
 {
     const size_t smem = filter_smem_bytes(P.set[pass]);
     auto kern = k_filter<W, G, CODING, PAIR>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
     int per_sm = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kFilterWarps * 32, smem);
+    cudaError_t e = blocks_per_sm_cached((const void *)kern, kFilterWarps * 32, smem, &per_sm);
     if (e != cudaSuccess) return e;
-    if (per_sm < 1) per_sm = 1;
     // persistent grid: a whole number of resident blocks per SM, capped by the work
     long long blocks = (long long)sm_count * per_sm;
     const long long need = ((long long)n + kFilterWarps - 1) / kFilterWarps;

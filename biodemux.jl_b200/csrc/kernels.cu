@@ -2,6 +2,9 @@
 // finalisation + DemuxStats counters, synthetic read generator, integer-ALU peak
 // microbenchmark.  sm_100a only.
 #include <algorithm>
+#include <map>
+#include <mutex>
+#include <tuple>
 #include <cstdio>
 #include <math_constants.h>
 
@@ -9,6 +12,44 @@
 #include "literal.cuh"
 
 namespace bdx {
+
+cudaError_t blocks_per_sm_cached(const void *kern, int threads, size_t smem, int *per_sm)
+{
+    static std::mutex mu;
+    static std::map<std::tuple<int, const void *, int, size_t>, int> occupancy;
+    static std::map<std::pair<int, const void *>, bool> limit_raised;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    const auto key = std::make_tuple(dev, kern, threads, smem);
+    bool raised;
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        auto it = occupancy.find(key);
+        if (it != occupancy.end()) {
+            *per_sm = it->second;
+            return cudaSuccess;
+        }
+        raised = limit_raised.count({dev, kern}) != 0;
+    }
+    if (!raised) {
+        // once per device and kernel, to the device maximum: configs with different table sizes share kernels
+        int optin = 0;
+        e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
+        if (e != cudaSuccess) return e;
+    }
+    int n = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, threads, smem);
+    if (e != cudaSuccess) return e;
+    if (n < 1) n = 1;
+    std::lock_guard<std::mutex> lk(mu);
+    limit_raised[{dev, kern}] = true;
+    occupancy[key] = n;
+    *per_sm = n;
+    return cudaSuccess;
+}
 
 // ---------------------------------------------------------------------------
 // k_literal: one thread per read walks barcodes in file order under the running
@@ -141,8 +182,8 @@ cudaError_t launch_literal(const DevParams &P, int pass, int from_filter, const 
                                                            sc.cand_cnt, list, n_list);
     } else if (max_m <= 64) {
         const size_t smem = (size_t)2 * (64 + 2) * threads * sizeof(int);
-        // per device (and cheap): a process-wide "done" flag would leave other GPUs of a bdx_pool without it
-        cudaError_t e = cudaFuncSetAttribute(k_literal<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        int unused = 0;     // raises the dynamic shared-memory limit once per device
+        cudaError_t e = blocks_per_sm_cached((const void *)k_literal<64, true>, threads, smem, &unused);
         if (e != cudaSuccess) return e;
         k_literal<64, true><<<blocks, threads, smem, st>>>(P, pass, from_filter, seq, off, n, out, prev, sc.cand,
                                                            sc.cand_cnt, list, n_list);

@@ -359,12 +359,9 @@ cudaError_t launch_seed(const DevParams &P, int pass, int level, const uint8_t *
     const bool tab = seed_tab_in_smem(S, L);
     const size_t smem = seed_smem(S, L, tab);
     auto kern = S.words == 1 ? (tab ? k_seed<true, 1> : k_seed<false, 1>) : (tab ? k_seed<true, 2> : k_seed<false, 2>);
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
     int per_sm = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kSeedThreads, smem);
+    cudaError_t e = blocks_per_sm_cached((const void *)kern, kSeedThreads, smem, &per_sm);
     if (e != cudaSuccess) return e;
-    if (per_sm < 1) per_sm = 1;
     const int groups = (n + kSeedThreads - 1) / kSeedThreads;     // upper bound: the worklist is <= n
     const int blocks = std::max(1, std::min(groups, sm_count * per_sm));
     e = cudaMemsetAsync(n_out, 0, sizeof(int), st);

@@ -304,12 +304,9 @@ cudaError_t launch_seed_deep(const DevParams &P, int pass, const uint8_t *seq, c
     const DevSet &S = P.set[pass];
     const size_t smem = deep_smem(S);
     auto kern = S.words == 1 ? k_seed_deep<1> : k_seed_deep<2>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
     int per_sm = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kSeedThreads, smem);
+    cudaError_t e = blocks_per_sm_cached((const void *)kern, kSeedThreads, smem, &per_sm);
     if (e != cudaSuccess) return e;
-    if (per_sm < 1) per_sm = 1;
     const int groups = (n + kSeedThreads - 1) / kSeedThreads;
     const int blocks = std::max(1, std::min(groups, sm_count * per_sm));
     e = cudaMemsetAsync(n_out, 0, sizeof(int), st);

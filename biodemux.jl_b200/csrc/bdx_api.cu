@@ -726,6 +726,13 @@ struct Slot {
     int32_t n = 0;
     uint64_t tag = 0;
     bool busy = false;
+    // the kernel sequence of a batch of graph_n reads on this slot's buffers, captured as a CUDA graph: small
+    // batches (the reference's 4000-read chunks) are bound by launch gaps, not by the kernels
+    cudaGraphExec_t graph = nullptr;
+    int32_t graph_n = -1;         // batch size the graph was captured for
+    bool graph_details = false;
+    int graph_launches = 0;       // kernel launches it holds
+    int uses = 0;                 // plain runs of this slot so far (the first warms the launch caches)
 };
 
 // stage of a profiled kernel launch (bdx_stream_profile_read_stages)
@@ -760,6 +767,7 @@ struct bdx_stream {
     int64_t launches = 0;
     // optional per-kernel timing of the dominant (filter) kernel, for roofline reporting
     bool profile = false;
+    bool graphs_ok = true;                     // cleared when a capture fails: plain launches from then on
     std::vector<ProfEvent> prof_events;
     DemuxState *demux = nullptr;               // device FASTQ block demultiplexer (demux.cu), created on first use
 };
@@ -817,6 +825,7 @@ extern "C" void bdx_stream_destroy(bdx_stream *s)
         if (sl.ev_h2d) cudaEventDestroy(sl.ev_h2d);
         if (sl.ev_kern) cudaEventDestroy(sl.ev_kern);
         if (sl.ev_done) cudaEventDestroy(sl.ev_done);
+        if (sl.graph) cudaGraphExecDestroy(sl.graph);
     }
     cudaFree(s->sc.pass[0]);
     cudaFree(s->sc.pass[1]);
@@ -1026,6 +1035,59 @@ static int enqueue_classify(bdx_stream *s, const uint8_t *d_seq, const int32_t *
     return BDX_OK;
 }
 
+// The kernels of one staged batch.  Batches up to kGraphMaxReads reads replay a CUDA graph captured on the
+// slot's second use with that size (the first use runs plainly and warms the per-kernel launch caches, so the
+// capture holds stream operations only); anything else -- other sizes, profiling, a failed capture -- launches
+// the kernels one by one.
+constexpr int32_t kGraphMaxReads = 100000;
+
+static int enqueue_batch(bdx_stream *s, Slot &sl)
+{
+    static const bool graphs_off = getenv("BDX_DISABLE_GRAPHS") != nullptr;
+    const int32_t n = sl.n;
+    bdx_pass_detail *det = s->details ? sl.d_det : nullptr;
+    const bool eligible = !graphs_off && s->graphs_ok && !s->profile && n > 0 && n <= kGraphMaxReads;
+    if (eligible && sl.graph && sl.graph_n == n && sl.graph_details == s->details) {
+        CU(cudaGraphLaunch(sl.graph, s->st_comp));
+        s->launches += sl.graph_launches;
+        return BDX_OK;
+    }
+    if (eligible && sl.uses >= 1 && n == s->max_reads) {          // full-size chunks are the ones that repeat
+        int rc = ensure_scratch(s, n);                            // allocation is not capturable
+        if (rc) return rc;
+        if (sl.graph) {
+            cudaGraphExecDestroy(sl.graph);
+            sl.graph = nullptr;
+        }
+        const int64_t l0 = s->launches;
+        cudaGraph_t g = nullptr;
+        bool ok = cudaStreamBeginCapture(s->st_comp, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+        if (ok) {
+            rc = enqueue_classify(s, sl.d_seq, sl.d_off, n, sl.d_res, det);
+            const cudaError_t ce = cudaStreamEndCapture(s->st_comp, &g);
+            ok = rc == BDX_OK && ce == cudaSuccess && g != nullptr;
+        }
+        if (ok) ok = cudaGraphInstantiate(&sl.graph, g, 0) == cudaSuccess;
+        if (g) cudaGraphDestroy(g);
+        if (ok) {
+            sl.graph_n = n;
+            sl.graph_details = s->details;
+            sl.graph_launches = (int)(s->launches - l0);
+            s->launches = l0;
+            CU(cudaGraphLaunch(sl.graph, s->st_comp));
+            s->launches += sl.graph_launches;
+            return BDX_OK;
+        }
+        // capture failed: clear the error state and never try again on this stream
+        cudaGetLastError();
+        s->launches = l0;
+        sl.graph = nullptr;
+        s->graphs_ok = false;
+    }
+    sl.uses++;
+    return enqueue_classify(s, sl.d_seq, sl.d_off, n, sl.d_res, det);
+}
+
 static int launch_slot(bdx_stream *s, Slot &sl, const uint8_t *h_seq, const int32_t *h_off)
 {
     CU(cudaSetDevice(s->device));
@@ -1037,7 +1099,7 @@ static int launch_slot(bdx_stream *s, Slot &sl, const uint8_t *h_seq, const int3
     }
     CU(cudaEventRecord(sl.ev_h2d, s->st_copy));
     CU(cudaStreamWaitEvent(s->st_comp, sl.ev_h2d, 0));
-    int rc = enqueue_classify(s, sl.d_seq, sl.d_off, n, sl.d_res, s->details ? sl.d_det : nullptr);
+    int rc = enqueue_batch(s, sl);
     if (rc) return rc;
     CU(cudaEventRecord(sl.ev_kern, s->st_comp));
     CU(cudaStreamWaitEvent(s->st_d2h, sl.ev_kern, 0));

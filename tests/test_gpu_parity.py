@@ -368,3 +368,38 @@ def test_long_reads_short_search_ranges(algo, rng_expr, at_end):
         pre, seed, auto = eng.stream.path_counters()
         if algo == "semiglobal":
             assert pre + seed > 0.4 * len(reads), (pre, seed, auto)   # ("30:180" cuts half of the planted barcodes)
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(trim_side=5, summary=True), dict(min_delta=0.1),
+                                dict(matching_algorithm="hamming")])
+def test_graph_replay_of_small_batches(kw):
+    """Full-size chunks on a stream replay a captured CUDA graph from the slot's second use on: 24 chunks of 512
+    reads through 4 slots must equal one big batch (never captured) read for read, stats included."""
+    rng = np.random.default_rng(77)
+    bcs = synth.random_barcodes(rng, 96, 24)
+    cfg = _cfg(bcs, **kw)
+    B, nb = 512, 24
+    reads = synth.random_reads(rng, B * nb, bcs, min_len=150)
+    blob, off = bdx.pack_reads(reads)
+    with capi.Engine(cfg, max_reads=B * nb + 1, max_bytes=int(off[-1]) + 16) as big:
+        want = big.classify_packed(blob, off)
+        want_stats = big.stream.stats() if kw.get("summary") else None
+    sub_off = np.ascontiguousarray(off[:B + 1])
+    with capi.Engine(cfg, max_reads=B, max_bytes=B * 150) as eng:
+        st, got, q = eng.stream, [], 0
+        l0 = st.launch_count
+        for k in range(nb):
+            st.submit(blob[k * B * 150:(k + 1) * B * 150], sub_off, tag=k)
+            q += 1
+            if q == 4:
+                got.append(st.fetch()[1])
+                q -= 1
+        while q:
+            got.append(st.fetch()[1])
+            q -= 1
+        assert st.launch_count - l0 >= nb * 2
+        res = np.concatenate(got)
+        for f in ("status", "bc1", "bc2", "keep_start", "keep_end"):
+            assert (res[f] == want[f]).all(), f
+        if want_stats is not None:
+            assert (st.stats() == want_stats).all()

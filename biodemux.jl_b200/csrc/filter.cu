@@ -832,8 +832,10 @@ bool prefilter_applies(const DevParams &P, int pass)
         return S.use_filter && S.pf_enabled && P.min_delta == 0.0 && P.max_error_rate >= 0.0;
     // :semiglobal -- with trimming / stats the resolved reads also need positions: a verbatim occurrence has
     // them (k_prefilter), a seed-resolved read gets them from k_literal run on its single winning barcode
-    return P.algo == BDX_SEMIGLOBAL && S.words > 0 && S.pf_enabled && P.unit_costs && P.min_delta == 0.0 &&
-           P.max_error_rate >= 0.0;
+    // Any positive edit costs will do (match = 0): a verbatim occurrence is the only way to score 0, whatever a
+    // mismatch or a gap costs, and score 0 beats every other barcode under the strict "<" of :658.
+    return P.algo == BDX_SEMIGLOBAL && S.words > 0 && S.pf_enabled && P.match == 0 && P.mismatch >= 1 && P.indel >= 1 &&
+           P.min_delta == 0.0 && P.max_error_rate >= 0.0;
 }
 
 static size_t filter_smem_bytes(const DevSet &S)

@@ -93,6 +93,8 @@ CONFIGS = {
     "delta_trim_stats": dict(n_bc=96, m=(24, 24), min_delta=0.08, trim_side=3, want_stats=True),
     "delta_close_pairs": dict(n_bc=96, m=(24, 24), min_delta=0.13, close_pairs=True),
     "weighted": dict(n_bc=48, m=(24, 24), max_error_rate=0.25, min_delta=0.15, mismatch=1, indel=2),
+    "weighted_nodelta_trim": dict(n_bc=96, m=(24, 24), mismatch=1, indel=2, trim_side=3, want_stats=True),
+    "weighted_nodelta": dict(n_bc=60, m=(16, 28), mismatch=2, indel=3, max_error_rate=0.3),
     "mismatch3": dict(n_bc=40, m=(16, 28), max_error_rate=0.3, mismatch=3, indel=1),
     "match1": dict(n_bc=20, m=(12, 20), max_error_rate=0.4, match=1, mismatch=2, indel=2),
     "negmatch": dict(n_bc=20, m=(12, 20), max_error_rate=0.3, match=-1, mismatch=2, indel=2),

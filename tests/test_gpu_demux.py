@@ -55,7 +55,7 @@ def _host_pipeline(cfg, eng, path1, path2, out_dir, p1, p2):
 
 
 @pytest.mark.parametrize("variant", ["plain", "crlf", "no_final_newline", "trim5", "trim3_dual", "blank_tail",
-                                     "paired_mates", "paired_both", "paired_unequal"])
+                                     "paired_mates", "paired_both", "paired_unequal", "dual_many_files"])
 def test_device_io_equals_host_pipeline(tmp_path, variant):
     rng = np.random.default_rng(zlib.crc32(variant.encode()))
     bcs = synth.random_barcodes(rng, 40, 12)
@@ -71,6 +71,12 @@ def test_device_io_equals_host_pipeline(tmp_path, variant):
         cfg = bdx.DemuxConfig(bc_seqs=bcs, bc_lengths_no_N=[12] * 40, ids=[f"s{i}" for i in range(40)],
                               is_dual=True, bc_seqs2=bcs2, bc_lengths_no_N2=[10] * 9, ids2=[f"t{i}" for i in range(9)],
                               trim_side=5, trim_side2=3, min_delta=0.05)
+    if variant == "dual_many_files":             # 300 x 300 output files: keys beyond 2^16, three radix passes
+        bcs = synth.random_barcodes(rng, 300, 12)
+        bcs2 = synth.random_barcodes(rng, 300, 10)
+        reads = [r + bcs2[int(rng.integers(0, 300))].encode() + b"AC" for r in synth.random_reads(rng, 900, bcs, min_len=20, max_len=60)]   # < 1024 output files stay open at once
+        cfg = bdx.DemuxConfig(bc_seqs=bcs, bc_lengths_no_N=[12] * 300, ids=[f"s{i}" for i in range(300)],
+                              is_dual=True, bc_seqs2=bcs2, bc_lengths_no_N2=[10] * 300, ids2=[f"t{i}" for i in range(300)])
     eol = b"\r\n" if variant == "crlf" else b"\n"
     text1 = _fastq_text(rng, reads, eol=eol, final_newline=variant != "no_final_newline",
                         ragged_qual=variant in ("trim5", "trim3_dual"))

@@ -1,29 +1,34 @@
 // seed.cu -- depth-limited seed-and-verify for :semiglobal in the exact regime.
 //
-// Setting: unit costs, score-only, no start/end constraint, min_delta = 0, a barcode set of one
-// common length m without wildcard rows (the regime k_prefilter<0> works in).  k_prefilter has
-// already resolved the reads with a verbatim barcode occurrence; this kernel resolves reads whose
-// best barcode is within K = sd_k edits, without running the full-range automaton:
+// Setting: unit costs, default barcode start / end ranges (a barcode's result then does not depend on the
+// running threshold), a barcode set of one common length m <= 64 without wildcard rows.  With min_delta = 0
+// k_prefilter has already resolved the reads with a verbatim barcode occurrence; otherwise the first level
+// takes every read.  A level resolves reads whose best barcode is within K edits, without running the
+// full-range automaton:
 //
 //   * Pigeonhole: cut every barcode into K + 1 disjoint segments.  An alignment with <= K edits
 //     leaves at least one segment untouched, so its first q bytes occur verbatim in the read at
 //     column p = s + o + shift, |shift| <= K (s = alignment start, o = segment offset).
-//   * Every read column's q-mer is hashed (rolling polynomial hash over class codes) into a
-//     first-level bitmap and a CSR bucket table of (barcode, o) entries; a hit fixes the
-//     diagonal delta = p - o.
-//   * Each hit is verified with the same Myers/Hyyro automaton as k_filter, but only over the
-//     window of columns [delta - K, delta + m + 2K] that can hold such an alignment.  A window is
-//     a sub-range of the search range with free start and end, so its minimum is >= the
-//     full-range distance d_b, and for d_b <= K some hit window contains an optimal alignment:
-//     min over the hit windows == d_b exactly whenever d_b <= K.
-//   * Hence the set {b : d_b <= K} and those distances are known exactly.  If it is non-empty the
-//     reference's answer (no min_delta: first barcode attaining the minimal score,
-//     classification.jl:658) is the lowest index among the minimal d_b.  If it is empty and
-//     K == allowed, no barcode is acceptable.  Otherwise (best distance in (K, allowed]) the read
-//     goes to the bit-parallel kernel via worklist2, like any read this kernel cannot stage.
+//   * Only the columns of the read's search range are staged (as class codes); every staged column's
+//     q-mer is hashed (rolling polynomial hash) into a first-level bitmap and a CSR bucket table of
+//     (barcode, o) entries; a hit fixes the diagonal delta = p - o.  Hits of one barcode on diagonals
+//     <= K apart join one record whose window is the union of theirs.
+//   * Each record is verified with the same Myers/Hyyro automaton as k_filter, but only over the
+//     window of columns that can hold such an alignment.  A window is a sub-range of the search range
+//     with free start and end, so its minimum is >= the full-range distance d_b, and for d_b <= K some
+//     hit window contains an optimal alignment: min over the hit windows == d_b exactly whenever
+//     d_b <= K.  The hits of a warp's 32 reads are pooled and spread evenly over the lanes
+//     (seed_common.cuh); the verified distance goes back into the record.
+//   * Hence the set {b : d_b <= K} and those distances are known exactly.  Non-empty: the reference's
+//     winner is the lowest index among the minimal d_b (classification.jl:658); with min_delta the
+//     read is decided when the runner-up is known (second-smallest d_b <= K) or provably far, else it
+//     moves on; with trimming / stats the winner is queued for k_literal together with the columns
+//     that hold all its best alignments.  Empty and K >= allowed at the last level: no barcode is
+//     acceptable.  Everything else goes on through the other worklist (next level, then k_filter).
 //
-// One thread per read; hits are first collected, then verified in lock step (verifying inside
-// the scan would serialise the lanes of a warp, see k_prefilter).
+// Two levels (bdx_config_create): long, very selective seeds first, then the deepest level that is still
+// selective.  One thread per read; wins and hits are first collected, then resolved / verified in lock
+// step (doing it inside the scan would serialise the lanes of a warp, see k_prefilter).
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>

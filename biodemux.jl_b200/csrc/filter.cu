@@ -369,8 +369,8 @@ k_filter(const __grid_constant__ DevParams P, const int pass, const uint8_t *__r
 // ---------------------------------------------------------------------------------------
 // k_prefilter: perfect-occurrence prefilter, one thread per read.
 //
-// In the exact regime without min_delta, a barcode that occurs verbatim inside the search
-// range scores 0, the running threshold drops to 0 and no later barcode can be accepted
+// With default start / end ranges, match = 0, positive edit costs and no min_delta, a barcode that occurs verbatim
+// inside the search range scores 0, the running threshold drops to 0 and no later barcode can be accepted
 // (score < min_score is strict, classification.jl:658); an earlier barcode wins only with a
 // score of 0 itself, i.e. if IT occurs verbatim.  So the answer for such a read is the
 // lowest-index barcode with a verbatim occurrence: found with a rolling polynomial hash of
@@ -611,8 +611,8 @@ k_prefilter(const __grid_constant__ DevParams P, const int pass, const uint8_t *
                     }
                 }
             } else if (g.valid && g.max_start_pos >= n && g.min_end_pos <= g.start_j && ncols >= seed) {
-                // same regime test as k_filter's `fast` (score-only / unit costs are config-level and
-                // checked by the launcher)
+                // same per-read regime test as k_filter's `fast` (the cost conditions are config-level and
+                // checked by the launcher, prefilter_applies)
                 // Positions (trimming / stats): every hit of the winning barcode scores 0, so the reference keeps
                 // the first one it meets (early exit for trim 5, no later hit is strictly better otherwise,
                 // classification.jl:419-436, :141-153) -- the leftmost occurrence -- or, trimming 3', the one

@@ -96,3 +96,39 @@ def test_host_path_equals_device_path(workload):
         q -= 1
     s2.close()
     assert (np.concatenate(got) == dev).all()
+
+
+@pytest.mark.parametrize("algo", ["hamming", "semiglobal"])
+def test_config5_scale_properties(algo):
+    """Config 5's barcode set (1 536 x 24 nt) at 2 M reads: idempotence, shard invariance (what the multi-GPU
+    dispatcher relies on) and oracle parity on sampled windows, for the packed Hamming scan and for the seed levels
+    whose bucket tables live in global memory."""
+    import torch
+    sys.path.insert(0, ROOT)
+    import bench_configs
+    cfg, sp, _ = bench_configs.configs()["5h" if algo == "hamming" else "5s"]
+    n = 2_000_000
+    config = capi.Config(cfg)
+    st = capi.Stream(config, device=0, max_reads=0, max_bytes=0)
+    d_seq = torch.empty(n * L, dtype=torch.uint8, device="cuda")
+    d_off = torch.empty(n + 1, dtype=torch.int32, device="cuda")
+    spec = capi.SynthSpec(seed=bench_configs.SEED, first_read=0, read_len=L, plant_permille=900, n_permille_x10=50, **sp)
+    st.synth_device(spec, n, d_seq.data_ptr(), d_off.data_ptr())
+    st.sync()
+    whole = _classify(st, d_seq.data_ptr(), d_off.data_ptr(), n)
+    again = _classify(st, d_seq.data_ptr(), d_off.data_ptr(), n)
+    assert hashlib.sha256(whole.tobytes()).digest() == hashlib.sha256(again.tobytes()).digest()
+    shard = n // 8
+    d_off_shard = d_off[:shard + 1].contiguous()
+    for k in range(8):
+        part = _classify(st, d_seq.data_ptr() + k * shard * L, d_off_shard.data_ptr(), shard)
+        assert (part == whole[k * shard:(k + 1) * shard]).all(), k
+    frac = float((whole["status"] == 0).mean())
+    assert (0.60 < frac < 0.72) if algo == "hamming" else (0.86 < frac < 0.91), frac
+    o = orc.Oracle(cfg)
+    for start in (0, n - 1500, 777_777):
+        blob = d_seq[start * L:(start + 1500) * L].cpu().numpy()
+        ref = o.classify(blob, np.arange(1501, dtype=np.int64) * L)
+        for f in ("status", "bc1", "bc2", "keep_start", "keep_end"):
+            assert (whole[f][start:start + 1500] == ref[f]).all(), (start, f)
+    st.close()

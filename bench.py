@@ -131,6 +131,36 @@ class ClockSampler:
                 "windows": "device-resident timed region + e2e timed region"}
 
 
+def bind_to_gpu_numa_node(local: int):
+    """Pin this rank's threads (and with them its pinned host allocations, which the kernel places on the local
+    node) to the NUMA node the GPU hangs off: H2D / D2H of several ranks then do not cross the socket
+    interconnect.  Best effort; returns a short description for the JSON line."""
+    if os.environ.get("BDX_NUMA_BIND", "1") == "0":
+        return "off"
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(local)).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        dev = bus.lower()
+        if len(dev.split(":")[0]) == 8:          # nvml prints an 8-digit domain, sysfs uses 4
+            dev = dev[4:]
+        node = int(open(f"/sys/bus/pci/devices/{dev}/numa_node").read())
+        if node < 0:
+            return "gpu has no NUMA node"
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return f"node {node}: none of its cpus allowed"
+        os.sched_setaffinity(0, cpus)
+        return f"node {node} ({len(cpus)} cpus)"
+    except Exception as exc:
+        return f"unavailable ({type(exc).__name__})"
+
+
 def oracle_rate(cfg, blob, off64, threads):
     """reads/s of the oracle port over (blob, off64) with `threads` workers, chunked like
     the reference (4000 reads per task)."""
@@ -230,6 +260,7 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product has no CPU path")
+    numa = bind_to_gpu_numa_node(local) if world > 1 else "single rank: not bound"
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -436,7 +467,7 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": nb * (B * READ_LEN + 4 * (B + 1)),
                     "d2h_bytes_per_step": nb * B * bdx.RESULT_DTYPE.itemsize,
                     "api": f"bdx_submit_pinned / bdx_fetch_view, {DEPTH} batches in flight",
-                    "h2d_gbs_achieved": e2e_value / world * (READ_LEN + 4) / 1e9,
+                    "h2d_gbs_achieved": e2e_value / world * (READ_LEN + 4) / 1e9, "numa_binding_rank0": numa,
                     "h2d_gbs_plain_memcpy": pcie_h2d_gbs,
                     "bound": "host link: every read is 154 B of H2D; a bare pinned cudaMemcpyAsync of the same "
                              "bytes runs at h2d_gbs_plain_memcpy on this box"},

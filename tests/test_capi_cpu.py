@@ -183,3 +183,14 @@ def test_stats_entries_bridge(dual, nindel):
     assert got == stats_from_counters(buf, lay, cfg)
     assert got == stats_from_passes(status, bc1, bc2, passes, cfg)
     config.close()
+
+
+def test_stats_overflow_merge():
+    """Exact overflow records (bdx_stats_overflow_fetch) land in the same Dicts as histogram bins."""
+    from bdx_b200.stats import DemuxStats, merge_overflow
+    ovf = np.array([(1, 3, 4000, 24), (1, 3, 4000, 25), (2, 1, 70000, 16)], dtype=capi.STATS_OVERFLOW_DTYPE)
+    st = merge_overflow(DemuxStats(), ovf)
+    assert st.bc1_pos_counts == {4000: 2} and st.bc1_len_counts == {24: 1, 25: 1}
+    assert st.bc1_per_bc_pos_counts == {3: {4000: 2}} and st.bc1_per_bc_len_counts == {3: {24: 1, 25: 1}}
+    assert st.bc2_pos_counts == {70000: 1} and st.bc2_per_bc_len_counts == {1: {16: 1}}
+    assert merge_overflow(DemuxStats(), None) == DemuxStats()

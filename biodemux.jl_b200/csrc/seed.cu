@@ -129,26 +129,7 @@ k_seed(const __grid_constant__ DevParams P, const int pass, const int level, con
         // all their global loads issued before the first table lookup / store ----
         uint8_t *my_slot = slot_s + (size_t)threadIdx.x * kSeedSlot;
         __syncwarp();
-        constexpr int kIt = (kSeedSlot + 31) / 32;
-        for (int r0 = 0; r0 < 32; r0 += 4) {
-            uint8_t v[4][kIt];
-            int rn4[4];
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const int rb = __shfl_sync(0xFFFFFFFFu, base + sbase, r0 + j);
-                rn4[j] = __shfl_sync(0xFFFFFFFFu, L, r0 + j);
-                const uint8_t *src = seq + rb;
-#pragma unroll
-                for (int it = 0; it < kIt; it++) v[j][it] = lane + 32 * it < rn4[j] ? src[lane + 32 * it] : (uint8_t)0;
-            }
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                uint8_t *dst = slot_s + (size_t)(warp * 32 + r0 + j) * kSeedSlot;
-#pragma unroll
-                for (int it = 0; it < kIt; it++)
-                    if (lane + 32 * it < rn4[j]) dst[lane + 32 * it] = class_s[v[j][it]];
-            }
-        }
+        seed_stage_warp(seq, (long long)base + sbase, L, slot_s + (size_t)warp * 32 * kSeedSlot, class_s, lane);
         __syncwarp();
 
         // ---- scan, phase 1: remember the columns whose q-mer passes the first-level bitmap.

@@ -16,6 +16,45 @@ constexpr int kSeedSlot = 180;      // staged class codes per read = columns of 
 constexpr int kSeedMaxHits = 28;    // distinct (barcode, diagonal group) hits remembered per read (more => next stage)
 constexpr int kSeedMaxWins = 32;    // bitmap-passing columns remembered per read (more => full path)
 
+// Stages, for each of the warp's 32 reads, `my_len` (<= kSeedSlot) bytes starting at seq + my_start as class codes
+// into that read's slot (lane l describes read l).  Four reads per round; a lane loads up to two ALIGNED 32-bit
+// words per read -- a range of 180 bytes spans at most 46 words including its misaligned head -- and all eight
+// loads of a round are issued before the first table lookup.  The aligned words never leave the allocation that
+// holds the bytes (allocations start and end on coarser boundaries).
+__device__ __forceinline__ void seed_stage_warp(const uint8_t *__restrict__ seq, long long my_start, int my_len,
+                                                uint8_t *warp_slots, const uint8_t *class_s, int lane)
+{
+    for (int r0 = 0; r0 < 32; r0 += 4) {
+        uint32_t w[4][2];
+        int mis[4], len[4], nw[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const long long start = __shfl_sync(0xFFFFFFFFu, my_start, r0 + j);
+            len[j] = __shfl_sync(0xFFFFFFFFu, my_len, r0 + j);
+            const uintptr_t addr = reinterpret_cast<uintptr_t>(seq + start);
+            mis[j] = (int)(addr & 3u);
+            nw[j] = len[j] ? (mis[j] + len[j] + 3) >> 2 : 0;
+            const uint32_t *base = reinterpret_cast<const uint32_t *>(addr - (uintptr_t)mis[j]);
+            w[j][0] = lane < nw[j] ? __ldg(base + lane) : 0u;
+            w[j][1] = lane + 32 < nw[j] ? __ldg(base + lane + 32) : 0u;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            uint8_t *dst = warp_slots + (size_t)(r0 + j) * kSeedSlot;
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const int wi = lane + 32 * h;
+                if (wi >= nw[j]) continue;
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const int idx = 4 * wi + k - mis[j];
+                    if (idx >= 0 && idx < len[j]) dst[idx] = class_s[(w[j][h] >> (8 * k)) & 0xFFu];
+                }
+            }
+        }
+    }
+}
+
 // Hit record: barcode << 13 | diagonal span << 10 | lowest diagonal + 256   (barcode < 2^14, span <= K <= 7)
 __device__ __forceinline__ uint32_t hit_pack(uint32_t b, int span, int dmin)
 {

@@ -38,10 +38,10 @@ OPS_PER_READ = 17 * N_BARCODES * ((BARCODE_LEN + 31) // 32) * READ_LEN   # algor
 BYTES_PER_READ = READ_LEN + 4 + 20                         # sequence + offset in, bdx_result out
 CHUNK = 4000                                               # reference chunk_size (core.jl:521)
 # DRAM traffic of the dominant kernel from the committed `ncu --set full` capture
-# (profiles/r01f_kernels_ncu_summary.txt: k_filter<1,3,0,1>, 4 M-read step, 516 667 reads through the
-# automaton): dram__bytes_read.sum 163.98 MB + dram__bytes_write.sum 15.58 MB.  Per read that is 2x the
+# (profiles/r01g_kernels_ncu_summary.txt: k_filter<1,3,0,1>, 4 M-read step, 516 667 reads through the
+# automaton): dram__bytes_read.sum 164.03 MB + dram__bytes_write.sum 16.11 MB.  Per read that is 2x the
 # algorithmic 174 B: worklist-scattered 150-byte reads touch 6 32-byte sectors, offsets / PassOut one each.
-NCU_FILTER_DRAM_BYTES_PER_READ = (163.981568e6 + 15.583488e6) / 516667
+NCU_FILTER_DRAM_BYTES_PER_READ = (164.026880e6 + 16.110336e6) / 516667
 
 
 def make_config():
@@ -453,7 +453,7 @@ def run_ours(args):
                          "unit": "Tint-op/s", "frac": achieved_ops / peak_ops.value if peak_ops.value else None,
                          "traffic": NCU_FILTER_DRAM_BYTES_PER_READ * auto_per_launch,
                          "traffic_unit": "DRAM bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum per "
-                                         "automaton read, profiles/r01f_kernels_ncu_summary.txt, x reads per launch here)",
+                                         "automaton read, profiles/r01g_kernels_ncu_summary.txt, x reads per launch here)",
                          "kernel": "k_filter<1,3>", "kernel_ms": filt_s * 1e3,
                          "kernel_share_of_step": filt_ms / ms if ms else None,
                          "stage_ms_per_step": {k: v[0] / args.steps for k, v in stages.items() if v[1]},

@@ -107,6 +107,13 @@ def main():
         st.sync()
         ms = e0.elapsed_time(e1) / args.steps
         launches = (st.launch_count - l0) // args.steps
+        # one more, profiled pass: CUDA-event time of every stage (bdx_stream_profile_read_stages)
+        st.profile(True)
+        st.path_counters(reset=True)
+        st.classify_device(d_seq.data_ptr(), d_off.data_ptr(), n, d_res.data_ptr())
+        stages = {k: round(v[0], 3) for k, v in st.profile_read_stages().items() if v[1]}
+        st.profile(False)
+        pre_r, seed_r, auto_r = st.path_counters(reset=True)
         res = np.frombuffer(d_res.cpu().numpy().tobytes(), dtype=bdx.RESULT_DTYPE)
         k = min(args.check if len(cfg.bc_seqs) < 1000 else args.check // 5, n)
         blob = d_seq[:k * READ_LEN].cpu().numpy()
@@ -115,7 +122,8 @@ def main():
         ok = all((res[f][:k] == ref[f]).all() for f in ("status", "bc1", "bc2", "keep_start", "keep_end"))
         rate = n / (ms * 1e-3)
         print(json.dumps({"config": name, "reads": n, "reads_per_sec": rate, "ms_per_step": ms,
-                          "gcups": rate * cell_updates(cfg) / 1e9, "launches_per_step": launches,
+                          "gcups": rate * cell_updates(cfg) / 1e9, "launches_per_step": launches, "stage_ms": stages,
+                          "reads_by_path": {"prefilter": pre_r, "seed": seed_r, "automaton": auto_r},
                           "matched_fraction": float((res["status"] == 0).mean()),
                           "ambiguous_fraction": float((res["status"] == 2).mean()),
                           "parity_checked_reads": k, "parity_bit_exact": bool(ok)}), flush=True)

@@ -88,6 +88,12 @@ struct HostSet {
     HostSeedLevel sd[2];
     int sdd_n = 0, sdd_k = 0;      // deepest level (seed_deep.cu): one table per seed length
     HostSeedLevel sdd[2];
+    // variable lengths / constrained geometries (seed_var.cu)
+    int sv_enabled = 0, sv_q = 0, sv_complete = 0;
+    double sv_sigma_min = 0.0;
+    std::vector<uint16_t> sv_bstart;
+    std::vector<uint32_t> sv_entries;
+    std::vector<uint8_t> sv_kdepth;
 };
 
 struct DeviceTables {
@@ -390,6 +396,66 @@ static int build_set(const bdx_params &p, const bdx_barcode_set &in, HostSet &hs
             }
         }
     }
+    // ---- seed-and-verify for sets of different lengths and constrained start / end geometries (seed_var.cu):
+    // K_b + 1 disjoint segments per barcode, K_b = min(m_b / q - 1, allowed_b), their first q bases in a
+    // direct-address table.  q = the shortest seed whose CHANCE hits on admissible diagonals stay within the hit
+    // list (estimated for a 150-base read): position constraints keep short seeds selective ----
+    if (sg && hs.words >= 1 && !p.has_nindel && hs.n_classes - 1 <= 4 && hs.n_bc < (1 << 14) && hs.max_m <= 64 &&
+        p.max_error_rate >= 0.0 && !getenv("BDX_DISABLE_SEED")) {
+        auto resolve = [](const DevRange &dr, int len, int &first, int &last) {      // classification.jl:96-100
+            const int s = dr.start_from_end ? len + dr.start_off : dr.start_off;
+            const int e = dr.end_from_end ? len + dr.end_off : dr.end_off;
+            first = std::max(1, s);
+            last = std::min(len, e);
+            if (last < first) last = first - 1;
+        };
+        const int n_nom = 150;
+        int rf, rl, bf, bl, ef, el;
+        resolve(hs.rs, n_nom, rf, rl);
+        resolve(hs.bs, n_nom, bf, bl);
+        resolve(hs.be, n_nom, ef, el);
+        const int start_j = std::max(rf, std::max(bf, 1)), end_j = std::min(rl, std::min(el, n_nom));
+        const int L = std::max(end_j - start_j + 1, 1), sbase = start_j - 1;
+        const int min_end_rel = ef - sbase, max_start_rel = bl - sbase;
+        for (int q = 4; q <= 8 && !hs.sv_enabled; q++) {
+            if (min_m < q) break;
+            double chance = 0.0;
+            size_t n_entries = 0;
+            for (int b = 0; b < hs.n_bc; b++) {
+                const int m = hs.off[b + 1] - hs.off[b], a0 = hs.allowed0[b];
+                const int K = std::min(m / q - 1, a0);
+                const int dlo = std::max(0, min_end_rel - m) - K, dhi = std::min(max_start_rel + a0, L - m + K);
+                chance += (double)(K + 1) * std::max(0, dhi - dlo + 1) / std::pow(4.0, q);
+                n_entries += (size_t)K + 1;
+            }
+            if (chance > 24.0 || n_entries > 65535) continue;
+            hs.sv_q = q;
+            hs.sv_kdepth.assign((size_t)hs.n_bc, 0);
+            std::vector<std::vector<uint32_t>> buckets((size_t)1 << (2 * q));
+            hs.sv_sigma_min = 1e300;
+            hs.sv_complete = 1;
+            for (int b = 0; b < hs.n_bc; b++) {
+                const int m = hs.off[b + 1] - hs.off[b], a0 = hs.allowed0[b];
+                const int K = std::min(m / q - 1, a0);
+                hs.sv_kdepth[(size_t)b] = (uint8_t)K;
+                if (K < a0) hs.sv_complete = 0;
+                hs.sv_sigma_min = std::min(hs.sv_sigma_min, (double)(K + 1) / (double)hs.norm[b]);
+                const int seg = m / (K + 1);                       // >= q: the segments are disjoint
+                for (int i = 0; i <= K; i++) {
+                    const int o = i * seg;
+                    uint32_t code = 0;
+                    for (int k = 0; k < q; k++) code |= ((uint32_t)(hs.bc_cls[hs.off[b] + o + k] - 1) & 3u) << (2 * k);
+                    buckets[code].push_back(((uint32_t)b << 8) | (uint32_t)o);
+                }
+            }
+            hs.sv_bstart.assign(buckets.size() + 1, 0);
+            for (size_t k = 0; k < buckets.size(); k++) {
+                hs.sv_bstart[k + 1] = (uint16_t)(hs.sv_bstart[k] + buckets[k].size());
+                hs.sv_entries.insert(hs.sv_entries.end(), buckets[k].begin(), buckets[k].end());
+            }
+            hs.sv_enabled = 1;
+        }
+    }
     // ---- :hamming on packed words (hamming.cu): uniform length <= 32, <= 4 distinct barcode bytes, no 'N' ----
     if (p.algorithm == BDX_HAMMING && min_m == hs.max_m && hs.max_m <= 32 && hs.n_classes - 1 <= 4 && hs.n_bc <= 65535 &&
         hs.allowed0[0] >= 0 && hs.allowed0[0] <= 7 && p.max_error_rate >= 0.0 &&
@@ -671,6 +737,15 @@ static int get_tables(bdx_config *cfg, int device, DeviceTables **out)
             if (e == cudaSuccess) e = upload(t, H.ekeys, &L.ekeys);
             if (e == cudaSuccess) e = upload(t, H.bitmap, &L.bitmap);
         }
+        D.sv.enabled = hs.sv_enabled;
+        D.sv.q = hs.sv_q;
+        D.sv.n_buckets = 1 << (2 * hs.sv_q);
+        D.sv.n_entries = (int)hs.sv_entries.size();
+        D.sv.complete = hs.sv_complete;
+        D.sv.sigma_min = hs.sv_sigma_min;
+        if (e == cudaSuccess) e = upload(t, hs.sv_bstart, &D.sv.bstart);
+        if (e == cudaSuccess) e = upload(t, hs.sv_entries, &D.sv.entries);
+        if (e == cudaSuccess) e = upload(t, hs.sv_kdepth, &D.sv.kdepth);
         D.hp.enabled = hs.hp_enabled;
         D.hp.m = hs.hp_m;
         D.hp.allowed = hs.hp_allowed;
@@ -979,7 +1054,16 @@ static int enqueue_classify(bdx_stream *s, const uint8_t *d_seq, const int32_t *
             {
                 // seed levels hand the reads they cannot finish from one worklist to the other; without a
                 // prefilter in front (min_delta != 0) the first level takes every read of the batch
-                const int levels = seed_levels(P, pass);
+                // barcodes of different lengths / constrained start or end: k_seed_var instead of the levels
+                const bool sv = seed_var_applies(P, pass);
+                if (sv) {
+                    const int *wl_in = wl == 0 ? nullptr : s->sc.worklist;
+                    const int *n_in = wl == 0 ? nullptr : s->sc.n_work;
+                    if ((rc = staged(kStSeed, [&] { return launch_seed_var(P, pass, d_seq, d_off, n, s->sc, wl_in, n_in, s->sc.worklist2, s->sc.n_work2,
+                                   s->tab->sm_count, s->d_counters, s->st_comp); }))) return rc;
+                    wl = 2;
+                }
+                const int levels = sv ? 0 : seed_levels(P, pass);
                 for (int l = 0; l < levels; l++) {
                     const int *wl_in = wl == 0 ? nullptr : (wl == 1 ? s->sc.worklist : s->sc.worklist2);
                     const int *n_in = wl == 0 ? nullptr : (wl == 1 ? s->sc.n_work : s->sc.n_work2);

@@ -54,6 +54,21 @@ struct HammingPacked {
     const uint2 *bcw;             // [n_bc] the two bit planes of the barcode's 2-bit base codes, base k in bit k
 };
 
+// seed-and-verify for variable-length sets / constrained geometries (seed_var.cu): every barcode is cut into
+// kdepth[b] + 1 disjoint segments whose first q bases sit in a direct-address table (4^q buckets, 2-bit codes)
+struct SeedVar {
+    int enabled;
+    int q;                        // seed length
+    int n_buckets;                // 4^q
+    int n_entries;
+    int complete;                 // kdepth[b] >= allowed0[b] for every barcode: the candidate sets are supersets
+    int pad;
+    double sigma_min;             // min_b (kdepth[b] + 1) / norm[b]: no barcode outside the candidate set scores below
+    const uint16_t *bstart;       // [n_buckets + 1] CSR row starts
+    const uint32_t *entries;      // [n_entries] (barcode index << 8) | seed offset
+    const uint8_t *kdepth;        // [n_bc] edit depth the barcode's seeds are complete for
+};
+
 struct DevSet {
     int n_bc;
     int n_bc_pad;     // n_bc rounded up to a multiple of 32
@@ -104,6 +119,7 @@ struct DevSet {
     int sdd_n;                    // 0 = off
     int sdd_k;
     SeedLevel sdd[2];
+    SeedVar sv;
 };
 
 constexpr int kPfMaxSeed = 12;
@@ -183,6 +199,10 @@ cudaError_t launch_seed(const DevParams &P, int pass, int level, const uint8_t *
 // reads of a worklist that no kernel resolved: queue them for k_literal over every barcode
 cudaError_t launch_mark_pending(const DevParams &P, int pass, int n, const Scratch &sc, const int *wl, const int *n_wl,
                                 cudaStream_t st);
+bool seed_var_applies(const DevParams &P, int pass);
+cudaError_t launch_seed_var(const DevParams &P, int pass, const uint8_t *seq, const int *off, int n, const Scratch &sc,
+                            const int *wl_in, const int *n_in, int *wl_out, int *n_out, int sm_count,
+                            unsigned long long *counters, cudaStream_t st);
 bool seed_deep_applies(const DevParams &P, int pass);
 cudaError_t launch_seed_deep(const DevParams &P, int pass, const uint8_t *seq, const int *off, int n, const Scratch &sc,
                              const int *wl_in, const int *n_in, int *wl_out, int *n_out, int sm_count,

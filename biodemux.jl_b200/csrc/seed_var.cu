@@ -1,0 +1,473 @@
+// seed_var.cu -- seed-and-verify for the sets and geometries k_seed (seed.cu) does not take: barcodes of
+// DIFFERENT lengths, and search geometries with a constrained barcode start or end (barcode_start_range /
+// barcode_end_range), where the reference's result for one barcode depends on the running threshold
+// (classification.jl:270: the start constraint is enforced through a band whose slack is the current allowed
+// distance).  Score-only passes with unit costs; one block works on groups of 128 reads.
+//
+//   scan    Every barcode b is cut into K_b + 1 disjoint segments of q bases (K_b = min(m_b / q - 1, allowed_b)),
+//           all (barcode, segment) q-mers sit in a direct-address table (4^q buckets: at most four distinct
+//           barcode bytes).  The q-mer at every column of every staged search range is looked up -- the pairs
+//           (read, column) are dealt to the threads of the block, not one read per thread -- and a table entry
+//           is a HIT when its diagonal is one an acceptable alignment can lie on: inside the search range,
+//           ending at or after min_end_pos, starting no later than max_start_pos + allowed_b (the reference's
+//           loose start bound), each widened by K_b.  Position constraints are what keeps short seeds
+//           selective here (config 3: 5-mers of 384 barcodes, 25 chance hits per read instead of 55).
+//   verify  The block's hits form one list; every thread verifies hits (two at a time) with the windowed
+//           Myers / Hyyro automaton of k_seed over the m_b + 2 K_b columns an alignment with that intact
+//           segment can occupy.  Pigeonhole: an alignment with <= K_b edits leaves a segment intact, so
+//           C = {b : unit distance d_b <= K_b} is found completely and with exact distances; a barcode outside
+//           C costs more than K_b edits under ANY threshold (the reference's finite results are costs of real
+//           alignments inside the range), i.e. scores at least sigma = min_b (K_b + 1) / m_b.
+//   decide  One thread per read replays find_best_matching_bc (classification.jl:632-713) over C in barcode
+//           order.  The value of a candidate is d_b / m_b if the reference finds that alignment whatever the
+//           running threshold is.  Default geometry: it does (k_filter's exact regime).  Constrained end only:
+//           the DP is threshold independent but the last row takes no insertion (:213), so the value comes
+//           from sg_literal at the initial threshold.  Constrained start: sg_literal run with allowed = d_b,
+//           the tightest band that can still accept the barcode; if it returns d_b the alignment lies inside
+//           every wider band as well (band(a) grows with a, the Ukkonen cut-off is exact for unit costs), so
+//           the value is d_b for every threshold >= d_b / m_b and "rejected" below -- which is all the replay
+//           needs.  Otherwise the read is left to the exact path.
+//           With best score s1 and runner-up s2 among C:  s1 < sigma is required (no unseen barcode can win or
+//           tie); without min_delta that decides the read; with min_delta it is ambiguous when s2 - s1 <
+//           min_delta (an unseen barcode can only lower the runner-up) and matched when both s2 - s1 and
+//           sigma - s1 are >= min_delta.  An unseen barcode accepted in the reference's run lowers the
+//           threshold to its score or to a candidate's, never below sigma or the runner-up, so the candidates'
+//           verdicts above are unchanged.  Everything else -- no candidate, best too close to sigma, too many
+//           hits -- goes on through the worklist to k_filter + k_literal, which are exact for any read.
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <math_constants.h>
+#include <type_traits>
+
+#include "bdx_internal.h"
+#include "literal.cuh"
+
+namespace bdx {
+
+constexpr int kSvThreads = 128;      // threads per block = reads per group
+constexpr int kSvHitsPerRead = 32;   // capacity of the block's hit list, per read of the group
+constexpr int kSvCand = 8;           // verified candidates kept per read
+constexpr int kSvDiagBias = 64;      // hit record: read << 22 | barcode << 8 | diagonal + bias
+constexpr int kSvMaxCols = 180;      // longest search range staged (longer ones take the exact path)
+constexpr int kSvBig = 1 << 20;
+
+// Stages `my_len` bytes starting at seq + my_start as class codes for each of the warp's 32 reads (lane l
+// describes read l) -- seed_stage_warp of seed_common.cuh with a runtime slot stride.
+__device__ __forceinline__ void sv_stage_warp(const uint8_t *__restrict__ seq, long long my_start, int my_len,
+                                              uint8_t *warp_slots, int stride, const uint8_t *class_s, int lane)
+{
+    for (int r0 = 0; r0 < 32; r0 += 4) {
+        uint32_t w[4][2];
+        int mis[4], len[4], nw[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const long long start = __shfl_sync(0xFFFFFFFFu, my_start, r0 + j);
+            len[j] = __shfl_sync(0xFFFFFFFFu, my_len, r0 + j);
+            const uintptr_t addr = reinterpret_cast<uintptr_t>(seq + start);
+            mis[j] = (int)(addr & 3u);
+            nw[j] = len[j] ? (mis[j] + len[j] + 3) >> 2 : 0;
+            const uint32_t *base = reinterpret_cast<const uint32_t *>(addr - (uintptr_t)mis[j]);
+            w[j][0] = lane < nw[j] ? __ldg(base + lane) : 0u;
+            w[j][1] = lane + 32 < nw[j] ? __ldg(base + lane + 32) : 0u;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            uint8_t *dst = warp_slots + (size_t)(r0 + j) * stride;
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const int wi = lane + 32 * h;
+                if (wi >= nw[j]) continue;
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const int idx = 4 * wi + k - mis[j];
+                    if (idx >= 0 && idx < len[j]) dst[idx] = class_s[(w[j][h] >> (8 * k)) & 0xFFu];
+                }
+            }
+        }
+    }
+}
+
+struct SvSmem {
+    uint32_t *peq, *hits, *cand, *entries;
+    int *rinfo, *cand_n, *ctr;
+    uint16_t *bstart;
+    uint8_t *len, *kd, *a0, *cls, *slot;
+};
+
+// words / bytes of the carve-up; the same arithmetic on the host (launch) and the device (kernel)
+__host__ __device__ inline size_t sv_smem_layout(int W, int plane, int n_pad, int n_entries, int n_buckets, int tab_smem,
+                                                 int slot_stride, size_t off[12])
+{
+    size_t o = 0;
+    off[0] = o; o += (size_t)W * plane * 4;                          // peq
+    off[1] = o; o += (size_t)kSvThreads * kSvHitsPerRead * 4;        // hits
+    off[2] = o; o += (size_t)kSvThreads * kSvCand * 4;               // cand
+    off[3] = o; o += (size_t)kSvThreads * 4 * 4;                     // rinfo: L, min_end_rel, max_start_rel, flags
+    off[4] = o; o += (size_t)kSvThreads * 4;                         // cand_n
+    off[5] = o; o += 16;                                             // ctr
+    off[6] = o; o += tab_smem ? (size_t)n_entries * 4 : 0;           // entries
+    off[7] = o; o += tab_smem ? (((size_t)n_buckets + 1) * 2 + 3) / 4 * 4 : 0;   // bstart
+    off[8] = o; o += (size_t)n_pad * 3;                              // len, kd, a0
+    o = (o + 3) / 4 * 4;
+    off[9] = o; o += 256;                                            // class_of
+    off[10] = o; o += (size_t)kSvThreads * slot_stride;              // slots
+    return (o + 15) / 16 * 16;
+}
+
+template <int W>
+__global__ void __launch_bounds__(kSvThreads)
+k_seed_var(const __grid_constant__ DevParams P, const int pass, const uint8_t *__restrict__ seq,
+           const int *__restrict__ off, const int n_reads, PassOut *__restrict__ out,
+           const PassOut *__restrict__ prev_pass, const int *__restrict__ wl_in, const int *__restrict__ n_in,
+           int *__restrict__ wl_out, int *__restrict__ n_out, unsigned long long *__restrict__ counters,
+           const int slot_stride, const int slot_cols, const int tab_smem)
+{
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    const DevSet &S = P.set[pass];
+    const SeedVar &V = S.sv;
+    const int n_pad = S.n_bc_pad;
+    const int plane = S.n_classes * n_pad;
+    const int q = V.q;
+    const int n_buckets = V.n_buckets;
+    size_t lo[12];
+    sv_smem_layout(W, plane, n_pad, V.n_entries, n_buckets, tab_smem, slot_stride, lo);
+    uint32_t *peq_s = reinterpret_cast<uint32_t *>(smem_raw + lo[0]);
+    uint32_t *hits_s = reinterpret_cast<uint32_t *>(smem_raw + lo[1]);
+    uint32_t *cand_s = reinterpret_cast<uint32_t *>(smem_raw + lo[2]);
+    int *rinfo_s = reinterpret_cast<int *>(smem_raw + lo[3]);
+    int *cand_n_s = reinterpret_cast<int *>(smem_raw + lo[4]);
+    int *ctr_s = reinterpret_cast<int *>(smem_raw + lo[5]);
+    const uint32_t *entries_s = tab_smem ? reinterpret_cast<const uint32_t *>(smem_raw + lo[6]) : V.entries;
+    const uint16_t *bstart_s = tab_smem ? reinterpret_cast<const uint16_t *>(smem_raw + lo[7]) : V.bstart;
+    uint8_t *len_s = smem_raw + lo[8];
+    uint8_t *kd_s = len_s + n_pad;
+    uint8_t *a0_s = kd_s + n_pad;
+    uint8_t *class_s = smem_raw + lo[9];
+    uint8_t *slot_s = smem_raw + lo[10];
+
+    for (int k = threadIdx.x; k < W * plane; k += blockDim.x) peq_s[k] = S.peq[k];
+    if (tab_smem) {
+        uint32_t *en = reinterpret_cast<uint32_t *>(smem_raw + lo[6]);
+        uint16_t *bs = reinterpret_cast<uint16_t *>(smem_raw + lo[7]);
+        for (int k = threadIdx.x; k < V.n_entries; k += blockDim.x) en[k] = V.entries[k];
+        for (int k = threadIdx.x; k <= n_buckets; k += blockDim.x) bs[k] = V.bstart[k];
+    }
+    for (int k = threadIdx.x; k < n_pad; k += blockDim.x) {
+        len_s[k] = (uint8_t)(k < S.n_bc ? S.bc_off[k + 1] - S.bc_off[k] : 0);
+        kd_s[k] = k < S.n_bc ? V.kdepth[k] : 0;
+        a0_s[k] = (uint8_t)(k < S.n_bc ? min(max(S.allowed0[k], 0), 255) : 0);
+    }
+    for (int k = threadIdx.x; k < 256; k += blockDim.x) class_s[k] = S.class_of[k];
+    __syncthreads();
+
+    using WT = typename std::conditional<W == 1, uint32_t, unsigned long long>::type;
+    constexpr int kMsb = (int)sizeof(WT) * 8 - 1;
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int n_items = wl_in ? *n_in : n_reads;
+    const int n_groups = (n_items + kSvThreads - 1) / kSvThreads;
+    const bool with_delta = P.min_delta != 0.0;
+    const int hit_cap = kSvThreads * kSvHitsPerRead;
+    const int n_pos = slot_cols - q + 1;                     // q-mer positions scanned per read (at most)
+    unsigned int n_done = 0;
+
+    for (int grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
+        const int item = grp * kSvThreads + threadIdx.x;
+        const bool have = item < n_items;
+        const int read = have ? (wl_in ? wl_in[item] : item) : 0;
+        const int base = have ? off[read] : 0;
+        const int n = have ? off[read + 1] - base : 0;
+
+        bool punt = !have;       // true => the read goes on to the exact path (or is not a read at all)
+        bool skip = false;       // nothing left to do for this read
+        Geometry g{};
+        if (have && pass == 1 && prev_pass[read].bc <= 0) {      // classification.jl:879-888
+            out[read] = PassOut{kBcNotRun, 0, -1, -1};
+            skip = true;
+            punt = true;
+        }
+        if (have && !skip) {
+            g = pass_geometry(S, n);
+            if (!g.valid) {                                      // :805-807
+                out[read] = PassOut{kBcUnknown, 0, -1, -1};
+                skip = true;
+                punt = true;
+            } else if (g.end_j - g.start_j + 1 > slot_cols) {
+                punt = true;
+            }
+        }
+        // columns RELATIVE to the search range: relative column c (1-based) is absolute column c + sbase
+        const int sbase = punt ? 0 : g.start_j - 1;
+        const int L = punt ? 0 : g.end_j - g.start_j + 1;
+        rinfo_s[threadIdx.x * 4 + 0] = L;
+        rinfo_s[threadIdx.x * 4 + 1] = punt ? 1 : max(g.min_end_pos - sbase, -kSvBig);
+        rinfo_s[threadIdx.x * 4 + 2] = punt ? 0 : min(g.max_start_pos - sbase, kSvBig);
+        rinfo_s[threadIdx.x * 4 + 3] = 0;                        // flags: 1 = hit list overflow
+        cand_n_s[threadIdx.x] = 0;
+        if (threadIdx.x == 0) ctr_s[0] = 0;
+        sv_stage_warp(seq, (long long)base + sbase, L, slot_s + (size_t)warp * 32 * slot_stride, slot_stride, class_s, lane);
+        __syncthreads();
+
+        // ---- scan: (read, column) pairs dealt to the threads; admissible table entries become hits ----
+        for (int i = threadIdx.x; i < kSvThreads * n_pos; i += kSvThreads) {
+            const int r = i / n_pos, p = i - r * n_pos;
+            const int Lr = rinfo_s[r * 4 + 0];
+            bool valid = p + q <= Lr;
+            uint32_t code = 0;
+            if (valid) {
+                const uint8_t *c = slot_s + (size_t)r * slot_stride + p;
+                for (int k = 0; k < q; k++) {
+                    const uint32_t cl = c[k];
+                    valid = valid && cl != 0;
+                    code |= ((cl - 1u) & 3u) << (2 * k);
+                }
+            }
+            int e = valid ? (int)bstart_s[code] : 0;
+            const int e1 = valid ? (int)bstart_s[code + 1] : 0;
+            const int min_end_rel = rinfo_s[r * 4 + 1], max_start_rel = rinfo_s[r * 4 + 2];
+            while (__any_sync(0xFFFFFFFFu, e < e1)) {
+                bool hit = false;
+                uint32_t rec = 0;
+                if (e < e1) {
+                    const uint32_t ent = entries_s[e++];
+                    const int b = (int)(ent >> 8), o = (int)(ent & 0xFFu);
+                    const int m = len_s[b], K = kd_s[b], a0 = a0_s[b];
+                    const int delta = p - o;                                  // 0-based relative diagonal
+                    const int dlo = max(0, min_end_rel - m) - K - 1;
+                    const int dhi = min(max_start_rel + a0, Lr - m) + K + 1;
+                    hit = delta >= dlo && delta <= dhi;
+                    rec = ((uint32_t)r << 22) | ((uint32_t)b << 8) | (uint32_t)(delta + kSvDiagBias);
+                }
+                const uint32_t hm = __ballot_sync(0xFFFFFFFFu, hit);
+                if (hm) {
+                    int hb = 0;
+                    if (lane == 0) hb = atomicAdd(&ctr_s[0], __popc(hm));
+                    hb = __shfl_sync(0xFFFFFFFFu, hb, 0);
+                    if (hit) {
+                        const int idx = hb + __popc(hm & ((1u << lane) - 1u));
+                        if (idx < hit_cap) hits_s[idx] = rec;
+                        else rinfo_s[r * 4 + 3] = 1;                           // this read's candidate set is incomplete
+                    }
+                }
+            }
+        }
+        __syncthreads();
+
+        // ---- verify: every thread takes hits of the block's list, two at a time ----
+        const int total = min(ctr_s[0], hit_cap);
+        for (int i0 = 0; i0 < total; i0 += 2 * kSvThreads) {
+            int hb[2], c0[2], c1[2], ct[2], score[2], best[2], hr[2], hk[2];
+            WT pv[2], mv[2];
+            const uint8_t *slot[2];
+            int wlen = 0;
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
+                const int i = i0 + u * kSvThreads + threadIdx.x;
+                const bool live = i < total;
+                const uint32_t rec = live ? hits_s[i] : 0u;
+                hr[u] = live ? (int)(rec >> 22) : 0;
+                hb[u] = (int)((rec >> 8) & 0x3FFFu);
+                const int delta = (int)(rec & 0xFFu) - kSvDiagBias;
+                const int m = len_s[hb[u]];
+                hk[u] = live ? (int)kd_s[hb[u]] : -1;
+                const int Lr = rinfo_s[hr[u] * 4 + 0], min_end_rel = rinfo_s[hr[u] * 4 + 1];
+                // 1-based relative columns an alignment with <= K edits and this segment intact can occupy
+                c0[u] = live ? max(1, delta - hk[u] + 1) : 1;
+                c1[u] = live ? min(Lr, delta + m + hk[u]) : 0;
+                ct[u] = max(c0[u], min_end_rel);                              // hits end at or after min_end_pos (:419)
+                slot[u] = slot_s + (size_t)hr[u] * slot_stride;
+                pv[u] = m > kMsb ? ~(WT)0 : (m <= 0 ? (WT)0 : (~(WT)0 << (kMsb + 1 - m)));   // barcode rows top-aligned
+                mv[u] = 0;
+                score[u] = m;
+                best[u] = kInf;
+                wlen = max(wlen, c1[u] - c0[u] + 1);
+            }
+            wlen = __reduce_max_sync(0xFFFFFFFFu, wlen);
+            for (int t = 0; t < wlen; t++) {
+                WT eq[2];
+                bool in[2];
+#pragma unroll
+                for (int u = 0; u < 2; u++) {
+                    const int c = c0[u] + t;
+                    in[u] = c <= c1[u];
+                    const uint32_t cls = in[u] ? (uint32_t)slot[u][c - 1] : 0u;   // outside the window: class 0
+                    eq[u] = peq_s[cls * n_pad + hb[u]];
+                    if (sizeof(WT) == 8) eq[u] |= (WT)peq_s[plane + cls * n_pad + hb[u]] << (kMsb - 31);
+                }
+#pragma unroll
+                for (int u = 0; u < 2; u++) {
+                    const WT xv = eq[u] | mv[u];
+                    const WT xh = ((((eq[u] & pv[u]) + pv[u]) ^ pv[u]) | eq[u]);
+                    const WT ph = mv[u] | ~(xh | pv[u]);
+                    const WT mh = pv[u] & xh;
+                    score[u] += (int)(ph >> kMsb) - (int)(mh >> kMsb);
+                    const WT phs = ph << 1, mhs = mh << 1;
+                    pv[u] = mhs | ~(xv | phs);
+                    mv[u] = phs & xv;
+                    best[u] = (in[u] && c0[u] + t >= ct[u]) ? min(best[u], score[u]) : best[u];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 2; u++)
+                if (hk[u] >= 0 && best[u] <= hk[u]) {
+                    const int k = atomicAdd(&cand_n_s[hr[u]], 1);
+                    if (k < kSvCand) cand_s[hr[u] * kSvCand + k] = ((uint32_t)hb[u] << 8) | (uint32_t)best[u];
+                }
+        }
+        __syncthreads();
+
+        // ---- decide: one thread per read ----
+        bool resolved = false;
+        if (!punt && rinfo_s[threadIdx.x * 4 + 3] == 0 && cand_n_s[threadIdx.x] <= kSvCand) {
+            int nc = cand_n_s[threadIdx.x];
+            uint32_t cl[kSvCand];
+#pragma unroll
+            for (int k = 0; k < kSvCand; k++) cl[k] = k < nc ? cand_s[threadIdx.x * kSvCand + k] : 0xFFFFFFFFu;
+            // ascending (barcode, distance): insertion sort of at most 8 records
+#pragma unroll
+            for (int a = 1; a < kSvCand; a++)
+#pragma unroll
+                for (int bq = a; bq > 0; bq--)
+                    if (cl[bq] < cl[bq - 1]) {
+                        const uint32_t t = cl[bq];
+                        cl[bq] = cl[bq - 1];
+                        cl[bq - 1] = t;
+                    }
+            const bool start_bound = g.max_start_pos < n;           // the reference's result depends on the threshold
+            const bool end_bound = g.min_end_pos > g.start_j;       // last row without insertion matters (:213)
+            const Costs c{P.match, P.mismatch, P.indel, P.nindel, P.has_n};
+            int dp_local[kMaxFilterWords * 32 + 2];
+            const WsCol DP{dp_local, 1};
+            BestState bs;
+            best_init(bs, P.max_error_rate);
+            bool ok = true;
+            int last_b = -1;
+#pragma unroll 1
+            for (int k = 0; k < nc && ok; k++) {
+                const int b = (int)(cl[k] >> 8);
+                if (b == last_b) continue;                           // same barcode through another hit: the smaller d came first
+                last_b = b;
+                int d = (int)(cl[k] & 0xFFu);
+                const int qo = S.bc_off[b];
+                const int m = S.bc_off[b + 1] - qo;
+                const int norm = S.norm[b];
+                if (start_bound || end_bound) {
+                    int s_, e_;
+                    const int a = start_bound ? d : S.allowed0[b];
+                    const int dl = sg_literal<false>(DP, DP, S.bc_bytes + qo - 1, seq + base - 1, m, n, a, c, 0, g.start_j, g.end_j,
+                                                     g.max_start_pos, g.min_end_pos, s_, e_);
+                    if (start_bound) {
+                        if (dl != d) ok = false;                     // not found in the tightest band: exact path
+                    } else {
+                        if (dl >= kInf) continue;                    // no alignment ends inside [min_end_pos, end_j]
+                        d = dl;
+                    }
+                }
+                const int allowed = allowed_from(bs.thr, norm);       // :254 with the running threshold
+                const double sc = d <= allowed ? __ddiv_rn((double)d, (double)norm) : CUDART_INF;
+                best_consider(bs, with_delta, sc, d, b + 1, -1, -1);
+            }
+            if (ok) {
+                if (V.complete) {
+                    out[read] = best_finish(bs, with_delta, P.min_delta);
+                    resolved = true;
+                } else if (bs.min_bc != 0 && bs.min_score < V.sigma_min) {
+                    if (!with_delta) {
+                        out[read] = best_finish(bs, false, 0.0);
+                        resolved = true;
+                    } else if (__dsub_rn(bs.sub_min, bs.min_score) < P.min_delta) {
+                        out[read] = PassOut{kBcAmbiguous, 0, -1, -1};
+                        resolved = true;
+                    } else if (__dsub_rn(V.sigma_min, bs.min_score) >= P.min_delta) {
+                        out[read] = PassOut{bs.min_bc, bs.min_dist, -1, -1};
+                        resolved = true;
+                    }
+                }
+            }
+        }
+        const bool todo = have && !resolved && !skip;
+        const uint32_t mask = __ballot_sync(0xFFFFFFFFu, todo);
+        int base_slot = 0;
+        if (lane == 0 && mask) base_slot = atomicAdd(n_out, __popc(mask));
+        base_slot = __shfl_sync(0xFFFFFFFFu, base_slot, 0);
+        if (todo) wl_out[base_slot + __popc(mask & ((1u << lane) - 1u))] = read;
+        n_done += __popc(__ballot_sync(0xFFFFFFFFu, resolved));
+        __syncthreads();                                             // the group's shared lists are reused
+    }
+    if (lane == 0 && n_done && counters) atomicAdd(counters + 2, (unsigned long long)n_done);
+}
+
+// longest search range any read can have (columns), or kSvMaxCols when it grows with the read
+static int sv_slot_cols(const DevSet &S)
+{
+    const DevRange &r = S.rs;
+    if (r.start_from_end == r.end_from_end) {
+        const long long len = (long long)r.end_off - r.start_off + 1;
+        if (len >= 1 && len <= kSvMaxCols) return (int)len;
+        if (len < 1) return 1;
+    }
+    return kSvMaxCols;
+}
+
+static bool sv_default_geometry(const DevSet &S)
+{
+    const DevRange &bs = S.bs, &be = S.be;
+    return bs.start_off <= 1 && !bs.start_from_end && bs.end_from_end && bs.end_off >= 0 && be.start_off <= 1 &&
+           !be.start_from_end;
+}
+
+struct SvLaunch {
+    int slot_cols, slot_stride, tab_smem;
+    size_t smem;
+};
+
+static SvLaunch sv_launch_params(const DevSet &S)
+{
+    SvLaunch L;
+    L.slot_cols = sv_slot_cols(S);
+    int words = (L.slot_cols + 3) / 4;
+    words |= 1;                                   // odd word stride: the slots of consecutive reads start in different banks
+    L.slot_stride = words * 4;
+    size_t off[12];
+    const int plane = S.n_classes * S.n_bc_pad;
+    L.tab_smem = 1;
+    L.smem = sv_smem_layout(S.words, plane, S.n_bc_pad, S.sv.n_entries, S.sv.n_buckets, 1, L.slot_stride, off);
+    if (L.smem > 100 * 1024) {
+        L.tab_smem = 0;
+        L.smem = sv_smem_layout(S.words, plane, S.n_bc_pad, S.sv.n_entries, S.sv.n_buckets, 0, L.slot_stride, off);
+    }
+    return L;
+}
+
+// Does k_seed_var take this pass?  Score-only :semiglobal passes with unit costs whose set has the tables, when
+// k_seed's levels do not apply (barcodes of different lengths) or would refuse every read (constrained start / end).
+bool seed_var_applies(const DevParams &P, int pass)
+{
+    const DevSet &S = P.set[pass];
+    if (P.algo != BDX_SEMIGLOBAL || !P.unit_costs || !S.sv.enabled || S.words < 1 || P.max_error_rate < 0.0) return false;
+    if (S.trim_side != 0 || P.want_stats) return false;
+    if (seed_levels(P, pass) > 0 && sv_default_geometry(S)) return false;
+    return sv_launch_params(S).smem <= 160 * 1024;
+}
+
+cudaError_t launch_seed_var(const DevParams &P, int pass, const uint8_t *seq, const int *off, int n, const Scratch &sc,
+                            const int *wl_in, const int *n_in, int *wl_out, int *n_out, int sm_count,
+                            unsigned long long *counters, cudaStream_t st)
+{
+    const DevSet &S = P.set[pass];
+    const SvLaunch L = sv_launch_params(S);
+    auto kern = S.words == 1 ? k_seed_var<1> : k_seed_var<2>;
+    int per_sm = 0;
+    cudaError_t e = blocks_per_sm_cached((const void *)kern, kSvThreads, L.smem, &per_sm);
+    if (e != cudaSuccess) return e;
+    const int groups = (n + kSvThreads - 1) / kSvThreads;
+    const int blocks = std::max(1, std::min(groups, sm_count * per_sm));
+    e = cudaMemsetAsync(n_out, 0, sizeof(int), st);
+    if (e != cudaSuccess) return e;
+    kern<<<blocks, kSvThreads, L.smem, st>>>(P, pass, seq, off, n, sc.pass[pass], sc.pass[0], wl_in, n_in, wl_out, n_out,
+                                             counters, L.slot_stride, L.slot_cols, L.tab_smem);
+    return cudaGetLastError();
+}
+
+}  // namespace bdx

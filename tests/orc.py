@@ -208,6 +208,24 @@ class Oracle:
         seq, off = pack_reads(reads)
         return self.classify(seq, off)
 
+    def classify_mt(self, seq_bytes: np.ndarray, offsets: np.ndarray, threads: Optional[int] = None,
+                    chunk: int = 4000) -> np.ndarray:
+        """classify() over chunks of `chunk` reads on `threads` host threads (ctypes releases the GIL):
+        the parity checks over >= 1 M reads use this."""
+        from concurrent.futures import ThreadPoolExecutor
+        off64 = np.ascontiguousarray(offsets, dtype=np.int64)
+        n = len(off64) - 1
+        out = np.zeros(n, dtype=RESULT_DTYPE)
+        spans = [(a, min(a + chunk, n)) for a in range(0, n, chunk)]
+
+        def work(span):
+            a, b = span
+            out[a:b] = self.classify(seq_bytes[off64[a]:off64[b]], off64[a:b + 1] - off64[a])
+
+        with ThreadPoolExecutor(threads or os.cpu_count() or 1) as ex:
+            list(ex.map(work, spans))
+        return out
+
     def find_best(self, read, rng, max_start_pos, min_end_pos, need_traceback=False, pass2=False):
         r = _b(read)
         ms, dl = C.c_double(), C.c_double()

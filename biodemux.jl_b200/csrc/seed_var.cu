@@ -21,8 +21,8 @@
 //   decide  One thread per read replays find_best_matching_bc (classification.jl:632-713) over C in barcode
 //           order.  The value of a candidate is d_b / m_b if the reference finds that alignment whatever the
 //           running threshold is.  Default geometry: it does (k_filter's exact regime).  Constrained end only:
-//           the DP is threshold independent but the last row takes no insertion (:213), so the value comes
-//           from sg_literal at the initial threshold.  Constrained start: sg_literal run with allowed = d_b,
+//           the DP is threshold independent but the last row takes no insertion (:213); the verification tracks
+//           D'[m][j] = min(D[m-1][j] + 1, D[m-1][j-1] + sub) then.  Constrained start: sg_literal run with allowed = d_b,
 //           the tightest band that can still accept the barcode; if it returns d_b the alignment lies inside
 //           every wider band as well (band(a) grows with a, the Ukkonen cut-off is exact for unit costs), so
 //           the value is d_b for every threshold >= d_b / m_b and "rejected" below -- which is all the replay
@@ -96,12 +96,14 @@ struct SvSmem {
 };
 
 // words / bytes of the carve-up; the same arithmetic on the host (launch) and the device (kernel)
+__host__ __device__ inline int sv_hit_rows(int max_m) { return max_m + 2 > kSvHitsPerRead ? max_m + 2 : kSvHitsPerRead; }
+
 __host__ __device__ inline size_t sv_smem_layout(int W, int plane, int n_pad, int n_entries, int n_buckets, int tab_smem,
-                                                 int slot_stride, size_t off[12])
+                                                 int slot_stride, int max_m, size_t off[12])
 {
     size_t o = 0;
     off[0] = o; o += (size_t)W * plane * 4;                          // peq
-    off[1] = o; o += (size_t)kSvThreads * kSvHitsPerRead * 4;        // hits
+    off[1] = o; o += (size_t)kSvThreads * sv_hit_rows(max_m) * 4;    // hits; the decide phase reuses it as DP columns [row][thread]
     off[2] = o; o += (size_t)kSvThreads * kSvCand * 4;               // cand
     off[3] = o; o += (size_t)kSvThreads * 4 * 4;                     // rinfo: L, min_end_rel, max_start_rel, flags
     off[4] = o; o += (size_t)kSvThreads * 4;                         // cand_n
@@ -131,7 +133,7 @@ k_seed_var(const __grid_constant__ DevParams P, const int pass, const uint8_t *_
     const int q = V.q;
     const int n_buckets = V.n_buckets;
     size_t lo[12];
-    sv_smem_layout(W, plane, n_pad, V.n_entries, n_buckets, tab_smem, slot_stride, lo);
+    sv_smem_layout(W, plane, n_pad, V.n_entries, n_buckets, tab_smem, slot_stride, S.max_m, lo);
     uint32_t *peq_s = reinterpret_cast<uint32_t *>(smem_raw + lo[0]);
     uint32_t *hits_s = reinterpret_cast<uint32_t *>(smem_raw + lo[1]);
     uint32_t *cand_s = reinterpret_cast<uint32_t *>(smem_raw + lo[2]);
@@ -168,7 +170,7 @@ k_seed_var(const __grid_constant__ DevParams P, const int pass, const uint8_t *_
     const int n_items = wl_in ? *n_in : n_reads;
     const int n_groups = (n_items + kSvThreads - 1) / kSvThreads;
     const bool with_delta = P.min_delta != 0.0;
-    const int hit_cap = kSvThreads * kSvHitsPerRead;
+    const int hit_cap = kSvThreads * sv_hit_rows(S.max_m);
     const int n_pos = slot_cols - q + 1;                     // q-mer positions scanned per read (at most)
     unsigned int n_done = 0;
 
@@ -207,7 +209,11 @@ k_seed_var(const __grid_constant__ DevParams P, const int pass, const uint8_t *_
         cand_n_s[threadIdx.x] = 0;
         if (threadIdx.x == 0) ctr_s[0] = 0;
         sv_stage_warp(seq, (long long)base + sbase, L, slot_s + (size_t)warp * 32 * slot_stride, slot_stride, class_s, lane);
-        __syncthreads();
+        // Constrained end (min_end_pos inside the range): the reference's last row takes no insertion
+        // (classification.jl:213), so a hit at column j is D'[m][j] = min(D[m-1][j] + 1, D[m-1][j-1] + sub), not
+        // the automaton's D[m][j].  Over ALL columns the two have the same minimum, over the columns
+        // >= min_end_pos they do not; D' is tracked for the whole group when any of its reads needs it.
+        const int last_row_rule = __syncthreads_or(!punt && g.min_end_pos > g.start_j);
 
         // ---- scan: (read, column) pairs dealt to the threads; admissible table entries become hits ----
         for (int i = threadIdx.x; i < kSvThreads * n_pos; i += kSvThreads) {
@@ -234,8 +240,12 @@ k_seed_var(const __grid_constant__ DevParams P, const int pass, const uint8_t *_
                     const int b = (int)(ent >> 8), o = (int)(ent & 0xFFu);
                     const int m = len_s[b], K = kd_s[b], a0 = a0_s[b];
                     const int delta = p - o;                                  // 0-based relative diagonal
-                    const int dlo = max(0, min_end_rel - m) - K - 1;
-                    const int dhi = min(max_start_rel + a0, Lr - m) + K + 1;
+                    // Diagonals (read column - barcode row) an acceptable alignment's intact segment can lie on:
+                    // the segment's own cells obey the reference's band j - i <= max_start_pos + steps
+                    // (classification.jl:270, :289-290; steps <= allowed_b); the rest of the barcode has to fit
+                    // between the range start and end with at most K edits, and to end at or after min_end_pos
+                    const int dlo = max(0, min_end_rel - m) - K;
+                    const int dhi = min(max_start_rel + a0, Lr - m + K);
                     hit = delta >= dlo && delta <= dhi;
                     rec = ((uint32_t)r << 22) | ((uint32_t)b << 8) | (uint32_t)(delta + kSvDiagBias);
                 }
@@ -297,6 +307,8 @@ k_seed_var(const __grid_constant__ DevParams P, const int pass, const uint8_t *_
                 }
 #pragma unroll
                 for (int u = 0; u < 2; u++) {
+                    // D[m-1][j-1] = D[m][j-1] - (vertical delta of row m in column j-1)
+                    const int up_prev = score[u] - (int)(pv[u] >> kMsb) + (int)(mv[u] >> kMsb);
                     const WT xv = eq[u] | mv[u];
                     const WT xh = ((((eq[u] & pv[u]) + pv[u]) ^ pv[u]) | eq[u]);
                     const WT ph = mv[u] | ~(xh | pv[u]);
@@ -305,7 +317,12 @@ k_seed_var(const __grid_constant__ DevParams P, const int pass, const uint8_t *_
                     const WT phs = ph << 1, mhs = mh << 1;
                     pv[u] = mhs | ~(xv | phs);
                     mv[u] = phs & xv;
-                    best[u] = (in[u] && c0[u] + t >= ct[u]) ? min(best[u], score[u]) : best[u];
+                    int hit_score = score[u];
+                    if (last_row_rule) {
+                        const int up = score[u] - (int)(pv[u] >> kMsb) + (int)(mv[u] >> kMsb);    // D[m-1][j]
+                        hit_score = min(up + 1, up_prev + 1 - (int)(eq[u] >> kMsb));
+                    }
+                    best[u] = (in[u] && c0[u] + t >= ct[u]) ? min(best[u], hit_score) : best[u];
                 }
             }
 #pragma unroll
@@ -335,10 +352,12 @@ k_seed_var(const __grid_constant__ DevParams P, const int pass, const uint8_t *_
                         cl[bq - 1] = t;
                     }
             const bool start_bound = g.max_start_pos < n;           // the reference's result depends on the threshold
-            const bool end_bound = g.min_end_pos > g.start_j;       // last row without insertion matters (:213)
             const Costs c{P.match, P.mismatch, P.indel, P.nindel, P.has_n};
-            int dp_local[kMaxFilterWords * 32 + 2];
-            const WsCol DP{dp_local, 1};
+            // DP column of sg_literal: element i of this thread at hits_s[i * 128 + thread] (the hit list is dead now)
+            const WsCol DP{reinterpret_cast<int *>(hits_s) + threadIdx.x, kSvThreads};
+            // the read's search range as class codes: equality of class codes == equality of bytes for barcode
+            // bytes (a read byte that occurs in no barcode is class 0); absolute column j at my_slot[j - 1 - sbase]
+            const uint8_t *r1 = slot_s + (size_t)threadIdx.x * slot_stride - sbase - 1;
             BestState bs;
             best_init(bs, P.max_error_rate);
             bool ok = true;
@@ -348,21 +367,17 @@ k_seed_var(const __grid_constant__ DevParams P, const int pass, const uint8_t *_
                 const int b = (int)(cl[k] >> 8);
                 if (b == last_b) continue;                           // same barcode through another hit: the smaller d came first
                 last_b = b;
-                int d = (int)(cl[k] & 0xFFu);
+                const int d = (int)(cl[k] & 0xFFu);
                 const int qo = S.bc_off[b];
                 const int m = S.bc_off[b + 1] - qo;
                 const int norm = S.norm[b];
-                if (start_bound || end_bound) {
+                if (start_bound) {
+                    // the tightest band that can still accept the barcode (allowed = d): found there => found in
+                    // every wider band; else the read takes the exact path
                     int s_, e_;
-                    const int a = start_bound ? d : S.allowed0[b];
-                    const int dl = sg_literal<false>(DP, DP, S.bc_bytes + qo - 1, seq + base - 1, m, n, a, c, 0, g.start_j, g.end_j,
+                    const int dl = sg_literal<false>(DP, DP, S.bc_cls + qo - 1, r1, m, n, d, c, 0, g.start_j, g.end_j,
                                                      g.max_start_pos, g.min_end_pos, s_, e_);
-                    if (start_bound) {
-                        if (dl != d) ok = false;                     // not found in the tightest band: exact path
-                    } else {
-                        if (dl >= kInf) continue;                    // no alignment ends inside [min_end_pos, end_j]
-                        d = dl;
-                    }
+                    if (dl != d) ok = false;
                 }
                 const int allowed = allowed_from(bs.thr, norm);       // :254 with the running threshold
                 const double sc = d <= allowed ? __ddiv_rn((double)d, (double)norm) : CUDART_INF;
@@ -432,10 +447,10 @@ static SvLaunch sv_launch_params(const DevSet &S)
     size_t off[12];
     const int plane = S.n_classes * S.n_bc_pad;
     L.tab_smem = 1;
-    L.smem = sv_smem_layout(S.words, plane, S.n_bc_pad, S.sv.n_entries, S.sv.n_buckets, 1, L.slot_stride, off);
+    L.smem = sv_smem_layout(S.words, plane, S.n_bc_pad, S.sv.n_entries, S.sv.n_buckets, 1, L.slot_stride, S.max_m, off);
     if (L.smem > 100 * 1024) {
         L.tab_smem = 0;
-        L.smem = sv_smem_layout(S.words, plane, S.n_bc_pad, S.sv.n_entries, S.sv.n_buckets, 0, L.slot_stride, off);
+        L.smem = sv_smem_layout(S.words, plane, S.n_bc_pad, S.sv.n_entries, S.sv.n_buckets, 0, L.slot_stride, S.max_m, off);
     }
     return L;
 }

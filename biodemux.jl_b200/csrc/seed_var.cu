@@ -88,33 +88,107 @@ __device__ __forceinline__ void sv_stage_warp(const uint8_t *__restrict__ seq, l
     }
 }
 
-struct SvSmem {
-    uint32_t *peq, *hits, *cand, *entries;
-    int *rinfo, *cand_n, *ctr;
-    uint16_t *bstart;
-    uint8_t *len, *kd, *a0, *cls, *slot;
-};
-
-// words / bytes of the carve-up; the same arithmetic on the host (launch) and the device (kernel)
+// Shared-memory carve-up (bytes); the same arithmetic on the host (launch) and the device (kernel).
 __host__ __device__ inline int sv_hit_rows(int max_m) { return max_m + 2 > kSvHitsPerRead ? max_m + 2 : kSvHitsPerRead; }
 
+enum { kSvPeq = 0, kSvHits, kSvCandL, kSvRinfo, kSvCandN, kSvCtr, kSvEntries, kSvBstart, kSvBinfo, kSvClass, kSvSlot, kSvParts };
+
 __host__ __device__ inline size_t sv_smem_layout(int W, int plane, int n_pad, int n_entries, int n_buckets, int tab_smem,
-                                                 int slot_stride, int max_m, size_t off[12])
+                                                 int slot_stride, int max_m, size_t off[kSvParts])
 {
     size_t o = 0;
-    off[0] = o; o += (size_t)W * plane * 4;                          // peq
-    off[1] = o; o += (size_t)kSvThreads * sv_hit_rows(max_m) * 4;    // hits; the decide phase reuses it as DP columns [row][thread]
-    off[2] = o; o += (size_t)kSvThreads * kSvCand * 4;               // cand
-    off[3] = o; o += (size_t)kSvThreads * 4 * 4;                     // rinfo: L, min_end_rel, max_start_rel, flags
-    off[4] = o; o += (size_t)kSvThreads * 4;                         // cand_n
-    off[5] = o; o += 16;                                             // ctr
-    off[6] = o; o += tab_smem ? (size_t)n_entries * 4 : 0;           // entries
-    off[7] = o; o += tab_smem ? (((size_t)n_buckets + 1) * 2 + 3) / 4 * 4 : 0;   // bstart
-    off[8] = o; o += (size_t)n_pad * 3;                              // len, kd, a0
-    o = (o + 3) / 4 * 4;
-    off[9] = o; o += 256;                                            // class_of
-    off[10] = o; o += (size_t)kSvThreads * slot_stride;              // slots
+    off[kSvPeq] = o; o += (size_t)W * plane * 4;                          // Peq, transposed to [word][barcode][class]
+    off[kSvHits] = o; o += (size_t)kSvThreads * sv_hit_rows(max_m) * 4;   // hit list; the decide phase reuses it as DP columns [row][thread]
+    off[kSvCandL] = o; o += (size_t)kSvThreads * kSvCand * 4;             // verified candidates per read
+    off[kSvRinfo] = o; o += (size_t)kSvThreads * 4 * 4;                   // per read: L, min_end_rel, max_start_rel, flags
+    off[kSvCandN] = o; o += (size_t)kSvThreads * 4;
+    off[kSvCtr] = o; o += 16;
+    off[kSvEntries] = o; o += tab_smem ? (size_t)n_entries * 4 : 0;
+    off[kSvBstart] = o; o += tab_smem ? (((size_t)n_buckets + 1) * 2 + 3) / 4 * 4 : 0;
+    off[kSvBinfo] = o; o += (size_t)n_pad * 4;                            // per barcode: m | K << 8 | allowed0 << 16
+    off[kSvClass] = o; o += 256;
+    off[kSvSlot] = o; o += (size_t)kSvThreads * slot_stride + 128;        // staged class codes (+ slack: windows are read past their end)
     return (o + 15) / 16 * 16;
+}
+
+// Windowed Myers / Hyyro verification of the block's hit list, two hits per thread and round.
+// LASTROW: hits are scored as D'[m][j] = min(D[m-1][j] + 1, D[m-1][j-1] + sub) (the reference's last row takes
+// no insertion, classification.jl:213) and only at columns >= min_end_pos.
+template <typename WT, bool LASTROW>
+__device__ __forceinline__ void sv_verify(const uint32_t *hits_s, int total, const int *rinfo_s, const uint32_t *binfo_s,
+                                          const uint32_t *peq_s, int n_classes, int plane, const uint8_t *slot_s,
+                                          int slot_stride, uint32_t *cand_s, int *cand_n_s)
+{
+    constexpr int kMsb = (int)sizeof(WT) * 8 - 1;
+    for (int i0 = 0; i0 < total; i0 += 2 * kSvThreads) {
+        int score[2], best[2], hr[2], hk[2], hb[2], wl[2], ts[2];
+        WT pv[2], mv[2];
+        const uint8_t *col[2];          // first column of the window
+        const uint32_t *row[2];         // the barcode's Peq words, indexed by class
+        int wlen = 0;
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+            const int i = i0 + u * kSvThreads + (int)threadIdx.x;
+            const bool live = i < total;
+            const uint32_t rec = live ? hits_s[i] : 0u;
+            hr[u] = live ? (int)(rec >> 22) : 0;
+            hb[u] = (int)((rec >> 8) & 0x3FFFu);
+            const int delta = (int)(rec & 0xFFu) - kSvDiagBias;
+            const uint32_t bi = binfo_s[hb[u]];
+            const int m = (int)(bi & 0xFFu);
+            hk[u] = live ? (int)((bi >> 8) & 0xFFu) : -1;
+            const int Lr = rinfo_s[hr[u] * 4 + 0], min_end_rel = rinfo_s[hr[u] * 4 + 1];
+            // 1-based relative columns an alignment with <= K edits and this segment intact can occupy
+            const int c0 = live ? max(1, delta - hk[u] + 1) : 1;
+            const int c1 = live ? min(Lr, delta + m + hk[u]) : 0;
+            wl[u] = c1 - c0 + 1;
+            ts[u] = LASTROW ? max(0, min_end_rel - c0) : 0;            // hits end at or after min_end_pos (:419)
+            col[u] = slot_s + (size_t)hr[u] * slot_stride + (c0 - 1);
+            row[u] = peq_s + hb[u] * n_classes;
+            pv[u] = m > kMsb ? ~(WT)0 : (m <= 0 ? (WT)0 : (~(WT)0 << (kMsb + 1 - m)));   // barcode rows top-aligned
+            mv[u] = 0;
+            score[u] = m;
+            best[u] = kInf;
+            wlen = max(wlen, wl[u]);
+        }
+        wlen = __reduce_max_sync(0xFFFFFFFFu, wlen);
+        // past its own window a lane keeps stepping on whatever is staged there (never read back: `best` is frozen)
+#pragma unroll 2
+        for (int t = 0; t < wlen; t++) {
+            WT eq[2];
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
+                const uint32_t cls = col[u][t];
+                eq[u] = row[u][cls];
+                if (sizeof(WT) == 8) eq[u] |= (WT)row[u][plane + cls] << (kMsb - 31);
+            }
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
+                int up_prev = 0;
+                if (LASTROW) up_prev = score[u] - (int)(pv[u] >> kMsb) + (int)(mv[u] >> kMsb);   // D[m-1][j-1]
+                const WT xv = eq[u] | mv[u];
+                const WT xh = ((((eq[u] & pv[u]) + pv[u]) ^ pv[u]) | eq[u]);
+                const WT ph = mv[u] | ~(xh | pv[u]);
+                const WT mh = pv[u] & xh;
+                score[u] += (int)(ph >> kMsb) - (int)(mh >> kMsb);
+                const WT phs = ph << 1, mhs = mh << 1;
+                pv[u] = mhs | ~(xv | phs);
+                mv[u] = phs & xv;
+                int hit_score = score[u];
+                if (LASTROW) {
+                    const int up = score[u] - (int)(pv[u] >> kMsb) + (int)(mv[u] >> kMsb);        // D[m-1][j]
+                    hit_score = min(up + 1, up_prev + 1 - (int)(eq[u] >> kMsb));
+                }
+                if ((unsigned)(t - ts[u]) < (unsigned)(wl[u] - ts[u])) best[u] = min(best[u], hit_score);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 2; u++)
+            if (hk[u] >= 0 && best[u] <= hk[u]) {
+                const int k = atomicAdd(&cand_n_s[hr[u]], 1);
+                if (k < kSvCand) cand_s[hr[u] * kSvCand + k] = ((uint32_t)hb[u] << 8) | (uint32_t)best[u];
+            }
+    }
 }
 
 template <int W>
@@ -129,49 +203,56 @@ k_seed_var(const __grid_constant__ DevParams P, const int pass, const uint8_t *_
     const DevSet &S = P.set[pass];
     const SeedVar &V = S.sv;
     const int n_pad = S.n_bc_pad;
-    const int plane = S.n_classes * n_pad;
+    const int n_classes = S.n_classes;
+    const int plane = n_classes * n_pad;
     const int q = V.q;
     const int n_buckets = V.n_buckets;
-    size_t lo[12];
+    size_t lo[kSvParts];
     sv_smem_layout(W, plane, n_pad, V.n_entries, n_buckets, tab_smem, slot_stride, S.max_m, lo);
-    uint32_t *peq_s = reinterpret_cast<uint32_t *>(smem_raw + lo[0]);
-    uint32_t *hits_s = reinterpret_cast<uint32_t *>(smem_raw + lo[1]);
-    uint32_t *cand_s = reinterpret_cast<uint32_t *>(smem_raw + lo[2]);
-    int *rinfo_s = reinterpret_cast<int *>(smem_raw + lo[3]);
-    int *cand_n_s = reinterpret_cast<int *>(smem_raw + lo[4]);
-    int *ctr_s = reinterpret_cast<int *>(smem_raw + lo[5]);
-    const uint32_t *entries_s = tab_smem ? reinterpret_cast<const uint32_t *>(smem_raw + lo[6]) : V.entries;
-    const uint16_t *bstart_s = tab_smem ? reinterpret_cast<const uint16_t *>(smem_raw + lo[7]) : V.bstart;
-    uint8_t *len_s = smem_raw + lo[8];
-    uint8_t *kd_s = len_s + n_pad;
-    uint8_t *a0_s = kd_s + n_pad;
-    uint8_t *class_s = smem_raw + lo[9];
-    uint8_t *slot_s = smem_raw + lo[10];
+    uint32_t *peq_s = reinterpret_cast<uint32_t *>(smem_raw + lo[kSvPeq]);
+    uint32_t *hits_s = reinterpret_cast<uint32_t *>(smem_raw + lo[kSvHits]);
+    uint32_t *cand_s = reinterpret_cast<uint32_t *>(smem_raw + lo[kSvCandL]);
+    int *rinfo_s = reinterpret_cast<int *>(smem_raw + lo[kSvRinfo]);
+    int *cand_n_s = reinterpret_cast<int *>(smem_raw + lo[kSvCandN]);
+    int *ctr_s = reinterpret_cast<int *>(smem_raw + lo[kSvCtr]);
+    const uint32_t *entries_s = tab_smem ? reinterpret_cast<const uint32_t *>(smem_raw + lo[kSvEntries]) : V.entries;
+    const uint16_t *bstart_s = tab_smem ? reinterpret_cast<const uint16_t *>(smem_raw + lo[kSvBstart]) : V.bstart;
+    uint32_t *binfo_s = reinterpret_cast<uint32_t *>(smem_raw + lo[kSvBinfo]);
+    uint8_t *class_s = smem_raw + lo[kSvClass];
+    uint8_t *slot_s = smem_raw + lo[kSvSlot];
 
-    for (int k = threadIdx.x; k < W * plane; k += blockDim.x) peq_s[k] = S.peq[k];
+    // Peq arrives as [word][class][barcode] (k_filter's lanes read consecutive barcodes); a verifying thread
+    // reads ONE barcode's words for changing classes, so it is kept as [word][barcode][class] here
+    for (int k = threadIdx.x; k < W * plane; k += blockDim.x) {
+        const int w = k / plane, rem = k - w * plane, c = rem / n_pad, b = rem - c * n_pad;
+        peq_s[w * plane + b * n_classes + c] = S.peq[k];
+    }
     if (tab_smem) {
-        uint32_t *en = reinterpret_cast<uint32_t *>(smem_raw + lo[6]);
-        uint16_t *bs = reinterpret_cast<uint16_t *>(smem_raw + lo[7]);
+        uint32_t *en = reinterpret_cast<uint32_t *>(smem_raw + lo[kSvEntries]);
+        uint16_t *bs = reinterpret_cast<uint16_t *>(smem_raw + lo[kSvBstart]);
         for (int k = threadIdx.x; k < V.n_entries; k += blockDim.x) en[k] = V.entries[k];
         for (int k = threadIdx.x; k <= n_buckets; k += blockDim.x) bs[k] = V.bstart[k];
     }
     for (int k = threadIdx.x; k < n_pad; k += blockDim.x) {
-        len_s[k] = (uint8_t)(k < S.n_bc ? S.bc_off[k + 1] - S.bc_off[k] : 0);
-        kd_s[k] = k < S.n_bc ? V.kdepth[k] : 0;
-        a0_s[k] = (uint8_t)(k < S.n_bc ? min(max(S.allowed0[k], 0), 255) : 0);
+        uint32_t v = 0;
+        if (k < S.n_bc)
+            v = (uint32_t)(S.bc_off[k + 1] - S.bc_off[k]) | ((uint32_t)V.kdepth[k] << 8) |
+                ((uint32_t)min(max(S.allowed0[k], 0), 255) << 16);
+        binfo_s[k] = v;
     }
     for (int k = threadIdx.x; k < 256; k += blockDim.x) class_s[k] = S.class_of[k];
+    for (int k = threadIdx.x; k < 128; k += blockDim.x) slot_s[(size_t)kSvThreads * slot_stride + k] = 0;
     __syncthreads();
 
     using WT = typename std::conditional<W == 1, uint32_t, unsigned long long>::type;
-    constexpr int kMsb = (int)sizeof(WT) * 8 - 1;
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int n_items = wl_in ? *n_in : n_reads;
     const int n_groups = (n_items + kSvThreads - 1) / kSvThreads;
     const bool with_delta = P.min_delta != 0.0;
     const int hit_cap = kSvThreads * sv_hit_rows(S.max_m);
-    const int n_pos = slot_cols - q + 1;                     // q-mer positions scanned per read (at most)
+    const int n_pos = max(slot_cols - q + 1, 1);             // q-mer positions scanned per read (at most)
+    const uint32_t pos_recip = 0xFFFFFFFFu / (uint32_t)n_pos + 1u;   // i / n_pos == umulhi(i, recip) for i < 2^16
     unsigned int n_done = 0;
 
     for (int grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
@@ -215,9 +296,10 @@ k_seed_var(const __grid_constant__ DevParams P, const int pass, const uint8_t *_
         // >= min_end_pos they do not; D' is tracked for the whole group when any of its reads needs it.
         const int last_row_rule = __syncthreads_or(!punt && g.min_end_pos > g.start_j);
 
-        // ---- scan: (read, column) pairs dealt to the threads; admissible table entries become hits ----
+        // ---- scan: (read, column) pairs dealt to the threads.  The table entries of a warp's 32 pairs are
+        // pooled (prefix sum of the bucket sizes) and dealt out evenly again, one entry per lane and round ----
         for (int i = threadIdx.x; i < kSvThreads * n_pos; i += kSvThreads) {
-            const int r = i / n_pos, p = i - r * n_pos;
+            const int r = (int)__umulhi((uint32_t)i, pos_recip), p = i - r * n_pos;
             const int Lr = rinfo_s[r * 4 + 0];
             bool valid = p + q <= Lr;
             uint32_t code = 0;
@@ -229,35 +311,59 @@ k_seed_var(const __grid_constant__ DevParams P, const int pass, const uint8_t *_
                     code |= ((cl - 1u) & 3u) << (2 * k);
                 }
             }
-            int e = valid ? (int)bstart_s[code] : 0;
-            const int e1 = valid ? (int)bstart_s[code + 1] : 0;
-            const int min_end_rel = rinfo_s[r * 4 + 1], max_start_rel = rinfo_s[r * 4 + 2];
-            while (__any_sync(0xFFFFFFFFu, e < e1)) {
+            const int e0 = valid ? (int)bstart_s[code] : 0;
+            const int cnt = valid ? (int)bstart_s[code + 1] - e0 : 0;
+            int incl = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            const int total_e = __shfl_sync(0xFFFFFFFFu, incl, 31);
+            const int my_first = e0 - (incl - cnt);                 // entry index of pooled item j owned by this lane: my_first + j
+            const int lane_i0 = i - lane;                           // pair index of lane 0
+            for (int j0 = 0; j0 < total_e; j0 += 32) {
+                const int j = j0 + lane;
+                // owner = first lane whose inclusive prefix exceeds j
+                int ow = 0;
+#pragma unroll
+                for (int step = 16; step >= 1; step >>= 1) {
+                    const int probe = __shfl_sync(0xFFFFFFFFu, incl, ow + step - 1);
+                    if (probe <= j) ow += step;
+                }
+                ow = min(ow, 31);
+                const int first = __shfl_sync(0xFFFFFFFFu, my_first, ow);
                 bool hit = false;
                 uint32_t rec = 0;
-                if (e < e1) {
-                    const uint32_t ent = entries_s[e++];
+                int hr = 0;
+                if (j < total_e) {
+                    const int oi = lane_i0 + ow;                                // the owner's (read, column) pair
+                    hr = (int)__umulhi((uint32_t)oi, pos_recip);
+                    const int op = oi - hr * n_pos;
+                    const uint32_t ent = entries_s[first + j];
                     const int b = (int)(ent >> 8), o = (int)(ent & 0xFFu);
-                    const int m = len_s[b], K = kd_s[b], a0 = a0_s[b];
-                    const int delta = p - o;                                  // 0-based relative diagonal
+                    const uint32_t bi = binfo_s[b];
+                    const int m = (int)(bi & 0xFFu), K = (int)((bi >> 8) & 0xFFu), a0 = (int)(bi >> 16);
+                    const int oL = rinfo_s[hr * 4 + 0], min_end_rel = rinfo_s[hr * 4 + 1], max_start_rel = rinfo_s[hr * 4 + 2];
+                    const int delta = op - o;                                   // 0-based relative diagonal
                     // Diagonals (read column - barcode row) an acceptable alignment's intact segment can lie on:
                     // the segment's own cells obey the reference's band j - i <= max_start_pos + steps
                     // (classification.jl:270, :289-290; steps <= allowed_b); the rest of the barcode has to fit
                     // between the range start and end with at most K edits, and to end at or after min_end_pos
                     const int dlo = max(0, min_end_rel - m) - K;
-                    const int dhi = min(max_start_rel + a0, Lr - m + K);
+                    const int dhi = min(max_start_rel + a0, oL - m + K);
                     hit = delta >= dlo && delta <= dhi;
-                    rec = ((uint32_t)r << 22) | ((uint32_t)b << 8) | (uint32_t)(delta + kSvDiagBias);
+                    rec = ((uint32_t)hr << 22) | ((uint32_t)b << 8) | (uint32_t)(delta + kSvDiagBias);
                 }
                 const uint32_t hm = __ballot_sync(0xFFFFFFFFu, hit);
                 if (hm) {
-                    int hb = 0;
-                    if (lane == 0) hb = atomicAdd(&ctr_s[0], __popc(hm));
-                    hb = __shfl_sync(0xFFFFFFFFu, hb, 0);
+                    int hbase = 0;
+                    if (lane == 0) hbase = atomicAdd(&ctr_s[0], __popc(hm));
+                    hbase = __shfl_sync(0xFFFFFFFFu, hbase, 0);
                     if (hit) {
-                        const int idx = hb + __popc(hm & ((1u << lane) - 1u));
+                        const int idx = hbase + __popc(hm & ((1u << lane) - 1u));
                         if (idx < hit_cap) hits_s[idx] = rec;
-                        else rinfo_s[r * 4 + 3] = 1;                           // this read's candidate set is incomplete
+                        else rinfo_s[hr * 4 + 3] = 1;                           // this read's candidate set is incomplete
                     }
                 }
             }
@@ -265,72 +371,12 @@ k_seed_var(const __grid_constant__ DevParams P, const int pass, const uint8_t *_
         __syncthreads();
 
         // ---- verify: every thread takes hits of the block's list, two at a time ----
-        const int total = min(ctr_s[0], hit_cap);
-        for (int i0 = 0; i0 < total; i0 += 2 * kSvThreads) {
-            int hb[2], c0[2], c1[2], ct[2], score[2], best[2], hr[2], hk[2];
-            WT pv[2], mv[2];
-            const uint8_t *slot[2];
-            int wlen = 0;
-#pragma unroll
-            for (int u = 0; u < 2; u++) {
-                const int i = i0 + u * kSvThreads + threadIdx.x;
-                const bool live = i < total;
-                const uint32_t rec = live ? hits_s[i] : 0u;
-                hr[u] = live ? (int)(rec >> 22) : 0;
-                hb[u] = (int)((rec >> 8) & 0x3FFFu);
-                const int delta = (int)(rec & 0xFFu) - kSvDiagBias;
-                const int m = len_s[hb[u]];
-                hk[u] = live ? (int)kd_s[hb[u]] : -1;
-                const int Lr = rinfo_s[hr[u] * 4 + 0], min_end_rel = rinfo_s[hr[u] * 4 + 1];
-                // 1-based relative columns an alignment with <= K edits and this segment intact can occupy
-                c0[u] = live ? max(1, delta - hk[u] + 1) : 1;
-                c1[u] = live ? min(Lr, delta + m + hk[u]) : 0;
-                ct[u] = max(c0[u], min_end_rel);                              // hits end at or after min_end_pos (:419)
-                slot[u] = slot_s + (size_t)hr[u] * slot_stride;
-                pv[u] = m > kMsb ? ~(WT)0 : (m <= 0 ? (WT)0 : (~(WT)0 << (kMsb + 1 - m)));   // barcode rows top-aligned
-                mv[u] = 0;
-                score[u] = m;
-                best[u] = kInf;
-                wlen = max(wlen, c1[u] - c0[u] + 1);
-            }
-            wlen = __reduce_max_sync(0xFFFFFFFFu, wlen);
-            for (int t = 0; t < wlen; t++) {
-                WT eq[2];
-                bool in[2];
-#pragma unroll
-                for (int u = 0; u < 2; u++) {
-                    const int c = c0[u] + t;
-                    in[u] = c <= c1[u];
-                    const uint32_t cls = in[u] ? (uint32_t)slot[u][c - 1] : 0u;   // outside the window: class 0
-                    eq[u] = peq_s[cls * n_pad + hb[u]];
-                    if (sizeof(WT) == 8) eq[u] |= (WT)peq_s[plane + cls * n_pad + hb[u]] << (kMsb - 31);
-                }
-#pragma unroll
-                for (int u = 0; u < 2; u++) {
-                    // D[m-1][j-1] = D[m][j-1] - (vertical delta of row m in column j-1)
-                    const int up_prev = score[u] - (int)(pv[u] >> kMsb) + (int)(mv[u] >> kMsb);
-                    const WT xv = eq[u] | mv[u];
-                    const WT xh = ((((eq[u] & pv[u]) + pv[u]) ^ pv[u]) | eq[u]);
-                    const WT ph = mv[u] | ~(xh | pv[u]);
-                    const WT mh = pv[u] & xh;
-                    score[u] += (int)(ph >> kMsb) - (int)(mh >> kMsb);
-                    const WT phs = ph << 1, mhs = mh << 1;
-                    pv[u] = mhs | ~(xv | phs);
-                    mv[u] = phs & xv;
-                    int hit_score = score[u];
-                    if (last_row_rule) {
-                        const int up = score[u] - (int)(pv[u] >> kMsb) + (int)(mv[u] >> kMsb);    // D[m-1][j]
-                        hit_score = min(up + 1, up_prev + 1 - (int)(eq[u] >> kMsb));
-                    }
-                    best[u] = (in[u] && c0[u] + t >= ct[u]) ? min(best[u], hit_score) : best[u];
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < 2; u++)
-                if (hk[u] >= 0 && best[u] <= hk[u]) {
-                    const int k = atomicAdd(&cand_n_s[hr[u]], 1);
-                    if (k < kSvCand) cand_s[hr[u] * kSvCand + k] = ((uint32_t)hb[u] << 8) | (uint32_t)best[u];
-                }
+        {
+            const int total = min(ctr_s[0], hit_cap);
+            if (last_row_rule)
+                sv_verify<WT, true>(hits_s, total, rinfo_s, binfo_s, peq_s, n_classes, plane, slot_s, slot_stride, cand_s, cand_n_s);
+            else
+                sv_verify<WT, false>(hits_s, total, rinfo_s, binfo_s, peq_s, n_classes, plane, slot_s, slot_stride, cand_s, cand_n_s);
         }
         __syncthreads();
 
@@ -444,7 +490,7 @@ static SvLaunch sv_launch_params(const DevSet &S)
     int words = (L.slot_cols + 3) / 4;
     words |= 1;                                   // odd word stride: the slots of consecutive reads start in different banks
     L.slot_stride = words * 4;
-    size_t off[12];
+    size_t off[kSvParts];
     const int plane = S.n_classes * S.n_bc_pad;
     L.tab_smem = 1;
     L.smem = sv_smem_layout(S.words, plane, S.n_bc_pad, S.sv.n_entries, S.sv.n_buckets, 1, L.slot_stride, S.max_m, off);

@@ -89,11 +89,15 @@ struct HostSet {
     int sdd_n = 0, sdd_k = 0;      // deepest level (seed_deep.cu): one table per seed length
     HostSeedLevel sdd[2];
     // variable lengths / constrained geometries (seed_var.cu)
-    int sv_enabled = 0, sv_q = 0, sv_complete = 0;
-    double sv_sigma_min = 0.0;
-    std::vector<uint16_t> sv_bstart;
-    std::vector<uint32_t> sv_entries;
-    std::vector<uint8_t> sv_kdepth;
+    struct HostSeedVar {
+        int q = 0, complete = 0, group_reads = 0;
+        double sigma_min = 0.0;
+        std::vector<uint16_t> bstart;
+        std::vector<uint32_t> entries;
+        std::vector<uint8_t> kdepth;
+    };
+    int sv_levels = 0;
+    HostSeedVar sv[2];
 };
 
 struct DeviceTables {
@@ -398,8 +402,11 @@ static int build_set(const bdx_params &p, const bdx_barcode_set &in, HostSet &hs
     }
     // ---- seed-and-verify for sets of different lengths and constrained start / end geometries (seed_var.cu):
     // K_b + 1 disjoint segments per barcode, K_b = min(m_b / q - 1, allowed_b), their first q bases in a
-    // direct-address table.  q = the shortest seed whose CHANCE hits on admissible diagonals stay within the hit
-    // list (estimated for a 150-base read): position constraints keep short seeds selective ----
+    // direct-address table.  Level 1: q = the shortest seed whose CHANCE hits on admissible diagonals (estimated
+    // for a 150-base read) stay around two dozen per read -- position constraints keep short seeds selective.
+    // Level 2 (reads level 1 could not decide): the longest seed that is COMPLETE (K_b = allowed_b for every
+    // barcode, so the candidates are a superset and every verdict is final), used while verifying its chance
+    // hits costs less than half the lane-per-barcode automaton over the whole range ----
     if (sg && hs.words >= 1 && !p.has_nindel && hs.n_classes - 1 <= 4 && hs.n_bc < (1 << 14) && hs.max_m <= 64 &&
         p.max_error_rate >= 0.0 && !getenv("BDX_DISABLE_SEED")) {
         auto resolve = [](const DevRange &dr, int len, int &first, int &last) {      // classification.jl:96-100
@@ -417,29 +424,34 @@ static int build_set(const bdx_params &p, const bdx_barcode_set &in, HostSet &hs
         const int start_j = std::max(rf, std::max(bf, 1)), end_j = std::min(rl, std::min(el, n_nom));
         const int L = std::max(end_j - start_j + 1, 1), sbase = start_j - 1;
         const int min_end_rel = ef - sbase, max_start_rel = bl - sbase;
-        for (int q = 4; q <= 8 && !hs.sv_enabled; q++) {
-            if (min_m < q) break;
-            double chance = 0.0;
-            size_t n_entries = 0;
+        struct Est { double chance, steps; size_t n_entries; bool complete; };
+        auto estimate = [&](int q) {
+            Est e{0.0, 0.0, 0, true};
             for (int b = 0; b < hs.n_bc; b++) {
                 const int m = hs.off[b + 1] - hs.off[b], a0 = hs.allowed0[b];
                 const int K = std::min(m / q - 1, a0);
                 const int dlo = std::max(0, min_end_rel - m) - K, dhi = std::min(max_start_rel + a0, L - m + K);
-                chance += (double)(K + 1) * std::max(0, dhi - dlo + 1) / std::pow(4.0, q);
-                n_entries += (size_t)K + 1;
+                const double c = (double)(K + 1) * std::max(0, dhi - dlo + 1) / std::pow(4.0, q);
+                e.chance += c;
+                e.steps += c * (m + 2 * K);          // columns verified for those hits
+                e.n_entries += (size_t)K + 1;
+                if (K < a0) e.complete = false;
             }
-            if (chance > 24.0 || n_entries > 65535) continue;
-            hs.sv_q = q;
-            hs.sv_kdepth.assign((size_t)hs.n_bc, 0);
+            return e;
+        };
+        auto build = [&](int q, double chance) {
+            HostSet::HostSeedVar &V = hs.sv[hs.sv_levels++];
+            V.q = q;
+            V.kdepth.assign((size_t)hs.n_bc, 0);
             std::vector<std::vector<uint32_t>> buckets((size_t)1 << (2 * q));
-            hs.sv_sigma_min = 1e300;
-            hs.sv_complete = 1;
+            V.sigma_min = 1e300;
+            V.complete = 1;
             for (int b = 0; b < hs.n_bc; b++) {
                 const int m = hs.off[b + 1] - hs.off[b], a0 = hs.allowed0[b];
                 const int K = std::min(m / q - 1, a0);
-                hs.sv_kdepth[(size_t)b] = (uint8_t)K;
-                if (K < a0) hs.sv_complete = 0;
-                hs.sv_sigma_min = std::min(hs.sv_sigma_min, (double)(K + 1) / (double)hs.norm[b]);
+                V.kdepth[(size_t)b] = (uint8_t)K;
+                if (K < a0) V.complete = 0;
+                V.sigma_min = std::min(V.sigma_min, (double)(K + 1) / (double)hs.norm[b]);
                 const int seg = m / (K + 1);                       // >= q: the segments are disjoint
                 for (int i = 0; i <= K; i++) {
                     const int o = i * seg;
@@ -448,12 +460,35 @@ static int build_set(const bdx_params &p, const bdx_barcode_set &in, HostSet &hs
                     buckets[code].push_back(((uint32_t)b << 8) | (uint32_t)o);
                 }
             }
-            hs.sv_bstart.assign(buckets.size() + 1, 0);
+            V.bstart.assign(buckets.size() + 1, 0);
             for (size_t k = 0; k < buckets.size(); k++) {
-                hs.sv_bstart[k + 1] = (uint16_t)(hs.sv_bstart[k] + buckets[k].size());
-                hs.sv_entries.insert(hs.sv_entries.end(), buckets[k].begin(), buckets[k].end());
+                V.bstart[k + 1] = (uint16_t)(V.bstart[k] + buckets[k].size());
+                V.entries.insert(V.entries.end(), buckets[k].begin(), buckets[k].end());
             }
-            hs.sv_enabled = 1;
+            // reads per group: their hits (chance + a handful of true ones) should fill the block's list
+            // (256 x 32 records, seed_var.cu) to about two thirds
+            int R = 256;
+            while (R > 32 && (chance + 6.0) * R > 0.66 * 256 * 32) R -= 32;
+            V.group_reads = R;
+        };
+        int q1 = 0;
+        for (int q = 4; q <= 8 && !q1; q++) {
+            if (min_m < q) break;
+            const Est e = estimate(q);
+            if (e.chance <= 24.0 && e.n_entries <= 65535) {
+                q1 = q;
+                build(q, e.chance);
+            }
+        }
+        if (q1 && !hs.sv[0].complete && !getenv("BDX_SEED_ONE_LEVEL")) {
+            int q2 = q1 - 1;
+            for (int b = 0; b < hs.n_bc; b++) q2 = std::min(q2, (hs.off[b + 1] - hs.off[b]) / (hs.allowed0[b] + 1));
+            if (q2 >= 3) {
+                const Est e = estimate(q2);
+                const double automaton_steps = (double)hs.n_bc * L;
+                if (e.complete && e.n_entries <= 65535 && e.steps < 0.5 * automaton_steps && e.chance <= 200.0)
+                    build(q2, e.chance);
+            }
         }
     }
     // ---- :hamming on packed words (hamming.cu): uniform length <= 32, <= 4 distinct barcode bytes, no 'N' ----
@@ -737,15 +772,21 @@ static int get_tables(bdx_config *cfg, int device, DeviceTables **out)
             if (e == cudaSuccess) e = upload(t, H.ekeys, &L.ekeys);
             if (e == cudaSuccess) e = upload(t, H.bitmap, &L.bitmap);
         }
-        D.sv.enabled = hs.sv_enabled;
-        D.sv.q = hs.sv_q;
-        D.sv.n_buckets = 1 << (2 * hs.sv_q);
-        D.sv.n_entries = (int)hs.sv_entries.size();
-        D.sv.complete = hs.sv_complete;
-        D.sv.sigma_min = hs.sv_sigma_min;
-        if (e == cudaSuccess) e = upload(t, hs.sv_bstart, &D.sv.bstart);
-        if (e == cudaSuccess) e = upload(t, hs.sv_entries, &D.sv.entries);
-        if (e == cudaSuccess) e = upload(t, hs.sv_kdepth, &D.sv.kdepth);
+        D.sv_levels = hs.sv_levels;
+        for (int l = 0; l < hs.sv_levels; l++) {
+            const HostSet::HostSeedVar &H = hs.sv[l];
+            SeedVar &V = D.sv[l];
+            V.enabled = 1;
+            V.q = H.q;
+            V.n_buckets = 1 << (2 * H.q);
+            V.n_entries = (int)H.entries.size();
+            V.complete = H.complete;
+            V.group_reads = H.group_reads;
+            V.sigma_min = H.sigma_min;
+            if (e == cudaSuccess) e = upload(t, H.bstart, &V.bstart);
+            if (e == cudaSuccess) e = upload(t, H.entries, &V.entries);
+            if (e == cudaSuccess) e = upload(t, H.kdepth, &V.kdepth);
+        }
         D.hp.enabled = hs.hp_enabled;
         D.hp.m = hs.hp_m;
         D.hp.allowed = hs.hp_allowed;
@@ -1055,15 +1096,17 @@ static int enqueue_classify(bdx_stream *s, const uint8_t *d_seq, const int32_t *
                 // seed levels hand the reads they cannot finish from one worklist to the other; without a
                 // prefilter in front (min_delta != 0) the first level takes every read of the batch
                 // barcodes of different lengths / constrained start or end: k_seed_var instead of the levels
-                const bool sv = seed_var_applies(P, pass);
-                if (sv) {
-                    const int *wl_in = wl == 0 ? nullptr : s->sc.worklist;
-                    const int *n_in = wl == 0 ? nullptr : s->sc.n_work;
-                    if ((rc = staged(kStSeed, [&] { return launch_seed_var(P, pass, d_seq, d_off, n, s->sc, wl_in, n_in, s->sc.worklist2, s->sc.n_work2,
+                const int sv_levels = seed_var_levels(P, pass);
+                for (int l = 0; l < sv_levels; l++) {
+                    const int *wl_in = wl == 0 ? nullptr : (wl == 1 ? s->sc.worklist : s->sc.worklist2);
+                    const int *n_in = wl == 0 ? nullptr : (wl == 1 ? s->sc.n_work : s->sc.n_work2);
+                    const bool to2 = wl != 2;
+                    if ((rc = staged(l == 0 ? kStSeed : kStSeedDeep, [&] { return launch_seed_var(P, pass, l, d_seq, d_off, n, s->sc, wl_in, n_in,
+                                   to2 ? s->sc.worklist2 : s->sc.worklist, to2 ? s->sc.n_work2 : s->sc.n_work,
                                    s->tab->sm_count, s->d_counters, s->st_comp); }))) return rc;
-                    wl = 2;
+                    wl = to2 ? 2 : 1;
                 }
-                const int levels = sv ? 0 : seed_levels(P, pass);
+                const int levels = sv_levels ? 0 : seed_levels(P, pass);
                 for (int l = 0; l < levels; l++) {
                     const int *wl_in = wl == 0 ? nullptr : (wl == 1 ? s->sc.worklist : s->sc.worklist2);
                     const int *n_in = wl == 0 ? nullptr : (wl == 1 ? s->sc.n_work : s->sc.n_work2);

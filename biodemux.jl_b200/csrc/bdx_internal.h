@@ -62,7 +62,7 @@ struct SeedVar {
     int n_buckets;                // 4^q
     int n_entries;
     int complete;                 // kdepth[b] >= allowed0[b] for every barcode: the candidate sets are supersets
-    int pad;
+    int group_reads;              // reads a block works on at a time (sized so that their hits fit the block's hit list)
     double sigma_min;             // min_b (kdepth[b] + 1) / norm[b]: no barcode outside the candidate set scores below
     const uint16_t *bstart;       // [n_buckets + 1] CSR row starts
     const uint32_t *entries;      // [n_entries] (barcode index << 8) | seed offset
@@ -119,7 +119,9 @@ struct DevSet {
     int sdd_n;                    // 0 = off
     int sdd_k;
     SeedLevel sdd[2];
-    SeedVar sv;
+    int sv_levels;                // 0 = off; level 1 (if any) is the complete one
+    int pad3;
+    SeedVar sv[2];
 };
 
 constexpr int kPfMaxSeed = 12;
@@ -199,8 +201,8 @@ cudaError_t launch_seed(const DevParams &P, int pass, int level, const uint8_t *
 // reads of a worklist that no kernel resolved: queue them for k_literal over every barcode
 cudaError_t launch_mark_pending(const DevParams &P, int pass, int n, const Scratch &sc, const int *wl, const int *n_wl,
                                 cudaStream_t st);
-bool seed_var_applies(const DevParams &P, int pass);
-cudaError_t launch_seed_var(const DevParams &P, int pass, const uint8_t *seq, const int *off, int n, const Scratch &sc,
+int seed_var_levels(const DevParams &P, int pass);     // number of k_seed_var levels that apply (0 = none)
+cudaError_t launch_seed_var(const DevParams &P, int pass, int level, const uint8_t *seq, const int *off, int n, const Scratch &sc,
                             const int *wl_in, const int *n_in, int *wl_out, int *n_out, int sm_count,
                             unsigned long long *counters, cudaStream_t st);
 bool seed_deep_applies(const DevParams &P, int pass);

@@ -45,7 +45,7 @@
 
 namespace bdx {
 
-constexpr int kSvThreads = 128;      // threads per block = reads per group
+constexpr int kSvThreads = 256;      // threads per block = reads per group
 constexpr int kSvHitsPerRead = 32;   // capacity of the block's hit list, per read of the group
 constexpr int kSvCand = 8;           // verified candidates kept per read
 constexpr int kSvDiagBias = 64;      // hit record: read << 22 | barcode << 8 | diagonal + bias
@@ -193,7 +193,7 @@ __device__ __forceinline__ void sv_verify(const uint32_t *hits_s, int total, con
 
 template <int W>
 __global__ void __launch_bounds__(kSvThreads)
-k_seed_var(const __grid_constant__ DevParams P, const int pass, const uint8_t *__restrict__ seq,
+k_seed_var(const __grid_constant__ DevParams P, const int pass, const int level, const uint8_t *__restrict__ seq,
            const int *__restrict__ off, const int n_reads, PassOut *__restrict__ out,
            const PassOut *__restrict__ prev_pass, const int *__restrict__ wl_in, const int *__restrict__ n_in,
            int *__restrict__ wl_out, int *__restrict__ n_out, unsigned long long *__restrict__ counters,
@@ -201,7 +201,8 @@ k_seed_var(const __grid_constant__ DevParams P, const int pass, const uint8_t *_
 {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const DevSet &S = P.set[pass];
-    const SeedVar &V = S.sv;
+    const SeedVar &V = S.sv[level];
+    const int R = V.group_reads;                             // reads per group: threads 0 .. R-1 own one each
     const int n_pad = S.n_bc_pad;
     const int n_classes = S.n_classes;
     const int plane = n_classes * n_pad;
@@ -248,7 +249,7 @@ k_seed_var(const __grid_constant__ DevParams P, const int pass, const uint8_t *_
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int n_items = wl_in ? *n_in : n_reads;
-    const int n_groups = (n_items + kSvThreads - 1) / kSvThreads;
+    const int n_groups = (n_items + R - 1) / R;
     const bool with_delta = P.min_delta != 0.0;
     const int hit_cap = kSvThreads * sv_hit_rows(S.max_m);
     const int n_pos = max(slot_cols - q + 1, 1);             // q-mer positions scanned per read (at most)
@@ -256,8 +257,8 @@ k_seed_var(const __grid_constant__ DevParams P, const int pass, const uint8_t *_
     unsigned int n_done = 0;
 
     for (int grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
-        const int item = grp * kSvThreads + threadIdx.x;
-        const bool have = item < n_items;
+        const int item = grp * R + threadIdx.x;
+        const bool have = (int)threadIdx.x < R && item < n_items;
         const int read = have ? (wl_in ? wl_in[item] : item) : 0;
         const int base = have ? off[read] : 0;
         const int n = have ? off[read + 1] - base : 0;
@@ -289,7 +290,8 @@ k_seed_var(const __grid_constant__ DevParams P, const int pass, const uint8_t *_
         rinfo_s[threadIdx.x * 4 + 3] = 0;                        // flags: 1 = hit list overflow
         cand_n_s[threadIdx.x] = 0;
         if (threadIdx.x == 0) ctr_s[0] = 0;
-        sv_stage_warp(seq, (long long)base + sbase, L, slot_s + (size_t)warp * 32 * slot_stride, slot_stride, class_s, lane);
+        if (warp * 32 < R)
+            sv_stage_warp(seq, (long long)base + sbase, L, slot_s + (size_t)warp * 32 * slot_stride, slot_stride, class_s, lane);
         // Constrained end (min_end_pos inside the range): the reference's last row takes no insertion
         // (classification.jl:213), so a hit at column j is D'[m][j] = min(D[m-1][j] + 1, D[m-1][j-1] + sub), not
         // the automaton's D[m][j].  Over ALL columns the two have the same minimum, over the columns
@@ -298,7 +300,7 @@ k_seed_var(const __grid_constant__ DevParams P, const int pass, const uint8_t *_
 
         // ---- scan: (read, column) pairs dealt to the threads.  The table entries of a warp's 32 pairs are
         // pooled (prefix sum of the bucket sizes) and dealt out evenly again, one entry per lane and round ----
-        for (int i = threadIdx.x; i < kSvThreads * n_pos; i += kSvThreads) {
+        for (int i = threadIdx.x; i < R * n_pos; i += kSvThreads) {
             const int r = (int)__umulhi((uint32_t)i, pos_recip), p = i - r * n_pos;
             const int Lr = rinfo_s[r * 4 + 0];
             bool valid = p + q <= Lr;
@@ -399,7 +401,7 @@ k_seed_var(const __grid_constant__ DevParams P, const int pass, const uint8_t *_
                     }
             const bool start_bound = g.max_start_pos < n;           // the reference's result depends on the threshold
             const Costs c{P.match, P.mismatch, P.indel, P.nindel, P.has_n};
-            // DP column of sg_literal: element i of this thread at hits_s[i * 128 + thread] (the hit list is dead now)
+            // DP column of sg_literal: element i of this thread at hits_s[i * kSvThreads + thread] (the hit list is dead now)
             const WsCol DP{reinterpret_cast<int *>(hits_s) + threadIdx.x, kSvThreads};
             // the read's search range as class codes: equality of class codes == equality of bytes for barcode
             // bytes (a read byte that occurs in no barcode is class 0); absolute column j at my_slot[j - 1 - sbase]
@@ -483,7 +485,7 @@ struct SvLaunch {
     size_t smem;
 };
 
-static SvLaunch sv_launch_params(const DevSet &S)
+static SvLaunch sv_launch_params(const DevSet &S, const SeedVar &V)
 {
     SvLaunch L;
     L.slot_cols = sv_slot_cols(S);
@@ -493,40 +495,43 @@ static SvLaunch sv_launch_params(const DevSet &S)
     size_t off[kSvParts];
     const int plane = S.n_classes * S.n_bc_pad;
     L.tab_smem = 1;
-    L.smem = sv_smem_layout(S.words, plane, S.n_bc_pad, S.sv.n_entries, S.sv.n_buckets, 1, L.slot_stride, S.max_m, off);
+    L.smem = sv_smem_layout(S.words, plane, S.n_bc_pad, V.n_entries, V.n_buckets, 1, L.slot_stride, S.max_m, off);
     if (L.smem > 100 * 1024) {
         L.tab_smem = 0;
-        L.smem = sv_smem_layout(S.words, plane, S.n_bc_pad, S.sv.n_entries, S.sv.n_buckets, 0, L.slot_stride, S.max_m, off);
+        L.smem = sv_smem_layout(S.words, plane, S.n_bc_pad, V.n_entries, V.n_buckets, 0, L.slot_stride, S.max_m, off);
     }
     return L;
 }
 
 // Does k_seed_var take this pass?  Score-only :semiglobal passes with unit costs whose set has the tables, when
 // k_seed's levels do not apply (barcodes of different lengths) or would refuse every read (constrained start / end).
-bool seed_var_applies(const DevParams &P, int pass)
+int seed_var_levels(const DevParams &P, int pass)
 {
     const DevSet &S = P.set[pass];
-    if (P.algo != BDX_SEMIGLOBAL || !P.unit_costs || !S.sv.enabled || S.words < 1 || P.max_error_rate < 0.0) return false;
-    if (S.trim_side != 0 || P.want_stats) return false;
-    if (seed_levels(P, pass) > 0 && sv_default_geometry(S)) return false;
-    return sv_launch_params(S).smem <= 160 * 1024;
+    if (P.algo != BDX_SEMIGLOBAL || !P.unit_costs || S.sv_levels < 1 || S.words < 1 || P.max_error_rate < 0.0) return 0;
+    if (S.trim_side != 0 || P.want_stats) return 0;
+    if (seed_levels(P, pass) > 0 && sv_default_geometry(S)) return 0;
+    for (int l = 0; l < S.sv_levels; l++)
+        if (sv_launch_params(S, S.sv[l]).smem > 160 * 1024) return l;
+    return S.sv_levels;
 }
 
-cudaError_t launch_seed_var(const DevParams &P, int pass, const uint8_t *seq, const int *off, int n, const Scratch &sc,
+cudaError_t launch_seed_var(const DevParams &P, int pass, int level, const uint8_t *seq, const int *off, int n, const Scratch &sc,
                             const int *wl_in, const int *n_in, int *wl_out, int *n_out, int sm_count,
                             unsigned long long *counters, cudaStream_t st)
 {
     const DevSet &S = P.set[pass];
-    const SvLaunch L = sv_launch_params(S);
+    const SeedVar &V = S.sv[level];
+    const SvLaunch L = sv_launch_params(S, V);
     auto kern = S.words == 1 ? k_seed_var<1> : k_seed_var<2>;
     int per_sm = 0;
     cudaError_t e = blocks_per_sm_cached((const void *)kern, kSvThreads, L.smem, &per_sm);
     if (e != cudaSuccess) return e;
-    const int groups = (n + kSvThreads - 1) / kSvThreads;
+    const int groups = (n + V.group_reads - 1) / V.group_reads;
     const int blocks = std::max(1, std::min(groups, sm_count * per_sm));
     e = cudaMemsetAsync(n_out, 0, sizeof(int), st);
     if (e != cudaSuccess) return e;
-    kern<<<blocks, kSvThreads, L.smem, st>>>(P, pass, seq, off, n, sc.pass[pass], sc.pass[0], wl_in, n_in, wl_out, n_out,
+    kern<<<blocks, kSvThreads, L.smem, st>>>(P, pass, level, seq, off, n, sc.pass[pass], sc.pass[0], wl_in, n_in, wl_out, n_out,
                                              counters, L.slot_stride, L.slot_cols, L.tab_smem);
     return cudaGetLastError();
 }

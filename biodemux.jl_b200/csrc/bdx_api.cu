@@ -90,7 +90,7 @@ struct HostSet {
     HostSeedLevel sdd[2];
     // variable lengths / constrained geometries (seed_var.cu)
     struct HostSeedVar {
-        int q = 0, complete = 0, group_reads = 0;
+        int q = 0, complete = 0, group_reads = 0, hit_rows = 0;
         double sigma_min = 0.0;
         std::vector<uint16_t> bstart;
         std::vector<uint32_t> entries;
@@ -465,10 +465,12 @@ static int build_set(const bdx_params &p, const bdx_barcode_set &in, HostSet &hs
                 V.bstart[k + 1] = (uint16_t)(V.bstart[k] + buckets[k].size());
                 V.entries.insert(V.entries.end(), buckets[k].begin(), buckets[k].end());
             }
-            // reads per group: their hits (chance + a handful of true ones) should fill the block's list
-            // (256 x 32 records, seed_var.cu) to about two thirds
-            int R = 256;
-            while (R > 32 && (chance + 6.0) * R > 0.66 * 256 * 32) R -= 32;
+            // 128 reads per group and a hit list of up to 64 rows x 128 records (seed_var.cu) that their hits -- chance
+            // + a handful of true ones -- fill to about 70 %; denser levels take fewer reads per group instead
+            const double per_read = chance + 6.0;
+            V.hit_rows = std::min(64, std::max(32, (int)std::ceil(per_read / 0.7)));
+            int R = 128;
+            while (R > 8 && per_read * R > 0.7 * 128 * V.hit_rows) R -= 8;
             V.group_reads = R;
         };
         int q1 = 0;
@@ -782,6 +784,7 @@ static int get_tables(bdx_config *cfg, int device, DeviceTables **out)
             V.n_entries = (int)H.entries.size();
             V.complete = H.complete;
             V.group_reads = H.group_reads;
+            V.hit_rows = H.hit_rows;
             V.sigma_min = H.sigma_min;
             if (e == cudaSuccess) e = upload(t, H.bstart, &V.bstart);
             if (e == cudaSuccess) e = upload(t, H.entries, &V.entries);

@@ -63,6 +63,8 @@ struct SeedVar {
     int n_entries;
     int complete;                 // kdepth[b] >= allowed0[b] for every barcode: the candidate sets are supersets
     int group_reads;              // reads a block works on at a time (sized so that their hits fit the block's hit list)
+    int hit_rows;                 // hit list capacity in rows of 128 records
+    int pad;
     double sigma_min;             // min_b (kdepth[b] + 1) / norm[b]: no barcode outside the candidate set scores below
     const uint16_t *bstart;       // [n_buckets + 1] CSR row starts
     const uint32_t *entries;      // [n_entries] (barcode index << 8) | seed offset

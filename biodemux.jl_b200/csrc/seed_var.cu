@@ -45,12 +45,12 @@
 
 namespace bdx {
 
-constexpr int kSvThreads = 256;      // threads per block = reads per group
-constexpr int kSvHitsPerRead = 32;   // capacity of the block's hit list, per read of the group
+constexpr int kSvThreads = 128;      // threads per block; a block works on groups of R <= 128 reads (SeedVar::group_reads)
 constexpr int kSvCand = 8;           // verified candidates kept per read
 constexpr int kSvDiagBias = 64;      // hit record: read << 22 | barcode << 8 | diagonal + bias
 constexpr int kSvMaxCols = 180;      // longest search range staged (longer ones take the exact path)
 constexpr int kSvBig = 1 << 20;
+constexpr int kSvRi = 5;             // ints per read in rinfo: L, min_end_rel, max_start_rel, flags, n_rel
 
 // Stages `my_len` bytes starting at seq + my_start as class codes for each of the warp's 32 reads (lane l
 // describes read l) -- seed_stage_warp of seed_common.cuh with a runtime slot stride.
@@ -89,25 +89,26 @@ __device__ __forceinline__ void sv_stage_warp(const uint8_t *__restrict__ seq, l
 }
 
 // Shared-memory carve-up (bytes); the same arithmetic on the host (launch) and the device (kernel).
-__host__ __device__ inline int sv_hit_rows(int max_m) { return max_m + 2 > kSvHitsPerRead ? max_m + 2 : kSvHitsPerRead; }
+// rows of kSvThreads records in the block's hit list; the decide phase reuses the list as DP columns [row][thread]
+__host__ __device__ inline int sv_hit_rows(int wanted, int max_m) { return max_m + 2 > wanted ? max_m + 2 : wanted; }
 
 enum { kSvPeq = 0, kSvHits, kSvCandL, kSvRinfo, kSvCandN, kSvCtr, kSvEntries, kSvBstart, kSvBinfo, kSvClass, kSvSlot, kSvParts };
 
 __host__ __device__ inline size_t sv_smem_layout(int W, int plane, int n_pad, int n_entries, int n_buckets, int tab_smem,
-                                                 int slot_stride, int max_m, size_t off[kSvParts])
+                                                 int slot_stride, int max_m, int R, int hit_rows, size_t off[kSvParts])
 {
     size_t o = 0;
     off[kSvPeq] = o; o += (size_t)W * plane * 4;                          // Peq, transposed to [word][barcode][class]
-    off[kSvHits] = o; o += (size_t)kSvThreads * sv_hit_rows(max_m) * 4;   // hit list; the decide phase reuses it as DP columns [row][thread]
-    off[kSvCandL] = o; o += (size_t)kSvThreads * kSvCand * 4;             // verified candidates per read
-    off[kSvRinfo] = o; o += (size_t)kSvThreads * 4 * 4;                   // per read: L, min_end_rel, max_start_rel, flags
-    off[kSvCandN] = o; o += (size_t)kSvThreads * 4;
-    off[kSvCtr] = o; o += 16;
+    off[kSvHits] = o; o += (size_t)kSvThreads * sv_hit_rows(hit_rows, max_m) * 4;   // hit list / DP columns [row][thread]
+    off[kSvCandL] = o; o += (size_t)R * kSvCand * 4;                      // verified candidates per read
+    off[kSvRinfo] = o; o += (size_t)kSvThreads * kSvRi * 4;               // per read: L, min_end_rel, max_start_rel, flags, n_rel
+    off[kSvCandN] = o; o += ((size_t)kSvThreads + 4) * 4;                 // per read: number of candidates; later their offsets
+    off[kSvCtr] = o; o += 32;
     off[kSvEntries] = o; o += tab_smem ? (size_t)n_entries * 4 : 0;
     off[kSvBstart] = o; o += tab_smem ? (((size_t)n_buckets + 1) * 2 + 3) / 4 * 4 : 0;
     off[kSvBinfo] = o; o += (size_t)n_pad * 4;                            // per barcode: m | K << 8 | allowed0 << 16
     off[kSvClass] = o; o += 256;
-    off[kSvSlot] = o; o += (size_t)kSvThreads * slot_stride + 128;        // staged class codes (+ slack: windows are read past their end)
+    off[kSvSlot] = o; o += (size_t)R * slot_stride + 128;                 // staged class codes (+ slack: windows are read past their end)
     return (o + 15) / 16 * 16;
 }
 
@@ -137,7 +138,7 @@ __device__ __forceinline__ void sv_verify(const uint32_t *hits_s, int total, con
             const uint32_t bi = binfo_s[hb[u]];
             const int m = (int)(bi & 0xFFu);
             hk[u] = live ? (int)((bi >> 8) & 0xFFu) : -1;
-            const int Lr = rinfo_s[hr[u] * 4 + 0], min_end_rel = rinfo_s[hr[u] * 4 + 1];
+            const int Lr = rinfo_s[hr[u] * kSvRi + 0], min_end_rel = rinfo_s[hr[u] * kSvRi + 1];
             // 1-based relative columns an alignment with <= K edits and this segment intact can occupy
             const int c0 = live ? max(1, delta - hk[u] + 1) : 1;
             const int c1 = live ? min(Lr, delta + m + hk[u]) : 0;
@@ -209,7 +210,7 @@ k_seed_var(const __grid_constant__ DevParams P, const int pass, const int level,
     const int q = V.q;
     const int n_buckets = V.n_buckets;
     size_t lo[kSvParts];
-    sv_smem_layout(W, plane, n_pad, V.n_entries, n_buckets, tab_smem, slot_stride, S.max_m, lo);
+    sv_smem_layout(W, plane, n_pad, V.n_entries, n_buckets, tab_smem, slot_stride, S.max_m, R, V.hit_rows, lo);
     uint32_t *peq_s = reinterpret_cast<uint32_t *>(smem_raw + lo[kSvPeq]);
     uint32_t *hits_s = reinterpret_cast<uint32_t *>(smem_raw + lo[kSvHits]);
     uint32_t *cand_s = reinterpret_cast<uint32_t *>(smem_raw + lo[kSvCandL]);
@@ -242,7 +243,7 @@ k_seed_var(const __grid_constant__ DevParams P, const int pass, const int level,
         binfo_s[k] = v;
     }
     for (int k = threadIdx.x; k < 256; k += blockDim.x) class_s[k] = S.class_of[k];
-    for (int k = threadIdx.x; k < 128; k += blockDim.x) slot_s[(size_t)kSvThreads * slot_stride + k] = 0;
+    for (int k = threadIdx.x; k < 128; k += blockDim.x) slot_s[(size_t)R * slot_stride + k] = 0;
     __syncthreads();
 
     using WT = typename std::conditional<W == 1, uint32_t, unsigned long long>::type;
@@ -251,7 +252,7 @@ k_seed_var(const __grid_constant__ DevParams P, const int pass, const int level,
     const int n_items = wl_in ? *n_in : n_reads;
     const int n_groups = (n_items + R - 1) / R;
     const bool with_delta = P.min_delta != 0.0;
-    const int hit_cap = kSvThreads * sv_hit_rows(S.max_m);
+    const int hit_cap = kSvThreads * sv_hit_rows(V.hit_rows, S.max_m);
     const int n_pos = max(slot_cols - q + 1, 1);             // q-mer positions scanned per read (at most)
     const uint32_t pos_recip = 0xFFFFFFFFu / (uint32_t)n_pos + 1u;   // i / n_pos == umulhi(i, recip) for i < 2^16
     unsigned int n_done = 0;
@@ -284,10 +285,11 @@ k_seed_var(const __grid_constant__ DevParams P, const int pass, const int level,
         // columns RELATIVE to the search range: relative column c (1-based) is absolute column c + sbase
         const int sbase = punt ? 0 : g.start_j - 1;
         const int L = punt ? 0 : g.end_j - g.start_j + 1;
-        rinfo_s[threadIdx.x * 4 + 0] = L;
-        rinfo_s[threadIdx.x * 4 + 1] = punt ? 1 : max(g.min_end_pos - sbase, -kSvBig);
-        rinfo_s[threadIdx.x * 4 + 2] = punt ? 0 : min(g.max_start_pos - sbase, kSvBig);
-        rinfo_s[threadIdx.x * 4 + 3] = 0;                        // flags: 1 = hit list overflow
+        rinfo_s[threadIdx.x * kSvRi + 0] = L;
+        rinfo_s[threadIdx.x * kSvRi + 1] = punt ? 1 : max(g.min_end_pos - sbase, -kSvBig);
+        rinfo_s[threadIdx.x * kSvRi + 2] = punt ? 0 : min(g.max_start_pos - sbase, kSvBig);
+        rinfo_s[threadIdx.x * kSvRi + 3] = 0;                        // flags: 1 = hit list overflow, 2 = a candidate is not robust
+        rinfo_s[threadIdx.x * kSvRi + 4] = n - sbase;                // read length seen from the range start
         cand_n_s[threadIdx.x] = 0;
         if (threadIdx.x == 0) ctr_s[0] = 0;
         if (warp * 32 < R)
@@ -300,10 +302,11 @@ k_seed_var(const __grid_constant__ DevParams P, const int pass, const int level,
 
         // ---- scan: (read, column) pairs dealt to the threads.  The table entries of a warp's 32 pairs are
         // pooled (prefix sum of the bucket sizes) and dealt out evenly again, one entry per lane and round ----
-        for (int i = threadIdx.x; i < R * n_pos; i += kSvThreads) {
-            const int r = (int)__umulhi((uint32_t)i, pos_recip), p = i - r * n_pos;
-            const int Lr = rinfo_s[r * 4 + 0];
-            bool valid = p + q <= Lr;
+        const int n_pairs = R * n_pos;
+        for (int i = threadIdx.x; i < ((n_pairs + 31) & ~31); i += kSvThreads) {     // whole warps: the loop body votes
+            const int r = min((int)__umulhi((uint32_t)i, pos_recip), R - 1), p = i - r * n_pos;
+            const int Lr = rinfo_s[r * kSvRi + 0];
+            bool valid = i < n_pairs && p + q <= Lr;
             uint32_t code = 0;
             if (valid) {
                 const uint8_t *c = slot_s + (size_t)r * slot_stride + p;
@@ -346,7 +349,7 @@ k_seed_var(const __grid_constant__ DevParams P, const int pass, const int level,
                     const int b = (int)(ent >> 8), o = (int)(ent & 0xFFu);
                     const uint32_t bi = binfo_s[b];
                     const int m = (int)(bi & 0xFFu), K = (int)((bi >> 8) & 0xFFu), a0 = (int)(bi >> 16);
-                    const int oL = rinfo_s[hr * 4 + 0], min_end_rel = rinfo_s[hr * 4 + 1], max_start_rel = rinfo_s[hr * 4 + 2];
+                    const int oL = rinfo_s[hr * kSvRi + 0], min_end_rel = rinfo_s[hr * kSvRi + 1], max_start_rel = rinfo_s[hr * kSvRi + 2];
                     const int delta = op - o;                                   // 0-based relative diagonal
                     // Diagonals (read column - barcode row) an acceptable alignment's intact segment can lie on:
                     // the segment's own cells obey the reference's band j - i <= max_start_pos + steps
@@ -365,7 +368,7 @@ k_seed_var(const __grid_constant__ DevParams P, const int pass, const int level,
                     if (hit) {
                         const int idx = hbase + __popc(hm & ((1u << lane) - 1u));
                         if (idx < hit_cap) hits_s[idx] = rec;
-                        else rinfo_s[hr * 4 + 3] = 1;                           // this read's candidate set is incomplete
+                        else rinfo_s[hr * kSvRi + 3] = 1;                           // this read's candidate set is incomplete
                     }
                 }
             }
@@ -382,10 +385,66 @@ k_seed_var(const __grid_constant__ DevParams P, const int pass, const int level,
         }
         __syncthreads();
 
-        // ---- decide: one thread per read ----
+        // ---- decide ----
+        // Constrained start: every candidate is re-aligned by sg_literal in the tightest band that can still accept
+        // it (allowed = d); found there => found in every wider band, i.e. its value does not depend on the running
+        // threshold.  One thread per CANDIDATE (the reads' lists are flattened by a prefix sum): a group of few
+        // reads would otherwise leave most of the block idle.
+        const bool usable = !punt && rinfo_s[threadIdx.x * kSvRi + 3] == 0 && cand_n_s[threadIdx.x] <= kSvCand;
+        const int my_nc = usable ? cand_n_s[threadIdx.x] : 0;
+        const bool start_bound = !punt && g.max_start_pos < n;      // the reference's result depends on the threshold
+        if (__syncthreads_or(start_bound && my_nc > 0)) {
+            // exclusive offsets of the reads' candidate lists (only reads with a constrained start take part)
+            const int cnt = start_bound ? my_nc : 0;
+            int incl = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            static_assert(kSvThreads == 128, "four warp totals in ctr_s[1..4]");
+            if (lane == 31) ctr_s[1 + warp] = incl;
+            __syncthreads();
+            int warp_off = 0;
+            for (int w = 0; w < warp; w++) warp_off += ctr_s[1 + w];
+            int *coff_s = cand_n_s;                                // counts become exclusive offsets; [kSvThreads] = total
+            __syncthreads();
+            const int total_c = ctr_s[1] + ctr_s[2] + ctr_s[3] + ctr_s[4];
+            coff_s[threadIdx.x] = warp_off + incl - cnt;
+            if (threadIdx.x == 0) coff_s[kSvThreads] = total_c;
+            __syncthreads();
+            const Costs c{P.match, P.mismatch, P.indel, P.nindel, P.has_n};
+            // DP column of sg_literal: element i of this thread at hits_s[i * kSvThreads + thread] (the hit list is dead now)
+            const WsCol DP{reinterpret_cast<int *>(hits_s) + threadIdx.x, kSvThreads};
+            for (int j = threadIdx.x; j < total_c; j += kSvThreads) {
+                // owner read: last r with coff[r] <= j
+                int lo_r = 0, hi_r = kSvThreads - 1;
+                while (lo_r < hi_r) {
+                    const int mid = (lo_r + hi_r + 1) >> 1;
+                    if (coff_s[mid] <= j) lo_r = mid;
+                    else hi_r = mid - 1;
+                }
+                const int r = lo_r, k = j - coff_s[r];
+                const uint32_t rec = cand_s[r * kSvCand + k];
+                const int b = (int)(rec >> 8), d = (int)(rec & 0xFFu);
+                const int qo = S.bc_off[b], m = S.bc_off[b + 1] - qo;
+                // the owner's geometry, rebuilt from what it left in shared memory: relative columns, read length L_r
+                // (sg_literal's column arithmetic is translation invariant: range, max_start_pos, min_end_pos and n all
+                // shift by sbase)
+                const int Lr = rinfo_s[r * kSvRi + 0], min_end_rel = rinfo_s[r * kSvRi + 1], max_start_rel = rinfo_s[r * kSvRi + 2];
+                const int n_rel = rinfo_s[r * kSvRi + 4];
+                const uint8_t *r1 = slot_s + (size_t)r * slot_stride - 1;     // relative column j at r1[j]
+                int s_, e_;
+                const int dl = sg_literal<false>(DP, DP, S.bc_cls + qo - 1, r1, m, n_rel, d, c, 0, 1, Lr, max_start_rel,
+                                                 min_end_rel, s_, e_);
+                if (dl != d) rinfo_s[r * kSvRi + 3] = 2;                          // not robust: the read takes the exact path
+            }
+            __syncthreads();
+            cand_n_s[threadIdx.x] = my_nc;                                     // (the offsets are not needed any more)
+        }
         bool resolved = false;
-        if (!punt && rinfo_s[threadIdx.x * 4 + 3] == 0 && cand_n_s[threadIdx.x] <= kSvCand) {
-            int nc = cand_n_s[threadIdx.x];
+        if (usable && rinfo_s[threadIdx.x * kSvRi + 3] == 0) {
+            const int nc = my_nc;
             uint32_t cl[kSvCand];
 #pragma unroll
             for (int k = 0; k < kSvCand; k++) cl[k] = k < nc ? cand_s[threadIdx.x * kSvCand + k] : 0xFFFFFFFFu;
@@ -399,53 +458,33 @@ k_seed_var(const __grid_constant__ DevParams P, const int pass, const int level,
                         cl[bq] = cl[bq - 1];
                         cl[bq - 1] = t;
                     }
-            const bool start_bound = g.max_start_pos < n;           // the reference's result depends on the threshold
-            const Costs c{P.match, P.mismatch, P.indel, P.nindel, P.has_n};
-            // DP column of sg_literal: element i of this thread at hits_s[i * kSvThreads + thread] (the hit list is dead now)
-            const WsCol DP{reinterpret_cast<int *>(hits_s) + threadIdx.x, kSvThreads};
-            // the read's search range as class codes: equality of class codes == equality of bytes for barcode
-            // bytes (a read byte that occurs in no barcode is class 0); absolute column j at my_slot[j - 1 - sbase]
-            const uint8_t *r1 = slot_s + (size_t)threadIdx.x * slot_stride - sbase - 1;
             BestState bs;
             best_init(bs, P.max_error_rate);
-            bool ok = true;
             int last_b = -1;
 #pragma unroll 1
-            for (int k = 0; k < nc && ok; k++) {
+            for (int k = 0; k < nc; k++) {
                 const int b = (int)(cl[k] >> 8);
                 if (b == last_b) continue;                           // same barcode through another hit: the smaller d came first
                 last_b = b;
                 const int d = (int)(cl[k] & 0xFFu);
-                const int qo = S.bc_off[b];
-                const int m = S.bc_off[b + 1] - qo;
                 const int norm = S.norm[b];
-                if (start_bound) {
-                    // the tightest band that can still accept the barcode (allowed = d): found there => found in
-                    // every wider band; else the read takes the exact path
-                    int s_, e_;
-                    const int dl = sg_literal<false>(DP, DP, S.bc_cls + qo - 1, r1, m, n, d, c, 0, g.start_j, g.end_j,
-                                                     g.max_start_pos, g.min_end_pos, s_, e_);
-                    if (dl != d) ok = false;
-                }
                 const int allowed = allowed_from(bs.thr, norm);       // :254 with the running threshold
                 const double sc = d <= allowed ? __ddiv_rn((double)d, (double)norm) : CUDART_INF;
                 best_consider(bs, with_delta, sc, d, b + 1, -1, -1);
             }
-            if (ok) {
-                if (V.complete) {
-                    out[read] = best_finish(bs, with_delta, P.min_delta);
+            if (V.complete) {
+                out[read] = best_finish(bs, with_delta, P.min_delta);
+                resolved = true;
+            } else if (bs.min_bc != 0 && bs.min_score < V.sigma_min) {
+                if (!with_delta) {
+                    out[read] = best_finish(bs, false, 0.0);
                     resolved = true;
-                } else if (bs.min_bc != 0 && bs.min_score < V.sigma_min) {
-                    if (!with_delta) {
-                        out[read] = best_finish(bs, false, 0.0);
-                        resolved = true;
-                    } else if (__dsub_rn(bs.sub_min, bs.min_score) < P.min_delta) {
-                        out[read] = PassOut{kBcAmbiguous, 0, -1, -1};
-                        resolved = true;
-                    } else if (__dsub_rn(V.sigma_min, bs.min_score) >= P.min_delta) {
-                        out[read] = PassOut{bs.min_bc, bs.min_dist, -1, -1};
-                        resolved = true;
-                    }
+                } else if (__dsub_rn(bs.sub_min, bs.min_score) < P.min_delta) {
+                    out[read] = PassOut{kBcAmbiguous, 0, -1, -1};
+                    resolved = true;
+                } else if (__dsub_rn(V.sigma_min, bs.min_score) >= P.min_delta) {
+                    out[read] = PassOut{bs.min_bc, bs.min_dist, -1, -1};
+                    resolved = true;
                 }
             }
         }
@@ -495,10 +534,10 @@ static SvLaunch sv_launch_params(const DevSet &S, const SeedVar &V)
     size_t off[kSvParts];
     const int plane = S.n_classes * S.n_bc_pad;
     L.tab_smem = 1;
-    L.smem = sv_smem_layout(S.words, plane, S.n_bc_pad, V.n_entries, V.n_buckets, 1, L.slot_stride, S.max_m, off);
+    L.smem = sv_smem_layout(S.words, plane, S.n_bc_pad, V.n_entries, V.n_buckets, 1, L.slot_stride, S.max_m, V.group_reads, V.hit_rows, off);
     if (L.smem > 100 * 1024) {
         L.tab_smem = 0;
-        L.smem = sv_smem_layout(S.words, plane, S.n_bc_pad, V.n_entries, V.n_buckets, 0, L.slot_stride, S.max_m, off);
+        L.smem = sv_smem_layout(S.words, plane, S.n_bc_pad, V.n_entries, V.n_buckets, 0, L.slot_stride, S.max_m, V.group_reads, V.hit_rows, off);
     }
     return L;
 }

@@ -186,26 +186,10 @@ def oracle_rate(cfg, blob, off64, threads):
 
 
 def sample_reads_host(cfg, n_sample, rank=0):
-    """First n_sample reads of the workload, on the host, as (uint8 blob, int64 offsets)."""
-    try:
-        import torch
-        from bdx_b200 import capi
-        if not torch.cuda.is_available():
-            raise RuntimeError("no cuda")
-        torch.cuda.set_device(0)
-        config = capi.Config(cfg)
-        st = capi.Stream(config, device=0, max_reads=0, max_bytes=0)
-        d_seq = torch.empty(n_sample * READ_LEN, dtype=torch.uint8, device="cuda")
-        d_off = torch.empty(n_sample + 1, dtype=torch.int32, device="cuda")
-        st.synth_device(synth_spec(0), n_sample, d_seq.data_ptr(), d_off.data_ptr())
-        st.sync()
-        blob = d_seq.cpu().numpy()
-        off = d_off.cpu().numpy().astype(np.int64)
-        st.close()
-        return blob, off, "device generator (Philox), first reads of the workload"
-    except Exception as exc:  # no GPU visible: same distribution from numpy
-        blob, off = numpy_reads(cfg, n_sample, SEED)
-        return blob, off, f"numpy generator, same distribution ({type(exc).__name__})"
+    """n_sample reads of the workload's distribution, on the host, as (uint8 blob, int64 offsets).  numpy only:
+    the reference arm maps no library of this repository other than the oracle it times."""
+    blob, off = numpy_reads(cfg, n_sample, SEED)
+    return blob, off, "numpy generator (same distribution as the device generator: 90 % planted, P(k edits) of SURVEY 8d)"
 
 
 def calibrate_sample(cfg, threads, seconds, lo=20000, hi=2_000_000):
@@ -214,6 +198,103 @@ def calibrate_sample(cfg, threads, seconds, lo=20000, hi=2_000_000):
     n = int(r1 * threads * seconds * 0.8)
     n = max(lo, min(hi, n))
     return (n + CHUNK - 1) // CHUNK * CHUNK, r1
+
+
+STATED_READS = {"3": 50_000_000, "4": 50_000_000, "5s": 200_000_000, "5h": 200_000_000, "5e": 200_000_000}
+CONFIG_BATCH = 10_000_000          # reads per device batch (offsets are int32: a batch stays below 2^31 bytes)
+
+
+def measure_config(key, cfg, sp, name, total_reads, rank, world, local, parity_seconds, parity_reads):
+    """One BASELINE.json config at its stated size: `total_reads` reads of READ_LEN bases, sharded contiguously
+    over the ranks, generated on the device batch by batch (not timed) and classified
+    device-resident (timed with CUDA events on the library's compute stream).  Rank 0 checks the first reads of
+    its shard against the multi-threaded oracle."""
+    import torch
+    import torch.distributed as dist
+    import bdx_b200 as bdx
+    from bdx_b200 import capi
+    import bench_configs
+    import orc
+
+    per_rank = total_reads // world
+    first = rank * per_rank
+    B = min(CONFIG_BATCH, per_rank)
+    config = capi.Config(cfg)
+    st = capi.Stream(config, device=local, max_reads=0, max_bytes=0)
+    ext = torch.cuda.ExternalStream(st.cuda_stream, device=torch.device("cuda", local))
+    d_seq = torch.empty(B * READ_LEN, dtype=torch.uint8, device="cuda")
+    d_off = torch.empty(B + 1, dtype=torch.int32, device="cuda")
+    d_res = torch.empty(B * bdx.RESULT_DTYPE.itemsize, dtype=torch.uint8, device="cuda")
+    res_i32 = d_res.view(torch.int32).view(-1, 5)
+
+    def gen(k, nb):
+        spec = capi.SynthSpec(seed=bench_configs.SEED, first_read=first + k * B, read_len=READ_LEN, plant_permille=900,
+                              n_permille_x10=50, **sp)
+        st.synth_device(spec, nb, d_seq.data_ptr(), d_off.data_ptr())
+        st.sync()
+
+    # warm-up on the first batch (also what the parity check looks at)
+    nb0 = min(B, per_rank)
+    gen(0, nb0)
+    for _ in range(2):
+        st.classify_device(d_seq.data_ptr(), d_off.data_ptr(), nb0, d_res.data_ptr())
+    st.sync()
+    parity = None
+    if rank == 0:
+        o = orc.Oracle(cfg)
+        k = parity_reads
+        if not k:                      # as many reads as the oracle finishes in about parity_seconds on this host
+            probe = 4000 if len(cfg.bc_seqs) < 1000 else 800
+            blob = d_seq[:probe * READ_LEN].cpu().numpy()
+            t0 = time.perf_counter()
+            o.classify_mt(blob, np.arange(probe + 1, dtype=np.int64) * READ_LEN)
+            rate = probe / (time.perf_counter() - t0)
+            k = int(max(20_000, min(1_000_000, rate * parity_seconds)))
+        k = min(k, nb0)
+        blob = d_seq[:k * READ_LEN].cpu().numpy()
+        got = np.frombuffer(d_res[:k * bdx.RESULT_DTYPE.itemsize].cpu().numpy().tobytes(), dtype=bdx.RESULT_DTYPE)
+        t0 = time.perf_counter()
+        want = o.classify_mt(blob, np.arange(k + 1, dtype=np.int64) * READ_LEN)
+        dt = time.perf_counter() - t0
+        ok = all((got[f] == want[f]).all() for f in ("status", "bc1", "bc2", "keep_start", "keep_end"))
+        parity = {"reads_checked": k, "bit_exact": bool(ok), "oracle_reads_per_s": k / dt, "oracle_threads": os.cpu_count()}
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms, matched, ambiguous, launches = 0.0, 0, 0, 0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    done = 0
+    k = 0
+    while done < per_rank:
+        nb = min(B, per_rank - done)
+        if k > 0 or nb != nb0:
+            gen(k, nb)
+        l0 = st.launch_count
+        e0.record(ext)
+        st.classify_device(d_seq.data_ptr(), d_off.data_ptr(), nb, d_res.data_ptr())
+        e1.record(ext)
+        st.sync()
+        ms += e0.elapsed_time(e1)
+        launches += st.launch_count - l0
+        stt = res_i32[:nb, 0]
+        matched += int((stt == 0).sum().item())
+        ambiguous += int((stt == 2).sum().item())
+        done += nb
+        k += 1
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    cnt = torch.tensor([matched, ambiguous, launches], dtype=torch.int64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    st.close()
+    del d_seq, d_off, d_res
+    secs = float(t.item()) * 1e-3
+    reads = per_rank * world
+    out = {"workload": name, "reads": reads, "reads_per_gpu": per_rank, "sharding": "contiguous shards, no data-path collective",
+           "scaling": "strong", "reads_per_sec": reads / secs, "gcups": reads / secs * bench_configs.cell_updates(cfg) / 1e9,
+           "seconds": secs, "matched_fraction": int(cnt[0].item()) / reads, "ambiguous_fraction": int(cnt[1].item()) / reads,
+           "gpu_launches": int(cnt[2].item()), "parity": parity}
+    return out
 
 
 def run_reference(args):
@@ -237,8 +318,9 @@ def run_reference(args):
         "gcups": value * CU_PER_READ / 1e9, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "int64", "data": "synthetic",
-        "config": {"workload": f"config2: {n_sample} x {READ_LEN}bp reads (bounded sample of the 10M-read job), "
-                               f"{N_BARCODES} barcodes x {BARCODE_LEN}nt, :semiglobal defaults",
+        "config": {"workload": f"config2: RATE over a {n_sample}-read sample of the 10M x {READ_LEN}bp job (a CPU step over all "
+                               f"10M reads would take minutes), {N_BARCODES} barcodes x {BARCODE_LEN}nt, :semiglobal defaults",
+                   "sample_reads": n_sample,
                    "note": "C restatement of BioDemuX.jl classification.jl (oracle port), all host threads; "
                            "Julia is not installed in this image so the reference itself cannot run"},
         "cpu_baseline": {"value": value, "unit": "reads/s", "cores": threads, "kind": "port",
@@ -428,6 +510,45 @@ def run_ours(args):
         assert int(counters[0].item()) == world * ns
         sst.close()
 
+    # ---- the data-dependence of the headline on record: the same workload with NO barcode planted, i.e. every read
+    # has to run the full-range automaton (k_filter) to prove "no barcode" ----
+    floor = None
+    if not args.no_floor:
+        nf = min(n, 2_000_000)
+        fspec = synth_spec(rank * n)
+        fspec.plant_permille = 0
+        stream.synth_device(fspec, nf, d_seq.data_ptr(), d_off.data_ptr())
+        stream.sync()
+        for _ in range(2):
+            stream.classify_device(d_seq.data_ptr(), d_off.data_ptr(), nf, d_res.data_ptr())
+        stream.sync()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record(ext)
+        for _ in range(3):
+            stream.classify_device(d_seq.data_ptr(), d_off.data_ptr(), nf, d_res.data_ptr())
+        f1.record(ext)
+        stream.sync()
+        tf = torch.tensor([f0.elapsed_time(f1) / 3], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tf, op=dist.ReduceOp.MAX)
+        floor = {"reads_per_sec": world * nf / (float(tf.item()) * 1e-3), "reads_per_gpu": nf,
+                 "workload": "config2 reads with plant_permille = 0: no read carries a barcode, all of them run the "
+                             "full-range automaton (the rate when nothing can be short-cut)"}
+    # ---- BASELINE.json configs 3, 4, 5 at their stated sizes (device-resident, sharded over the ranks) ----
+    others = None
+    if not args.no_configs:
+        import bench_configs
+        del d_seq, d_off, d_res
+        torch.cuda.empty_cache()
+        others = {}
+        for key, (ocfg, sp, name) in bench_configs.configs().items():
+            if args.configs and key not in args.configs:
+                continue
+            total = int(STATED_READS[key] * args.config_scale)
+            total -= total % world
+            others[key] = measure_config(key, ocfg, sp, name, total, rank, world, local, args.parity_seconds,
+                                         args.parity_reads)
+
     if rank == 0:
         filt_s = filt_ms * 1e-3 / max(filt_n, 1)          # average duration of one filter launch
         # only reads that ran the bit-parallel automaton are credited with its int-ops; reads the
@@ -439,7 +560,9 @@ def run_ours(args):
             hbm_src = "MEASURED_PEAKS.json"
         except Exception:
             hbm_peak, hbm_src = 6650.0, "fallback (B200_PROFILING.md)"
-        hbm_gbs = BYTES_PER_READ * n / filt_s / 1e9 if filt_s > 0 else 0.0
+        # algorithmic bytes of the reads the kernel actually touched (sequence + offset in, PassOut out) over its time
+        hbm_gbs = BYTES_PER_READ * auto_per_launch / filt_s / 1e9 if filt_s > 0 else 0.0
+        step_gbs = BYTES_PER_READ * n / (ms_max / args.steps * 1e-3) / 1e9
         line = {
             "metric": "reads_per_sec", "value": value, "unit": "reads/s", "gcups": value * CU_PER_READ / 1e9,
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps,
@@ -463,7 +586,8 @@ def run_ours(args):
                          "peak_source": "bdx_int_alu_peak: LOP3/IADD3 chains measured live on this GPU",
                          "hbm": {"achieved": hbm_gbs, "peak": hbm_peak, "unit": "GB/s",
                                  "frac": hbm_gbs / hbm_peak, "peak_source": hbm_src,
-                                 "bytes_per_read": BYTES_PER_READ}},
+                                 "bytes_per_read": BYTES_PER_READ, "what": "k_filter: algorithmic bytes of ITS reads / its time",
+                                 "whole_step_gbs": step_gbs}},
             "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": nb * (B * READ_LEN + 4 * (B + 1)),
                     "d2h_bytes_per_step": nb * B * bdx.RESULT_DTYPE.itemsize,
                     "api": f"bdx_submit_pinned / bdx_fetch_view, {DEPTH} batches in flight",
@@ -475,6 +599,10 @@ def run_ours(args):
         }
         if stats_ms is not None:
             line["stats_allreduce_ms"] = stats_ms
+        if floor is not None:
+            line["floor"] = floor
+        if others is not None:
+            line["configs"] = others
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             n_sample, r1 = calibrate_sample(cfg, threads, 12.0)
@@ -502,6 +630,12 @@ def main():
     ap.add_argument("--e2e-batch", type=int, default=500_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="device-resident timing only (kernel experiments)")
+    ap.add_argument("--no-floor", action="store_true", help="skip the no-barcode (all-automaton) rate")
+    ap.add_argument("--no-configs", action="store_true", help="skip BASELINE.json configs 3 / 4 / 5")
+    ap.add_argument("--configs", nargs="*", default=None, help="subset of 3 4 5s 5h 5e")
+    ap.add_argument("--config-scale", type=float, default=1.0, help="fraction of the stated read counts (1.0 = 50 M / 50 M / 200 M)")
+    ap.add_argument("--parity-seconds", type=float, default=15.0, help="oracle time per config for the parity sample")
+    ap.add_argument("--parity-reads", type=int, default=0, help="parity sample size per config (0 = by --parity-seconds)")
     args = ap.parse_args()
     if args.reads % args.e2e_batch:
         args.e2e_batch = args.reads

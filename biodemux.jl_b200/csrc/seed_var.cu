@@ -394,53 +394,58 @@ k_seed_var(const __grid_constant__ DevParams P, const int pass, const int level,
         const int my_nc = usable ? cand_n_s[threadIdx.x] : 0;
         const bool start_bound = !punt && g.max_start_pos < n;      // the reference's result depends on the threshold
         if (__syncthreads_or(start_bound && my_nc > 0)) {
-            // exclusive offsets of the reads' candidate lists (only reads with a constrained start take part)
-            const int cnt = start_bound ? my_nc : 0;
-            int incl = cnt;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-                if (lane >= o) incl += t;
-            }
-            static_assert(kSvThreads == 128, "four warp totals in ctr_s[1..4]");
-            if (lane == 31) ctr_s[1 + warp] = incl;
-            __syncthreads();
-            int warp_off = 0;
-            for (int w = 0; w < warp; w++) warp_off += ctr_s[1 + w];
-            int *coff_s = cand_n_s;                                // counts become exclusive offsets; [kSvThreads] = total
-            __syncthreads();
-            const int total_c = ctr_s[1] + ctr_s[2] + ctr_s[3] + ctr_s[4];
-            coff_s[threadIdx.x] = warp_off + incl - cnt;
-            if (threadIdx.x == 0) coff_s[kSvThreads] = total_c;
-            __syncthreads();
             const Costs c{P.match, P.mismatch, P.indel, P.nindel, P.has_n};
             // DP column of sg_literal: element i of this thread at hits_s[i * kSvThreads + thread] (the hit list is dead now)
             const WsCol DP{reinterpret_cast<int *>(hits_s) + threadIdx.x, kSvThreads};
-            for (int j = threadIdx.x; j < total_c; j += kSvThreads) {
-                // owner read: last r with coff[r] <= j
-                int lo_r = 0, hi_r = kSvThreads - 1;
-                while (lo_r < hi_r) {
-                    const int mid = (lo_r + hi_r + 1) >> 1;
-                    if (coff_s[mid] <= j) lo_r = mid;
-                    else hi_r = mid - 1;
-                }
-                const int r = lo_r, k = j - coff_s[r];
+            auto check = [&](int r, int k) {
                 const uint32_t rec = cand_s[r * kSvCand + k];
                 const int b = (int)(rec >> 8), d = (int)(rec & 0xFFu);
                 const int qo = S.bc_off[b], m = S.bc_off[b + 1] - qo;
-                // the owner's geometry, rebuilt from what it left in shared memory: relative columns, read length L_r
-                // (sg_literal's column arithmetic is translation invariant: range, max_start_pos, min_end_pos and n all
-                // shift by sbase)
+                // the owner's geometry in RELATIVE columns, as it left it in shared memory (sg_literal's column
+                // arithmetic is translation invariant: range, max_start_pos, min_end_pos and n all shift by sbase)
                 const int Lr = rinfo_s[r * kSvRi + 0], min_end_rel = rinfo_s[r * kSvRi + 1], max_start_rel = rinfo_s[r * kSvRi + 2];
                 const int n_rel = rinfo_s[r * kSvRi + 4];
                 const uint8_t *r1 = slot_s + (size_t)r * slot_stride - 1;     // relative column j at r1[j]
                 int s_, e_;
                 const int dl = sg_literal<false>(DP, DP, S.bc_cls + qo - 1, r1, m, n_rel, d, c, 0, 1, Lr, max_start_rel,
                                                  min_end_rel, s_, e_);
-                if (dl != d) rinfo_s[r * kSvRi + 3] = 2;                          // not robust: the read takes the exact path
+                if (dl != d) rinfo_s[r * kSvRi + 3] = 2;                       // not robust: the read takes the exact path
+            };
+            if (R > 64) {
+                // a full group: most reads have exactly one candidate, a thread checks its own read's
+                if (start_bound)
+                    for (int k = 0; k < my_nc; k++) check(threadIdx.x, k);
+            } else {
+                // exclusive offsets of the reads' candidate lists (only reads with a constrained start take part)
+                const int cnt = start_bound ? my_nc : 0;
+                int incl = cnt;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+                    if (lane >= o) incl += t;
+                }
+                static_assert(kSvThreads == 128, "four warp totals in ctr_s[1..4]");
+                if (lane == 31) ctr_s[1 + warp] = incl;
+                __syncthreads();
+                int warp_off = 0;
+                for (int w = 0; w < warp; w++) warp_off += ctr_s[1 + w];
+                int *coff_s = cand_n_s;                                // counts become exclusive offsets
+                const int total_c = ctr_s[1] + ctr_s[2] + ctr_s[3] + ctr_s[4];
+                coff_s[threadIdx.x] = warp_off + incl - cnt;
+                __syncthreads();
+                for (int j = threadIdx.x; j < total_c; j += kSvThreads) {
+                    int lo_r = 0, hi_r = kSvThreads - 1;               // owner read: last r with coff[r] <= j
+                    while (lo_r < hi_r) {
+                        const int mid = (lo_r + hi_r + 1) >> 1;
+                        if (coff_s[mid] <= j) lo_r = mid;
+                        else hi_r = mid - 1;
+                    }
+                    check(lo_r, j - coff_s[lo_r]);
+                }
+                __syncthreads();
+                cand_n_s[threadIdx.x] = my_nc;                         // (the offsets are not needed any more)
             }
             __syncthreads();
-            cand_n_s[threadIdx.x] = my_nc;                                     // (the offsets are not needed any more)
         }
         bool resolved = false;
         if (usable && rinfo_s[threadIdx.x * kSvRi + 3] == 0) {

@@ -417,8 +417,7 @@ def run_ours(args):
                               "matched_fraction": matched / n, "peak_Tops": peak_ops.value / 1e12,
                               "achieved_Tops": OPS_PER_READ * auto_per_launch / filt_s / 1e12,
                               "prefilter_fraction": pre_reads / max(pre_reads + seed_reads + auto_reads, 1),
-                              "seed_fraction": seed_reads / max(pre_reads + seed_reads + auto_reads, 1), "clocks": clocks,
-                              "variant": os.environ.get("BDX_FILTER_VARIANT")}))
+                              "seed_fraction": seed_reads / max(pre_reads + seed_reads + auto_reads, 1), "clocks": clocks}))
         stream.close()
         return
 

@@ -23,8 +23,11 @@ ABI_VERSION = 1
 BDX_OK, BDX_ERR_INVALID, BDX_ERR_CUDA, BDX_ERR_NOMEM, BDX_ERR_STATE, BDX_ERR_TOO_LARGE = 0, -1, -2, -3, -4, -5
 
 # every symbol include/bdx.h declares (tests check that the library exports all of them)
+DEBUG_NO_FILTER, DEBUG_NO_PREFILTER, DEBUG_NO_SEEDS, DEBUG_NO_SEED_DEEP = 1, 2, 4, 8
+DEBUG_ONE_SEED_LEVEL, DEBUG_NO_GRAPHS, DEBUG_NO_HAMMING_PACKED = 16, 32, 64
+
 EXPORTS = [
-    "bdx_last_error", "bdx_abi_version", "bdx_device_count", "bdx_config_create", "bdx_config_destroy",
+    "bdx_last_error", "bdx_abi_version", "bdx_device_count", "bdx_config_create", "bdx_config_create_debug", "bdx_config_destroy",
     "bdx_stream_create", "bdx_stream_destroy", "bdx_submit", "bdx_acquire", "bdx_commit",
     "bdx_submit_pinned", "bdx_host_alloc", "bdx_host_free", "bdx_stream_enable_details",
     "bdx_fetch", "bdx_fetch_view", "bdx_classify", "bdx_classify_device", "bdx_stream_sync",
@@ -118,6 +121,7 @@ def load_library():
     L.bdx_abi_version.restype = C.c_int
     L.bdx_device_count.restype = C.c_int
     L.bdx_config_create.argtypes = [C.POINTER(Params), C.POINTER(vp)]
+    L.bdx_config_create_debug.argtypes = [C.POINTER(Params), C.c_uint32, C.POINTER(vp)]
     L.bdx_config_destroy.argtypes = [vp]
     L.bdx_config_destroy.restype = None
     L.bdx_stream_create.argtypes = [vp, C.c_int, i32, i64, C.POINTER(vp)]
@@ -254,7 +258,8 @@ def load_barcode_table(path: str, complement: bool = False, rev: bool = False):
 class Config:
     """Owns a ``bdx_config`` (immutable; shareable across streams)."""
 
-    def __init__(self, cfg: DemuxConfig, want_stats: Optional[bool] = None):
+    def __init__(self, cfg: DemuxConfig, want_stats: Optional[bool] = None, debug: int = 0):
+        """debug: BDX_DEBUG_* flags (tests only: single pipeline stages switched off)."""
         self.lib = load_library()
         self.cfg = cfg
         self._keep = []
@@ -276,7 +281,10 @@ class Config:
                                cfg.barcode_start_range2, cfg.barcode_end_range2, cfg.trim_side2)
         self.params = p
         self.handle = C.c_void_p()
-        _check(self.lib.bdx_config_create(C.byref(p), C.byref(self.handle)))
+        if debug:
+            _check(self.lib.bdx_config_create_debug(C.byref(p), int(debug), C.byref(self.handle)))
+        else:
+            _check(self.lib.bdx_config_create(C.byref(p), C.byref(self.handle)))
         self.layout = StatsLayout()
         _check(self.lib.bdx_stats_layout_get(self.handle, C.byref(self.layout)))
 
@@ -539,17 +547,48 @@ class Engine:
     """Config + one stream: what a single reference worker thread would own."""
 
     def __init__(self, cfg: DemuxConfig, device: int = 0, max_reads: int = 4000,
-                 max_bytes: Optional[int] = None, want_stats: Optional[bool] = None):
+                 max_bytes: Optional[int] = None, want_stats: Optional[bool] = None, debug: int = 0):
         self.cfg = cfg
-        self.config = Config(cfg, want_stats=want_stats)
+        self.config = Config(cfg, want_stats=want_stats, debug=debug)
+        self._device = device
         self.stream = Stream(self.config, device=device, max_reads=max_reads, max_bytes=max_bytes)
 
     def classify_reads(self, seqs: Sequence[bytes]) -> np.ndarray:
         blob, off = pack_reads(seqs)
-        return self.stream.classify(blob, off)
+        return self.classify_packed(blob, off)
 
     def classify_packed(self, blob: np.ndarray, off: np.ndarray, want_details: bool = False):
-        return self.stream.classify(blob, off, want_details=want_details)
+        """Any number of reads of any length (the reference has no limits either): the batch is split into
+        sub-batches that fit the stream's staging buffers, and a single read longer than max_bytes makes the
+        engine re-create its stream with larger buffers."""
+        off = np.ascontiguousarray(off, dtype=np.int64)
+        n = len(off) - 1
+        st = self.stream
+        lens = np.diff(off)
+        if n and int(lens.max()) > st.max_bytes:
+            new_bytes = max(2 * st.max_bytes, int(lens.max()))
+            details, dev = st.details, self._device
+            st.close()
+            self.stream = st = Stream(self.config, device=dev, max_reads=st.max_reads, max_bytes=new_bytes)
+            if details != st.details:
+                st.enable_details(details)
+        if n <= st.max_reads and (n == 0 or int(off[-1]) <= st.max_bytes):
+            return st.classify(blob, off.astype(np.int32), want_details=want_details)
+        res = np.zeros(n, RESULT_DTYPE)
+        det = np.zeros((2, n), DETAIL_DTYPE) if want_details else None
+        a = 0
+        while a < n:
+            # the longest run of reads from a that fits both limits
+            b = min(n, a + st.max_reads)
+            b = min(b, int(np.searchsorted(off, off[a] + st.max_bytes, side="right")) - 1)
+            b = max(b, a + 1)
+            out = st.classify(blob[off[a]:off[b]], (off[a:b + 1] - off[a]).astype(np.int32), want_details=want_details)
+            if want_details:
+                res[a:b], det[:, a:b] = out
+            else:
+                res[a:b] = out
+            a = b
+        return (res, det) if want_details else res
 
     def demux_stats(self):
         from .stats import stats_from_counters

@@ -99,16 +99,6 @@ struct DevSet {
     const uint32_t *pf_keys;      // [size] hash of the first pf_seed class codes
     const uint32_t *pf_vals;      // [size] (len << 16) | barcode index (lowest of identical sequences); kPfEmpty
     const uint8_t *bc_cls;        // barcode bytes mapped through class_of (same offsets as bc_bytes)
-    // :hamming pigeonhole seeds (filter.cu, k_seed_hamming): allowed_b + 1 disjoint segments per
-    // barcode, the first hs_q bytes of each hashed into a CSR bucket table
-    int hs_enabled;
-    int hs_q;                     // seed length (4..8)
-    uint32_t hs_pow;              // kPfBase^(hs_q-1)
-    int hs_log2;                  // number of buckets = 1 << hs_log2
-    int hs_n_entries;
-    int hs_max_off;               // largest seed offset inside a barcode
-    const uint32_t *hs_bstart;    // [buckets + 1] CSR row starts
-    const uint32_t *hs_entries;   // [n_entries] (barcode index << 8) | seed offset
     // :semiglobal depth-limited seeds (seed.cu, k_seed): for uniform-length sets, every alignment
     // with <= k edits leaves one of k + 1 disjoint barcode segments intact.  Up to two levels: a
     // shallow one with long, very selective seeds, then the deepest level that is still selective.
@@ -150,7 +140,7 @@ struct DevParams {
     int algo, is_dual, want_stats;
     int filter_ok;    // costs allow the unit-cost filter to be a superset
     int unit_costs;   // match 0, mismatch 1, indel 1 (and nindel 1): filter distance is the score
-    int two;          // the constant 2, opaque to ptxas (keeps IMAD.HI on the fma pipe, filter.cu)
+    int two;          // (reserved)
     int pad1;
     DevSet set[2];
 };
@@ -162,12 +152,13 @@ struct PassOut {
     int start, end;
 };
 
-constexpr int kStatsOvfCap = 1 << 20;   // overflow records kept per stream
+constexpr int kStatsOvfCap = 1 << 20;   // initial capacity of a stream's overflow list (it is drained / grown, never dropped)
 struct StatsDev {
     unsigned long long *buf;  // layout: bdx_stats_layout
     bdx_stats_layout lay;
-    bdx_stats_overflow *ovf;  // [kStatsOvfCap] passes whose start / length do not fit the histograms
-    unsigned int *n_ovf;      // [2] records appended (may exceed the capacity), records lost
+    bdx_stats_overflow *ovf;  // [ovf_cap] passes whose start / length do not fit the histograms
+    unsigned int *n_ovf;      // [2] records appended, records lost (stays 0: the host reserves room per batch)
+    unsigned int ovf_cap;
 };
 
 struct Scratch {
@@ -215,11 +206,8 @@ cudaError_t launch_prefilter(const DevParams &P, int pass, const uint8_t *seq, c
                              const Scratch &sc, int sm_count, unsigned long long *counters, cudaStream_t st);
 bool prefilter_applies(const DevParams &P, int pass);
 bool exact_hash_applies(const DevParams &P, int pass);
-bool hamming_seed_applies(const DevParams &P, int pass);
 bool hamming_packed_applies(const DevParams &P, int pass);
 cudaError_t launch_hamming_scan(const DevParams &P, int pass, const uint8_t *seq, const int *off, int n,
-                                const Scratch &sc, int sm_count, cudaStream_t st);
-cudaError_t launch_seed_hamming(const DevParams &P, int pass, const uint8_t *seq, const int *off, int n,
                                 const Scratch &sc, int sm_count, cudaStream_t st);
 cudaError_t launch_finalize(const DevParams &P, const int *off, int n, const Scratch &sc,
                             bdx_result *res, bdx_pass_detail *det, StatsDev stats, cudaStream_t st);

@@ -24,7 +24,6 @@
 //     (classification.jl:632-713) is replayed in-warp over the candidates;
 //   * otherwise the candidates are queued for the literal kernel.
 #include <algorithm>
-#include <cstdlib>
 #include <math_constants.h>
 
 #include "bdx_internal.h"
@@ -44,53 +43,20 @@ struct BV {
 // D[m][j] - D[m][j-1] is +1 when the MSB of Ph is set, -1 when the MSB of Mh is set.
 // `mid` = score - msb(mh) is min(D[m][j-1], D[m][j]) (the score moves by at most one per
 // column), so taking the running minimum of `mid` at every SECOND column covers both.
-// Codings of "mid = score - msb(mh); score = mid + msb(ph); ph <<= 1; mh <<= 1",
-// selectable for measurement (BDX_FILTER_VARIANT); they differ in how the work splits
-// between the alu pipe (LOP3/IADD3/LEA) and the fma pipe (IMAD*):
-//   kPlain : plain C, the compiler picks (LEA.HI on the alu pipe)
-//   kCarry : add.cc ph+ph / addc, sub.cc 0x7fffffff-mh / subc (borrow = msb(mh))
-//   kMadHi : mad.hi.s32(mh, two, score) subtracts msb(mh) (the signed high half of 2*mh is
-//            -1 exactly when the MSB is set), mad.hi.u32(ph, two, mid) adds msb(ph); `two`
-//            is a kernel parameter (DevParams::two) so that ptxas cannot fold it into LEA.HI
-enum { kPlain = 0, kCarry = 1, kMadHi = 2, kMadHiP = 3, kMadHiM = 4,  // 3/4: only one of the two on the fma pipe
-       kShiftAnd = 5 };  // :exact -- Shift-And automaton instead of the edit-distance automaton
+// ptxas turns the two updates into LEA.HI on the alu pipe and the shifts into IMAD.IADD on the fma
+// pipe; carry-chain (add.cc / subc) and mad.hi codings of the same update measured slower on B200
+// (profiles/r01_filter_variants.jsonl) and are gone.
+enum { kMyers = 0, kShiftAnd = 5 };  // kShiftAnd: :exact -- Shift-And automaton instead of the edit-distance automaton
 
 template <int CODING>
 __device__ __forceinline__ void shift_score(uint32_t ph, uint32_t mh, uint32_t two, uint32_t &phs,
                                             uint32_t &mhs, int &score, int &mid)
 {
-    if (CODING == kMadHi) {
-        asm("mad.hi.s32 %0, %1, %2, %3;" : "=r"(mid) : "r"(mh), "r"(two), "r"(score));
-        asm("mad.hi.u32 %0, %1, %2, %3;" : "=r"(score) : "r"(ph), "r"(two), "r"(mid));
-        phs = ph << 1;
-        mhs = mh << 1;
-    } else if (CODING == kMadHiP) {
-        mid = score - (int)(mh >> 31);
-        asm("mad.hi.u32 %0, %1, %2, %3;" : "=r"(score) : "r"(ph), "r"(two), "r"(mid));
-        phs = ph << 1;
-        mhs = mh << 1;
-    } else if (CODING == kMadHiM) {
-        asm("mad.hi.s32 %0, %1, %2, %3;" : "=r"(mid) : "r"(mh), "r"(two), "r"(score));
-        score = mid + (int)(ph >> 31);
-        phs = ph << 1;
-        mhs = mh << 1;
-    } else if (CODING == kCarry) {
-        uint32_t dummy;
-        asm("{\n\t"
-            "sub.cc.u32 %1, 0x7fffffff, %5;\n\t"
-            "subc.u32 %3, %2, 0;\n\t"
-            "add.cc.u32 %0, %4, %4;\n\t"
-            "addc.u32 %2, %3, 0;\n\t"
-            "}"
-            : "=&r"(phs), "=&r"(dummy), "+r"(score), "=&r"(mid)
-            : "r"(ph), "r"(mh));
-        mhs = mh << 1;
-    } else {
-        mid = score - (int)(mh >> 31);
-        score = mid + (int)(ph >> 31);
-        phs = ph << 1;
-        mhs = mh << 1;
-    }
+    (void)two;
+    mid = score - (int)(mh >> 31);
+    score = mid + (int)(ph >> 31);
+    phs = ph << 1;
+    mhs = mh << 1;
 }
 
 // One column of the automaton for one barcode.  Eq: match mask of this read byte.
@@ -378,6 +344,8 @@ k_filter(const __grid_constant__ DevParams P, const int pass, const uint8_t *__r
 // and byte-wise verification on a hit.  Resolved reads get their PassOut here; all other
 // reads are appended to the worklist the bit-parallel kernel then walks.
 // ---------------------------------------------------------------------------------------
+size_t prefilter_smem_bytes_for(const DevSet &S);
+
 constexpr int kPfThreads = 256;
 constexpr int kPfStageBytes = 48 * 1024;   // raw bytes of one group of 256 reads (<= 192 bases each)
 constexpr int kPfMaxCand = 2;              // table hits remembered per read; more => leave it to the DP
@@ -648,7 +616,7 @@ cudaError_t launch_prefilter(const DevParams &P, int pass, const uint8_t *seq, c
                              const Scratch &sc, int sm_count, unsigned long long *counters, cudaStream_t st)
 {
     const DevSet &S = P.set[pass];
-    const size_t smem = kPfStageBytes + 16 + ((size_t)8 << S.pf_log2) + ((size_t)4 << (S.pf_bm_log2 - 5));
+    const size_t smem = prefilter_smem_bytes_for(S);
     auto kern = P.algo == BDX_EXACT ? k_prefilter<1> : (P.algo == BDX_HAMMING ? k_prefilter<2> : k_prefilter<0>);
     int per_sm = 0;
     cudaError_t e = blocks_per_sm_cached((const void *)kern, kPfThreads, smem, &per_sm);
@@ -660,161 +628,6 @@ cudaError_t launch_prefilter(const DevParams &P, int pass, const uint8_t *seq, c
     kern<<<blocks, kPfThreads, smem, st>>>(P, pass, seq, off, n, sc.pass[pass], sc.pass[0], sc.worklist, sc.n_work,
                                            counters, sc.cand, sc.cand_cnt);
     return cudaGetLastError();
-}
-
-// ---------------------------------------------------------------------------------------
-// k_seed_hamming: candidate generation for :hamming by pigeonhole seeds, one thread per read.
-// A placement of barcode b with at most allowed_b mismatches leaves at least one of its
-// allowed_b + 1 disjoint segments untouched, hence the first hs_q bytes of that segment occur
-// verbatim at the corresponding read column.  Every read column's q-mer is hashed (rolling)
-// into a CSR bucket table of (barcode, seed offset) entries; each entry fixes the placement
-// (Hamming distance has no shifts), which is checked against the start/end constraints of
-// hamming_align (classification.jl:570-586) and verified by counting mismatches with the
-// reference's early break (:592-604).  Barcodes with a verified placement form the read's
-// candidate list (distinct, ascending); hamming_literal then computes exactly what the
-// reference would for those barcodes, and all other barcodes return Inf in the reference.
-// ---------------------------------------------------------------------------------------
-template <typename BytePtr>
-__device__ __forceinline__ int seed_scan_hamming(BytePtr rd, int n, const Geometry &g, const DevSet &S,
-                                                 const uint32_t *bstart_s, const uint32_t *entries_s,
-                                                 uint16_t *list)
-{
-    const int q = S.hs_q;
-    const uint32_t pw = S.hs_pow;
-    const int p0 = g.start_j - 1;                                    // 0-based column of the first q-mer
-    const int p1 = min(n - q, g.end_j - 1 + S.hs_max_off);           // last q-mer that can belong to a valid start
-    if (p1 < p0) return 0;
-    uint32_t h = 0;
-    for (int i = 0; i < q; i++) h = h * kPfBase + (uint32_t)rd[p0 + i];
-    int nc = 0, last_b = -1;
-    for (int p = p0;;) {
-        const uint32_t bucket = pf_slot(h, S.hs_log2);
-        const uint32_t e1 = bstart_s[bucket + 1];
-        for (uint32_t e = bstart_s[bucket]; e < e1; e++) {
-            const uint32_t ent = entries_s[e];
-            const int b = (int)(ent >> 8);
-            const int s0 = p - (int)(ent & 0xFFu);                   // 0-based start of the barcode
-            if (b == last_b || s0 < p0) continue;
-            const int qo = S.bc_off[b];
-            const int m = S.bc_off[b + 1] - qo;
-            // start in [first, min(last(range), max_start_pos, n - m + 1)], end >= min_end_pos (:570-586)
-            if (s0 + 1 > min(g.end_j, min(g.max_start_pos, n - m + 1)) || s0 + m < g.min_end_pos) continue;
-            const int allowed = S.allowed0[b];
-            const uint8_t *bc = S.bc_bytes + qo;
-            int mm = 0;
-            for (int k = 0; k < m; k++) {
-                if (bc[k] != rd[s0 + k] && ++mm > allowed) break;
-            }
-            if (mm > allowed) continue;
-            last_b = b;
-            if (nc == kCandOverflow) continue;
-            int pos = 0;                                             // sorted insert, skip duplicates
-            while (pos < nc && list[pos] < b) pos++;
-            if (pos == nc || list[pos] != b) {
-                if (nc == kCandMax) {
-                    nc = kCandOverflow;
-                } else {
-                    for (int k = nc; k > pos; k--) list[k] = list[k - 1];
-                    list[pos] = (uint16_t)b;
-                    nc++;
-                }
-            }
-        }
-        if (++p > p1) break;
-        h = (h - (uint32_t)rd[p - 1] * pw) * kPfBase + (uint32_t)rd[p - 1 + q];
-    }
-    return nc;
-}
-
-__global__ void __launch_bounds__(kPfThreads)
-k_seed_hamming(const __grid_constant__ DevParams P, const int pass, const uint8_t *__restrict__ seq,
-               const int *__restrict__ off, const int n_reads, PassOut *__restrict__ out,
-               const PassOut *__restrict__ prev_pass, uint16_t *__restrict__ cand, uint8_t *__restrict__ cand_cnt)
-{
-    extern __shared__ __align__(16) uint32_t smem[];
-    const DevSet &S = P.set[pass];
-    const int n_buckets = 1 << S.hs_log2;
-    uint8_t *stage = reinterpret_cast<uint8_t *>(smem);                     // kPfStageBytes + 16
-    uint32_t *bstart_s = smem + (kPfStageBytes + 16) / 4;
-    uint32_t *entries_s = bstart_s + n_buckets + 1;
-    for (int k = threadIdx.x; k <= n_buckets; k += blockDim.x) bstart_s[k] = S.hs_bstart[k];
-    for (int k = threadIdx.x; k < S.hs_n_entries; k += blockDim.x) entries_s[k] = S.hs_entries[k];
-
-    const int n_groups = (n_reads + kPfThreads - 1) / kPfThreads;
-    for (int grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
-        const int r0 = grp * kPfThreads;
-        const int r1 = min(r0 + kPfThreads, n_reads);
-        const int blk_base = off[r0];
-        const int blk_end = off[r1];
-        const uintptr_t g0 = reinterpret_cast<uintptr_t>(seq + blk_base);
-        const int skew = (int)(g0 & 15);
-        const bool staged = blk_end - blk_base + skew <= kPfStageBytes;
-        __syncthreads();
-        if (staged) {
-            const uint8_t *src = seq + blk_base - skew;
-            const int total = blk_end - blk_base + skew;
-            const int vecs = total >> 4;
-            const uint4 *src16 = reinterpret_cast<const uint4 *>(src);
-            uint4 *dst16 = reinterpret_cast<uint4 *>(stage);
-            for (int k = threadIdx.x; k < vecs; k += blockDim.x) dst16[k] = __ldg(src16 + k);
-            for (int k = (vecs << 4) + threadIdx.x; k < total; k += blockDim.x) stage[k] = src[k];
-        }
-        __syncthreads();
-        const int read = r0 + threadIdx.x;
-        if (read >= n_reads) continue;
-        if (pass == 1 && prev_pass[read].bc <= 0) {
-            out[read] = PassOut{kBcNotRun, 0, -1, -1};
-            continue;
-        }
-        const int base = off[read];
-        const int n = off[read + 1] - base;
-        const Geometry g = pass_geometry(S, n);
-        int nc = 0;
-        uint16_t *list = cand + (size_t)read * kCandMax;
-        if (g.valid) {
-            if (staged)
-                nc = seed_scan_hamming(stage + skew + (base - blk_base), n, g, S, bstart_s, entries_s, list);
-            else
-                nc = seed_scan_hamming(seq + base, n, g, S, bstart_s, entries_s, list);
-        }
-        if (nc == 0) {
-            out[read] = PassOut{kBcUnknown, 0, -1, -1};
-        } else {
-            cand_cnt[read] = (uint8_t)nc;
-            out[read] = PassOut{kBcPending, 0, -1, -1};
-        }
-    }
-}
-
-static size_t seed_hamming_smem(const DevSet &S)
-{
-    return kPfStageBytes + 16 + ((size_t)(1 << S.hs_log2) + 1 + (size_t)S.hs_n_entries) * 4;
-}
-
-cudaError_t launch_seed_hamming(const DevParams &P, int pass, const uint8_t *seq, const int *off, int n,
-                                const Scratch &sc, int sm_count, cudaStream_t st)
-{
-    const DevSet &S = P.set[pass];
-    const size_t smem = seed_hamming_smem(S);
-    int per_sm = 0;
-    cudaError_t e = blocks_per_sm_cached((const void *)k_seed_hamming, kPfThreads, smem, &per_sm);
-    if (e != cudaSuccess) return e;
-    const int groups = (n + kPfThreads - 1) / kPfThreads;
-    const int blocks = std::min(groups, sm_count * per_sm);
-    k_seed_hamming<<<blocks, kPfThreads, smem, st>>>(P, pass, seq, off, n, sc.pass[pass], sc.pass[0], sc.cand,
-                                                     sc.cand_cnt);
-    return cudaGetLastError();
-}
-
-// Measured on B200 (config 5, 1 536 barcodes, q = 4): 4.7 M reads/s against 7.4 M reads/s for the
-// bit-parallel filter -- ~30 table entries per column make the per-thread byte-wise verification
-// diverge badly.  Kept for experiments (BDX_HAMMING_SEEDS=1) until the verification is rewritten
-// on 2-bit packed words; off by default.
-bool hamming_seed_applies(const DevParams &P, int pass)
-{
-    static const bool on = getenv("BDX_HAMMING_SEEDS") != nullptr;
-    const DevSet &S = P.set[pass];
-    return on && P.algo == BDX_HAMMING && S.hs_enabled && seed_hamming_smem(S) <= 200 * 1024;
 }
 
 // :exact with a hash table: k_prefilter<1> replaces the Shift-And filter kernel altogether
@@ -870,39 +683,14 @@ static cudaError_t launch_wgv(const DevParams &P, int pass, const uint8_t *seq, 
     return cudaGetLastError();
 }
 
-// BDX_FILTER_VARIANT (measurement only): 0 plain, 1 plain+pair, 2 carry, 3 carry+pair,
-// 4 mad.hi, 5 mad.hi+pair, 6 mad.hi for +msb(ph) only (+pair), 7 mad.hi for -msb(mh) only (+pair).  Variants other than the default exist for one word per barcode.
-constexpr int kDefaultVariant = 1;
-static int filter_variant()
-{
-    static int v = -1;
-    if (v < 0) {
-        const char *e = getenv("BDX_FILTER_VARIANT");
-        v = (e && e[0] >= '0' && e[0] <= '7') ? e[0] - '0' : kDefaultVariant;
-    }
-    return v;
-}
-
 template <int W, int G>
 static cudaError_t launch_wg(const DevParams &P, int pass, const uint8_t *seq, const int *off, int n,
                              const Scratch &sc, int sm_count, unsigned long long *counters, int use_worklist,
                              cudaStream_t st)
 {
-    if (P.algo == BDX_EXACT && !getenv("BDX_EXACT_VIA_MYERS"))
+    if (P.algo == BDX_EXACT)
         return launch_wgv<W, G, kShiftAnd, false>(P, pass, seq, off, n, sc, sm_count, counters, use_worklist, st);
-    if (W == 1) {
-        switch (filter_variant()) {
-        case 0: return launch_wgv<W, G, kPlain, false>(P, pass, seq, off, n, sc, sm_count, counters, use_worklist, st);
-        case 2: return launch_wgv<W, G, kCarry, false>(P, pass, seq, off, n, sc, sm_count, counters, use_worklist, st);
-        case 3: return launch_wgv<W, G, kCarry, true>(P, pass, seq, off, n, sc, sm_count, counters, use_worklist, st);
-        case 4: return launch_wgv<W, G, kMadHi, false>(P, pass, seq, off, n, sc, sm_count, counters, use_worklist, st);
-        case 5: return launch_wgv<W, G, kMadHi, true>(P, pass, seq, off, n, sc, sm_count, counters, use_worklist, st);
-        case 6: return launch_wgv<W, G, kMadHiP, true>(P, pass, seq, off, n, sc, sm_count, counters, use_worklist, st);
-        case 7: return launch_wgv<W, G, kMadHiM, true>(P, pass, seq, off, n, sc, sm_count, counters, use_worklist, st);
-        default: break;
-        }
-    }
-    return launch_wgv<W, G, kPlain, true>(P, pass, seq, off, n, sc, sm_count, counters, use_worklist, st);
+    return launch_wgv<W, G, kMyers, true>(P, pass, seq, off, n, sc, sm_count, counters, use_worklist, st);
 }
 
 cudaError_t launch_filter(const DevParams &P, int pass, const uint8_t *seq, const int *off, int n,
@@ -922,5 +710,11 @@ cudaError_t launch_filter(const DevParams &P, int pass, const uint8_t *seq, cons
 }
 
 size_t filter_smem_bytes_for(const DevSet &S) { return filter_smem_bytes(S); }
+
+// k_prefilter's dynamic shared memory: read staging + hash table (keys, values) + first-level bitmap
+size_t prefilter_smem_bytes_for(const DevSet &S)
+{
+    return kPfStageBytes + 16 + ((size_t)8 << S.pf_log2) + ((size_t)4 << (S.pf_bm_log2 - 5));
+}
 
 }  // namespace bdx

@@ -208,7 +208,7 @@ static size_t hamming_scan_smem(const DevSet &S)
 
 bool hamming_packed_applies(const DevParams &P, int pass)
 {
-    static const bool off = getenv("BDX_DISABLE_HAMMING_PACKED") != nullptr;
+    const bool off = false;   // (switched off through BDX_DEBUG_* at config creation: the tables are not built then)
     const DevSet &S = P.set[pass];
     return !off && P.algo == BDX_HAMMING && S.hp.enabled && hamming_scan_smem(S) <= 200 * 1024;
 }

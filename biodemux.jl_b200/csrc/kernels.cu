@@ -250,7 +250,7 @@ __device__ void stats_pass(const DevParams &P, const StatsDev &st, int pass, con
     if (pos < 0 || pos >= L.pos_bins || len < 0 || len >= L.len_bins) {
         // outside the histograms (a long read searched near its end): keep the exact record instead
         const unsigned int k = atomicAdd(st.n_ovf, 1u);
-        if (k < (unsigned int)kStatsOvfCap)
+        if (k < st.ovf_cap)
             st.ovf[k] = bdx_stats_overflow{pass + 1, o.bc, o.start, len};
         else
             atomicAdd(st.n_ovf + 1, 1u);

@@ -326,7 +326,7 @@ static bool seed_tab_in_smem(const DevSet &S, const SeedLevel &L) { return seed_
 
 int seed_levels(const DevParams &P, int pass)
 {
-    static const bool off = getenv("BDX_DISABLE_SEED") != nullptr;
+    const bool off = false;   // (switched off through BDX_DEBUG_* at config creation: the tables are not built then)
     const DevSet &S = P.set[pass];
     // the exact regime of k_filter (unit costs, uniform length, no wildcard rows: the tables exist only then);
     // min_delta is handled, trimming / stats go through k_literal for the positions

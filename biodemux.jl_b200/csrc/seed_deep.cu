@@ -273,7 +273,7 @@ static size_t deep_smem(const DevSet &S)
 // the deep level runs after k_seed's levels, for min_delta = 0 (it keeps no runner-up)
 bool seed_deep_applies(const DevParams &P, int pass)
 {
-    static const bool off = getenv("BDX_DISABLE_SEED_DEEP") != nullptr;
+    const bool off = false;   // (switched off through BDX_DEBUG_* at config creation: the tables are not built then)
     const DevSet &S = P.set[pass];
     return !off && S.sdd_n > 0 && seed_levels(P, pass) > 0 && P.min_delta == 0.0 && deep_smem(S) <= 96 * 1024;
 }

@@ -260,8 +260,19 @@ def execute_demultiplexing(fastq1: str, a: str, b: str, c: Optional[str] = None,
         execute_demultiplexing(FASTQ_file1, FASTQ_file2, barcode_file, output_directory; ...)
 
     Returns the DemuxStats-like dict when ``summary`` is set, else None.
+
+    Reporting is out of scope here (SURVEY.md section 2, rows 11-12 stay with the Julia host): the reference
+    writes summary.{html,txt,json} / stdout through generate_summary_report (reporting.jl:567-577) and a run
+    log to stderr with ``log=true``; this mirror returns the counters instead and says so when either is asked for.
     """
+    import warnings
     from .capi import Engine  # needs libbdx + a CUDA device; fails loudly otherwise
+
+    if summary:
+        warnings.warn(f"summary=True: the DemuxStats counters are returned; the reference's summary.{summary_format} "
+                      "report is written by the Julia host (reporting.jl), not by this mirror", stacklevel=2)
+    if log:
+        warnings.warn("log=True is ignored: the run log is printed by the Julia host (core.jl:531-543)", stacklevel=2)
 
     if c is None:
         fastq2, barcode_file, output_directory = None, a, b

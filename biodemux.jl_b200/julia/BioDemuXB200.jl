@@ -132,61 +132,94 @@ function filename_of(c::DemuxConfig, r::BdxResult)
 end
 
 """
-    gpu_worker_task(input_channel, output_channel, gcfg; device=0, chunk_size=4000)
+    gpu_worker_task(input_channel, output_channel, gcfg; device=0, chunk_size=4000, max_read_len=1024)
 
-Drop-in for `BioDemuX.worker_task` (core.jl:226-279).  One bdx_stream per worker task;
-two chunks are kept in flight so H2D copies overlap the kernels.  Returns the stream's
-DemuxStats (from the device counters) when `config.summary`, else `nothing`.
+Drop-in for `BioDemuX.worker_task` (core.jl:226-279).  One bdx_stream per worker task; up to three batches are
+kept in flight so H2D copies overlap the kernels.  The stream's pinned staging holds `chunk_size` reads /
+`chunk_size * max_read_len` sequence bytes per batch: a chunk that does not fit (long reads, or a reader chunk
+larger than the worker's) is split into several batches -- nothing is ever written past the staging buffers --
+and only a single read longer than the whole staging buffer is an error (raise `max_read_len`).  Returns the
+stream's DemuxStats (from the device counters) when `config.summary`, else `nothing`.
 """
 function gpu_worker_task(input_channel::Channel{Chunk}, output_channel::Channel{ResultChunk}, g::GpuConfig;
                          device::Int=0, chunk_size::Int=4000, max_read_len::Int=1024)
     c = g.config
+    max_bytes = chunk_size * max_read_len
     sref = Ref{Ptr{Cvoid}}(C_NULL)
     check(ccall((:bdx_stream_create, libbdx), Cint, (Ptr{Cvoid}, Cint, Int32, Int64, Ref{Ptr{Cvoid}}),
-                g.handle, device, chunk_size, chunk_size * max_read_len, sref))
+                g.handle, device, chunk_size, max_bytes, sref))
     s = sref[]
     do_trim = !isnothing(c.trim_side) || !isnothing(c.trim_side2)
-    pending = Chunk[]
+    # a chunk and the result arrays its batches fill; `left` = batches of it not yet fetched
+    pending = Tuple{Chunk,Vector{String},Union{Vector{Union{UnitRange{Int},Nothing}},Nothing},Base.RefValue{Int}}[]
+    in_flight = Tuple{Int,UnitRange{Int}}[]          # (index into pending, reads of that chunk), oldest first
     results = Vector{BdxResult}(undef, chunk_size)
 
     function finish_oldest()
-        chunk = popfirst!(pending)
-        n = length(chunk.data.headers)
+        (_, rng) = popfirst!(in_flight)
+        chunk, filenames, trim_ranges, left = pending[1]
         tag = Ref{UInt64}(0); nn = Ref{Int32}(0)
         check(ccall((:bdx_fetch, libbdx), Cint, (Ptr{Cvoid}, Ref{UInt64}, Ref{Int32}, Ptr{BdxResult}, Ptr{Cvoid}),
                     s, tag, nn, results, C_NULL))
-        filenames = Vector{String}(undef, n)
-        trim_ranges = do_trim ? Vector{Union{UnitRange{Int},Nothing}}(undef, n) : nothing
-        @inbounds for i in 1:n
-            r = results[i]
+        nn[] == length(rng) || error("libbdx: batch of $(length(rng)) reads came back with $(nn[]) results")
+        @inbounds for (k, i) in enumerate(rng)
+            r = results[k]
             filenames[i] = filename_of(c, r)
             if do_trim                                   # core.jl:249-255
                 trim_ranges[i] = r.keep_start != -1 ? (Int(r.keep_start):Int(r.keep_end)) : nothing
             end
         end
-        put!(output_channel, ResultChunk(chunk, filenames, trim_ranges))
+        left[] -= 1
+        if left[] == 0                                   # batches come back in submission order: chunks stay ordered
+            popfirst!(pending)
+            put!(output_channel, ResultChunk(chunk, filenames, trim_ranges))
+        end
     end
 
     try
         for chunk in input_channel
             seqs = chunk.data.seqs
             n = length(seqs)
-            # zero-copy: write straight into the stream's pinned staging
-            pseq = Ref{Ptr{UInt8}}(C_NULL); poff = Ref{Ptr{Int32}}(C_NULL)
-            check(ccall((:bdx_acquire, libbdx), Cint, (Ptr{Cvoid}, Ref{Ptr{UInt8}}, Ref{Ptr{Int32}}), s, pseq, poff))
-            off = 0
-            unsafe_store!(poff[], Int32(0), 1)
-            @inbounds for i in 1:n
+            # split the chunk into batches that fit the staging buffers (usually exactly one)
+            ranges = UnitRange{Int}[]
+            first_i, bytes = 1, 0
+            for i in 1:n
                 len = ncodeunits(seqs[i])
-                GC.@preserve seqs unsafe_copyto!(pseq[] + off, pointer(seqs[i]), len)
-                off += len
-                unsafe_store!(poff[], Int32(off), i + 1)
+                len > max_bytes && error("libbdx: a read of $len bases exceeds the worker's staging buffer " *
+                                         "($max_bytes bytes); create it with a larger max_read_len")
+                if i - first_i >= chunk_size || bytes + len > max_bytes
+                    push!(ranges, first_i:i-1)
+                    first_i, bytes = i, 0
+                end
+                bytes += len
             end
-            check(ccall((:bdx_commit, libbdx), Cint, (Ptr{Cvoid}, Int32, UInt64), s, n, chunk.id))
-            push!(pending, chunk)
-            length(pending) == 2 && finish_oldest()
+            push!(ranges, first_i:n)
+            push!(pending, (chunk, Vector{String}(undef, n),
+                            do_trim ? Vector{Union{UnitRange{Int},Nothing}}(undef, n) : nothing, Ref(length(ranges))))
+            for rng in ranges
+                while length(in_flight) >= 3                 # BDX_MAX_IN_FLIGHT is 4
+                    finish_oldest()
+                end
+                # zero-copy: write straight into the stream's pinned staging (bounds established above)
+                pseq = Ref{Ptr{UInt8}}(C_NULL); poff = Ref{Ptr{Int32}}(C_NULL)
+                check(ccall((:bdx_acquire, libbdx), Cint, (Ptr{Cvoid}, Ref{Ptr{UInt8}}, Ref{Ptr{Int32}}), s, pseq, poff))
+                off = 0
+                unsafe_store!(poff[], Int32(0), 1)
+                @inbounds for (k, i) in enumerate(rng)
+                    len = ncodeunits(seqs[i])
+                    @assert off + len <= max_bytes && k <= chunk_size
+                    GC.@preserve seqs unsafe_copyto!(pseq[] + off, pointer(seqs[i]), len)
+                    off += len
+                    unsafe_store!(poff[], Int32(off), k + 1)
+                end
+                check(ccall((:bdx_commit, libbdx), Cint, (Ptr{Cvoid}, Int32, UInt64), s, length(rng), chunk.id))
+                push!(in_flight, (length(pending), rng))
+            end
+            while length(in_flight) > 2
+                finish_oldest()
+            end
         end
-        while !isempty(pending)
+        while !isempty(in_flight)
             finish_oldest()
         end
         return c.summary ? fetch_stats(s, g) : nothing

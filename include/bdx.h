@@ -132,6 +132,21 @@ int bdx_device_count(void);
 int bdx_config_create(const bdx_params *params, bdx_config **out);
 void bdx_config_destroy(bdx_config *cfg);
 
+/* Test / debug hook (not part of the reference boundary): bdx_config_create with single stages of the device
+ * pipeline switched off, so that tests can compare the paths against each other.  The results are the same for
+ * every flag combination; only the kernels that produce them differ.  The library reads no environment
+ * variables. */
+enum {
+    BDX_DEBUG_NO_FILTER = 1,          /* no bit-parallel kernel: k_literal over every barcode */
+    BDX_DEBUG_NO_PREFILTER = 2,       /* no perfect-occurrence / exact-hash tables */
+    BDX_DEBUG_NO_SEEDS = 4,           /* no k_seed / k_seed_var levels */
+    BDX_DEBUG_NO_SEED_DEEP = 8,       /* no k_seed_deep level */
+    BDX_DEBUG_ONE_SEED_LEVEL = 16,    /* only the first seed level */
+    BDX_DEBUG_NO_GRAPHS = 32,         /* plain launches instead of CUDA-graph replay of small batches */
+    BDX_DEBUG_NO_HAMMING_PACKED = 64  /* :hamming through the edit-distance filter instead of k_hamming_scan */
+};
+int bdx_config_create_debug(const bdx_params *params, uint32_t debug_flags, bdx_config **out);
+
 /* One per host worker.  Owns three CUDA streams (H2D / kernels / D2H), a ring of
  * BDX_MAX_IN_FLIGHT staging slots (pinned host + device buffers for max_reads reads /
  * max_bytes sequence bytes per batch) and device scratch. */

@@ -16,10 +16,10 @@ def has_gpu() -> bool:
         return False
 
 
-def run_cuda(cfg, reads, want_stats=False, details=True):
+def run_cuda(cfg, reads, want_stats=False, details=True, debug=0):
     blob, off = bdx.pack_reads(reads)
     with capi.Engine(cfg, max_reads=max(len(reads), 1), max_bytes=max(int(off[-1]), 16),
-                     want_stats=want_stats) as eng:
+                     want_stats=want_stats, debug=debug) as eng:
         if details:
             eng.stream.enable_details(True)
         out = eng.classify_packed(blob, off, want_details=details)

@@ -193,7 +193,7 @@ def test_random_parity_dual(name):
     compare(cfg, reads, want_stats=want_stats, label=name)
 
 
-def test_filter_matches_literal_only(monkeypatch):
+def test_filter_matches_literal_only():
     """The bit-parallel filter path and the literal-only path must agree read for read."""
     rng = np.random.default_rng(7)
     bcs = synth.random_barcodes(rng, 96, 24)
@@ -201,9 +201,7 @@ def test_filter_matches_literal_only(monkeypatch):
     for kw in (dict(), dict(min_delta=0.1), dict(trim_side=3), dict(mismatch=2, indel=3, max_error_rate=0.3)):
         cfg = _cfg(bcs, **kw)
         a, _, _, _ = run_cuda(cfg, reads)
-        monkeypatch.setenv("BDX_DISABLE_FILTER", "1")
-        b, _, _, _ = run_cuda(cfg, reads)
-        monkeypatch.delenv("BDX_DISABLE_FILTER")
+        b, _, _, _ = run_cuda(cfg, reads, debug=capi.DEBUG_NO_FILTER)
         assert (a == b).all(), kw
 
 
@@ -244,7 +242,7 @@ def test_streaming_double_buffer_and_errors():
         assert st.launch_count > 0
 
 
-def test_prefilter_edge_cases(monkeypatch):
+def test_prefilter_edge_cases():
     """Perfect-occurrence prefilter: duplicate barcodes (lowest index wins), barcodes that are
     substrings of longer ones, several lengths, occurrences cut by the search range, and the
     prefilter-off path must agree."""
@@ -257,9 +255,7 @@ def test_prefilter_edge_cases(monkeypatch):
                dict(max_error_rate=0.0), dict(min_delta=0.1)):
         cfg = _cfg(bcs, **kw)
         res, _ = compare(cfg, reads, label=f"prefilter {kw}")
-        monkeypatch.setenv("BDX_DISABLE_PREFILTER", "1")
-        off, _, _, _ = run_cuda(cfg, reads)
-        monkeypatch.delenv("BDX_DISABLE_PREFILTER")
+        off, _, _, _ = run_cuda(cfg, reads, debug=capi.DEBUG_NO_PREFILTER)
         assert (res == off).all(), kw
 
 
@@ -277,7 +273,7 @@ def test_prefilter_counters():
     assert pre >= 1000 and pre + seed + auto == 2000
 
 
-def test_hash_paths_with_repeats_and_duplicates(monkeypatch):
+def test_hash_paths_with_repeats_and_duplicates():
     """:hamming / :exact hash paths on adversarial inputs: duplicated barcodes, barcodes that are
     prefixes of others, reads with the same barcode several times (rightmost / leftmost rules),
     low-complexity reads with many table hits; hash paths off must agree."""
@@ -294,9 +290,7 @@ def test_hash_paths_with_repeats_and_duplicates(monkeypatch):
                    dict(min_delta=0.2), dict(barcode_end_range=R("30:end"), trim_side=3)):
             cfg = _cfg(bcs, matching_algorithm=algo, max_error_rate=0.1, **kw)
             res, _ = compare(cfg, reads, label=f"{algo} {kw}")
-            monkeypatch.setenv("BDX_DISABLE_PREFILTER", "1")
-            off, _, _, _ = run_cuda(cfg, reads)
-            monkeypatch.delenv("BDX_DISABLE_PREFILTER")
+            off, _, _, _ = run_cuda(cfg, reads, debug=capi.DEBUG_NO_PREFILTER)
             assert (res == off).all(), (algo, kw)
 
 

@@ -28,6 +28,7 @@ DEBUG_ONE_SEED_LEVEL, DEBUG_NO_GRAPHS, DEBUG_NO_HAMMING_PACKED = 16, 32, 64
 
 EXPORTS = [
     "bdx_last_error", "bdx_abi_version", "bdx_device_count", "bdx_config_create", "bdx_config_create_debug", "bdx_config_destroy",
+    "bdx_config_code_table", "bdx_pack_reads4", "bdx_submit_packed4", "bdx_submit_packed4_pinned",
     "bdx_stream_create", "bdx_stream_destroy", "bdx_submit", "bdx_acquire", "bdx_commit",
     "bdx_submit_pinned", "bdx_host_alloc", "bdx_host_free", "bdx_stream_enable_details",
     "bdx_fetch", "bdx_fetch_view", "bdx_classify", "bdx_classify_device", "bdx_stream_sync",
@@ -122,6 +123,10 @@ def load_library():
     L.bdx_device_count.restype = C.c_int
     L.bdx_config_create.argtypes = [C.POINTER(Params), C.POINTER(vp)]
     L.bdx_config_create_debug.argtypes = [C.POINTER(Params), C.c_uint32, C.POINTER(vp)]
+    L.bdx_config_code_table.argtypes = [vp, vp]
+    L.bdx_pack_reads4.argtypes = [vp, vp, i64, vp]
+    L.bdx_submit_packed4.argtypes = [vp, vp, vp, C.c_int32, C.c_uint64]
+    L.bdx_submit_packed4_pinned.argtypes = [vp, vp, vp, C.c_int32, C.c_uint64]
     L.bdx_config_destroy.argtypes = [vp]
     L.bdx_config_destroy.restype = None
     L.bdx_stream_create.argtypes = [vp, C.c_int, i32, i64, C.POINTER(vp)]
@@ -288,6 +293,22 @@ class Config:
         self.layout = StatsLayout()
         _check(self.lib.bdx_stats_layout_get(self.handle, C.byref(self.layout)))
 
+    def code_table(self) -> np.ndarray:
+        """byte -> 4-bit code of the packed input (raises when the config has > 15 distinct barcode bytes)."""
+        t = np.zeros(256, np.uint8)
+        rc = self.lib.bdx_config_code_table(self.handle, t.ctypes.data)
+        if rc < 0:
+            _check(rc)
+        return t
+
+    def pack4(self, seq: np.ndarray, out: Optional[np.ndarray] = None) -> np.ndarray:
+        """bdx_pack_reads4: the concatenated read bytes as 4-bit codes, two per byte."""
+        seq = np.ascontiguousarray(seq, dtype=np.uint8)
+        if out is None:
+            out = np.zeros((seq.size + 1) // 2, np.uint8)
+        _check(self.lib.bdx_pack_reads4(self.handle, seq.ctypes.data, seq.size, out.ctypes.data))
+        return out
+
     def _set(self, seqs: Sequence[str], lens: Sequence[int], rs, bs, be, trim) -> BarcodeSet:
         raw = [s.encode("latin-1") if isinstance(s, str) else bytes(s) for s in seqs]
         blob = np.frombuffer(b"".join(raw) + b"\0", dtype=np.uint8).copy()
@@ -339,6 +360,11 @@ class Stream:
         n = len(off) - 1
         fn = self.lib.bdx_submit_pinned if pinned else self.lib.bdx_submit
         _check(fn(self.handle, seq.ctypes.data, off.ctypes.data, n, tag))
+
+    def submit_packed4(self, packed: np.ndarray, off: np.ndarray, tag: int = 0, pinned: bool = False):
+        """4-bit packed reads (Config.pack4) + the offsets of the unpacked reads."""
+        fn = self.lib.bdx_submit_packed4_pinned if pinned else self.lib.bdx_submit_packed4
+        _check(fn(self.handle, packed.ctypes.data, off.ctypes.data, len(off) - 1, tag))
 
     def fetch(self, want_details: bool = False, copy: bool = True):
         """Oldest in-flight batch.  copy=False returns views into the stream's pinned result

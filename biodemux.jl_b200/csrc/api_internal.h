@@ -72,6 +72,10 @@ struct DeviceTables {
 
 struct bdx_config {
     uint32_t debug = 0;  // BDX_DEBUG_* (bdx_config_create_debug); 0 in production
+    // 4-bit packed input (packed.cu): byte -> code over the barcode bytes of both sets, code -> representative byte
+    int n_codes = 0;     // codes incl. 0; 0 = more than 15 distinct barcode bytes, packed input unavailable
+    uint8_t code_of[256] = {};
+    uint8_t rep_of[16] = {};
     DevParams base{};  // device pointers unset
     HostSet set[2];
     bdx_stats_layout lay{};
@@ -88,6 +92,8 @@ struct Slot {
     int32_t *h_off = nullptr;
     bdx_result *h_res = nullptr;
     bdx_pass_detail *h_det = nullptr;
+    uint8_t *d_packed = nullptr;  // 4-bit packed input of the batch (allocated on first packed submit)
+    uint8_t *h_packed = nullptr;  // its pinned staging (bdx_submit_packed4 only)
     uint8_t *d_seq = nullptr;
     int32_t *d_off = nullptr;
     bdx_result *d_res = nullptr;

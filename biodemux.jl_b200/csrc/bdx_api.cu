@@ -79,6 +79,28 @@ extern "C" int bdx_config_create_debug(const bdx_params *p, uint32_t debug, bdx_
         delete cfg;
         return rc;
     }
+    {   // 4-bit codes of the packed input: the distinct barcode bytes of both sets, in order of first appearance
+        int n_codes = 1;
+        bool used[256] = {};
+        for (int k = 0; k < (p->is_dual ? 2 : 1) && n_codes; k++)
+            for (uint8_t b : cfg->set[k].bytes)
+                if (!cfg->code_of[b]) {
+                    if (n_codes == 16) {                 // too many distinct bytes: no packed input for this config
+                        n_codes = 0;
+                        memset(cfg->code_of, 0, sizeof(cfg->code_of));
+                        break;
+                    }
+                    cfg->code_of[b] = (uint8_t)n_codes;
+                    cfg->rep_of[n_codes++] = b;
+                    used[b] = true;
+                }
+        cfg->n_codes = n_codes;
+        for (int b = 0; b < 256 && n_codes; b++)
+            if (!used[b]) {                              // code 0 expands to a byte that is in no barcode
+                cfg->rep_of[0] = (uint8_t)b;
+                break;
+            }
+    }
     DevParams &P = cfg->base;
     P.max_error_rate = p->max_error_rate;
     P.min_delta = p->min_delta;
@@ -349,6 +371,8 @@ extern "C" void bdx_stream_destroy(bdx_stream *s)
         cudaFreeHost(sl.h_off);
         cudaFreeHost(sl.h_res);
         cudaFreeHost(sl.h_det);
+        cudaFree(sl.d_packed);
+        cudaFreeHost(sl.h_packed);
         cudaFree(sl.d_seq);
         cudaFree(sl.d_off);
         cudaFree(sl.d_res);
@@ -394,7 +418,7 @@ static int stream_create_impl(bdx_stream *s)
         for (Slot &sl : s->slot) {
             CU(cudaHostAlloc(&sl.h_res, (size_t)s->max_reads * sizeof(bdx_result), cudaHostAllocDefault));
             CU(cudaHostAlloc(&sl.h_det, (size_t)s->max_reads * 2 * sizeof(bdx_pass_detail), cudaHostAllocDefault));
-            CU(cudaMalloc(&sl.d_seq, (size_t)std::max<int64_t>(s->max_bytes, 16)));
+            CU(cudaMalloc(&sl.d_seq, (size_t)std::max<int64_t>(s->max_bytes, 16) + 32));   // (+ slack: k_unpack4 stores 16-byte vectors)
             CU(cudaMalloc(&sl.d_off, ((size_t)s->max_reads + 1) * 4));
             CU(cudaMalloc(&sl.d_res, (size_t)s->max_reads * sizeof(bdx_result)));
             CU(cudaMalloc(&sl.d_det, (size_t)s->max_reads * 2 * sizeof(bdx_pass_detail)));
@@ -627,17 +651,23 @@ static int enqueue_batch(bdx_stream *s, Slot &sl)
     return bdx_enqueue_classify(s, sl.d_seq, sl.d_off, n, sl.d_res, det);
 }
 
-static int launch_slot(bdx_stream *s, Slot &sl, const uint8_t *h_seq, const int32_t *h_off)
+// h_seq: the batch's sequence bytes, or -- packed -- their 4-bit codes (packed.cu)
+static int launch_slot(bdx_stream *s, Slot &sl, const uint8_t *h_seq, const int32_t *h_off, bool packed = false)
 {
     CU(cudaSetDevice(s->device));
     const int32_t n = sl.n;
     const size_t bytes = n ? (size_t)h_off[n] : 0;
     if (n) {
         CU(cudaMemcpyAsync(sl.d_off, h_off, ((size_t)n + 1) * 4, cudaMemcpyHostToDevice, s->st_copy));
-        if (bytes) CU(cudaMemcpyAsync(sl.d_seq, h_seq, bytes, cudaMemcpyHostToDevice, s->st_copy));
+        if (bytes && !packed) CU(cudaMemcpyAsync(sl.d_seq, h_seq, bytes, cudaMemcpyHostToDevice, s->st_copy));
+        if (bytes && packed) CU(cudaMemcpyAsync(sl.d_packed, h_seq, (bytes + 1) / 2, cudaMemcpyHostToDevice, s->st_copy));
     }
     CU(cudaEventRecord(sl.ev_h2d, s->st_copy));
     CU(cudaStreamWaitEvent(s->st_comp, sl.ev_h2d, 0));
+    if (packed && bytes) {
+        CU(launch_unpack4(sl.d_packed, sl.d_seq, sl.d_off, n, (long long)bytes, s->cfg->rep_of, s->tab->sm_count, s->st_comp));
+        s->launches++;
+    }
     int rc = enqueue_batch(s, sl);
     if (rc) return rc;
     CU(cudaEventRecord(sl.ev_kern, s->st_comp));
@@ -661,8 +691,8 @@ static int ensure_host_staging(bdx_stream *s)
     if (s->host_staging) return BDX_OK;
     CU(cudaSetDevice(s->device));
     for (Slot &sl : s->slot) {
-        CU(cudaHostAlloc(&sl.h_seq, (size_t)std::max<int64_t>(s->max_bytes, 16), cudaHostAllocDefault));
-        CU(cudaHostAlloc(&sl.h_off, ((size_t)s->max_reads + 1) * 4, cudaHostAllocDefault));
+        if (!sl.h_seq) CU(cudaHostAlloc(&sl.h_seq, (size_t)std::max<int64_t>(s->max_bytes, 16), cudaHostAllocDefault));
+        if (!sl.h_off) CU(cudaHostAlloc(&sl.h_off, ((size_t)s->max_reads + 1) * 4, cudaHostAllocDefault));
     }
     s->host_staging = true;
     return BDX_OK;
@@ -720,6 +750,68 @@ extern "C" int bdx_submit_pinned(bdx_stream *s, const uint8_t *seq, const int32_
     sl.n = n;
     sl.tag = tag;
     return launch_slot(s, sl, seq, offsets);
+}
+
+// ---- 4-bit packed input ----
+void bdx_pack4_bytes(const uint8_t code[256], const uint8_t *in, int64_t n, uint8_t *out);   // pack.cpp
+
+extern "C" int bdx_config_code_table(const bdx_config *cfg, uint8_t table[256])
+{
+    if (!cfg || !table) return fail(BDX_ERR_INVALID, "null argument");
+    if (!cfg->n_codes) return fail(BDX_ERR_INVALID, "more than 15 distinct barcode bytes: no 4-bit packed input for this config");
+    memcpy(table, cfg->code_of, 256);
+    return cfg->n_codes;
+}
+
+extern "C" int bdx_pack_reads4(const bdx_config *cfg, const uint8_t *seq, int64_t n_bytes, uint8_t *packed)
+{
+    if (!cfg || n_bytes < 0 || (n_bytes > 0 && (!seq || !packed))) return fail(BDX_ERR_INVALID, "bad argument");
+    if (!cfg->n_codes) return fail(BDX_ERR_INVALID, "more than 15 distinct barcode bytes: no 4-bit packed input for this config");
+    bdx_pack4_bytes(cfg->code_of, seq, n_bytes, packed);
+    return BDX_OK;
+}
+
+static int ensure_packed_buffers(bdx_stream *s, bool host)
+{
+    CU(cudaSetDevice(s->device));
+    const size_t cap = (size_t)std::max<int64_t>(s->max_bytes, 16) / 2 + 32;
+    for (Slot &sl : s->slot) {
+        if (!sl.d_packed) CU(cudaMalloc(&sl.d_packed, cap));
+        if (host && !sl.h_packed) CU(cudaHostAlloc(&sl.h_packed, cap, cudaHostAllocDefault));
+        if (host && !sl.h_off) CU(cudaHostAlloc(&sl.h_off, ((size_t)s->max_reads + 1) * 4, cudaHostAllocDefault));
+    }
+    return BDX_OK;
+}
+
+static int submit_packed(bdx_stream *s, const uint8_t *packed, const int32_t *offsets, int32_t n, uint64_t tag, bool pinned)
+{
+    if (!s || (n > 0 && (!packed || !offsets))) return fail(BDX_ERR_INVALID, "null argument");
+    if (!s->cfg->n_codes) return fail(BDX_ERR_INVALID, "more than 15 distinct barcode bytes: no 4-bit packed input for this config");
+    if (s->max_reads <= 0) return fail(BDX_ERR_STATE, "stream has no staging (max_reads = 0)");
+    if (s->acquired) return fail(BDX_ERR_STATE, "bdx_acquire pending; call bdx_commit");
+    if (s->in_flight >= BDX_MAX_IN_FLIGHT) return fail(BDX_ERR_STATE, "BDX_MAX_IN_FLIGHT batches already in flight; call bdx_fetch");
+    int rc = check_batch(s, offsets, n);
+    if (rc) return rc;
+    if ((rc = ensure_packed_buffers(s, !pinned))) return rc;
+    Slot &sl = s->slot[s->head];
+    sl.n = n;
+    sl.tag = tag;
+    if (pinned) return launch_slot(s, sl, packed, offsets, true);
+    if (n) {
+        memcpy(sl.h_off, offsets, ((size_t)n + 1) * 4);
+        memcpy(sl.h_packed, packed, ((size_t)offsets[n] + 1) / 2);
+    }
+    return launch_slot(s, sl, sl.h_packed, sl.h_off, true);
+}
+
+extern "C" int bdx_submit_packed4(bdx_stream *s, const uint8_t *packed, const int32_t *offsets, int32_t n, uint64_t tag)
+{
+    return submit_packed(s, packed, offsets, n, tag, false);
+}
+
+extern "C" int bdx_submit_packed4_pinned(bdx_stream *s, const uint8_t *packed, const int32_t *offsets, int32_t n, uint64_t tag)
+{
+    return submit_packed(s, packed, offsets, n, tag, true);
 }
 
 extern "C" int bdx_acquire(bdx_stream *s, uint8_t **seq, int32_t **offsets)

@@ -211,6 +211,8 @@ cudaError_t launch_hamming_scan(const DevParams &P, int pass, const uint8_t *seq
                                 const Scratch &sc, int sm_count, cudaStream_t st);
 cudaError_t launch_finalize(const DevParams &P, const int *off, int n, const Scratch &sc,
                             bdx_result *res, bdx_pass_detail *det, StatsDev stats, cudaStream_t st);
+cudaError_t launch_unpack4(const uint8_t *d_packed, uint8_t *d_seq, const int *d_off, int n_reads, long long max_bytes,
+                           const uint8_t rep[16], int sm_count, cudaStream_t st);
 cudaError_t launch_synth(const DevParams &P, const bdx_synth_spec &spec, int n, uint8_t *seq, int *off,
                          cudaStream_t st);
 cudaError_t run_int_alu_peak(int device, double *ops_per_second);

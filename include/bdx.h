@@ -173,6 +173,22 @@ int bdx_submit_pinned(bdx_stream *s, const uint8_t *seq_bytes, const int32_t *of
 void *bdx_host_alloc(size_t bytes);
 void bdx_host_free(void *p);
 
+/* ---- packed input: half the host->device bytes ---------------------------------------------------------
+ * All the path asks of a read byte is whether it equals a barcode byte, so reads may travel as 4-bit codes:
+ * 0 = a byte that occurs in no barcode of the config, 1..15 = its distinct barcode bytes (both sets together;
+ * bdx_config_code_table).  Layout: byte k of the batch's concatenated reads is nibble k of the packed stream, low
+ * nibble first; `offsets` are those of the UNPACKED reads, exactly as for bdx_submit.  The device expands the codes
+ * to representative bytes and classifies as usual: the results are identical to bdx_submit on the original bytes.
+ * BDX_ERR_INVALID when the config has more than 15 distinct barcode bytes.
+ * bdx_pack_reads4 is the host helper a reader calls INSTEAD of copying sequence bytes (AVX2 for letter alphabets;
+ * thread-safe, no CUDA): n_bytes input bytes -> (n_bytes + 1) / 2 output bytes. */
+int bdx_config_code_table(const bdx_config *cfg, uint8_t table[256]);   /* returns the number of codes incl. 0 */
+int bdx_pack_reads4(const bdx_config *cfg, const uint8_t *seq_bytes, int64_t n_bytes, uint8_t *packed_out);
+int bdx_submit_packed4(bdx_stream *s, const uint8_t *packed, const int32_t *offsets, int32_t n_reads, uint64_t tag);
+/* like bdx_submit_pinned: packed / offsets are page-locked and stay untouched until the batch has been fetched */
+int bdx_submit_packed4_pinned(bdx_stream *s, const uint8_t *packed, const int32_t *offsets, int32_t n_reads,
+                              uint64_t tag);
+
 /* Per-pass details are copied back only when enabled (default: on iff want_stats). */
 int bdx_stream_enable_details(bdx_stream *s, int on);
 

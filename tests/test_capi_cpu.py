@@ -194,3 +194,38 @@ def test_stats_overflow_merge():
     assert st.bc1_per_bc_pos_counts == {3: {4000: 2}} and st.bc1_per_bc_len_counts == {3: {24: 1, 25: 1}}
     assert st.bc2_pos_counts == {70000: 1} and st.bc2_per_bc_len_counts == {1: {16: 1}}
     assert merge_overflow(DemuxStats(), None) == DemuxStats()
+
+
+def test_pack4_matches_numpy_reference():
+    """bdx_pack_reads4 (AVX2 and scalar paths) against a numpy restatement: code table = distinct barcode bytes of
+    both sets in order of appearance, nibble k = code of byte k, low nibble first; no CUDA needed."""
+    rng = np.random.default_rng(5)
+    for bcs, bcs2 in ((["ACGTACGT", "TTGGCCAA"], None), (["ACGTN", "RYKM"], ["ACGU", "acgt"]), (["AC.T", "A-GT"], None)):
+        cfg = bdx.DemuxConfig(bc_seqs=bcs, bc_lengths_no_N=[len(b) for b in bcs], ids=[str(i) for i in range(len(bcs))])
+        if bcs2:
+            cfg.is_dual, cfg.bc_seqs2, cfg.bc_lengths_no_N2 = True, bcs2, [len(b) for b in bcs2]
+            cfg.ids2 = [str(i) for i in range(len(bcs2))]
+        config = capi.Config(cfg)
+        table = config.code_table()
+        order = []
+        for b in "".join(bcs + (bcs2 or [])).encode("latin-1"):
+            if b not in order:
+                order.append(b)
+        want_table = np.zeros(256, np.uint8)
+        for k, b in enumerate(order):
+            want_table[b] = k + 1
+        assert (table == want_table).all()
+        for n in (0, 1, 2, 63, 64, 65, 1000, 4097):
+            seq = rng.choice(np.frombuffer(b"ACGTNacgtRYKMU.-\n\x00\xff", dtype=np.uint8), n).astype(np.uint8)
+            got = config.pack4(seq)
+            codes = want_table[seq]
+            if n % 2:
+                codes = np.append(codes, 0)
+            want = (codes[0::2] | (codes[1::2] << 4)).astype(np.uint8)
+            assert (got == want).all(), (bcs, n)
+        config.close()
+    many = ["".join(chr(65 + k) for k in range(16))]          # 16 distinct barcode bytes: no packed input
+    config = capi.Config(bdx.DemuxConfig(bc_seqs=many, bc_lengths_no_N=[16], ids=["x"]))
+    with pytest.raises(capi.BdxError):
+        config.code_table()
+    config.close()

@@ -434,7 +434,10 @@ def run_ours(args):
 
     DEPTH = int(os.environ.get("BDX_E2E_DEPTH", "4"))  # batches kept in flight (BDX_MAX_IN_FLIGHT = 4)
 
-    def e2e_steps(n_steps):
+    def submit_bytes(k):
+        stream.submit(seq_np[k * B * READ_LEN:(k + 1) * B * READ_LEN], off_np, tag=k, pinned=True)
+
+    def e2e_steps(n_steps, submit=submit_bytes):
         """n_steps passes over the workload as ONE pipeline of batches: every batch is copied H2D from pinned
         host memory, classified, its results copied D2H and read by the host; DEPTH batches are in flight,
         the pipeline is drained at the end (inside the timed region), not between steps."""
@@ -443,7 +446,7 @@ def run_ours(args):
         queued = 0
         for _ in range(n_steps):
             for k in range(nb):
-                stream.submit(seq_np[k * B * READ_LEN:(k + 1) * B * READ_LEN], off_np, tag=k, pinned=True)
+                submit(k)
                 queued += 1
                 if queued == DEPTH:
                     _, r = stream.fetch(copy=False)
@@ -467,6 +470,19 @@ def run_ours(args):
     p1.record()
     torch.cuda.synchronize()
     pcie_h2d_gbs = 4 * B * READ_LEN / (p0.elapsed_time(p1) * 1e-3) / 1e9
+    # the same copy issued by ALL ranks at once (barrier first): what the box's host memory / PCIe complex gives N
+    # GPUs together is the ceiling the N-GPU e2e number has to be read against
+    barrier()
+    p0.record()
+    for k in range(8):
+        d_probe.copy_(h_seq[(k % nb) * B * READ_LEN:(k % nb + 1) * B * READ_LEN], non_blocking=True)
+    p1.record()
+    torch.cuda.synchronize()
+    conc = torch.tensor([8 * B * READ_LEN / (p0.elapsed_time(p1) * 1e-3) / 1e9], dtype=torch.float64, device="cuda")
+    conc_all = [conc.clone() for _ in range(world)]
+    if world > 1:
+        dist.all_gather(conc_all, conc)
+    conc_per_rank = [float(x.item()) for x in conc_all]
     del d_probe
     barrier()
     sampler.begin()                           # second sampling window: the e2e timed region
@@ -482,6 +498,83 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = world * nb * B * args.steps / float(t.item())
     assert e2e_matched == args.steps * int((res["status"][:nb * B] == 0).sum()), "e2e and device-resident results disagree"
+
+    # ---- the same pipeline fed with 4-bit packed reads (bdx_submit_packed4_pinned): half the H2D bytes.  The reads
+    # are packed once, outside the timed region -- packing is what a reader does INSTEAD of copying the sequence
+    # bytes into the staging buffer (bdx_pack_reads4 runs at memcpy speed; its rate is reported) ----
+    e2e_packed = None
+    if not args.no_packed:
+        h_packed = torch.empty(n * READ_LEN // 2 + 16, dtype=torch.uint8, pin_memory=True)
+        packed_np = h_packed.numpy()
+        tp = time.perf_counter()
+        for k in range(nb):
+            config.pack4(seq_np[k * B * READ_LEN:(k + 1) * B * READ_LEN], packed_np[k * B * READ_LEN // 2:(k + 1) * B * READ_LEN // 2])
+        pack_gbs = nb * B * READ_LEN / (time.perf_counter() - tp) / 1e9
+
+        def submit_packed(k):
+            stream.submit_packed4(packed_np[k * B * READ_LEN // 2:(k + 1) * B * READ_LEN // 2], off_np, tag=k, pinned=True)
+
+        e2e_steps(1, submit_packed)
+        barrier()
+        t0 = time.perf_counter()
+        e2e_steps(args.steps, submit_packed)
+        torch.cuda.synchronize()
+        tpk = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tpk, op=dist.ReduceOp.MAX)
+        assert e2e_matched == args.steps * int((res["status"][:nb * B] == 0).sum()), "packed e2e and device-resident results disagree"
+        e2e_packed = {"value": world * nb * B * args.steps / float(tpk.item()), "unit": "reads/s",
+                      "h2d_bytes_per_step": nb * (B * READ_LEN // 2 + 4 * (B + 1)),
+                      "d2h_bytes_per_step": nb * B * bdx.RESULT_DTYPE.itemsize,
+                      "api": "bdx_submit_packed4_pinned / bdx_fetch_view", "host_pack_gbs_one_thread": pack_gbs,
+                      "note": "reads packed to 4-bit codes by the reader (bdx_pack_reads4, outside the timed region: it replaces "
+                              "the reader's copy into the staging buffer); results identical to the byte input"}
+        del h_packed
+
+    # ---- one host process driving all GPUs of the job through bdx_pool (the Julia host's shape, core.jl:454-466):
+    # rank 0 deals the batches round-robin over the ranks' devices while the other ranks wait ----
+    pool_line = None
+    if not args.no_pool:
+        barrier()
+        if rank == 0:
+            devs = list(range(world))
+            pool = capi.Pool(config, devs, streams_per_device=2, max_reads=B, max_bytes=B * READ_LEN)
+            cap = len(devs) * 2 * 3
+
+            readers = ThreadPoolExecutor(4)       # the host still reads every result record (numpy drops the GIL)
+
+            def pool_pass(n_steps):
+                counts, queued = [], 0
+                for _ in range(n_steps):
+                    for k in range(nb):
+                        pool.submit(seq_np[k * B * READ_LEN:(k + 1) * B * READ_LEN], off_np, tag=k, pinned=True)
+                        queued += 1
+                        if queued == cap:
+                            _, r = pool.fetch(copy=False)
+                            counts.append(readers.submit(lambda v: int(np.count_nonzero(v["bc1"])), r))
+                            queued -= 1
+                while queued:
+                    _, r = pool.fetch(copy=False)
+                    counts.append(readers.submit(lambda v: int(np.count_nonzero(v["bc1"])), r))
+                    queued -= 1
+                return sum(c.result() for c in counts)
+
+            pool_pass(1)
+            for dv in devs:
+                torch.cuda.synchronize(dv)
+            t0 = time.perf_counter()
+            steps_pool = max(args.steps, 2 * world)
+            m = pool_pass(steps_pool)
+            for dv in devs:
+                torch.cuda.synchronize(dv)
+            dtp = time.perf_counter() - t0
+            assert m == steps_pool * int((res["status"][:nb * B] == 0).sum())
+            pool_line = {"n_gpus": world, "reads_per_sec": steps_pool * nb * B / dtp, "streams_per_device": 2,
+                         "batches_in_flight": cap, "api": "bdx_pool_submit_pinned / bdx_pool_fetch_view, ONE host process and "
+                         "thread, one pinned copy of the workload on rank 0's NUMA node"}
+            pool.close()
+            torch.cuda.set_device(local)
+        barrier()
 
     # ---- N > 1: the one collective of the path -- DemuxStats counters summed over GPUs ------
     stats_ms = None
@@ -592,12 +685,18 @@ def run_ours(args):
                     "api": f"bdx_submit_pinned / bdx_fetch_view, {DEPTH} batches in flight",
                     "h2d_gbs_achieved": e2e_value / world * (READ_LEN + 4) / 1e9, "numa_binding_rank0": numa,
                     "h2d_gbs_plain_memcpy": pcie_h2d_gbs,
+                    "h2d_gbs_concurrent_per_rank": conc_per_rank, "h2d_gbs_concurrent_aggregate": sum(conc_per_rank),
+                    "reads_per_sec_at_concurrent_h2d_ceiling": sum(conc_per_rank) * 1e9 / (READ_LEN + 4),
                     "bound": "host link: every read is 154 B of H2D; a bare pinned cudaMemcpyAsync of the same "
                              "bytes runs at h2d_gbs_plain_memcpy on this box"},
             "gpu_launches": launches, "clocks": clocks,
         }
         if stats_ms is not None:
             line["stats_allreduce_ms"] = stats_ms
+        if e2e_packed is not None:
+            line["e2e_packed"] = e2e_packed
+        if pool_line is not None:
+            line["pool_single_process"] = pool_line
         if floor is not None:
             line["floor"] = floor
         if others is not None:
@@ -630,6 +729,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="device-resident timing only (kernel experiments)")
     ap.add_argument("--no-floor", action="store_true", help="skip the no-barcode (all-automaton) rate")
+    ap.add_argument("--no-packed", action="store_true", help="skip the 4-bit packed-input e2e leg")
+    ap.add_argument("--no-pool", action="store_true", help="skip the single-process bdx_pool leg")
     ap.add_argument("--no-configs", action="store_true", help="skip BASELINE.json configs 3 / 4 / 5")
     ap.add_argument("--configs", nargs="*", default=None, help="subset of 3 4 5s 5h 5e")
     ap.add_argument("--config-scale", type=float, default=1.0, help="fraction of the stated read counts (1.0 = 50 M / 50 M / 200 M)")

@@ -538,14 +538,17 @@ class Pool:
                 return False
             raise
 
-    def fetch(self):
+    def fetch(self, copy: bool = True):
+        """Oldest batch of the pool.  copy=False: a view into the owning stream's pinned result staging (valid
+        until that stream has taken BDX_MAX_IN_FLIGHT - 1 further batches)."""
         tag, n = C.c_uint64(), C.c_int32()
         res_p, det_p = C.c_void_p(), C.c_void_p()
         _check(self.lib.bdx_pool_fetch_view(self.handle, C.byref(tag), C.byref(n), C.byref(res_p), C.byref(det_p)))
         if n.value == 0:
             return tag.value, np.zeros(0, RESULT_DTYPE)
         buf = (C.c_char * (n.value * RESULT_DTYPE.itemsize)).from_address(res_p.value)
-        return tag.value, np.frombuffer(buf, dtype=RESULT_DTYPE, count=n.value).copy()
+        res = np.frombuffer(buf, dtype=RESULT_DTYPE, count=n.value)
+        return tag.value, (res.copy() if copy else res)
 
     @property
     def in_flight(self) -> int:

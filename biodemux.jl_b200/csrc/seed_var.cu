@@ -154,7 +154,7 @@ __device__ __forceinline__ void sv_verify(const uint32_t *hits_s, int total, con
         }
         wlen = __reduce_max_sync(0xFFFFFFFFu, wlen);
         // past its own window a lane keeps stepping on whatever is staged there (never read back: `best` is frozen)
-#pragma unroll 2
+#pragma unroll 4
         for (int t = 0; t < wlen; t++) {
             WT eq[2];
 #pragma unroll
@@ -391,7 +391,31 @@ k_seed_var(const __grid_constant__ DevParams P, const int pass, const int level,
         // threshold.  One thread per CANDIDATE (the reads' lists are flattened by a prefix sum): a group of few
         // reads would otherwise leave most of the block idle.
         const bool usable = !punt && rinfo_s[threadIdx.x * kSvRi + 3] == 0 && cand_n_s[threadIdx.x] <= kSvCand;
-        const int my_nc = usable ? cand_n_s[threadIdx.x] : 0;
+        // the read's verified candidates, ascending by (barcode, distance), one record per barcode: several intact
+        // segments of one alignment are several hits of the same barcode
+        int my_nc = 0;
+        uint32_t cl[kSvCand];
+        if (usable) {
+            const int nc = cand_n_s[threadIdx.x];
+#pragma unroll
+            for (int k = 0; k < kSvCand; k++) cl[k] = k < nc ? cand_s[threadIdx.x * kSvCand + k] : 0xFFFFFFFFu;
+#pragma unroll
+            for (int a = 1; a < kSvCand; a++)
+#pragma unroll
+                for (int bq = a; bq > 0; bq--)
+                    if (cl[bq] < cl[bq - 1]) {
+                        const uint32_t t = cl[bq];
+                        cl[bq] = cl[bq - 1];
+                        cl[bq - 1] = t;
+                    }
+            uint32_t last = 0xFFFFFFFFu;
+#pragma unroll
+            for (int k = 0; k < kSvCand; k++)
+                if (k < nc && (cl[k] >> 8) != last) {                 // the smaller distance of a barcode came first
+                    last = cl[k] >> 8;
+                    cand_s[threadIdx.x * kSvCand + my_nc++] = cl[k];
+                }
+        }
         const bool start_bound = !punt && g.max_start_pos < n;      // the reference's result depends on the threshold
         if (__syncthreads_or(start_bound && my_nc > 0)) {
             const Costs c{P.match, P.mismatch, P.indel, P.nindel, P.has_n};
@@ -450,28 +474,12 @@ k_seed_var(const __grid_constant__ DevParams P, const int pass, const int level,
         bool resolved = false;
         if (usable && rinfo_s[threadIdx.x * kSvRi + 3] == 0) {
             const int nc = my_nc;
-            uint32_t cl[kSvCand];
-#pragma unroll
-            for (int k = 0; k < kSvCand; k++) cl[k] = k < nc ? cand_s[threadIdx.x * kSvCand + k] : 0xFFFFFFFFu;
-            // ascending (barcode, distance): insertion sort of at most 8 records
-#pragma unroll
-            for (int a = 1; a < kSvCand; a++)
-#pragma unroll
-                for (int bq = a; bq > 0; bq--)
-                    if (cl[bq] < cl[bq - 1]) {
-                        const uint32_t t = cl[bq];
-                        cl[bq] = cl[bq - 1];
-                        cl[bq - 1] = t;
-                    }
             BestState bs;
             best_init(bs, P.max_error_rate);
-            int last_b = -1;
 #pragma unroll 1
             for (int k = 0; k < nc; k++) {
-                const int b = (int)(cl[k] >> 8);
-                if (b == last_b) continue;                           // same barcode through another hit: the smaller d came first
-                last_b = b;
-                const int d = (int)(cl[k] & 0xFFu);
+                const uint32_t rec = cand_s[threadIdx.x * kSvCand + k];
+                const int b = (int)(rec >> 8), d = (int)(rec & 0xFFu);
                 const int norm = S.norm[b];
                 const int allowed = allowed_from(bs.thr, norm);       // :254 with the running threshold
                 const double sc = d <= allowed ? __ddiv_rn((double)d, (double)norm) : CUDART_INF;

@@ -348,7 +348,7 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     n = args.reads
     cfg = make_config()
-    config = capi.Config(cfg)
+    config = capi.Config(cfg, debug=args.debug_flags)
     stream = capi.Stream(config, device=local, max_reads=args.e2e_batch, max_bytes=args.e2e_batch * READ_LEN)
     ext = torch.cuda.ExternalStream(stream.cuda_stream, device=torch.device("cuda", local))
 
@@ -417,7 +417,8 @@ def run_ours(args):
                               "matched_fraction": matched / n, "peak_Tops": peak_ops.value / 1e12,
                               "achieved_Tops": OPS_PER_READ * auto_per_launch / filt_s / 1e12,
                               "prefilter_fraction": pre_reads / max(pre_reads + seed_reads + auto_reads, 1),
-                              "seed_fraction": seed_reads / max(pre_reads + seed_reads + auto_reads, 1), "clocks": clocks}))
+                              "seed_fraction": seed_reads / max(pre_reads + seed_reads + auto_reads, 1), "clocks": clocks,
+                              "stage_ms_per_step": {k: v[0] / args.steps for k, v in stages.items() if v[1]}}))
         stream.close()
         return
 
@@ -728,6 +729,7 @@ def main():
     ap.add_argument("--e2e-batch", type=int, default=500_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="device-resident timing only (kernel experiments)")
+    ap.add_argument("--debug-flags", type=int, default=0, help="BDX_DEBUG_* (kernel experiments only)")
     ap.add_argument("--no-floor", action="store_true", help="skip the no-barcode (all-automaton) rate")
     ap.add_argument("--no-packed", action="store_true", help="skip the 4-bit packed-input e2e leg")
     ap.add_argument("--no-pool", action="store_true", help="skip the single-process bdx_pool leg")

@@ -114,6 +114,7 @@ extern "C" int bdx_config_create_debug(const bdx_params *p, uint32_t debug, bdx_
     P.want_stats = p->want_stats ? 1 : 0;
     P.filter_ok = cfg->set[0].use_filter && (!p->is_dual || cfg->set[1].use_filter);
     P.two = 2;
+    P.debug = (int)debug;
     P.unit_costs = p->match == 0 && p->mismatch == 1 && p->indel == 1 && (!p->has_nindel || p->nindel == 1);
 
     // stats layout (classification.jl:736-758)

@@ -141,7 +141,7 @@ struct DevParams {
     int filter_ok;    // costs allow the unit-cost filter to be a superset
     int unit_costs;   // match 0, mismatch 1, indel 1 (and nindel 1): filter distance is the score
     int two;          // (reserved)
-    int pad1;
+    int debug;        // BDX_DEBUG_* flags of the config (test hooks)
     DevSet set[2];
 };
 

@@ -562,7 +562,7 @@ int seed_var_levels(const DevParams &P, int pass)
     const DevSet &S = P.set[pass];
     if (P.algo != BDX_SEMIGLOBAL || !P.unit_costs || S.sv_levels < 1 || S.words < 1 || P.max_error_rate < 0.0) return 0;
     if (S.trim_side != 0 || P.want_stats) return 0;
-    if (seed_levels(P, pass) > 0 && sv_default_geometry(S)) return 0;
+    if (seed_levels(P, pass) > 0 && sv_default_geometry(S) && !(P.debug & BDX_DEBUG_PREFER_SEED_VAR)) return 0;
     for (int l = 0; l < S.sv_levels; l++)
         if (sv_launch_params(S, S.sv[l]).smem > 160 * 1024) return l;
     return S.sv_levels;

@@ -151,3 +151,27 @@ def _fuzz_case(seed):
 def test_seed_var_fuzz(seed):
     cfg, reads = _fuzz_case(7000 + seed)
     compare(cfg, reads, label=f"seedvar fuzz {seed}")
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_seed_var_on_uniform_default_geometry(seed):
+    """k_seed_var forced (BDX_DEBUG_PREFER_SEED_VAR) onto the sets k_seed's levels normally take -- uniform length,
+    default start / end ranges, 150-column search ranges, with and without min_delta: the exact regime, where a
+    candidate's value is its verified distance itself."""
+    rng = np.random.default_rng(9000 + seed)
+    m = int(rng.choice([12, 16, 20, 24, 28, 32]))
+    n_bc = int(rng.choice([24, 96, 200, 384]))
+    bcs = synth.random_barcodes(rng, n_bc, m, m)
+    kw = dict(max_error_rate=float(rng.choice([0.1, 0.2, 0.25])), min_delta=float(rng.choice([0.0, 0.0, 0.1])))
+    if rng.random() < 0.4:
+        kw["ref_search_range"] = R(f"{int(rng.integers(1, 20))}:{int(rng.integers(60, 170))}")
+    cfg = _cfg(bcs, **kw)
+    reads = synth.random_reads(rng, 3000, bcs, min_len=int(rng.choice([60, 150])), max_len=int(rng.choice([150, 175, 200])),
+                               max_edits=5, n_prob=0.02, lower_prob=0.02)
+    blob, off = bdx.pack_reads(reads)
+    want = orc.Oracle(cfg).classify_mt(blob, off)
+    with capi.Engine(cfg, max_reads=len(reads), max_bytes=int(off[-1]) + 16, debug=capi.DEBUG_PREFER_SEED_VAR) as eng:
+        got = eng.classify_packed(blob, off)
+    for f in ("status", "bc1", "bc2", "keep_start", "keep_end"):
+        bad = np.nonzero(got[f] != want[f])[0]
+        assert bad.size == 0, (f, int(bad[0]), got[bad[0]], want[bad[0]], reads[bad[0]])

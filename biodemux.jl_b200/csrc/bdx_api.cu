@@ -263,7 +263,9 @@ static int get_tables(bdx_config *cfg, int device, DeviceTables **out)
             SeedVar &V = D.sv[l];
             V.enabled = 1;
             V.q = H.q;
-            V.n_buckets = 1 << (2 * H.q);
+            V.q2 = H.q2;
+            V.bstart2 = (1 << (2 * H.q)) + 1;
+            V.n_bstart = (int)H.bstart.size();
             V.n_entries = (int)H.entries.size();
             V.complete = H.complete;
             V.group_reads = H.group_reads;
@@ -552,7 +554,17 @@ int bdx_enqueue_classify(bdx_stream *s, const uint8_t *d_seq, const int32_t *d_o
                                    to2 ? s->sc.n_work2 : s->sc.n_work, s->tab->sm_count, s->d_counters, s->st_comp); }))) return rc;
                     wl = to2 ? 2 : 1;
                 }
-                if (levels > 0 && seed_deep_applies(P, pass)) {
+                const int tail = levels > 0 ? seed_var_tail_level(P, pass) : -1;
+                if (tail >= 0) {
+                    // k_seed_var's complete level on what k_seed's levels left: verdicts are final, k_filter sees only
+                    // the reads it hands on (hit-list overflow)
+                    const bool to2 = wl != 2;
+                    if ((rc = staged(kStSeedDeep, [&] { return launch_seed_var(P, pass, tail, d_seq, d_off, n, s->sc, wl == 1 ? s->sc.worklist : s->sc.worklist2,
+                                        wl == 1 ? s->sc.n_work : s->sc.n_work2, to2 ? s->sc.worklist2 : s->sc.worklist,
+                                        to2 ? s->sc.n_work2 : s->sc.n_work, s->tab->sm_count, s->d_counters, s->st_comp); }))) return rc;
+                    wl = to2 ? 2 : 1;
+                }
+                if (levels > 0 && tail < 0 && seed_deep_applies(P, pass)) {
                     const bool to2 = wl != 2;
                     if ((rc = staged(kStSeedDeep, [&] { return launch_seed_deep(P, pass, d_seq, d_off, n, s->sc, wl == 1 ? s->sc.worklist : s->sc.worklist2,
                                         wl == 1 ? s->sc.n_work : s->sc.n_work2, to2 ? s->sc.worklist2 : s->sc.worklist,

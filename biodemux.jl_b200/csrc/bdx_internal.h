@@ -58,15 +58,17 @@ struct HammingPacked {
 // kdepth[b] + 1 disjoint segments whose first q bases sit in a direct-address table (4^q buckets, 2-bit codes)
 struct SeedVar {
     int enabled;
-    int q;                        // seed length
-    int n_buckets;                // 4^q
+    int q;                        // seed length of table 0
+    int q2;                       // seed length of table 1 (0 = one table): segments one base longer use it
+    int bstart2;                  // first bstart element of table 1 (= 4^q + 1)
+    int n_bstart;                 // elements of bstart: (4^q + 1) [+ (4^q2 + 1)]
     int n_entries;
     int complete;                 // kdepth[b] >= allowed0[b] for every barcode: the candidate sets are supersets
     int group_reads;              // reads a block works on at a time (sized so that their hits fit the block's hit list)
     int hit_rows;                 // hit list capacity in rows of 128 records
     int pad;
     double sigma_min;             // min_b (kdepth[b] + 1) / norm[b]: no barcode outside the candidate set scores below
-    const uint16_t *bstart;       // [n_buckets + 1] CSR row starts
+    const uint16_t *bstart;       // [n_bstart] CSR row starts of both tables, absolute indices into entries
     const uint32_t *entries;      // [n_entries] (barcode index << 8) | seed offset
     const uint8_t *kdepth;        // [n_bc] edit depth the barcode's seeds are complete for
 };
@@ -195,6 +197,7 @@ cudaError_t launch_seed(const DevParams &P, int pass, int level, const uint8_t *
 cudaError_t launch_mark_pending(const DevParams &P, int pass, int n, const Scratch &sc, const int *wl, const int *n_wl,
                                 cudaStream_t st);
 int seed_var_levels(const DevParams &P, int pass);     // number of k_seed_var levels that apply (0 = none)
+int seed_var_tail_level(const DevParams &P, int pass); // the complete level, usable behind k_seed's levels (-1 = none)
 cudaError_t launch_seed_var(const DevParams &P, int pass, int level, const uint8_t *seq, const int *off, int n, const Scratch &sc,
                             const int *wl_in, const int *n_in, int *wl_out, int *n_out, int sm_count,
                             unsigned long long *counters, cudaStream_t st);

@@ -94,7 +94,7 @@ __host__ __device__ inline int sv_hit_rows(int wanted, int max_m) { return max_m
 
 enum { kSvPeq = 0, kSvHits, kSvCandL, kSvRinfo, kSvCandN, kSvCtr, kSvEntries, kSvBstart, kSvBinfo, kSvClass, kSvSlot, kSvParts };
 
-__host__ __device__ inline size_t sv_smem_layout(int W, int plane, int n_pad, int n_entries, int n_buckets, int tab_smem,
+__host__ __device__ inline size_t sv_smem_layout(int W, int plane, int n_pad, int n_entries, int n_bstart, int tab_smem,
                                                  int slot_stride, int max_m, int R, int hit_rows, size_t off[kSvParts])
 {
     size_t o = 0;
@@ -105,7 +105,7 @@ __host__ __device__ inline size_t sv_smem_layout(int W, int plane, int n_pad, in
     off[kSvCandN] = o; o += ((size_t)kSvThreads + 4) * 4;                 // per read: number of candidates; later their offsets
     off[kSvCtr] = o; o += 32;
     off[kSvEntries] = o; o += tab_smem ? (size_t)n_entries * 4 : 0;
-    off[kSvBstart] = o; o += tab_smem ? (((size_t)n_buckets + 1) * 2 + 3) / 4 * 4 : 0;
+    off[kSvBstart] = o; o += tab_smem ? ((size_t)n_bstart * 2 + 3) / 4 * 4 : 0;
     off[kSvBinfo] = o; o += (size_t)n_pad * 4;                            // per barcode: m | K << 8 | allowed0 << 16
     off[kSvClass] = o; o += 256;
     off[kSvSlot] = o; o += (size_t)R * slot_stride + 128;                 // staged class codes (+ slack: windows are read past their end)
@@ -207,10 +207,8 @@ k_seed_var(const __grid_constant__ DevParams P, const int pass, const int level,
     const int n_pad = S.n_bc_pad;
     const int n_classes = S.n_classes;
     const int plane = n_classes * n_pad;
-    const int q = V.q;
-    const int n_buckets = V.n_buckets;
     size_t lo[kSvParts];
-    sv_smem_layout(W, plane, n_pad, V.n_entries, n_buckets, tab_smem, slot_stride, S.max_m, R, V.hit_rows, lo);
+    sv_smem_layout(W, plane, n_pad, V.n_entries, V.n_bstart, tab_smem, slot_stride, S.max_m, R, V.hit_rows, lo);
     uint32_t *peq_s = reinterpret_cast<uint32_t *>(smem_raw + lo[kSvPeq]);
     uint32_t *hits_s = reinterpret_cast<uint32_t *>(smem_raw + lo[kSvHits]);
     uint32_t *cand_s = reinterpret_cast<uint32_t *>(smem_raw + lo[kSvCandL]);
@@ -233,7 +231,7 @@ k_seed_var(const __grid_constant__ DevParams P, const int pass, const int level,
         uint32_t *en = reinterpret_cast<uint32_t *>(smem_raw + lo[kSvEntries]);
         uint16_t *bs = reinterpret_cast<uint16_t *>(smem_raw + lo[kSvBstart]);
         for (int k = threadIdx.x; k < V.n_entries; k += blockDim.x) en[k] = V.entries[k];
-        for (int k = threadIdx.x; k <= n_buckets; k += blockDim.x) bs[k] = V.bstart[k];
+        for (int k = threadIdx.x; k < V.n_bstart; k += blockDim.x) bs[k] = V.bstart[k];
     }
     for (int k = threadIdx.x; k < n_pad; k += blockDim.x) {
         uint32_t v = 0;
@@ -253,8 +251,6 @@ k_seed_var(const __grid_constant__ DevParams P, const int pass, const int level,
     const int n_groups = (n_items + R - 1) / R;
     const bool with_delta = P.min_delta != 0.0;
     const int hit_cap = kSvThreads * sv_hit_rows(V.hit_rows, S.max_m);
-    const int n_pos = max(slot_cols - q + 1, 1);             // q-mer positions scanned per read (at most)
-    const uint32_t pos_recip = 0xFFFFFFFFu / (uint32_t)n_pos + 1u;   // i / n_pos == umulhi(i, recip) for i < 2^16
     unsigned int n_done = 0;
 
     for (int grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
@@ -302,6 +298,11 @@ k_seed_var(const __grid_constant__ DevParams P, const int pass, const int level,
 
         // ---- scan: (read, column) pairs dealt to the threads.  The table entries of a warp's 32 pairs are
         // pooled (prefix sum of the bucket sizes) and dealt out evenly again, one entry per lane and round ----
+        for (int tb = 0; tb < (V.q2 ? 2 : 1); tb++) {                // one or two seed tables (lengths q, q + 1)
+        const int q = tb ? V.q2 : V.q;
+        const uint16_t *bstart_t = bstart_s + (tb ? V.bstart2 : 0);
+        const int n_pos = max(slot_cols - q + 1, 1);             // q-mer positions scanned per read (at most)
+        const uint32_t pos_recip = 0xFFFFFFFFu / (uint32_t)n_pos + 1u;   // i / n_pos == umulhi(i, recip) for i < 2^16
         const int n_pairs = R * n_pos;
         for (int i = threadIdx.x; i < ((n_pairs + 31) & ~31); i += kSvThreads) {     // whole warps: the loop body votes
             const int r = min((int)__umulhi((uint32_t)i, pos_recip), R - 1), p = i - r * n_pos;
@@ -316,8 +317,8 @@ k_seed_var(const __grid_constant__ DevParams P, const int pass, const int level,
                     code |= ((cl - 1u) & 3u) << (2 * k);
                 }
             }
-            const int e0 = valid ? (int)bstart_s[code] : 0;
-            const int cnt = valid ? (int)bstart_s[code + 1] - e0 : 0;
+            const int e0 = valid ? (int)bstart_t[code] : 0;
+            const int cnt = valid ? (int)bstart_t[code + 1] - e0 : 0;
             int incl = cnt;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
@@ -372,6 +373,7 @@ k_seed_var(const __grid_constant__ DevParams P, const int pass, const int level,
                     }
                 }
             }
+        }
         }
         __syncthreads();
 
@@ -547,10 +549,10 @@ static SvLaunch sv_launch_params(const DevSet &S, const SeedVar &V)
     size_t off[kSvParts];
     const int plane = S.n_classes * S.n_bc_pad;
     L.tab_smem = 1;
-    L.smem = sv_smem_layout(S.words, plane, S.n_bc_pad, V.n_entries, V.n_buckets, 1, L.slot_stride, S.max_m, V.group_reads, V.hit_rows, off);
+    L.smem = sv_smem_layout(S.words, plane, S.n_bc_pad, V.n_entries, V.n_bstart, 1, L.slot_stride, S.max_m, V.group_reads, V.hit_rows, off);
     if (L.smem > 100 * 1024) {
         L.tab_smem = 0;
-        L.smem = sv_smem_layout(S.words, plane, S.n_bc_pad, V.n_entries, V.n_buckets, 0, L.slot_stride, S.max_m, V.group_reads, V.hit_rows, off);
+        L.smem = sv_smem_layout(S.words, plane, S.n_bc_pad, V.n_entries, V.n_bstart, 0, L.slot_stride, S.max_m, V.group_reads, V.hit_rows, off);
     }
     return L;
 }
@@ -566,6 +568,18 @@ int seed_var_levels(const DevParams &P, int pass)
     for (int l = 0; l < S.sv_levels; l++)
         if (sv_launch_params(S, S.sv[l]).smem > 160 * 1024) return l;
     return S.sv_levels;
+}
+
+// The complete level behind k_seed's own levels (uniform-length sets in the default geometry): it takes the reads
+// they could not finish -- best barcode at the allowed distance, or none at all -- instead of k_filter.
+int seed_var_tail_level(const DevParams &P, int pass)
+{
+    const DevSet &S = P.set[pass];
+    if (P.algo != BDX_SEMIGLOBAL || !P.unit_costs || S.sv_levels < 1 || S.words < 1 || P.max_error_rate < 0.0) return -1;
+    if (S.trim_side != 0 || P.want_stats) return -1;
+    const int l = S.sv_levels - 1;
+    if (!S.sv[l].complete || sv_launch_params(S, S.sv[l]).smem > 160 * 1024) return -1;
+    return l;
 }
 
 cudaError_t launch_seed_var(const DevParams &P, int pass, int level, const uint8_t *seq, const int *off, int n, const Scratch &sc,

@@ -341,13 +341,17 @@ void build_seed_var(const Build &B)
         const int L = std::max(end_j - start_j + 1, 1), sbase = start_j - 1;
         const int min_end_rel = ef - sbase, max_start_rel = bl - sbase;
         struct Est { double chance, steps; size_t n_entries; bool complete; };
+        // admissible diagonals of barcode b at depth K (seed_var.cu, scan)
+        auto n_diag = [&](int m, int a0, int K) {
+            const int dlo = std::max(0, min_end_rel - m) - K, dhi = std::min(max_start_rel + a0, L - m + K);
+            return std::max(0, dhi - dlo + 1);
+        };
         auto estimate = [&](int q) {
             Est e{0.0, 0.0, 0, true};
             for (int b = 0; b < hs.n_bc; b++) {
                 const int m = hs.off[b + 1] - hs.off[b], a0 = hs.allowed0[b];
                 const int K = std::min(m / q - 1, a0);
-                const int dlo = std::max(0, min_end_rel - m) - K, dhi = std::min(max_start_rel + a0, L - m + K);
-                const double c = (double)(K + 1) * std::max(0, dhi - dlo + 1) / std::pow(4.0, q);
+                const double c = (double)(K + 1) * n_diag(m, a0, K) / std::pow(4.0, q);
                 e.chance += c;
                 e.steps += c * (m + 2 * K);          // columns verified for those hits
                 e.n_entries += (size_t)K + 1;
@@ -355,9 +359,20 @@ void build_seed_var(const Build &B)
             }
             return e;
         };
+        // reads per group: 128 and a hit list of up to 64 rows x 128 records (seed_var.cu) that their hits -- chance
+        // + a handful of true ones -- fill to about 70 %; denser levels take fewer reads per group instead
+        auto size_groups = [&](HostSet::HostSeedVar &V, double chance) {
+            const double per_read = chance + 6.0;
+            V.hit_rows = std::min(64, std::max(32, (int)std::ceil(per_read / 0.7)));
+            int R = 128;
+            while (R > 8 && per_read * R > 0.7 * 128 * V.hit_rows) R -= 8;
+            V.group_reads = R;
+        };
+        // level with ONE seed length q: K_b + 1 segments of m_b / (K_b + 1) >= q bases, K_b = min(m_b / q - 1, allowed_b)
         auto build = [&](int q, double chance) {
             HostSet::HostSeedVar &V = hs.sv[hs.sv_levels++];
             V.q = q;
+            V.q2 = 0;
             V.kdepth.assign((size_t)hs.n_bc, 0);
             std::vector<std::vector<uint32_t>> buckets((size_t)1 << (2 * q));
             V.sigma_min = 1e300;
@@ -381,13 +396,61 @@ void build_seed_var(const Build &B)
                 V.bstart[k + 1] = (uint16_t)(V.bstart[k] + buckets[k].size());
                 V.entries.insert(V.entries.end(), buckets[k].begin(), buckets[k].end());
             }
-            // 128 reads per group and a hit list of up to 64 rows x 128 records (seed_var.cu) that their hits -- chance
-            // + a handful of true ones -- fill to about 70 %; denser levels take fewer reads per group instead
-            const double per_read = chance + 6.0;
-            V.hit_rows = std::min(64, std::max(32, (int)std::ceil(per_read / 0.7)));
-            int R = 128;
-            while (R > 8 && per_read * R > 0.7 * 128 * V.hit_rows) R -= 8;
-            V.group_reads = R;
+            size_groups(V, chance);
+        };
+        // COMPLETE level (K_b = allowed_b): barcode b is cut into allowed_b + 1 segments of m_b / (allowed_b + 1) bases,
+        // the first m_b % (allowed_b + 1) of them one base longer; every segment is a seed of its own length, kept
+        // in one of two tables (q and q + 1: e.g. 24 nt at depth 4 = four 5-mers and one 4-mer, 2.5 x fewer chance
+        // hits than five 4-mers)
+        struct Seg { int b, o, q; };
+        auto complete_segments = [&](int q_lo, std::vector<Seg> &segs) {
+            Est e{0.0, 0.0, 0, true};
+            for (int b = 0; b < hs.n_bc; b++) {
+                const int m = hs.off[b + 1] - hs.off[b], a0 = hs.allowed0[b];
+                const int n_seg = a0 + 1, base = m / n_seg, extra = m % n_seg;
+                int o = 0;
+                for (int i = 0; i < n_seg; i++) {
+                    const int len = base + (i < extra ? 1 : 0);
+                    const int q = (len > q_lo && q_lo < 8) ? q_lo + 1 : q_lo;
+                    segs.push_back(Seg{b, o, q});
+                    const double c = (double)n_diag(m, a0, a0) / std::pow(4.0, q);
+                    e.chance += c;
+                    e.steps += c * (m + 2 * a0);
+                    o += len;
+                }
+            }
+            e.n_entries = segs.size();
+            return e;
+        };
+        auto build_complete = [&](int q_lo, const std::vector<Seg> &segs, double chance) {
+            HostSet::HostSeedVar &V = hs.sv[hs.sv_levels++];
+            bool two = false;
+            for (const Seg &sg2 : segs) two = two || sg2.q != q_lo;
+            V.q = q_lo;
+            V.q2 = two ? q_lo + 1 : 0;
+            V.kdepth.assign((size_t)hs.n_bc, 0);
+            V.sigma_min = 1e300;
+            V.complete = 1;
+            for (int b = 0; b < hs.n_bc; b++) {
+                V.kdepth[(size_t)b] = (uint8_t)hs.allowed0[b];
+                V.sigma_min = std::min(V.sigma_min, (double)(hs.allowed0[b] + 1) / (double)hs.norm[b]);
+            }
+            for (int t = 0; t < (two ? 2 : 1); t++) {
+                const int q = t ? q_lo + 1 : q_lo;
+                std::vector<std::vector<uint32_t>> buckets((size_t)1 << (2 * q));
+                for (const Seg &sg2 : segs) {
+                    if (sg2.q != q) continue;
+                    uint32_t code = 0;
+                    for (int k = 0; k < q; k++) code |= ((uint32_t)(hs.bc_cls[hs.off[sg2.b] + sg2.o + k] - 1) & 3u) << (2 * k);
+                    buckets[code].push_back(((uint32_t)sg2.b << 8) | (uint32_t)sg2.o);
+                }
+                for (size_t k = 0; k < buckets.size(); k++) {
+                    V.bstart.push_back((uint16_t)V.entries.size());
+                    V.entries.insert(V.entries.end(), buckets[k].begin(), buckets[k].end());
+                }
+                V.bstart.push_back((uint16_t)V.entries.size());
+            }
+            size_groups(V, chance);
         };
         int q1 = 0;
         for (int q = 4; q <= 8 && !q1; q++) {
@@ -399,13 +462,14 @@ void build_seed_var(const Build &B)
             }
         }
         if (q1 && !hs.sv[0].complete && !(B.debug & BDX_DEBUG_ONE_SEED_LEVEL)) {
-            int q2 = q1 - 1;
-            for (int b = 0; b < hs.n_bc; b++) q2 = std::min(q2, (hs.off[b + 1] - hs.off[b]) / (hs.allowed0[b] + 1));
-            if (q2 >= 3) {
-                const Est e = estimate(q2);
+            int q_lo = 8;
+            for (int b = 0; b < hs.n_bc; b++) q_lo = std::min(q_lo, (hs.off[b + 1] - hs.off[b]) / (hs.allowed0[b] + 1));
+            if (q_lo >= 3) {
+                std::vector<Seg> segs;
+                const Est e = complete_segments(q_lo, segs);
                 const double automaton_steps = (double)hs.n_bc * L;
-                if (e.complete && e.n_entries <= 65535 && e.steps < 0.5 * automaton_steps && e.chance <= 200.0)
-                    build(q2, e.chance);
+                if (e.n_entries <= 65535 && e.steps < 0.5 * automaton_steps && e.chance <= 200.0)
+                    build_complete(q_lo, segs, e.chance);
             }
         }
     }

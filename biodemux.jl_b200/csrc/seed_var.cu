@@ -242,6 +242,7 @@ k_seed_var(const __grid_constant__ DevParams P, const int pass, const int level,
     }
     for (int k = threadIdx.x; k < 256; k += blockDim.x) class_s[k] = S.class_of[k];
     for (int k = threadIdx.x; k < 128; k += blockDim.x) slot_s[(size_t)R * slot_stride + k] = 0;
+    if (threadIdx.x == 0) ctr_s[5] = 0;
     __syncthreads();
 
     using WT = typename std::conditional<W == 1, uint32_t, unsigned long long>::type;
@@ -288,6 +289,7 @@ k_seed_var(const __grid_constant__ DevParams P, const int pass, const int level,
         rinfo_s[threadIdx.x * kSvRi + 4] = n - sbase;                // read length seen from the range start
         cand_n_s[threadIdx.x] = 0;
         if (threadIdx.x == 0) ctr_s[0] = 0;
+        if (L > 0) atomicMax(&ctr_s[5], L);                      // the group's longest search range (reset at the group's end)
         if (warp * 32 < R)
             sv_stage_warp(seq, (long long)base + sbase, L, slot_s + (size_t)warp * 32 * slot_stride, slot_stride, class_s, lane);
         // Constrained end (min_end_pos inside the range): the reference's last row takes no insertion
@@ -296,84 +298,111 @@ k_seed_var(const __grid_constant__ DevParams P, const int pass, const int level,
         // >= min_end_pos they do not; D' is tracked for the whole group when any of its reads needs it.
         const int last_row_rule = __syncthreads_or(!punt && g.min_end_pos > g.start_j);
 
-        // ---- scan: (read, column) pairs dealt to the threads.  The table entries of a warp's 32 pairs are
+        // ---- scan: (read, column) pairs dealt to the lanes, two consecutive pairs each.  A pair looks its q-mer up
+        // in table 0 and, with one more base, its (q + 1)-mer in table 1; the entries of a warp's 64 pairs are
         // pooled (prefix sum of the bucket sizes) and dealt out evenly again, one entry per lane and round ----
-        for (int tb = 0; tb < (V.q2 ? 2 : 1); tb++) {                // one or two seed tables (lengths q, q + 1)
-        const int q = tb ? V.q2 : V.q;
-        const uint16_t *bstart_t = bstart_s + (tb ? V.bstart2 : 0);
-        const int n_pos = max(slot_cols - q + 1, 1);             // q-mer positions scanned per read (at most)
-        const uint32_t pos_recip = 0xFFFFFFFFu / (uint32_t)n_pos + 1u;   // i / n_pos == umulhi(i, recip) for i < 2^16
-        const int n_pairs = R * n_pos;
-        for (int i = threadIdx.x; i < ((n_pairs + 31) & ~31); i += kSvThreads) {     // whole warps: the loop body votes
-            const int r = min((int)__umulhi((uint32_t)i, pos_recip), R - 1), p = i - r * n_pos;
-            const int Lr = rinfo_s[r * kSvRi + 0];
-            bool valid = i < n_pairs && p + q <= Lr;
-            uint32_t code = 0;
-            if (valid) {
-                const uint8_t *c = slot_s + (size_t)r * slot_stride + p;
-                for (int k = 0; k < q; k++) {
-                    const uint32_t cl = c[k];
-                    valid = valid && cl != 0;
-                    code |= ((cl - 1u) & 3u) << (2 * k);
-                }
-            }
-            const int e0 = valid ? (int)bstart_t[code] : 0;
-            const int cnt = valid ? (int)bstart_t[code + 1] - e0 : 0;
-            int incl = cnt;
+        {
+            const int q0 = V.q, q1 = V.q2;                               // q1 = 0: one table
+            const uint16_t *bst0 = bstart_s, *bst1 = bstart_s + V.bstart2;
+            const int n_pos = max(ctr_s[5] - q0 + 1, 0);                 // positions of the group's longest search range
+            const uint32_t pos_recip = 0xFFFFFFFFu / (uint32_t)max(n_pos, 1) + 1u;   // i / n_pos == umulhi(i, recip) for i < 2^16
+            const int n_pairs = R * n_pos;
+            for (int base = warp * 64; base < n_pairs; base += (kSvThreads / 32) * 64) {
+                uint32_t ea = 0, eb = 0, c4 = 0;   // first entries of (pair 0: table 0 | table 1 << 16), (pair 1: ...); the four bucket sizes, a byte each
+                int lane_total = 0;
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-                if (lane >= o) incl += t;
-            }
-            const int total_e = __shfl_sync(0xFFFFFFFFu, incl, 31);
-            const int my_first = e0 - (incl - cnt);                 // entry index of pooled item j owned by this lane: my_first + j
-            const int lane_i0 = i - lane;                           // pair index of lane 0
-            for (int j0 = 0; j0 < total_e; j0 += 32) {
-                const int j = j0 + lane;
-                // owner = first lane whose inclusive prefix exceeds j
-                int ow = 0;
+                for (int u = 0; u < 2; u++) {
+                    const int i = base + 2 * lane + u;
+                    uint32_t e00 = 0, c00 = 0, e01 = 0, c01 = 0;
+                    if (i < n_pairs) {
+                        const int r = min((int)__umulhi((uint32_t)i, pos_recip), R - 1), p = i - r * n_pos;
+                        const int Lr = rinfo_s[r * kSvRi + 0];
+                        if (p + q0 <= Lr) {
+                            const uint8_t *c = slot_s + (size_t)r * slot_stride + p;
+                            uint32_t code = 0;
+                            bool ok = true;
+                            for (int k = 0; k < q0; k++) {
+                                const uint32_t cl = c[k];
+                                ok = ok && cl != 0;                       // a byte that occurs in no barcode: no seed here
+                                code |= ((cl - 1u) & 3u) << (2 * k);
+                            }
+                            if (ok) {
+                                e00 = bst0[code];
+                                c00 = bst0[code + 1] - e00;
+                                if (q1 && p + q1 <= Lr && c[q0] != 0) {
+                                    const uint32_t code1 = code | ((((uint32_t)c[q0] - 1u) & 3u) << (2 * q0));
+                                    e01 = bst1[code1];
+                                    c01 = bst1[code1 + 1] - e01;
+                                }
+                            }
+                        }
+                    }
+                    if (u == 0) ea = e00 | (e01 << 16);
+                    else eb = e00 | (e01 << 16);
+                    c4 |= (c00 | (c01 << 8)) << (16 * u);
+                    lane_total += (int)(c00 + c01);
+                }
+                int incl = lane_total;
 #pragma unroll
-                for (int step = 16; step >= 1; step >>= 1) {
-                    const int probe = __shfl_sync(0xFFFFFFFFu, incl, ow + step - 1);
-                    if (probe <= j) ow += step;
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+                    if (lane >= o) incl += t;
                 }
-                ow = min(ow, 31);
-                const int first = __shfl_sync(0xFFFFFFFFu, my_first, ow);
-                bool hit = false;
-                uint32_t rec = 0;
-                int hr = 0;
-                if (j < total_e) {
-                    const int oi = lane_i0 + ow;                                // the owner's (read, column) pair
-                    hr = (int)__umulhi((uint32_t)oi, pos_recip);
-                    const int op = oi - hr * n_pos;
-                    const uint32_t ent = entries_s[first + j];
-                    const int b = (int)(ent >> 8), o = (int)(ent & 0xFFu);
-                    const uint32_t bi = binfo_s[b];
-                    const int m = (int)(bi & 0xFFu), K = (int)((bi >> 8) & 0xFFu), a0 = (int)(bi >> 16);
-                    const int oL = rinfo_s[hr * kSvRi + 0], min_end_rel = rinfo_s[hr * kSvRi + 1], max_start_rel = rinfo_s[hr * kSvRi + 2];
-                    const int delta = op - o;                                   // 0-based relative diagonal
-                    // Diagonals (read column - barcode row) an acceptable alignment's intact segment can lie on:
-                    // the segment's own cells obey the reference's band j - i <= max_start_pos + steps
-                    // (classification.jl:270, :289-290; steps <= allowed_b); the rest of the barcode has to fit
-                    // between the range start and end with at most K edits, and to end at or after min_end_pos
-                    const int dlo = max(0, min_end_rel - m) - K;
-                    const int dhi = min(max_start_rel + a0, oL - m + K);
-                    hit = delta >= dlo && delta <= dhi;
-                    rec = ((uint32_t)hr << 22) | ((uint32_t)b << 8) | (uint32_t)(delta + kSvDiagBias);
-                }
-                const uint32_t hm = __ballot_sync(0xFFFFFFFFu, hit);
-                if (hm) {
-                    int hbase = 0;
-                    if (lane == 0) hbase = atomicAdd(&ctr_s[0], __popc(hm));
-                    hbase = __shfl_sync(0xFFFFFFFFu, hbase, 0);
-                    if (hit) {
-                        const int idx = hbase + __popc(hm & ((1u << lane) - 1u));
-                        if (idx < hit_cap) hits_s[idx] = rec;
-                        else rinfo_s[hr * kSvRi + 3] = 1;                           // this read's candidate set is incomplete
+                const int total_e = __shfl_sync(0xFFFFFFFFu, incl, 31);
+                const int my_excl = incl - lane_total;
+                for (int j0 = 0; j0 < total_e; j0 += 32) {
+                    const int j = j0 + lane;
+                    int ow = 0;                                            // owner = first lane whose inclusive prefix exceeds j
+#pragma unroll
+                    for (int step = 16; step >= 1; step >>= 1) {
+                        const int probe = __shfl_sync(0xFFFFFFFFu, incl, ow + step - 1);
+                        if (probe <= j) ow += step;
+                    }
+                    ow = min(ow, 31);
+                    const int o_excl = __shfl_sync(0xFFFFFFFFu, my_excl, ow);
+                    const uint32_t oc4 = __shfl_sync(0xFFFFFFFFu, c4, ow);
+                    const uint32_t oea = __shfl_sync(0xFFFFFFFFu, ea, ow), oeb = __shfl_sync(0xFFFFFFFFu, eb, ow);
+                    bool hit = false;
+                    uint32_t rec = 0;
+                    int hr = 0;
+                    if (j < total_e) {
+                        // which of the owner's four buckets, and which entry of it
+                        int jj = j - o_excl, which = 0;
+                        const int n0 = (int)(oc4 & 0xFFu), n1 = (int)((oc4 >> 8) & 0xFFu), n2 = (int)((oc4 >> 16) & 0xFFu);
+                        if (jj >= n0) { jj -= n0; which = 1; if (jj >= n1) { jj -= n1; which = 2; if (jj >= n2) { jj -= n2; which = 3; } } }
+                        const uint32_t esel = which < 2 ? oea : oeb;
+                        const int e0 = (int)((which & 1) ? (esel >> 16) : (esel & 0xFFFFu));
+                        const int oi = base + 2 * ow + (which >> 1);                // the owner's (read, column) pair
+                        hr = min((int)__umulhi((uint32_t)oi, pos_recip), R - 1);
+                        const int op = oi - hr * n_pos;
+                        const uint32_t ent = entries_s[e0 + jj];
+                        const int b = (int)(ent >> 8), o = (int)(ent & 0xFFu);
+                        const uint32_t bi = binfo_s[b];
+                        const int m = (int)(bi & 0xFFu), K = (int)((bi >> 8) & 0xFFu), a0 = (int)(bi >> 16);
+                        const int oL = rinfo_s[hr * kSvRi + 0], min_end_rel = rinfo_s[hr * kSvRi + 1], max_start_rel = rinfo_s[hr * kSvRi + 2];
+                        const int delta = op - o;                                   // 0-based relative diagonal
+                        // Diagonals (read column - barcode row) an acceptable alignment's intact segment can lie on:
+                        // the segment's own cells obey the reference's band j - i <= max_start_pos + steps
+                        // (classification.jl:270, :289-290; steps <= allowed_b); the rest of the barcode has to fit
+                        // between the range start and end with at most K edits, and to end at or after min_end_pos
+                        const int dlo = max(0, min_end_rel - m) - K;
+                        const int dhi = min(max_start_rel + a0, oL - m + K);
+                        hit = delta >= dlo && delta <= dhi;
+                        rec = ((uint32_t)hr << 22) | ((uint32_t)b << 8) | (uint32_t)(delta + kSvDiagBias);
+                    }
+                    const uint32_t hm = __ballot_sync(0xFFFFFFFFu, hit);
+                    if (hm) {
+                        int hbase = 0;
+                        if (lane == 0) hbase = atomicAdd(&ctr_s[0], __popc(hm));
+                        hbase = __shfl_sync(0xFFFFFFFFu, hbase, 0);
+                        if (hit) {
+                            const int idx = hbase + __popc(hm & ((1u << lane) - 1u));
+                            if (idx < hit_cap) hits_s[idx] = rec;
+                            else rinfo_s[hr * kSvRi + 3] = 1;                       // this read's candidate set is incomplete
+                        }
                     }
                 }
             }
-        }
         }
         __syncthreads();
 
@@ -510,6 +539,7 @@ k_seed_var(const __grid_constant__ DevParams P, const int pass, const int level,
         base_slot = __shfl_sync(0xFFFFFFFFu, base_slot, 0);
         if (todo) wl_out[base_slot + __popc(mask & ((1u << lane) - 1u))] = read;
         n_done += __popc(__ballot_sync(0xFFFFFFFFu, resolved));
+        if (threadIdx.x == 0) ctr_s[5] = 0;
         __syncthreads();                                             // the group's shared lists are reused
     }
     if (lane == 0 && n_done && counters) atomicAdd(counters + 2, (unsigned long long)n_done);

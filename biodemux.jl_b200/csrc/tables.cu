@@ -393,6 +393,11 @@ void build_seed_var(const Build &B)
             }
             V.bstart.assign(buckets.size() + 1, 0);
             for (size_t k = 0; k < buckets.size(); k++) {
+                if (buckets[k].size() > 255) {                     // the scan keeps bucket sizes in a byte
+                    V = HostSet::HostSeedVar();
+                    hs.sv_levels--;
+                    return;
+                }
                 V.bstart[k + 1] = (uint16_t)(V.bstart[k] + buckets[k].size());
                 V.entries.insert(V.entries.end(), buckets[k].begin(), buckets[k].end());
             }
@@ -445,6 +450,11 @@ void build_seed_var(const Build &B)
                     buckets[code].push_back(((uint32_t)sg2.b << 8) | (uint32_t)sg2.o);
                 }
                 for (size_t k = 0; k < buckets.size(); k++) {
+                    if (buckets[k].size() > 255) {                 // the scan keeps bucket sizes in a byte
+                        V = HostSet::HostSeedVar();
+                        hs.sv_levels--;
+                        return;
+                    }
                     V.bstart.push_back((uint16_t)V.entries.size());
                     V.entries.insert(V.entries.end(), buckets[k].begin(), buckets[k].end());
                 }
@@ -457,8 +467,8 @@ void build_seed_var(const Build &B)
             if (min_m < q) break;
             const Est e = estimate(q);
             if (e.chance <= 24.0 && e.n_entries <= 65535) {
-                q1 = q;
                 build(q, e.chance);
+                if (hs.sv_levels > 0) q1 = q;
             }
         }
         if (q1 && !hs.sv[0].complete && !(B.debug & BDX_DEBUG_ONE_SEED_LEVEL)) {

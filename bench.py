@@ -42,6 +42,9 @@ CHUNK = 4000                                               # reference chunk_siz
 # automaton): dram__bytes_read.sum 164.03 MB + dram__bytes_write.sum 16.11 MB.  Per read that is 2x the
 # algorithmic 174 B: worklist-scattered 150-byte reads touch 6 32-byte sectors, offsets / PassOut one each.
 NCU_FILTER_DRAM_BYTES_PER_READ = (164.026880e6 + 16.110336e6) / 516667
+# the same for k_seed_var's complete level, the kernel that now takes those reads in config 2
+# (profiles/r02_kernels_ncu_summary.txt: 4 M-read step, 516 667 reads: 163.31 MB read + 15.72 MB written)
+NCU_SEEDVAR_DRAM_BYTES_PER_READ = (163.314176e6 + 15.723520e6) / 516667
 
 
 def make_config():
@@ -281,6 +284,13 @@ def measure_config(key, cfg, sp, name, total_reads, rank, world, local, parity_s
         ambiguous += int((stt == 2).sum().item())
         done += nb
         k += 1
+    # one more pass over the last batch with per-stage CUDA events and the work counters (not timed above)
+    st.profile(True)
+    st.work_counters(reset=True)
+    st.classify_device(d_seq.data_ptr(), d_off.data_ptr(), nb, d_res.data_ptr())
+    stage_ms = {k2: v[0] for k2, v in st.profile_read_stages().items() if v[1]}
+    st.profile(False)
+    wc = st.work_counters(reset=True)
     t = torch.tensor([ms], dtype=torch.float64, device="cuda")
     cnt = torch.tensor([matched, ambiguous, launches], dtype=torch.int64, device="cuda")
     if world > 1:
@@ -293,7 +303,10 @@ def measure_config(key, cfg, sp, name, total_reads, rank, world, local, parity_s
     out = {"workload": name, "reads": reads, "reads_per_gpu": per_rank, "sharding": "contiguous shards, no data-path collective",
            "scaling": "strong", "reads_per_sec": reads / secs, "gcups": reads / secs * bench_configs.cell_updates(cfg) / 1e9,
            "seconds": secs, "matched_fraction": int(cnt[0].item()) / reads, "ambiguous_fraction": int(cnt[1].item()) / reads,
-           "gpu_launches": int(cnt[2].item()), "parity": parity}
+           "gpu_launches": int(cnt[2].item()), "parity": parity,
+           "last_batch": {"reads": nb, "stage_ms": stage_ms,
+                          "reads_by_path": {"prefilter": wc[0], "seed": wc[1], "automaton": wc[2]},
+                          "verified_hit_columns": wc[3]}}
     return out
 
 
@@ -395,7 +408,7 @@ def run_ours(args):
     stages = stream.profile_read_stages()
     filt_ms, filt_n = stages["k_filter"]
     stream.profile(False)
-    pre_reads, seed_reads, auto_reads = stream.path_counters(reset=True)
+    pre_reads, seed_reads, auto_reads, hit_cols, sv_in_reads = stream.work_counters(reset=True)
     auto_per_launch = auto_reads / max(filt_n, 1)       # reads that actually ran the DP automaton
     clocks = None
     if args.no_e2e and rank == 0:
@@ -643,19 +656,66 @@ def run_ours(args):
                                          args.parity_reads)
 
     if rank == 0:
-        filt_s = filt_ms * 1e-3 / max(filt_n, 1)          # average duration of one filter launch
-        # only reads that ran the bit-parallel automaton are credited with its int-ops; reads the
-        # perfect-occurrence prefilter resolved cost (almost) no ALU work and are not counted
-        achieved_ops = OPS_PER_READ * auto_per_launch / filt_s if filt_s > 0 else 0.0
         hbm_peak = None
         try:
             hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
             hbm_src = "MEASURED_PEAKS.json"
         except Exception:
             hbm_peak, hbm_src = 6650.0, "fallback (B200_PROFILING.md)"
-        # algorithmic bytes of the reads the kernel actually touched (sequence + offset in, PassOut out) over its time
-        hbm_gbs = BYTES_PER_READ * auto_per_launch / filt_s / 1e9 if filt_s > 0 else 0.0
+        # ---- roofline of the DOMINANT kernel of the step (the stage with the most CUDA-event time).  Both candidates
+        # are bound by integer-ALU issue; their algorithmic unit is one bit-parallel column step of 17 int-ops
+        # (SURVEY.md section 8d):
+        #   k_filter              17 x barcodes x columns for every read that ran the full-range automaton
+        #   k_seed_var (complete) 17 x the window columns it stepped its verified hits over (device counter) -- the
+        #                         work it really did; the reads it decides would have cost 244 800 int-ops each in
+        #                         k_filter, which is reported next to it as the survey-convention figure
+        stage_names = {"k_seed_deep": "k_seed_var (complete level)", "k_seed": "k_seed (levels 1-2)"}
+        dom = max((k for k in stages if stages[k][1]), key=lambda k: stages[k][0])
+        dom_ms, dom_n = stages[dom]
+        dom_s = dom_ms * 1e-3 / max(dom_n, 1)             # average duration of one launch of it
+        if dom == "k_filter":
+            units = OPS_PER_READ * auto_reads / max(dom_n, 1)
+            dom_reads = auto_reads / max(dom_n, 1)
+            traffic = NCU_FILTER_DRAM_BYTES_PER_READ * dom_reads
+            how = "17 int-ops x 96 barcodes x 150 columns x reads that ran the automaton (device counter)"
+        elif dom == "k_seed_deep":
+            units = 17.0 * hit_cols / max(dom_n, 1)
+            dom_reads = sv_in_reads / max(dom_n, 1)           # what k_prefilter and k_seed's levels left: it decides nearly all
+            traffic = NCU_SEEDVAR_DRAM_BYTES_PER_READ * dom_reads
+            how = "17 int-ops x window columns stepped over verified seed hits (device counter bdx_stream_work_counters[3])"
+        else:
+            units, dom_reads, traffic, how = None, None, None, "no algorithmic unit defined for this stage"
+        achieved_ops = units / dom_s if units and dom_s > 0 else 0.0
+        roof = {"bound": "int_alu", "achieved": achieved_ops / 1e12, "peak": peak_ops.value / 1e12, "unit": "Tint-op/s",
+                "frac": achieved_ops / peak_ops.value if peak_ops.value else None,
+                "kernel": stage_names.get(dom, dom), "kernel_ms": dom_s * 1e3, "kernel_share_of_step": dom_ms / ms if ms else None,
+                "algorithmic_unit": how,
+                "stage_ms_per_step": {k: v[0] / args.steps for k, v in stages.items() if v[1]},
+                "reads_by_path_per_step": {"prefilter": pre_reads / args.steps, "seed_kernels": seed_reads / args.steps,
+                                           "automaton": auto_reads / args.steps},
+                "peak_source": "bdx_int_alu_peak: LOP3/IADD3 chains measured live on this GPU (dual-pipe issue peak)"}
+        roof["traffic"] = traffic
+        roof["traffic_unit"] = ("DRAM bytes per launch: ncu dram__bytes_read.sum + dram__bytes_write.sum per read of this kernel "
+                                "(profiles/r02_kernels_ncu_summary.txt) x its reads per launch here")
+        roof["reads_per_launch"] = dom_reads
+        if dom == "k_seed_deep":
+            roof["verified_hit_columns_per_launch"] = hit_cols / max(dom_n, 1)
+            roof["survey_convention"] = {"achieved": OPS_PER_READ * dom_reads / dom_s / 1e12 if dom_s > 0 else None,
+                                         "what": "244 800 int-ops (the full 96 x 150 matrix, SURVEY 8d) per read this kernel decides / its "
+                                                 "time: what the lane-per-barcode automaton would have had to do for the same reads"}
+        hbm_gbs = BYTES_PER_READ * (dom_reads or 0) / dom_s / 1e9 if dom_s > 0 else 0.0
         step_gbs = BYTES_PER_READ * n / (ms_max / args.steps * 1e-3) / 1e9
+        roof["hbm"] = {"achieved": hbm_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_gbs / hbm_peak, "peak_source": hbm_src,
+                       "bytes_per_read": BYTES_PER_READ, "what": "the dominant kernel: algorithmic bytes of ITS reads / its time",
+                       "whole_step_gbs": step_gbs}
+        # the lane-per-barcode automaton where it still dominates: config 5 :semiglobal (1 536 barcodes)
+        if others and "5s" in others and "k_filter" in others["5s"]["last_batch"]["stage_ms"]:
+            lb = others["5s"]["last_batch"]
+            ops5 = 17 * 1536 * READ_LEN
+            a5 = ops5 * lb["reads_by_path"]["automaton"] / (lb["stage_ms"]["k_filter"] * 1e-3)
+            roof["k_filter_on_config5"] = {"achieved": a5 / 1e12, "frac": a5 / peak_ops.value if peak_ops.value else None,
+                                           "kernel_ms": lb["stage_ms"]["k_filter"], "reads": lb["reads_by_path"]["automaton"],
+                                           "ops_per_read": ops5, "share_of_its_step": lb["stage_ms"]["k_filter"] / sum(lb["stage_ms"].values())}
         line = {
             "metric": "reads_per_sec", "value": value, "unit": "reads/s", "gcups": value * CU_PER_READ / 1e9,
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps,
@@ -665,22 +725,7 @@ def run_ours(args):
                                    f"{BARCODE_LEN}nt, :semiglobal defaults (max_error_rate 0.2, unit costs)",
                        "reads_per_gpu": n, "l2": "inputs (1.5 GB of reads per step) exceed the 126 MB L2",
                        "matched_fraction": matched / n, "e2e_batch_reads": B},
-            "roofline": {"bound": "int_alu", "achieved": achieved_ops / 1e12, "peak": peak_ops.value / 1e12,
-                         "unit": "Tint-op/s", "frac": achieved_ops / peak_ops.value if peak_ops.value else None,
-                         "traffic": NCU_FILTER_DRAM_BYTES_PER_READ * auto_per_launch,
-                         "traffic_unit": "DRAM bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum per "
-                                         "automaton read, profiles/r01g_kernels_ncu_summary.txt, x reads per launch here)",
-                         "kernel": "k_filter<1,3>", "kernel_ms": filt_s * 1e3,
-                         "kernel_share_of_step": filt_ms / ms if ms else None,
-                         "stage_ms_per_step": {k: v[0] / args.steps for k, v in stages.items() if v[1]},
-                         "ops_per_read": OPS_PER_READ, "reads_through_automaton_per_launch": auto_per_launch,
-                         "reads_resolved_by_prefilter_per_launch": pre_reads / max(filt_n, 1),
-                         "reads_resolved_by_seed_kernel_per_launch": seed_reads / max(filt_n, 1),
-                         "peak_source": "bdx_int_alu_peak: LOP3/IADD3 chains measured live on this GPU",
-                         "hbm": {"achieved": hbm_gbs, "peak": hbm_peak, "unit": "GB/s",
-                                 "frac": hbm_gbs / hbm_peak, "peak_source": hbm_src,
-                                 "bytes_per_read": BYTES_PER_READ, "what": "k_filter: algorithmic bytes of ITS reads / its time",
-                                 "whole_step_gbs": step_gbs}},
+            "roofline": roof,
             "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": nb * (B * READ_LEN + 4 * (B + 1)),
                     "d2h_bytes_per_step": nb * B * bdx.RESULT_DTYPE.itemsize,
                     "api": f"bdx_submit_pinned / bdx_fetch_view, {DEPTH} batches in flight",

@@ -28,7 +28,7 @@ DEBUG_ONE_SEED_LEVEL, DEBUG_NO_GRAPHS, DEBUG_NO_HAMMING_PACKED, DEBUG_PREFER_SEE
 
 EXPORTS = [
     "bdx_last_error", "bdx_abi_version", "bdx_device_count", "bdx_config_create", "bdx_config_create_debug", "bdx_config_destroy",
-    "bdx_config_code_table", "bdx_pack_reads4", "bdx_submit_packed4", "bdx_submit_packed4_pinned",
+    "bdx_stream_work_counters", "bdx_config_code_table", "bdx_pack_reads4", "bdx_submit_packed4", "bdx_submit_packed4_pinned",
     "bdx_stream_create", "bdx_stream_destroy", "bdx_submit", "bdx_acquire", "bdx_commit",
     "bdx_submit_pinned", "bdx_host_alloc", "bdx_host_free", "bdx_stream_enable_details",
     "bdx_fetch", "bdx_fetch_view", "bdx_classify", "bdx_classify_device", "bdx_stream_sync",
@@ -429,6 +429,7 @@ class Stream:
         _check(self.lib.bdx_stream_profile_read(self.handle, C.byref(ms), C.byref(n)))
         return ms.value, n.value
 
+    # "k_seed": k_seed levels / k_seed_var level 1; "k_seed_deep": k_seed_deep / k_seed_var's complete level
     STAGES = ("k_prefilter", "k_seed", "k_seed_deep", "k_filter", "k_literal", "k_hamming_scan", "k_finalize", "other")
 
     def profile_read_stages(self):
@@ -443,6 +444,12 @@ class Stream:
         a, b, c = C.c_int64(), C.c_int64(), C.c_int64()
         _check(self.lib.bdx_stream_path_counters(self.handle, C.byref(a), C.byref(b), C.byref(c), int(reset)))
         return a.value, b.value, c.value
+
+    def work_counters(self, reset: bool = False):
+        """(prefilter reads, seed reads, automaton reads, verified hit-columns of k_seed_var, its input reads)."""
+        out = (C.c_int64 * 6)()
+        _check(self.lib.bdx_stream_work_counters(self.handle, out, int(reset)))
+        return tuple(int(x) for x in out)[:5]
 
     def demux_block(self, fastq1, fastq2=None, final_block: int = 1, mode: int = DEMUX_SINGLE):
         """bdx_demux_block over host uint8 arrays (or ``(device_ptr, length)`` pairs with

@@ -116,11 +116,12 @@ __host__ __device__ inline size_t sv_smem_layout(int W, int plane, int n_pad, in
 // LASTROW: hits are scored as D'[m][j] = min(D[m-1][j] + 1, D[m-1][j-1] + sub) (the reference's last row takes
 // no insertion, classification.jl:213) and only at columns >= min_end_pos.
 template <typename WT, bool LASTROW>
-__device__ __forceinline__ void sv_verify(const uint32_t *hits_s, int total, const int *rinfo_s, const uint32_t *binfo_s,
+__device__ __forceinline__ int sv_verify(const uint32_t *hits_s, int total, const int *rinfo_s, const uint32_t *binfo_s,
                                           const uint32_t *peq_s, int n_classes, int plane, const uint8_t *slot_s,
                                           int slot_stride, uint32_t *cand_s, int *cand_n_s)
 {
     constexpr int kMsb = (int)sizeof(WT) * 8 - 1;
+    int cols = 0;                       // window columns this thread stepped its hits over (work counter)
     for (int i0 = 0; i0 < total; i0 += 2 * kSvThreads) {
         int score[2], best[2], hr[2], hk[2], hb[2], wl[2], ts[2];
         WT pv[2], mv[2];
@@ -151,6 +152,7 @@ __device__ __forceinline__ void sv_verify(const uint32_t *hits_s, int total, con
             score[u] = m;
             best[u] = kInf;
             wlen = max(wlen, wl[u]);
+            cols += max(wl[u], 0);
         }
         wlen = __reduce_max_sync(0xFFFFFFFFu, wlen);
         // past its own window a lane keeps stepping on whatever is staged there (never read back: `best` is frozen)
@@ -190,6 +192,7 @@ __device__ __forceinline__ void sv_verify(const uint32_t *hits_s, int total, con
                 if (k < kSvCand) cand_s[hr[u] * kSvCand + k] = ((uint32_t)hb[u] << 8) | (uint32_t)best[u];
             }
     }
+    return cols;
 }
 
 template <int W>
@@ -253,6 +256,7 @@ k_seed_var(const __grid_constant__ DevParams P, const int pass, const int level,
     const bool with_delta = P.min_delta != 0.0;
     const int hit_cap = kSvThreads * sv_hit_rows(V.hit_rows, S.max_m);
     unsigned int n_done = 0;
+    unsigned long long n_cols = 0;      // verified hit-columns (one Myers / Hyyro column step each), for the roofline
 
     for (int grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
         const int item = grp * R + threadIdx.x;
@@ -410,9 +414,9 @@ k_seed_var(const __grid_constant__ DevParams P, const int pass, const int level,
         {
             const int total = min(ctr_s[0], hit_cap);
             if (last_row_rule)
-                sv_verify<WT, true>(hits_s, total, rinfo_s, binfo_s, peq_s, n_classes, plane, slot_s, slot_stride, cand_s, cand_n_s);
+                n_cols += sv_verify<WT, true>(hits_s, total, rinfo_s, binfo_s, peq_s, n_classes, plane, slot_s, slot_stride, cand_s, cand_n_s);
             else
-                sv_verify<WT, false>(hits_s, total, rinfo_s, binfo_s, peq_s, n_classes, plane, slot_s, slot_stride, cand_s, cand_n_s);
+                n_cols += sv_verify<WT, false>(hits_s, total, rinfo_s, binfo_s, peq_s, n_classes, plane, slot_s, slot_stride, cand_s, cand_n_s);
         }
         __syncthreads();
 
@@ -543,6 +547,12 @@ k_seed_var(const __grid_constant__ DevParams P, const int pass, const int level,
         __syncthreads();                                             // the group's shared lists are reused
     }
     if (lane == 0 && n_done && counters) atomicAdd(counters + 2, (unsigned long long)n_done);
+    if (counters) {
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) n_cols += __shfl_down_sync(0xFFFFFFFFu, n_cols, o);
+        if (lane == 0 && n_cols) atomicAdd(counters + 3, n_cols);
+        if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(counters + 4, (unsigned long long)n_items);
+    }
 }
 
 // longest search range any read can have (columns), or kSvMaxCols when it grows with the read

@@ -233,6 +233,11 @@ int bdx_stream_profile_read_stages(bdx_stream *s, double ms[BDX_PROFILE_STAGES],
  * since the last reset (syncs the stream). */
 int bdx_stream_path_counters(bdx_stream *s, int64_t *prefilter_reads, int64_t *seed_reads,
                              int64_t *automaton_reads, int reset);
+/* The same three counters plus the work of the seed-and-verify kernel k_seed_var: [3] window columns it stepped its
+ * verified hits over -- one bit-parallel column step each, the unit of its integer-ALU roofline -- and [4] reads
+ * it took in (summed over its launches).  out = {prefilter reads, seed reads, automaton reads, verified
+ * hit-columns, k_seed_var input reads, 0}. */
+int bdx_stream_work_counters(bdx_stream *s, int64_t out[6], int reset);
 /* number of kernel launches this stream has issued so far */
 int64_t bdx_stream_launch_count(const bdx_stream *s);
 

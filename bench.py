@@ -43,8 +43,8 @@ CHUNK = 4000                                               # reference chunk_siz
 # algorithmic 174 B: worklist-scattered 150-byte reads touch 6 32-byte sectors, offsets / PassOut one each.
 NCU_FILTER_DRAM_BYTES_PER_READ = (164.026880e6 + 16.110336e6) / 516667
 # the same for k_seed_var's complete level, the kernel that now takes those reads in config 2
-# (profiles/r02_kernels_ncu_summary.txt: 4 M-read step, 516 667 reads: 163.31 MB read + 15.72 MB written)
-NCU_SEEDVAR_DRAM_BYTES_PER_READ = (163.314176e6 + 15.723520e6) / 516667
+# (profiles/r02_kernels_ncu_summary.txt: 4 M-read step, 516 667 reads: 162.06 MB read + 14.85 MB written)
+NCU_SEEDVAR_DRAM_BYTES_PER_READ = (162.063104e6 + 14.851328e6) / 516667
 
 
 def make_config():

@@ -46,6 +46,7 @@
 namespace bdx {
 
 constexpr int kSvThreads = 128;      // threads per block; a block works on groups of R <= 128 reads (SeedVar::group_reads)
+constexpr int kSvChains = 2;         // hits a thread verifies at a time (independent dependency chains)
 constexpr int kSvCand = 8;           // verified candidates kept per read
 constexpr int kSvDiagBias = 64;      // hit record: read << 22 | barcode << 8 | diagonal + bias
 constexpr int kSvMaxCols = 180;      // longest search range staged (longer ones take the exact path)
@@ -112,7 +113,7 @@ __host__ __device__ inline size_t sv_smem_layout(int W, int plane, int n_pad, in
     return (o + 15) / 16 * 16;
 }
 
-// Windowed Myers / Hyyro verification of the block's hit list, two hits per thread and round.
+// Windowed Myers / Hyyro verification of the block's hit list, kSvChains hits per thread and round.
 // LASTROW: hits are scored as D'[m][j] = min(D[m-1][j] + 1, D[m-1][j-1] + sub) (the reference's last row takes
 // no insertion, classification.jl:213) and only at columns >= min_end_pos.
 template <typename WT, bool LASTROW>
@@ -122,14 +123,14 @@ __device__ __forceinline__ int sv_verify(const uint32_t *hits_s, int total, cons
 {
     constexpr int kMsb = (int)sizeof(WT) * 8 - 1;
     int cols = 0;                       // window columns this thread stepped its hits over (work counter)
-    for (int i0 = 0; i0 < total; i0 += 2 * kSvThreads) {
-        int score[2], best[2], hr[2], hk[2], hb[2], wl[2], ts[2];
-        WT pv[2], mv[2];
-        const uint8_t *col[2];          // first column of the window
-        const uint32_t *row[2];         // the barcode's Peq words, indexed by class
+    for (int i0 = 0; i0 < total; i0 += kSvChains * kSvThreads) {
+        int score[kSvChains], best[kSvChains], hr[kSvChains], hk[kSvChains], hb[kSvChains], wl[kSvChains], ts[kSvChains];
+        WT pv[kSvChains], mv[kSvChains];
+        const uint8_t *col[kSvChains];          // first column of the window
+        const uint32_t *row[kSvChains];         // the barcode's Peq words, indexed by class
         int wlen = 0;
 #pragma unroll
-        for (int u = 0; u < 2; u++) {
+        for (int u = 0; u < kSvChains; u++) {
             const int i = i0 + u * kSvThreads + (int)threadIdx.x;
             const bool live = i < total;
             const uint32_t rec = live ? hits_s[i] : 0u;
@@ -156,17 +157,17 @@ __device__ __forceinline__ int sv_verify(const uint32_t *hits_s, int total, cons
         }
         wlen = __reduce_max_sync(0xFFFFFFFFu, wlen);
         // past its own window a lane keeps stepping on whatever is staged there (never read back: `best` is frozen)
-#pragma unroll 4
+#pragma unroll 2
         for (int t = 0; t < wlen; t++) {
-            WT eq[2];
+            WT eq[kSvChains];
 #pragma unroll
-            for (int u = 0; u < 2; u++) {
+            for (int u = 0; u < kSvChains; u++) {
                 const uint32_t cls = col[u][t];
                 eq[u] = row[u][cls];
                 if (sizeof(WT) == 8) eq[u] |= (WT)row[u][plane + cls] << (kMsb - 31);
             }
 #pragma unroll
-            for (int u = 0; u < 2; u++) {
+            for (int u = 0; u < kSvChains; u++) {
                 int up_prev = 0;
                 if (LASTROW) up_prev = score[u] - (int)(pv[u] >> kMsb) + (int)(mv[u] >> kMsb);   // D[m-1][j-1]
                 const WT xv = eq[u] | mv[u];
@@ -186,7 +187,7 @@ __device__ __forceinline__ int sv_verify(const uint32_t *hits_s, int total, cons
             }
         }
 #pragma unroll
-        for (int u = 0; u < 2; u++)
+        for (int u = 0; u < kSvChains; u++)
             if (hk[u] >= 0 && best[u] <= hk[u]) {
                 const int k = atomicAdd(&cand_n_s[hr[u]], 1);
                 if (k < kSvCand) cand_s[hr[u] * kSvCand + k] = ((uint32_t)hb[u] << 8) | (uint32_t)best[u];

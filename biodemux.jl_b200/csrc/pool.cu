@@ -44,16 +44,26 @@ extern "C" int bdx_pool_create(const bdx_config *cfg, const int *devices, int n_
     return BDX_OK;
 }
 
+// The next batch goes to the stream with the fewest batches in flight (ties: the one after the last used, i.e.
+// round-robin over equally loaded streams): GPUs that drain their queues faster -- a shorter path to the host
+// memory the batches come from, a less loaded device -- take more of the work, and the pool's rate approaches the
+// sum of the GPUs' rates instead of N times the slowest.  Results still come back in submission order.
 template <typename Submit>
 static int pool_submit(bdx_pool *p, Submit submit)
 {
     if (!p) return bdx_fail(BDX_ERR_INVALID, "null pool");
-    bdx_stream *s = p->streams[p->next];
-    if (s->in_flight >= BDX_MAX_IN_FLIGHT) return bdx_fail(BDX_ERR_STATE, "the next stream of the pool is full; call bdx_pool_fetch");
-    const int rc = submit(s);
+    const size_t n = p->streams.size();
+    size_t best = n;
+    for (size_t k = 0; k < n; k++) {
+        const size_t i = (p->next + k) % n;
+        if (p->streams[i]->in_flight >= BDX_MAX_IN_FLIGHT) continue;
+        if (best == n || p->streams[i]->in_flight < p->streams[best]->in_flight) best = i;
+    }
+    if (best == n) return bdx_fail(BDX_ERR_STATE, "every stream of the pool is full; call bdx_pool_fetch");
+    const int rc = submit(p->streams[best]);
     if (rc) return rc;
-    p->order.push_back((int)p->next);
-    p->next = (p->next + 1) % p->streams.size();
+    p->order.push_back((int)best);
+    p->next = (best + 1) % n;
     return BDX_OK;
 }
 

@@ -363,7 +363,7 @@ void build_seed_var(const Build &B)
         // + a handful of true ones -- fill to about 70 %; denser levels take fewer reads per group instead
         auto size_groups = [&](HostSet::HostSeedVar &V, double chance) {
             const double per_read = chance + 6.0;
-            V.hit_rows = std::min(64, std::max(32, (int)std::ceil(per_read / 0.7)));
+            V.hit_rows = std::min(40, std::max(32, (int)std::ceil(per_read / 0.7)));
             int R = 128;
             while (R > 8 && per_read * R > 0.7 * 128 * V.hit_rows) R -= 8;
             V.group_reads = R;

@@ -318,11 +318,12 @@ int bdx_fastq_pack(const uint8_t *buf, const bdx_fastq_record *recs, int32_t n, 
                    int64_t seq_cap, int32_t *offsets_out);
 
 /* ---- dispatcher over several GPUs ------------------------------------------
- * Reads are independent, so batches are dealt round-robin to streams on the given devices (barcode tables
- * replicated per device, no data-path collective) and come back in submission order -- what a host that
- * owns the writers needs (core.jl:139-148).  A pool belongs to one thread at a time, like a stream.
- * bdx_pool_submit returns BDX_ERR_STATE when the stream whose turn it is already has BDX_MAX_IN_FLIGHT
- * batches in flight: fetch first.  At most n_devices * streams_per_device * BDX_MAX_IN_FLIGHT batches can
+ * Reads are independent, so batches are dealt to streams on the given devices (barcode tables replicated per
+ * device, no data-path collective) -- each to the stream with the fewest batches in flight, round-robin among
+ * equally loaded ones -- and come back in submission order: what a host that owns the writers needs
+ * (core.jl:139-148).  A pool belongs to one thread at a time, like a stream.
+ * bdx_pool_submit returns BDX_ERR_STATE when every stream already has BDX_MAX_IN_FLIGHT batches in flight:
+ * fetch first.  At most n_devices * streams_per_device * BDX_MAX_IN_FLIGHT batches can
  * be in flight.  bdx_pool_stats_fetch sums the DemuxStats counters of all streams (across processes the
  * host sums the buffers with one all-reduce, see bdx_stats_device_ptr). */
 typedef struct bdx_pool bdx_pool;

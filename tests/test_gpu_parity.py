@@ -399,3 +399,30 @@ def test_graph_replay_of_small_batches(kw):
             assert (res[f] == want[f]).all(), f
         if want_stats is not None:
             assert (st.stats() == want_stats).all()
+
+
+def test_bad_offsets_are_refused_before_anything_runs():
+    """A batch whose offsets decrease would be a negative read length on the device: refused with BDX_ERR_INVALID
+    on every host entry (bdx_submit, bdx_submit_pinned via the same check, bdx_commit)."""
+    rng = np.random.default_rng(3)
+    bcs = synth.random_barcodes(rng, 24, 20)
+    cfg = _cfg(bcs)
+    blob = np.frombuffer(b"ACGT" * 100, dtype=np.uint8).copy()
+    with capi.Engine(cfg, max_reads=16, max_bytes=4096) as eng:
+        for off in ([0, 100, 50, 400], [0, 100, 200, 150], [5, 100, 200, 400]):
+            with pytest.raises(capi.BdxError) as ei:
+                eng.stream.submit(blob, np.asarray(off, np.int32))
+            assert ei.value.code == capi.BDX_ERR_INVALID, off
+        res = eng.classify_packed(blob, np.asarray([0, 100, 100, 400], np.int64))     # an empty read is fine
+        assert len(res) == 3
+
+
+@pytest.mark.parametrize("algo", ["semiglobal", "exact"])
+def test_thousands_of_short_barcodes(algo):
+    """~ 9 000 short barcodes: the prefilter's hash table + bitmap would need more shared memory than a block may
+    have (the launch used to fail); the stage is dropped for such sets and the results stay the oracle's."""
+    rng = np.random.default_rng(77)
+    bcs = sorted(set(synth.random_barcodes(rng, 9000, 10, 12)))
+    cfg = _cfg(bcs, matching_algorithm=algo, max_error_rate=0.1)
+    reads = synth.random_reads(rng, 400, bcs, min_len=40, max_len=60, max_edits=1)
+    compare(cfg, reads, label=f"9000 barcodes {algo}")

@@ -367,27 +367,51 @@ __device__ __forceinline__ int pf_scan(BytePtr c0, int ncols, const DevSet &S, c
     const uint32_t size_mask = (1u << S.pf_log2) - 1u;
     uint32_t h = 0;
     for (int i = 0; i < seed; i++) h = h * kPfBase + (uint32_t)c0[i];
-    int cb[kPfMaxCand], cw[kPfMaxCand], nc = 0;
     const int nwin = ncols - seed + 1;
-    for (int w = 0;;) {
+    // The loop only REMEMBERS the (few) columns whose hash passes the first-level bitmap; the table is probed
+    // after the loop, when the lanes of a warp probe together.  Probing inside the loop ran the probe for one lane
+    // at a time -- each lane passes the bitmap at a different column -- and cost a fifth of the kernel's
+    // instructions (ncu source view, profiles/r02_kernels_ncu_summary.txt).
+    constexpr int kRec = 4;
+    int rw0 = 0, rw1 = 0, rw2 = 0, rw3 = 0, n_rec = 0;
+    uint32_t rh0 = 0, rh1 = 0, rh2 = 0, rh3 = 0;
+    auto probe = [&](int w) {
         const uint32_t bit = pf_bit(h, bm_log2);
         if ((bitmap_s[bit >> 5] >> (bit & 31)) & 1u) {       // rare: some barcode prefix hashes here
-            uint32_t slot = pf_slot(h, S.pf_log2);
-            for (;;) {
-                const uint32_t v = vals_s[slot];
-                if (v == kPfEmpty) break;
-                if (keys_s[slot] == h && w + (int)(v >> 16) <= ncols) {
-                    if (nc < kPfMaxCand) {
-                        cb[nc] = (int)(v & 0xFFFFu);
-                        cw[nc] = w;
-                    }
-                    nc++;
-                }
-                slot = (slot + 1) & size_mask;
-            }
+            if (n_rec == 0) { rw0 = w; rh0 = h; }
+            else if (n_rec == 1) { rw1 = w; rh1 = h; }
+            else if (n_rec == 2) { rw2 = w; rh2 = h; }
+            else if (n_rec == 3) { rw3 = w; rh3 = h; }
+            n_rec++;
         }
-        if (++w >= nwin) break;
-        h = (h - (uint32_t)c0[w - 1] * pw) * kPfBase + (uint32_t)c0[w - 1 + seed];
+    };
+    const auto *c_in = c0 + seed;
+#pragma unroll 4
+    for (int w = 0; w < nwin - 1; w++) {
+        probe(w);
+        h = (h - (uint32_t)c0[w] * pw) * kPfBase + (uint32_t)c_in[w];
+    }
+    if (nwin > 0) probe(nwin - 1);
+    if (n_rec > kRec) return -1;                              // more bitmap hits than remembered: leave it to the DP
+    int cb[kPfMaxCand], cw[kPfMaxCand], nc = 0;
+#pragma unroll
+    for (int k = 0; k < kRec; k++) {
+        if (k >= n_rec) continue;
+        const int w = k == 0 ? rw0 : (k == 1 ? rw1 : (k == 2 ? rw2 : rw3));
+        const uint32_t hk = k == 0 ? rh0 : (k == 1 ? rh1 : (k == 2 ? rh2 : rh3));
+        uint32_t slot = pf_slot(hk, S.pf_log2);
+        for (;;) {
+            const uint32_t v = vals_s[slot];
+            if (v == kPfEmpty) break;
+            if (keys_s[slot] == hk && w + (int)(v >> 16) <= ncols) {
+                if (nc < kPfMaxCand) {
+                    cb[nc] = (int)(v & 0xFFFFu);
+                    cw[nc] = w;
+                }
+                nc++;
+            }
+            slot = (slot + 1) & size_mask;
+        }
     }
     if (nc > kPfMaxCand) return -1;
     int found = 0x7FFFFFFF;

@@ -117,7 +117,7 @@ k_seed(const __grid_constant__ DevParams P, const int pass, const int level, con
             g = pass_geometry(S, n);
             // the regime test of k_filter's `fast` / k_prefilter<0>; the search range has to fit the slot
             // (the read itself may be much longer: only the columns of its search range are staged)
-            if (!(g.valid && g.max_start_pos >= n && g.min_end_pos <= g.start_j) || g.end_j - g.start_j + 1 > kSeedSlot)
+            if (!(g.valid && g.max_start_pos >= n && g.min_end_pos <= g.start_j) || g.end_j - g.start_j + 1 > kSeedSlot - 3)
                 punt = true;
         }
         // From here on columns are RELATIVE to the search range: column c of the range (1-based, 1 = start_j)
@@ -127,7 +127,8 @@ k_seed(const __grid_constant__ DevParams P, const int pass, const int level, con
 
         // ---- stage the search ranges of the warp's 32 reads as class codes, coalesced: four reads at a time,
         // all their global loads issued before the first table lookup / store ----
-        uint8_t *my_slot = slot_s + (size_t)threadIdx.x * kSeedSlot;
+        const int skew = seed_slot_skew(seq, (long long)base + sbase);          // the slot keeps the source alignment
+        uint8_t *my_slot = slot_s + (size_t)threadIdx.x * kSeedSlot + skew;
         __syncwarp();
         seed_stage_warp(seq, (long long)base + sbase, L, slot_s + (size_t)warp * 32 * kSeedSlot, class_s, lane);
         __syncwarp();
@@ -214,8 +215,8 @@ k_seed(const __grid_constant__ DevParams P, const int pass, const int level, con
             const SeedVerifyCtx vc{hits_s + warp * 32, peq_s, slot_s + (size_t)warp * 32 * kSeedSlot, n_pad, plane, m, K, win,
                                    total_hits};
             int i0 = 0;
-            for (; i0 + 32 < total_hits; i0 += 64) seed_verify<2, WT>(vc, i0, lane, incl, 1, L);
-            if (i0 < total_hits) seed_verify<1, WT>(vc, i0, lane, incl, 1, L);
+            for (; i0 + 32 < total_hits; i0 += 64) seed_verify<2, WT>(vc, i0, lane, incl, 1, L, skew);
+            if (i0 < total_hits) seed_verify<1, WT>(vc, i0, lane, incl, 1, L, skew);
         }
         __syncwarp();
         // ---- the read's own hits, now with distances: d_b = min over the hit groups of barcode b.

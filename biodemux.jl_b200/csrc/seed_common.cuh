@@ -10,46 +10,52 @@
 namespace bdx {
 
 constexpr int kSeedThreads = 128;
-constexpr int kSeedSlot = 180;      // staged class codes per read = columns of its search range (longer ranges take the
+constexpr int kSeedSlot = 180;      // slot bytes per read: its search range + up to 3 bytes of skew (longer ranges take the
                                     // full path); 45 words:
                                     // an odd word stride keeps the lock-step scan free of bank conflicts
 constexpr int kSeedMaxHits = 28;    // distinct (barcode, diagonal group) hits remembered per read (more => next stage)
 constexpr int kSeedMaxWins = 32;    // bitmap-passing columns remembered per read (more => full path)
 
-// Stages, for each of the warp's 32 reads, `my_len` (<= kSeedSlot) bytes starting at seq + my_start as class codes
-// into that read's slot (lane l describes read l).  Four reads per round; a lane loads up to two ALIGNED 32-bit
-// words per read -- a range of 180 bytes spans at most 46 words including its misaligned head -- and all eight
-// loads of a round are issued before the first table lookup.  The aligned words never leave the allocation that
-// holds the bytes (allocations start and end on coarser boundaries).
+// Stages, for each of the warp's 32 reads, `my_len` bytes starting at seq + my_start as class codes into that read's
+// slot (lane l describes read l).  Four reads per round; a lane loads up to two ALIGNED 32-bit words per read -- a
+// range spans at most 46 words including its misaligned head -- and all eight loads of a round are issued before the
+// first table lookup.  The slot keeps the SOURCE alignment: word w of the slot = the class codes of aligned source
+// word w, one 32-bit store per word, so the read's first byte sits at slot[mis] with mis = (address of its first
+// byte) & 3 (seed_slot_skew), and a range needs mis + len <= kSeedSlot.  The bytes in front of and behind the range
+// inside its first / last word belong to neighbouring reads and are never looked at.  The aligned words never leave
+// the allocation that holds the bytes (allocations start and end on coarser boundaries).
+__device__ __forceinline__ int seed_slot_skew(const uint8_t *seq, long long start)
+{
+    return (int)(reinterpret_cast<uintptr_t>(seq + start) & 3u);
+}
+
 __device__ __forceinline__ void seed_stage_warp(const uint8_t *__restrict__ seq, long long my_start, int my_len,
                                                 uint8_t *warp_slots, const uint8_t *class_s, int lane)
 {
     for (int r0 = 0; r0 < 32; r0 += 4) {
         uint32_t w[4][2];
-        int mis[4], len[4], nw[4];
+        int nw[4];
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             const long long start = __shfl_sync(0xFFFFFFFFu, my_start, r0 + j);
-            len[j] = __shfl_sync(0xFFFFFFFFu, my_len, r0 + j);
+            const int len = __shfl_sync(0xFFFFFFFFu, my_len, r0 + j);
             const uintptr_t addr = reinterpret_cast<uintptr_t>(seq + start);
-            mis[j] = (int)(addr & 3u);
-            nw[j] = len[j] ? (mis[j] + len[j] + 3) >> 2 : 0;
-            const uint32_t *base = reinterpret_cast<const uint32_t *>(addr - (uintptr_t)mis[j]);
+            const int mis = (int)(addr & 3u);
+            nw[j] = len ? (mis + len + 3) >> 2 : 0;
+            const uint32_t *base = reinterpret_cast<const uint32_t *>(addr - (uintptr_t)mis);
             w[j][0] = lane < nw[j] ? __ldg(base + lane) : 0u;
             w[j][1] = lane + 32 < nw[j] ? __ldg(base + lane + 32) : 0u;
         }
 #pragma unroll
         for (int j = 0; j < 4; j++) {
-            uint8_t *dst = warp_slots + (size_t)(r0 + j) * kSeedSlot;
+            uint32_t *dst = reinterpret_cast<uint32_t *>(warp_slots + (size_t)(r0 + j) * kSeedSlot);
 #pragma unroll
             for (int h = 0; h < 2; h++) {
                 const int wi = lane + 32 * h;
                 if (wi >= nw[j]) continue;
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    const int idx = 4 * wi + k - mis[j];
-                    if (idx >= 0 && idx < len[j]) dst[idx] = class_s[(w[j][h] >> (8 * k)) & 0xFFu];
-                }
+                const uint32_t v = w[j][h];
+                dst[wi] = (uint32_t)class_s[v & 0xFFu] | ((uint32_t)class_s[(v >> 8) & 0xFFu] << 8) |
+                          ((uint32_t)class_s[(v >> 16) & 0xFFu] << 16) | ((uint32_t)class_s[v >> 24] << 24);
             }
         }
     }
@@ -75,7 +81,7 @@ struct SeedVerifyCtx {
 // has work whatever its own read found; the distance goes back into the hit record for its owner.  Branch-free so that the ILP chains of a lane interleave: past the
 // end of its window a chain keeps stepping on class 0 and its minimum is not updated.
 template <int ILP, typename WT>      // WT: uint32_t for barcodes up to 32 nt, unsigned long long up to 64
-__device__ __forceinline__ void seed_verify(const SeedVerifyCtx &v, int i0, int lane, int incl, int start_j, int end_j)
+__device__ __forceinline__ void seed_verify(const SeedVerifyCtx &v, int i0, int lane, int incl, int start_j, int end_j, int my_skew)
 {
     constexpr int kMsb = (int)sizeof(WT) * 8 - 1;
     const WT row_mask = v.m > kMsb ? ~(WT)0 : (~(WT)0 << (kMsb + 1 - v.m));     // barcode rows top-aligned
@@ -107,7 +113,7 @@ __device__ __forceinline__ void seed_verify(const SeedVerifyCtx &v, int i0, int 
         // 1-based columns an alignment with <= K edits on these diagonals can occupy
         c0[u] = live ? max(sj, dmin + 1 - v.K) : 1;
         c1[u] = live ? min(ej, dmin + span + v.m + 2 * v.K) : 0;
-        slot[u] = v.warp_slots + (size_t)owner[u] * kSeedSlot;
+        slot[u] = v.warp_slots + (size_t)owner[u] * kSeedSlot + __shfl_sync(0xFFFFFFFFu, my_skew, owner[u]);
         pv[u] = row_mask;
         mv[u] = 0;
         score[u] = v.m;

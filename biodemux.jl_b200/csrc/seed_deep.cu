@@ -100,14 +100,15 @@ k_seed_deep(const __grid_constant__ DevParams P, const int pass, const uint8_t *
         }
         if (have && !skip) {
             g = pass_geometry(S, n);
-            if (!(g.valid && g.max_start_pos >= n && g.min_end_pos <= g.start_j) || g.end_j - g.start_j + 1 > kSeedSlot)
+            if (!(g.valid && g.max_start_pos >= n && g.min_end_pos <= g.start_j) || g.end_j - g.start_j + 1 > kSeedSlot - 3)
                 punt = true;
         }
         // columns relative to the search range, as in k_seed
         const int sbase = punt ? 0 : g.start_j - 1;
         const int L = punt ? 0 : g.end_j - g.start_j + 1;
 
-        uint8_t *my_slot = slot_s + (size_t)threadIdx.x * kSeedSlot;
+        const int skew = seed_slot_skew(seq, (long long)base + sbase);          // the slot keeps the source alignment
+        uint8_t *my_slot = slot_s + (size_t)threadIdx.x * kSeedSlot + skew;
         __syncwarp();
         seed_stage_warp(seq, (long long)base + sbase, L, slot_s + (size_t)warp * 32 * kSeedSlot, class_s, lane);
         __syncwarp();
@@ -194,8 +195,8 @@ k_seed_deep(const __grid_constant__ DevParams P, const int pass, const uint8_t *
                 const SeedVerifyCtx vc{hits_s + warp * 32, peq_s, slot_s + (size_t)warp * 32 * kSeedSlot, n_pad, plane, m, K,
                                        m + 4 * K + 1, total_hits};
                 int i0 = 0;
-                for (; i0 + 32 < total_hits; i0 += 64) seed_verify<2, WT>(vc, i0, lane, incl, 1, L);
-                if (i0 < total_hits) seed_verify<1, WT>(vc, i0, lane, incl, 1, L);
+                for (; i0 + 32 < total_hits; i0 += 64) seed_verify<2, WT>(vc, i0, lane, incl, 1, L, skew);
+                if (i0 < total_hits) seed_verify<1, WT>(vc, i0, lane, incl, 1, L, skew);
             }
             __syncwarp();
             // ---- fold into the read's running best (smallest distance, lowest index among equals) and the

@@ -175,22 +175,25 @@ k_seed(const __grid_constant__ DevParams P, const int pass, const int level, con
                     // 32-bit hash collisions are harmless: a false hit only costs a verification
                     const int delta = p - (int)(ent & 0xFFu);           // 0-based diagonal
                     const uint32_t b = ent >> 8;
-                    // Several intact segments of one alignment hit the same barcode on diagonals at most K
-                    // apart: they join one record whose window is the union of theirs (still a sub-range
-                    // with free ends, and it contains every alignment either window contained).
-                    bool merged = false;
-                    const int have_hits = min(n_hits, kSeedMaxHits);
-                    for (int j = 0; j < have_hits && !merged; j++) {
-                        const uint32_t old = hits_s[j * kSeedThreads + threadIdx.x];
-                        if ((old >> 13) != b) continue;
-                        const int dmin = (int)(old & 0x3FFu) - 256, span = (int)((old >> 10) & 0x7u);
-                        const int lo = min(dmin, delta), hi = max(dmin + span, delta);
-                        if (hi - lo <= K) {
-                            hits_s[j * kSeedThreads + threadIdx.x] = hit_pack(b, hi - lo, lo);
-                            merged = true;
+                    // Several intact segments of one alignment hit the same barcode on diagonals at most K apart.
+                    // When such a hit follows directly on the previous one of this read (the usual case: a read
+                    // has one real match and few chance hits) it joins that record, whose window becomes the
+                    // union of theirs (still a sub-range with free ends, and it contains every alignment either
+                    // window contained).  Otherwise it gets a record of its own: every record is verified in its
+                    // own window and the barcode's distance is the minimum over its records, so a missed merge
+                    // only costs a verification.  (Searching ALL earlier records for a partner ran at 5 of 32
+                    // lanes and cost 12 % of the kernel's instructions, profiles/r02_kernels_ncu_summary.txt.)
+                    if (n_hits > 0 && n_hits <= kSeedMaxHits) {
+                        const uint32_t old = hits_s[(n_hits - 1) * kSeedThreads + threadIdx.x];
+                        if ((old >> 13) == b) {
+                            const int dmin = (int)(old & 0x3FFu) - 256, span = (int)((old >> 10) & 0x7u);
+                            const int lo = min(dmin, delta), hi = max(dmin + span, delta);
+                            if (hi - lo <= K) {
+                                hits_s[(n_hits - 1) * kSeedThreads + threadIdx.x] = hit_pack(b, hi - lo, lo);
+                                continue;
+                            }
                         }
                     }
-                    if (merged) continue;
                     if (n_hits < kSeedMaxHits) hits_s[n_hits * kSeedThreads + threadIdx.x] = hit_pack(b, 0, delta);
                     n_hits++;
                 }

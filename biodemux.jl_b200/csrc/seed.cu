@@ -143,15 +143,20 @@ k_seed(const __grid_constant__ DevParams P, const int pass, const int level, con
             if (p1 >= p0) {
                 uint32_t h = 0;
                 for (int i = 0; i < q; i++) h = h * kPfBase + (uint32_t)my_slot[p0 + i];
-                for (int p = p0;;) {
+                auto probe = [&](int p) {
                     const uint32_t bit = pf_bit(h, bm_log2);
                     if ((bitmap_s[bit >> 5] >> (bit & 31)) & 1u) {
                         if (n_wins < kSeedMaxWins) wins_s[n_wins * kSeedThreads + threadIdx.x] = (uint8_t)p;
                         n_wins++;
                     }
-                    if (++p > p1) break;
-                    h = (h - (uint32_t)my_slot[p - 1] * pw) * kPfBase + (uint32_t)my_slot[p - 1 + q];
+                };
+                const uint8_t *c_in = my_slot + q;
+#pragma unroll 4
+                for (int p = p0; p < p1; p++) {
+                    probe(p);
+                    h = (h - (uint32_t)my_slot[p] * pw) * kPfBase + (uint32_t)c_in[p];
                 }
+                probe(p1);
             }
             if (n_wins > kSeedMaxWins) punt = true;
         }

@@ -25,6 +25,7 @@ BDX_OK, BDX_ERR_INVALID, BDX_ERR_CUDA, BDX_ERR_NOMEM, BDX_ERR_STATE, BDX_ERR_TOO
 # every symbol include/bdx.h declares (tests check that the library exports all of them)
 DEBUG_NO_FILTER, DEBUG_NO_PREFILTER, DEBUG_NO_SEEDS, DEBUG_NO_SEED_DEEP = 1, 2, 4, 8
 DEBUG_ONE_SEED_LEVEL, DEBUG_NO_GRAPHS, DEBUG_NO_HAMMING_PACKED, DEBUG_PREFER_SEED_VAR = 16, 32, 64, 128
+DEBUG_NO_QGRAM_FILTER = 256
 
 EXPORTS = [
     "bdx_last_error", "bdx_abi_version", "bdx_device_count", "bdx_config_create", "bdx_config_create_debug", "bdx_config_destroy",

@@ -54,7 +54,7 @@ struct HostSet {
     HostSeedLevel sdd[2];
     // variable lengths / constrained geometries (seed_var.cu)
     struct HostSeedVar {
-        int q = 0, q2 = 0, complete = 0, group_reads = 0, hit_rows = 0;
+        int q = 0, q2 = 0, complete = 0, group_reads = 0, hit_rows = 0, qgram_filter = 0;
         double sigma_min = 0.0;
         std::vector<uint16_t> bstart;
         std::vector<uint32_t> entries;

@@ -270,6 +270,7 @@ static int get_tables(bdx_config *cfg, int device, DeviceTables **out)
             V.complete = H.complete;
             V.group_reads = H.group_reads;
             V.hit_rows = H.hit_rows;
+            V.qgram_filter = H.qgram_filter;
             V.sigma_min = H.sigma_min;
             if (e == cudaSuccess) e = upload(t, H.bstart, &V.bstart);
             if (e == cudaSuccess) e = upload(t, H.entries, &V.entries);

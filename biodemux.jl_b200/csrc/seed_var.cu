@@ -196,6 +196,73 @@ __device__ __forceinline__ int sv_verify(const uint32_t *hits_s, int total, cons
     return cols;
 }
 
+// q-gram filter in front of the verification (one word per barcode row vector, i.e. barcodes up to 32 nt).
+// An alignment with <= K edits that contains the hit's intact segment on diagonal delta keeps all its cells on the
+// diagonals delta - K .. delta + K, and every edit destroys at most three of the barcode's m - 2 overlapping 3-grams;
+// so at least (m - 2) - 3 K barcode positions i must see their 3-gram in the read at a column c with
+// c - i in [delta - K, delta + K].  The count is taken bit-parallel over the rows: with E_c = the rows whose base
+// equals the read's base at column c (the Peq word), G_c = E_c & (E_c+1 >> 1) & (E_c+2 >> 2) marks the rows whose
+// 3-gram occurs at column c, a band of 2 K + 1 rows slides up one row per column, and covered |= G_c & band.
+// Ten instructions per window column instead of the automaton's twenty -- and nine of ten chance hits end here
+// (a random window shares ~6 of 22 3-grams with the barcode where 10 are needed).  A necessary condition only:
+// whatever passes is verified as before; hits of barcodes with (m - 2) - 3 K <= 0 all pass.
+// The survivors are compacted to the front of the list, round by round; returns their number.
+__device__ __forceinline__ int sv_qgram_filter(uint32_t *hits_s, int total, const int *rinfo_s, const uint32_t *binfo_s,
+                                               const uint32_t *peq_s, int n_classes, const uint8_t *slot_s, int slot_stride,
+                                               int *ctr_s)
+{
+    // ctr_s[6]: survivors written so far (reset by the caller before the first round)
+    const int lane = threadIdx.x & 31;
+    for (int i0 = 0; i0 < total; i0 += kSvThreads) {
+        const int i = i0 + (int)threadIdx.x;
+        const bool live = i < total;
+        const uint32_t rec = live ? hits_s[i] : 0u;
+        bool keep = false;
+        int wlen = 0;
+        const uint8_t *col = slot_s;
+        const uint32_t *row = peq_s;
+        unsigned long long wide = 0;
+        uint32_t rows3 = 0;
+        int need = 0;
+        if (live) {
+            const int hr = (int)(rec >> 22), hb = (int)((rec >> 8) & 0x3FFFu);
+            const int delta = (int)(rec & 0xFFu) - kSvDiagBias;
+            const uint32_t bi = binfo_s[hb];
+            const int m = (int)(bi & 0xFFu), K = (int)((bi >> 8) & 0xFFu);
+            const int Lr = rinfo_s[hr * kSvRi + 0];
+            need = (m - 2) - 3 * K;
+            const int w0 = max(0, delta - K), w1 = min(Lr - 1, delta + m - 1 + K);      // 0-based window columns
+            wlen = need > 0 ? w1 - w0 - 1 : 0;                                           // 3-grams starting inside it
+            col = slot_s + (size_t)hr * slot_stride + w0;
+            row = peq_s + hb * n_classes;
+            // rows are top-aligned: row r (0-based) is bit 32 - m + r; the band of column w0 starts at row w0 - delta - K
+            const int bitpos = 32 - m + (w0 - delta - K);                               // >= -2 K - 32 + ... > -32
+            wide = ((1ull << (2 * K + 1)) - 1ull) << (bitpos + 32);
+            rows3 = m >= 3 ? (0xFFFFFFFFu << (32 - m)) & (0xFFFFFFFFu >> 2) : 0u;        // rows that start a 3-gram
+            keep = need <= 0;
+        }
+        const int trips = __reduce_max_sync(0xFFFFFFFFu, wlen);
+        uint32_t e0 = row[col[0]], e1 = row[col[1]], covered = 0;
+        for (int t = 0; t < trips; t++) {
+            const uint32_t e2 = row[col[t + 2]];
+            const uint32_t g = e0 & (e1 >> 1) & (e2 >> 2);
+            if (t < wlen) covered |= g & (uint32_t)(wide >> 32);
+            wide <<= 1;
+            e0 = e1;
+            e1 = e2;
+        }
+        if (live && !keep) keep = __popc(covered & rows3) >= need;
+        __syncthreads();                                             // every hit of this round has been read
+        const uint32_t km = __ballot_sync(0xFFFFFFFFu, keep);
+        int base = 0;
+        if (lane == 0 && km) base = atomicAdd(&ctr_s[6], __popc(km));
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        if (keep) hits_s[base + __popc(km & ((1u << lane) - 1u))] = rec;   // base + rank <= hits read so far
+        __syncthreads();
+    }
+    return ctr_s[6];
+}
+
 template <int W>
 __global__ void __launch_bounds__(kSvThreads)
 k_seed_var(const __grid_constant__ DevParams P, const int pass, const int level, const uint8_t *__restrict__ seq,
@@ -413,7 +480,12 @@ k_seed_var(const __grid_constant__ DevParams P, const int pass, const int level,
 
         // ---- verify: every thread takes hits of the block's list, two at a time ----
         {
-            const int total = min(ctr_s[0], hit_cap);
+            int total = min(ctr_s[0], hit_cap);
+            if (W == 1 && V.qgram_filter) {
+                if (threadIdx.x == 0) ctr_s[6] = 0;
+                __syncthreads();
+                total = sv_qgram_filter(hits_s, total, rinfo_s, binfo_s, peq_s, n_classes, slot_s, slot_stride, ctr_s);
+            }
             if (last_row_rule)
                 n_cols += sv_verify<WT, true>(hits_s, total, rinfo_s, binfo_s, peq_s, n_classes, plane, slot_s, slot_stride, cand_s, cand_n_s);
             else

@@ -367,6 +367,11 @@ void build_seed_var(const Build &B)
             int R = 128;
             while (R > 8 && per_read * R > 0.7 * 128 * V.hit_rows) R -= 8;
             V.group_reads = R;
+            // the 3-gram filter in front of the verification pays when most hits can fail it: (m - 2) - 3 K > 0
+            int strong = 0;
+            for (int b = 0; b < hs.n_bc; b++)
+                strong += (hs.off[b + 1] - hs.off[b] - 2) - 3 * (int)V.kdepth[(size_t)b] >= 4;
+            V.qgram_filter = hs.max_m <= 32 && 2 * strong >= hs.n_bc && !(B.debug & BDX_DEBUG_NO_QGRAM_FILTER);
         };
         // level with ONE seed length q: K_b + 1 segments of m_b / (K_b + 1) >= q bases, K_b = min(m_b / q - 1, allowed_b)
         auto build = [&](int q, double chance) {

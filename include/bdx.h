@@ -144,7 +144,8 @@ enum {
     BDX_DEBUG_ONE_SEED_LEVEL = 16,    /* only the first seed level */
     BDX_DEBUG_NO_GRAPHS = 32,         /* plain launches instead of CUDA-graph replay of small batches */
     BDX_DEBUG_NO_HAMMING_PACKED = 64, /* :hamming through the edit-distance filter instead of k_hamming_scan */
-    BDX_DEBUG_PREFER_SEED_VAR = 128   /* k_seed_var also for the sets / geometries k_seed's levels take */
+    BDX_DEBUG_PREFER_SEED_VAR = 128,  /* k_seed_var also for the sets / geometries k_seed's levels take */
+    BDX_DEBUG_NO_QGRAM_FILTER = 256   /* k_seed_var verifies every hit (no 3-gram filter in front) */
 };
 int bdx_config_create_debug(const bdx_params *params, uint32_t debug_flags, bdx_config **out);
 

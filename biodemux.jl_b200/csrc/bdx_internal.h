@@ -66,7 +66,7 @@ struct SeedVar {
     int complete;                 // kdepth[b] >= allowed0[b] for every barcode: the candidate sets are supersets
     int group_reads;              // reads a block works on at a time (sized so that their hits fit the block's hit list)
     int hit_rows;                 // hit list capacity in rows of 128 records
-    int qgram_filter;             // run the 3-gram filter in front of the verification (enough barcodes have (m - 2) - 3 K > 0)
+    int qgram_filter;             // 3-gram filter in front of the verification: 0 = off, 1 = inside the scan, 2 = over the finished hit list
     double sigma_min;             // min_b (kdepth[b] + 1) / norm[b]: no barcode outside the candidate set scores below
     const uint16_t *bstart;       // [n_bstart] CSR row starts of both tables, absolute indices into entries
     const uint32_t *entries;      // [n_entries] (barcode index << 8) | seed offset

@@ -90,17 +90,21 @@ __device__ __forceinline__ void sv_stage_warp(const uint8_t *__restrict__ seq, l
 }
 
 // Shared-memory carve-up (bytes); the same arithmetic on the host (launch) and the device (kernel).
-// rows of kSvThreads records in the block's hit list; the decide phase reuses the list as DP columns [row][thread]
-__host__ __device__ inline int sv_hit_rows(int wanted, int max_m) { return max_m + 2 > wanted ? max_m + 2 : wanted; }
+// The block's hit list holds hit_rows rows of kSvThreads records; the decide phase reuses it as sg_literal's DP
+// columns [row][thread], max_m + 2 rows (sets whose geometry can bound the start get at least that many: tables.cu).
 
-enum { kSvPeq = 0, kSvHits, kSvCandL, kSvRinfo, kSvCandN, kSvCtr, kSvEntries, kSvBstart, kSvBinfo, kSvClass, kSvSlot, kSvParts };
+enum { kSvPeq = 0, kSvHits, kSvCandL, kSvRinfo, kSvCandN, kSvCtr, kSvEntries, kSvBstart, kSvBinfo, kSvClass, kSvPlanes, kSvBplanes, kSvSlot, kSvParts };
+
+// words of one bit plane of a read's search range (3-gram filter): the columns -32 .. slot_cols + 63, odd so that the
+// planes of consecutive reads start in different banks; 0 = no filter
+__host__ __device__ inline int sv_plane_words(int slot_cols, int qgram_filter) { return qgram_filter ? ((slot_cols + 32) / 32 + 3) | 1 : 0; }
 
 __host__ __device__ inline size_t sv_smem_layout(int W, int plane, int n_pad, int n_entries, int n_bstart, int tab_smem,
-                                                 int slot_stride, int max_m, int R, int hit_rows, size_t off[kSvParts])
+                                                 int slot_stride, int R, int hit_rows, int pl_words, size_t off[kSvParts])
 {
     size_t o = 0;
     off[kSvPeq] = o; o += (size_t)W * plane * 4;                          // Peq, transposed to [word][barcode][class]
-    off[kSvHits] = o; o += (size_t)kSvThreads * sv_hit_rows(hit_rows, max_m) * 4;   // hit list / DP columns [row][thread]
+    off[kSvHits] = o; o += (size_t)kSvThreads * hit_rows * 4;                     // hit list / DP columns [row][thread]
     off[kSvCandL] = o; o += (size_t)R * kSvCand * 4;                      // verified candidates per read
     off[kSvRinfo] = o; o += (size_t)kSvThreads * kSvRi * 4;               // per read: L, min_end_rel, max_start_rel, flags, n_rel
     off[kSvCandN] = o; o += ((size_t)kSvThreads + 4) * 4;                 // per read: number of candidates; later their offsets
@@ -109,6 +113,9 @@ __host__ __device__ inline size_t sv_smem_layout(int W, int plane, int n_pad, in
     off[kSvBstart] = o; o += tab_smem ? ((size_t)n_bstart * 2 + 3) / 4 * 4 : 0;
     off[kSvBinfo] = o; o += (size_t)n_pad * 4;                            // per barcode: m | K << 8 | allowed0 << 16
     off[kSvClass] = o; o += 256;
+    off[kSvPlanes] = o; o += (size_t)R * 3 * pl_words * 4;                // per read: bit planes (absent, code bit 0, code bit 1) of the staged range
+    o = (o + 7) / 8 * 8;
+    off[kSvBplanes] = o; o += pl_words ? (size_t)n_pad * 8 : 0;           // per barcode: code bit 0 / bit 1 of its rows, row i at bit i
     off[kSvSlot] = o; o += (size_t)R * slot_stride + 128;                 // staged class codes (+ slack: windows are read past their end)
     return (o + 15) / 16 * 16;
 }
@@ -119,9 +126,19 @@ __host__ __device__ inline size_t sv_smem_layout(int W, int plane, int n_pad, in
 template <typename WT, bool LASTROW>
 __device__ __forceinline__ int sv_verify(const uint32_t *hits_s, int total, const int *rinfo_s, const uint32_t *binfo_s,
                                           const uint32_t *peq_s, int n_classes, int plane, const uint8_t *slot_s,
-                                          int slot_stride, uint32_t *cand_s, int *cand_n_s)
+                                          int slot_stride, uint32_t *cand_s, int *cand_n_s, int seg, const int *cnt)
 {
     constexpr int kMsb = (int)sizeof(WT) * 8 - 1;
+    // seg != 0: the list is four segments of seg records whose first cnt[0..3] are live (sv_qgram_compact)
+    const int n0 = seg ? cnt[0] : 0, n1 = seg ? cnt[1] : 0, n2 = seg ? cnt[2] : 0;
+    auto fetch = [&](int i) {
+        if (seg) {
+            int w = 0;
+            if (i >= n0) { i -= n0; w = 1; if (i >= n1) { i -= n1; w = 2; if (i >= n2) { i -= n2; w = 3; } } }
+            i += w * seg;
+        }
+        return hits_s[i];
+    };
     int cols = 0;                       // window columns this thread stepped its hits over (work counter)
     for (int i0 = 0; i0 < total; i0 += kSvChains * kSvThreads) {
         int score[kSvChains], best[kSvChains], hr[kSvChains], hk[kSvChains], hb[kSvChains], wl[kSvChains], ts[kSvChains];
@@ -133,7 +150,7 @@ __device__ __forceinline__ int sv_verify(const uint32_t *hits_s, int total, cons
         for (int u = 0; u < kSvChains; u++) {
             const int i = i0 + u * kSvThreads + (int)threadIdx.x;
             const bool live = i < total;
-            const uint32_t rec = live ? hits_s[i] : 0u;
+            const uint32_t rec = live ? fetch(i) : 0u;
             hr[u] = live ? (int)(rec >> 22) : 0;
             hb[u] = (int)((rec >> 8) & 0x3FFFu);
             const int delta = (int)(rec & 0xFFu) - kSvDiagBias;
@@ -196,71 +213,72 @@ __device__ __forceinline__ int sv_verify(const uint32_t *hits_s, int total, cons
     return cols;
 }
 
-// q-gram filter in front of the verification (one word per barcode row vector, i.e. barcodes up to 32 nt).
+// 3-gram filter between the hit test and the verification (barcodes up to 32 nt over at most four bases).
 // An alignment with <= K edits that contains the hit's intact segment on diagonal delta keeps all its cells on the
 // diagonals delta - K .. delta + K, and every edit destroys at most three of the barcode's m - 2 overlapping 3-grams;
-// so at least (m - 2) - 3 K barcode positions i must see their 3-gram in the read at a column c with
-// c - i in [delta - K, delta + K].  The count is taken bit-parallel over the rows: with E_c = the rows whose base
-// equals the read's base at column c (the Peq word), G_c = E_c & (E_c+1 >> 1) & (E_c+2 >> 2) marks the rows whose
-// 3-gram occurs at column c, a band of 2 K + 1 rows slides up one row per column, and covered |= G_c & band.
-// Ten instructions per window column instead of the automaton's twenty -- and nine of ten chance hits end here
-// (a random window shares ~6 of 22 3-grams with the barcode where 10 are needed).  A necessary condition only:
-// whatever passes is verified as before; hits of barcodes with (m - 2) - 3 K <= 0 all pass.
-// The survivors are compacted to the front of the list, round by round; returns their number.
-__device__ __forceinline__ int sv_qgram_filter(uint32_t *hits_s, int total, const int *rinfo_s, const uint32_t *binfo_s,
-                                               const uint32_t *peq_s, int n_classes, const uint8_t *slot_s, int slot_stride,
-                                               int *ctr_s)
+// so at least (m - 2) - 3 K barcode rows i must see rows i, i + 1, i + 2 matched on ONE of those diagonals.
+// Bit-parallel over the rows: the read's range is kept as three bit planes (no-barcode-base, code bit 0, code bit 1;
+// columns outside the range count as no-barcode-base), the barcode as two; a diagonal's match vector is
+// ~((R0 ^ B0) | (R1 ^ B1) | RA) with the read planes shifted by the diagonal, its 3-gram vector M & M>>1 & M>>2,
+// the union over the 2 K + 1 diagonals is counted.  ~10 instructions per diagonal where the automaton steps ~20 per
+// window COLUMN (m + 2 K of them), and nine of ten chance hits end here (a random window shares ~6 of a 24-nt
+// barcode's 22 3-grams where 10 are needed).  A necessary condition only: whatever passes is verified.
+__device__ __forceinline__ bool sv_qgram_pass(const uint32_t *planes_s, int pl_words, const uint2 *bplanes_s, int hr, int b,
+                                              int m, int K, int delta)
 {
-    // ctr_s[6]: survivors written so far (reset by the caller before the first round)
-    const int lane = threadIdx.x & 31;
-    for (int i0 = 0; i0 < total; i0 += kSvThreads) {
-        const int i = i0 + (int)threadIdx.x;
-        const bool live = i < total;
-        const uint32_t rec = live ? hits_s[i] : 0u;
-        bool keep = false;
-        int wlen = 0;
-        const uint8_t *col = slot_s;
-        const uint32_t *row = peq_s;
-        unsigned long long wide = 0;
-        uint32_t rows3 = 0;
-        int need = 0;
-        if (live) {
-            const int hr = (int)(rec >> 22), hb = (int)((rec >> 8) & 0x3FFFu);
-            const int delta = (int)(rec & 0xFFu) - kSvDiagBias;
-            const uint32_t bi = binfo_s[hb];
-            const int m = (int)(bi & 0xFFu), K = (int)((bi >> 8) & 0xFFu);
-            const int Lr = rinfo_s[hr * kSvRi + 0];
-            need = (m - 2) - 3 * K;
-            const int w0 = max(0, delta - K), w1 = min(Lr - 1, delta + m - 1 + K);      // 0-based window columns
-            wlen = need > 0 ? w1 - w0 - 1 : 0;                                           // 3-grams starting inside it
-            col = slot_s + (size_t)hr * slot_stride + w0;
-            row = peq_s + hb * n_classes;
-            // rows are top-aligned: row r (0-based) is bit 32 - m + r; the band of column w0 starts at row w0 - delta - K
-            const int bitpos = 32 - m + (w0 - delta - K);                               // >= -2 K - 32 + ... > -32
-            wide = ((1ull << (2 * K + 1)) - 1ull) << (bitpos + 32);
-            rows3 = m >= 3 ? (0xFFFFFFFFu << (32 - m)) & (0xFFFFFFFFu >> 2) : 0u;        // rows that start a 3-gram
-            keep = need <= 0;
-        }
-        const int trips = __reduce_max_sync(0xFFFFFFFFu, wlen);
-        uint32_t e0 = row[col[0]], e1 = row[col[1]], covered = 0;
-        for (int t = 0; t < trips; t++) {
-            const uint32_t e2 = row[col[t + 2]];
-            const uint32_t g = e0 & (e1 >> 1) & (e2 >> 2);
-            if (t < wlen) covered |= g & (uint32_t)(wide >> 32);
-            wide <<= 1;
-            e0 = e1;
-            e1 = e2;
-        }
-        if (live && !keep) keep = __popc(covered & rows3) >= need;
-        __syncthreads();                                             // every hit of this round has been read
-        const uint32_t km = __ballot_sync(0xFFFFFFFFu, keep);
-        int base = 0;
-        if (lane == 0 && km) base = atomicAdd(&ctr_s[6], __popc(km));
-        base = __shfl_sync(0xFFFFFFFFu, base, 0);
-        if (keep) hits_s[base + __popc(km & ((1u << lane) - 1u))] = rec;   // base + rank <= hits read so far
-        __syncthreads();
+    const int need = (m - 2) - 3 * K;
+    if (need <= 0) return true;
+    const int biased = delta - K + 32;                      // first diagonal's column of row 0, plane bit index
+    const uint32_t *pl = planes_s + (size_t)hr * 3 * pl_words + (biased >> 5);
+    const int sh = biased & 31;
+    const uint32_t a_lo = __funnelshift_r(pl[0], pl[1], sh), a_hi = __funnelshift_r(pl[1], pl[2], sh);
+    pl += pl_words;
+    const uint32_t p_lo = __funnelshift_r(pl[0], pl[1], sh), p_hi = __funnelshift_r(pl[1], pl[2], sh);
+    pl += pl_words;
+    const uint32_t q_lo = __funnelshift_r(pl[0], pl[1], sh), q_hi = __funnelshift_r(pl[1], pl[2], sh);
+    const uint2 bp = bplanes_s[b];
+    const uint32_t rows = m >= 32 ? 0xFFFFFFFFu : (1u << m) - 1u;
+    uint32_t cover = 0;
+    for (int k = 0; k <= 2 * K; k++) {                       // 2 K <= 2 (m - 3) / 3 < 31
+        const uint32_t mis = (__funnelshift_r(p_lo, p_hi, k) ^ bp.x) | (__funnelshift_r(q_lo, q_hi, k) ^ bp.y) |
+                             __funnelshift_r(a_lo, a_hi, k);
+        const uint32_t mt = ~mis & rows;
+        cover |= mt & (mt >> 1) & (mt >> 2);
     }
-    return ctr_s[6];
+    return __popc(cover) >= need;
+}
+
+// The same test over the finished hit list (mode 2: geometries whose admissible diagonals are few, where testing inside
+// the scan would run it for two or three lanes of a warp at a time).  No block-wide barrier per round: the list is cut
+// into one segment per warp, each warp tests its segment 32 hits at a time and compacts the survivors to the
+// segment's front (its write cursor never passes its read cursor); cnt[w] = survivors of warp w's segment.
+// sv_verify then walks the four segment fronts as one list.  Returns the segment length.
+__device__ __forceinline__ int sv_qgram_compact(uint32_t *hits_s, int total, const uint32_t *planes_s, int pl_words,
+                                                const uint2 *bplanes_s, const uint32_t *binfo_s, int *cnt)
+{
+    static_assert(kSvThreads == 128, "four segments");
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int seg = ((total + 3) / 4 + 31) & ~31;
+    const int s0 = warp * seg, s1 = min(total, s0 + seg);
+    int kept = 0;
+    for (int i0 = s0; i0 < s1; i0 += 32) {
+        const int i = i0 + lane;
+        uint32_t rec = 0;
+        bool keep = false;
+        if (i < s1) {
+            rec = hits_s[i];
+            const int b = (int)((rec >> 8) & 0x3FFFu);
+            const uint32_t bi = binfo_s[b];
+            keep = sv_qgram_pass(planes_s, pl_words, bplanes_s, (int)(rec >> 22), b, (int)(bi & 0xFFu), (int)((bi >> 8) & 0xFFu),
+                                 (int)(rec & 0xFFu) - kSvDiagBias);
+        }
+        const uint32_t km = __ballot_sync(0xFFFFFFFFu, keep);        // (every lane has read its hit by now)
+        if (keep) hits_s[s0 + kept + __popc(km & ((1u << lane) - 1u))] = rec;
+        kept += __popc(km);
+        __syncwarp();
+    }
+    if (lane == 0) cnt[warp] = kept;
+    return seg;
 }
 
 template <int W>
@@ -279,7 +297,8 @@ k_seed_var(const __grid_constant__ DevParams P, const int pass, const int level,
     const int n_classes = S.n_classes;
     const int plane = n_classes * n_pad;
     size_t lo[kSvParts];
-    sv_smem_layout(W, plane, n_pad, V.n_entries, V.n_bstart, tab_smem, slot_stride, S.max_m, R, V.hit_rows, lo);
+    const int pl_words = sv_plane_words(slot_cols, W == 1 && V.qgram_filter);
+    sv_smem_layout(W, plane, n_pad, V.n_entries, V.n_bstart, tab_smem, slot_stride, R, V.hit_rows, pl_words, lo);
     uint32_t *peq_s = reinterpret_cast<uint32_t *>(smem_raw + lo[kSvPeq]);
     uint32_t *hits_s = reinterpret_cast<uint32_t *>(smem_raw + lo[kSvHits]);
     uint32_t *cand_s = reinterpret_cast<uint32_t *>(smem_raw + lo[kSvCandL]);
@@ -291,6 +310,8 @@ k_seed_var(const __grid_constant__ DevParams P, const int pass, const int level,
     uint32_t *binfo_s = reinterpret_cast<uint32_t *>(smem_raw + lo[kSvBinfo]);
     uint8_t *class_s = smem_raw + lo[kSvClass];
     uint8_t *slot_s = smem_raw + lo[kSvSlot];
+    uint32_t *planes_s = reinterpret_cast<uint32_t *>(smem_raw + lo[kSvPlanes]);
+    uint2 *bplanes_s = reinterpret_cast<uint2 *>(smem_raw + lo[kSvBplanes]);
 
     // Peq arrives as [word][class][barcode] (k_filter's lanes read consecutive barcodes); a verifying thread
     // reads ONE barcode's words for changing classes, so it is kept as [word][barcode][class] here
@@ -312,6 +333,14 @@ k_seed_var(const __grid_constant__ DevParams P, const int pass, const int level,
         binfo_s[k] = v;
     }
     for (int k = threadIdx.x; k < 256; k += blockDim.x) class_s[k] = S.class_of[k];
+    if (pl_words)                                            // the barcodes' bit planes, row i at bit i (class c = code c - 1)
+        for (int k = threadIdx.x; k < n_pad; k += blockDim.x) {
+            const int m = k < S.n_bc ? S.bc_off[k + 1] - S.bc_off[k] : 0;
+            uint32_t e[5] = {0u, 0u, 0u, 0u, 0u};
+            for (int c = 1; c < n_classes && c < 5; c++) e[c] = S.peq[c * n_pad + k];
+            const int sh = 32 - m;                           // Peq rows are top-aligned, phantom rows below them
+            bplanes_s[k] = m >= 1 && m <= 32 ? make_uint2((e[2] | e[4]) >> sh, (e[3] | e[4]) >> sh) : make_uint2(0u, 0u);
+        }
     for (int k = threadIdx.x; k < 128; k += blockDim.x) slot_s[(size_t)R * slot_stride + k] = 0;
     if (threadIdx.x == 0) ctr_s[5] = 0;
     __syncthreads();
@@ -322,7 +351,9 @@ k_seed_var(const __grid_constant__ DevParams P, const int pass, const int level,
     const int n_items = wl_in ? *n_in : n_reads;
     const int n_groups = (n_items + R - 1) / R;
     const bool with_delta = P.min_delta != 0.0;
-    const int hit_cap = kSvThreads * sv_hit_rows(V.hit_rows, S.max_m);
+    const int hit_cap = kSvThreads * V.hit_rows;
+    const bool in_scan_filter = pl_words && V.qgram_filter == 1;
+    const bool dp_fits = V.hit_rows >= S.max_m + 2;          // sg_literal's column fits the (dead) hit list
     unsigned int n_done = 0;
     unsigned long long n_cols = 0;      // verified hit-columns (one Myers / Hyyro column step each), for the roofline
 
@@ -369,6 +400,29 @@ k_seed_var(const __grid_constant__ DevParams P, const int pass, const int level,
         // the automaton's D[m][j].  Over ALL columns the two have the same minimum, over the columns
         // >= min_end_pos they do not; D' is tracked for the whole group when any of its reads needs it.
         const int last_row_rule = __syncthreads_or(!punt && g.min_end_pos > g.start_j);
+        if (pl_words) {
+            // the staged ranges as bit planes, 32 columns per ballot; plane bit 32 + c is relative column c (0-based)
+            for (int r = warp; r < R; r += kSvThreads / 32) {
+                const int Lr = rinfo_s[r * kSvRi + 0];
+                uint32_t *pl = planes_s + (size_t)r * 3 * pl_words;
+                for (int w = 0; w < pl_words; w++) {
+                    const int c = (w - 1) * 32 + lane;
+                    uint32_t a = 0xFFFFFFFFu, b0 = 0u, b1 = 0u;
+                    if (w >= 1 && (w - 1) * 32 < Lr) {
+                        const uint32_t cls = c < Lr ? slot_s[(size_t)r * slot_stride + c] : 0u;
+                        a = __ballot_sync(0xFFFFFFFFu, cls == 0u);
+                        b0 = __ballot_sync(0xFFFFFFFFu, cls != 0u && ((cls - 1u) & 1u));
+                        b1 = __ballot_sync(0xFFFFFFFFu, cls != 0u && ((cls - 1u) & 2u));
+                    }
+                    if (lane == 0) {
+                        pl[w] = a;
+                        pl[pl_words + w] = b0;
+                        pl[2 * pl_words + w] = b1;
+                    }
+                }
+            }
+            __syncthreads();
+        }
 
         // ---- scan: (read, column) pairs dealt to the lanes, two consecutive pairs each.  A pair looks its q-mer up
         // in table 0 and, with one more base, its (q + 1)-mer in table 1; the entries of a warp's 64 pairs are
@@ -460,6 +514,7 @@ k_seed_var(const __grid_constant__ DevParams P, const int pass, const int level,
                         const int dlo = max(0, min_end_rel - m) - K;
                         const int dhi = min(max_start_rel + a0, oL - m + K);
                         hit = delta >= dlo && delta <= dhi;
+                        if (hit && in_scan_filter) hit = sv_qgram_pass(planes_s, pl_words, bplanes_s, hr, b, m, K, delta);
                         rec = ((uint32_t)hr << 22) | ((uint32_t)b << 8) | (uint32_t)(delta + kSvDiagBias);
                     }
                     const uint32_t hm = __ballot_sync(0xFFFFFFFFu, hit);
@@ -480,16 +535,16 @@ k_seed_var(const __grid_constant__ DevParams P, const int pass, const int level,
 
         // ---- verify: every thread takes hits of the block's list, two at a time ----
         {
-            int total = min(ctr_s[0], hit_cap);
-            if (W == 1 && V.qgram_filter) {
-                if (threadIdx.x == 0) ctr_s[6] = 0;
+            int total = min(ctr_s[0], hit_cap), seg = 0;
+            if (pl_words && !in_scan_filter) {
+                seg = sv_qgram_compact(hits_s, total, planes_s, pl_words, bplanes_s, binfo_s, ctr_s + 1);
                 __syncthreads();
-                total = sv_qgram_filter(hits_s, total, rinfo_s, binfo_s, peq_s, n_classes, slot_s, slot_stride, ctr_s);
+                total = ctr_s[1] + ctr_s[2] + ctr_s[3] + ctr_s[4];
             }
             if (last_row_rule)
-                n_cols += sv_verify<WT, true>(hits_s, total, rinfo_s, binfo_s, peq_s, n_classes, plane, slot_s, slot_stride, cand_s, cand_n_s);
+                n_cols += sv_verify<WT, true>(hits_s, total, rinfo_s, binfo_s, peq_s, n_classes, plane, slot_s, slot_stride, cand_s, cand_n_s, seg, ctr_s + 1);
             else
-                n_cols += sv_verify<WT, false>(hits_s, total, rinfo_s, binfo_s, peq_s, n_classes, plane, slot_s, slot_stride, cand_s, cand_n_s);
+                n_cols += sv_verify<WT, false>(hits_s, total, rinfo_s, binfo_s, peq_s, n_classes, plane, slot_s, slot_stride, cand_s, cand_n_s, seg, ctr_s + 1);
         }
         __syncthreads();
 
@@ -532,6 +587,10 @@ k_seed_var(const __grid_constant__ DevParams P, const int pass, const int level,
             auto check = [&](int r, int k) {
                 const uint32_t rec = cand_s[r * kSvCand + k];
                 const int b = (int)(rec >> 8), d = (int)(rec & 0xFFu);
+                if (!dp_fits) {                                                // (never sized that way; the read takes the exact path)
+                    rinfo_s[r * kSvRi + 3] = 2;
+                    return;
+                }
                 const int qo = S.bc_off[b], m = S.bc_off[b + 1] - qo;
                 // the owner's geometry in RELATIVE columns, as it left it in shared memory (sg_literal's column
                 // arithmetic is translation invariant: range, max_start_pos, min_end_pos and n all shift by sbase)
@@ -662,10 +721,12 @@ static SvLaunch sv_launch_params(const DevSet &S, const SeedVar &V)
     size_t off[kSvParts];
     const int plane = S.n_classes * S.n_bc_pad;
     L.tab_smem = 1;
-    L.smem = sv_smem_layout(S.words, plane, S.n_bc_pad, V.n_entries, V.n_bstart, 1, L.slot_stride, S.max_m, V.group_reads, V.hit_rows, off);
+    L.smem = sv_smem_layout(S.words, plane, S.n_bc_pad, V.n_entries, V.n_bstart, 1, L.slot_stride, V.group_reads, V.hit_rows,
+                            sv_plane_words(L.slot_cols, S.words == 1 && V.qgram_filter), off);
     if (L.smem > 100 * 1024) {
         L.tab_smem = 0;
-        L.smem = sv_smem_layout(S.words, plane, S.n_bc_pad, V.n_entries, V.n_bstart, 0, L.slot_stride, S.max_m, V.group_reads, V.hit_rows, off);
+        L.smem = sv_smem_layout(S.words, plane, S.n_bc_pad, V.n_entries, V.n_bstart, 0, L.slot_stride, V.group_reads, V.hit_rows,
+                            sv_plane_words(L.slot_cols, S.words == 1 && V.qgram_filter), off);
     }
     return L;
 }

@@ -359,19 +359,42 @@ void build_seed_var(const Build &B)
             }
             return e;
         };
-        // reads per group: 128 and a hit list of up to 64 rows x 128 records (seed_var.cu) that their hits -- chance
-        // + a handful of true ones -- fill to about 70 %; denser levels take fewer reads per group instead
+        // reads per group: 128 and a hit list of up to 40 rows x 128 records (seed_var.cu) that their hits -- chance
+        // + a handful of true ones -- fill to about 70 %; denser levels take fewer reads per group instead.
+        // The 3-gram filter between the hit test and the list pays when most hits can fail it ((m - 2) - 3 K >= 4
+        // for most barcodes); about one chance hit in seven passes it then (measured: one in ten for 24 nt, K = 4).
         auto size_groups = [&](HostSet::HostSeedVar &V, double chance) {
-            const double per_read = chance + 6.0;
-            V.hit_rows = std::min(40, std::max(32, (int)std::ceil(per_read / 0.7)));
-            int R = 128;
-            while (R > 8 && per_read * R > 0.7 * 128 * V.hit_rows) R -= 8;
-            V.group_reads = R;
-            // the 3-gram filter in front of the verification pays when most hits can fail it: (m - 2) - 3 K > 0
             int strong = 0;
             for (int b = 0; b < hs.n_bc; b++)
                 strong += (hs.off[b + 1] - hs.off[b] - 2) - 3 * (int)V.kdepth[(size_t)b] >= 4;
             V.qgram_filter = hs.max_m <= 32 && 2 * strong >= hs.n_bc && !(B.debug & BDX_DEBUG_NO_QGRAM_FILTER);
+            // mode 1 tests inside the scan (only survivors reach the list), mode 2 over the finished list: with few
+            // admissible diagonals per barcode (constrained start / end) the scan's lanes rarely hold a hit at the
+            // same time and the test would run for two or three lanes of a warp
+            if (V.qgram_filter) {
+                double adm = 0.0, all = 0.0;
+                for (int b = 0; b < hs.n_bc; b++) {
+                    const int m = hs.off[b + 1] - hs.off[b], K = V.kdepth[(size_t)b];
+                    adm += (double)(K + 1) * n_diag(m, hs.allowed0[b], K);
+                    all += (double)(K + 1) * L;
+                }
+                V.qgram_filter = adm >= 0.5 * all ? 1 : 2;
+            }
+            const double pass = V.qgram_filter == 1 ? (0.15 * strong + (hs.n_bc - strong)) / hs.n_bc : 1.0;
+            const double per_read = chance * pass + 6.0;
+            // shared memory per read (staged range, its bit planes, candidates, bookkeeping) kept to ~20 KB per block:
+            // five or six blocks per SM hide the scan's shuffle and shared-memory latencies, three do not
+            // (measured: 0.50 -> issue slots used with three resident blocks)
+            const int per_read_bytes = (L + 8) + (V.qgram_filter ? 12 * ((L + 32) / 32 + 3) : 0) + 64;
+            int R = 128;
+            while (R > 32 && R * per_read_bytes > 20 * 1024) R -= 32;
+            auto rows_for = [&](int r) { return (int)std::ceil(per_read * r / (0.7 * 128)); };
+            while (R > 8 && rows_for(R) > 40) R -= R > 32 ? 32 : 8;          // (whole warps of reads while there are several)
+            V.group_reads = R;
+            V.hit_rows = std::max(8, std::min(40, rows_for(R)));
+            // a constrained start is re-checked by sg_literal, whose DP column (max_m + 2 entries per thread) reuses the list
+            const bool can_bound_start = !(hs.bs.end_from_end && hs.bs.end_off >= 0);
+            if (can_bound_start) V.hit_rows = std::max(V.hit_rows, hs.max_m + 2);
         };
         // level with ONE seed length q: K_b + 1 segments of m_b / (K_b + 1) >= q bases, K_b = min(m_b / q - 1, allowed_b)
         auto build = [&](int q, double chance) {

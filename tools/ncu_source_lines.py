@@ -28,9 +28,13 @@ def main():
             hdr = r
         elif hdr and r[0] != "" and r[0].isdigit():
             i_s, i_i = hdr.index("# Samples"), hdr.index("Instructions Executed")
+            try:                                   # header text with embedded quotes (inline asm) splits oddly
+                smp, ins = int(r[i_s] or 0), int(r[i_i] or 0)
+            except (ValueError, IndexError):
+                continue
             a = agg[func][(fpath.split("/")[-1], int(r[0]))]
-            a[0] += int(r[i_s] or 0)
-            a[1] += int(r[i_i] or 0)
+            a[0] += smp
+            a[1] += ins
             a[2] = r[1].strip()
     for func, lines in agg.items():
         if want not in func:

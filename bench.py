@@ -45,6 +45,9 @@ NCU_FILTER_DRAM_BYTES_PER_READ = (164.026880e6 + 16.110336e6) / 516667
 # the same for k_seed_var's complete level, the kernel that now takes those reads in config 2
 # (profiles/r02_kernels_ncu_summary.txt: 4 M-read step, 516 667 reads: 162.06 MB read + 14.85 MB written)
 NCU_SEEDVAR_DRAM_BYTES_PER_READ = (162.063104e6 + 14.851328e6) / 516667
+# k_seed, average of its two launches, per read of the first level's input (same capture: 4 M-read step, 2 155 000
+# reads left by the prefilter; level 1 496.77 + 38.71 MB, level 2 211.38 + 9.30 MB)
+NCU_SEED_DRAM_BYTES_PER_READ = (496.767744e6 + 38.713088e6 + 211.380224e6 + 9.296640e6) / 2 / 2155000
 
 
 def make_config():
@@ -408,7 +411,8 @@ def run_ours(args):
     stages = stream.profile_read_stages()
     filt_ms, filt_n = stages["k_filter"]
     stream.profile(False)
-    pre_reads, seed_reads, auto_reads, hit_cols, sv_in_reads = stream.work_counters(reset=True)
+    (pre_reads, seed_reads, auto_reads, hit_cols, sv_in_reads, seed_qmers, seed_ver_cols, sv_positions,
+     sv_filter_diags) = stream.work_counters(reset=True)
     auto_per_launch = auto_reads / max(filt_n, 1)       # reads that actually ran the DP automaton
     clocks = None
     if args.no_e2e and rank == 0:
@@ -664,13 +668,16 @@ def run_ours(args):
             hbm_src = "MEASURED_PEAKS.json"
         except Exception:
             hbm_peak, hbm_src = 6650.0, "fallback (B200_PROFILING.md)"
-        # ---- roofline of the DOMINANT kernel of the step (the stage with the most CUDA-event time).  Both candidates
-        # are bound by integer-ALU issue; their algorithmic unit is one bit-parallel column step of 17 int-ops
-        # (SURVEY.md section 8d):
-        #   k_filter              17 x barcodes x columns for every read that ran the full-range automaton
-        #   k_seed_var (complete) 17 x the window columns it stepped its verified hits over (device counter) -- the
-        #                         work it really did; the reads it decides would have cost 244 800 int-ops each in
-        #                         k_filter, which is reported next to it as the survey-convention figure
+        # ---- roofline of the DOMINANT kernel of the step (the stage with the most CUDA-event time).  All candidates
+        # are bound by integer-ALU issue, not by HBM (1.5 GB of reads per step is 0.2 ms of HBM time).  Their
+        # algorithmic units, counted on the device (bdx_stream_work_counters) and priced in int-ops:
+        #   k_filter              17 x barcodes x columns for every read that ran the full-range automaton (SURVEY 8d)
+        #   k_seed (levels 1-2)    8 x q-mers probed (rolling-hash step + bitmap test) + 17 x window columns verified
+        #   k_seed_var (complete) 24 x (read, position) pairs scanned (a 5-mer code, two table look-ups)
+        #                         + 10 x diagonals the 3-gram filter tested + 17 x window columns verified
+        # The seed kernels do far LESS arithmetic than the automaton they replace -- that is their point -- so their
+        # fraction of the ALU peak is small by construction; the reads they decide would have cost 244 800 int-ops
+        # each in k_filter, which is reported next to it as the survey-convention figure.
         stage_names = {"k_seed_deep": "k_seed_var (complete level)", "k_seed": "k_seed (levels 1-2)"}
         dom = max((k for k in stages if stages[k][1]), key=lambda k: stages[k][0])
         dom_ms, dom_n = stages[dom]
@@ -681,10 +688,17 @@ def run_ours(args):
             traffic = NCU_FILTER_DRAM_BYTES_PER_READ * dom_reads
             how = "17 int-ops x 96 barcodes x 150 columns x reads that ran the automaton (device counter)"
         elif dom == "k_seed_deep":
-            units = 17.0 * hit_cols / max(dom_n, 1)
+            units = (24.0 * sv_positions + 10.0 * sv_filter_diags + 17.0 * hit_cols) / max(dom_n, 1)
             dom_reads = sv_in_reads / max(dom_n, 1)           # what k_prefilter and k_seed's levels left: it decides nearly all
             traffic = NCU_SEEDVAR_DRAM_BYTES_PER_READ * dom_reads
-            how = "17 int-ops x window columns stepped over verified seed hits (device counter bdx_stream_work_counters[3])"
+            how = ("24 int-ops x (read, position) pairs scanned + 10 x 3-gram-filter diagonals + 17 x window columns verified "
+                   "(device counters bdx_stream_work_counters[7], [8], [3])")
+        elif dom == "k_seed":
+            units = (8.0 * seed_qmers + 17.0 * seed_ver_cols) / max(dom_n, 1)
+            dom_reads = (n - pre_reads / max(stages["k_prefilter"][1], 1)) if stages.get("k_prefilter", (0, 0))[1] else n
+            traffic = NCU_SEED_DRAM_BYTES_PER_READ * dom_reads
+            how = ("8 int-ops x q-mers probed + 17 x window columns verified, average of its launches (two levels per step; "
+                   "device counters bdx_stream_work_counters[5], [6]); reads_per_launch = the first level's input")
         else:
             units, dom_reads, traffic, how = None, None, None, "no algorithmic unit defined for this stage"
         achieved_ops = units / dom_s if units and dom_s > 0 else 0.0
@@ -700,8 +714,11 @@ def run_ours(args):
         roof["traffic_unit"] = ("DRAM bytes per launch: ncu dram__bytes_read.sum + dram__bytes_write.sum per read of this kernel "
                                 "(profiles/r02_kernels_ncu_summary.txt) x its reads per launch here")
         roof["reads_per_launch"] = dom_reads
-        if dom == "k_seed_deep":
-            roof["verified_hit_columns_per_launch"] = hit_cols / max(dom_n, 1)
+        roof["work_units_per_step"] = {k: v / args.steps for k, v in {
+            "k_seed_qmers_probed": seed_qmers, "k_seed_columns_verified": seed_ver_cols,
+            "k_seed_var_positions_scanned": sv_positions, "k_seed_var_filter_diagonals": sv_filter_diags,
+            "k_seed_var_columns_verified": hit_cols, "k_seed_var_input_reads": sv_in_reads}.items()}
+        if dom in ("k_seed_deep", "k_seed"):
             roof["survey_convention"] = {"achieved": OPS_PER_READ * dom_reads / dom_s / 1e12 if dom_s > 0 else None,
                                          "what": "244 800 int-ops (the full 96 x 150 matrix, SURVEY 8d) per read this kernel decides / its "
                                                  "time: what the lane-per-barcode automaton would have had to do for the same reads"}

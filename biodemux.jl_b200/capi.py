@@ -447,10 +447,12 @@ class Stream:
         return a.value, b.value, c.value
 
     def work_counters(self, reset: bool = False):
-        """(prefilter reads, seed reads, automaton reads, verified hit-columns of k_seed_var, its input reads)."""
-        out = (C.c_int64 * 6)()
+        """(prefilter reads, seed reads, automaton reads, verified hit-columns of k_seed_var, its input reads,
+        q-mers probed by k_seed, hit-columns verified by k_seed, positions scanned by k_seed_var, diagonals its
+        3-gram filter tested) -- include/bdx.h."""
+        out = (C.c_int64 * 12)()
         _check(self.lib.bdx_stream_work_counters(self.handle, out, int(reset)))
-        return tuple(int(x) for x in out)[:5]
+        return tuple(int(x) for x in out)[:9]
 
     def demux_block(self, fastq1, fastq2=None, final_block: int = 1, mode: int = DEMUX_SINGLE):
         """bdx_demux_block over host uint8 arrays (or ``(device_ptr, length)`` pairs with

@@ -433,8 +433,8 @@ static int stream_create_impl(bdx_stream *s)
         int rc = ensure_scratch(s, s->max_reads);
         if (rc) return rc;
     }
-    CU(cudaMalloc(&s->d_counters, 8 * sizeof(unsigned long long)));
-    CU(cudaMemset(s->d_counters, 0, 8 * sizeof(unsigned long long)));
+    CU(cudaMalloc(&s->d_counters, 12 * sizeof(unsigned long long)));
+    CU(cudaMemset(s->d_counters, 0, 12 * sizeof(unsigned long long)));
     if (s->cfg->base.want_stats) {
         CU(cudaMalloc(&s->d_stats, (size_t)s->cfg->lay.total_len * 8));
         CU(cudaMemset(s->d_stats, 0, (size_t)s->cfg->lay.total_len * 8));
@@ -966,7 +966,7 @@ extern "C" int bdx_stream_path_counters(bdx_stream *s, int64_t *prefilter_reads,
     if (!s) return fail(BDX_ERR_INVALID, "null stream");
     CU(cudaSetDevice(s->device));
     CU(cudaStreamSynchronize(s->st_comp));
-    unsigned long long h[8];
+    unsigned long long h[12];
     CU(cudaMemcpy(h, s->d_counters, sizeof(h), cudaMemcpyDeviceToHost));
     if (prefilter_reads) *prefilter_reads = (int64_t)h[0];
     if (seed_reads) *seed_reads = (int64_t)h[2];
@@ -975,19 +975,20 @@ extern "C" int bdx_stream_path_counters(bdx_stream *s, int64_t *prefilter_reads,
     return BDX_OK;
 }
 
-extern "C" int bdx_stream_work_counters(bdx_stream *s, int64_t out[6], int reset)
+extern "C" int bdx_stream_work_counters(bdx_stream *s, int64_t out[12], int reset)
 {
     if (!s || !out) return fail(BDX_ERR_INVALID, "null argument");
     CU(cudaSetDevice(s->device));
     CU(cudaStreamSynchronize(s->st_comp));
-    unsigned long long h[8];
+    unsigned long long h[12];
     CU(cudaMemcpy(h, s->d_counters, sizeof(h), cudaMemcpyDeviceToHost));
     out[0] = (int64_t)h[0];
     out[1] = (int64_t)h[2];
     out[2] = (int64_t)h[1];
     out[3] = (int64_t)h[3];
     out[4] = (int64_t)h[4];
-    out[5] = 0;
+    for (int k = 5; k < 9; k++) out[k] = (int64_t)h[k];
+    out[9] = out[10] = out[11] = 0;
     if (reset) CU(cudaMemset(s->d_counters, 0, sizeof(h)));
     return BDX_OK;
 }

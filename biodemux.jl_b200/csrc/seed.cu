@@ -98,6 +98,7 @@ k_seed(const __grid_constant__ DevParams P, const int pass, const int level, con
     const int n_groups = (n_items + kSeedThreads - 1) / kSeedThreads;
     unsigned int n_done = 0;
 
+    unsigned long long scan_cols = 0, ver_cols = 0;      // work counters for the roofline: q-mers probed, window columns verified
     for (int grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
         const int item = grp * kSeedThreads + threadIdx.x;
         const bool have = item < n_items;
@@ -141,6 +142,7 @@ k_seed(const __grid_constant__ DevParams P, const int pass, const int level, con
             const int p0 = 0;                          // 0-based (relative) column of the first q-mer
             const int p1 = L - q;                      // last one that lies inside the search range
             if (p1 >= p0) {
+                scan_cols += (unsigned)(p1 - p0 + 1);
                 uint32_t h = 0;
                 for (int i = 0; i < q; i++) h = h * kPfBase + (uint32_t)my_slot[p0 + i];
                 auto probe = [&](int p) {
@@ -216,6 +218,7 @@ k_seed(const __grid_constant__ DevParams P, const int pass, const int level, con
             if (lane >= o) incl += t;
         }
         const int total_hits = __shfl_sync(0xFFFFFFFFu, incl, 31);
+        if (lane == 0) ver_cols += (unsigned)(total_hits * (m + 2 * K));    // the least window a hit has to be stepped over
         __syncwarp();
         {
             const int win = m + 4 * K + 1;                   // columns [dmin + 1 - K, dmin + span + m + 2K], span <= K
@@ -319,6 +322,14 @@ k_seed(const __grid_constant__ DevParams P, const int pass, const int level, con
         n_done += __popc(__ballot_sync(0xFFFFFFFFu, resolved));
     }
     if (lane == 0 && n_done && counters) atomicAdd(counters + 2, (unsigned long long)n_done);
+    if (counters) {
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) scan_cols += __shfl_down_sync(0xFFFFFFFFu, scan_cols, o);
+        if (lane == 0) {
+            if (scan_cols) atomicAdd(counters + 5, scan_cols);
+            if (ver_cols) atomicAdd(counters + 6, ver_cols);
+        }
+    }
 }
 
 static size_t seed_tab_words(const SeedLevel &L) { return ((size_t)1 << L.log2) + 1 + 2 * (size_t)L.n_entries; }

@@ -254,7 +254,7 @@ __device__ __forceinline__ bool sv_qgram_pass(const uint32_t *planes_s, int pl_w
 // segment's front (its write cursor never passes its read cursor); cnt[w] = survivors of warp w's segment.
 // sv_verify then walks the four segment fronts as one list.  Returns the segment length.
 __device__ __forceinline__ int sv_qgram_compact(uint32_t *hits_s, int total, const uint32_t *planes_s, int pl_words,
-                                                const uint2 *bplanes_s, const uint32_t *binfo_s, int *cnt)
+                                                const uint2 *bplanes_s, const uint32_t *binfo_s, int *cnt, unsigned &n_diag)
 {
     static_assert(kSvThreads == 128, "four segments");
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -269,6 +269,7 @@ __device__ __forceinline__ int sv_qgram_compact(uint32_t *hits_s, int total, con
             rec = hits_s[i];
             const int b = (int)((rec >> 8) & 0x3FFFu);
             const uint32_t bi = binfo_s[b];
+            n_diag += 2u * ((bi >> 8) & 0xFFu) + 1u;
             keep = sv_qgram_pass(planes_s, pl_words, bplanes_s, (int)(rec >> 22), b, (int)(bi & 0xFFu), (int)((bi >> 8) & 0xFFu),
                                  (int)(rec & 0xFFu) - kSvDiagBias);
         }
@@ -282,7 +283,7 @@ __device__ __forceinline__ int sv_qgram_compact(uint32_t *hits_s, int total, con
 }
 
 template <int W>
-__global__ void __launch_bounds__(kSvThreads)
+__global__ void __launch_bounds__(kSvThreads, 7)
 k_seed_var(const __grid_constant__ DevParams P, const int pass, const int level, const uint8_t *__restrict__ seq,
            const int *__restrict__ off, const int n_reads, PassOut *__restrict__ out,
            const PassOut *__restrict__ prev_pass, const int *__restrict__ wl_in, const int *__restrict__ n_in,
@@ -356,6 +357,8 @@ k_seed_var(const __grid_constant__ DevParams P, const int pass, const int level,
     const bool dp_fits = V.hit_rows >= S.max_m + 2;          // sg_literal's column fits the (dead) hit list
     unsigned int n_done = 0;
     unsigned long long n_cols = 0;      // verified hit-columns (one Myers / Hyyro column step each), for the roofline
+    unsigned long long n_scan = 0;      // (read, position) pairs scanned (thread 0 counts for the block)
+    unsigned n_diag = 0;                // diagonals the 3-gram filter tested
 
     for (int grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
         const int item = grp * R + threadIdx.x;
@@ -433,6 +436,7 @@ k_seed_var(const __grid_constant__ DevParams P, const int pass, const int level,
             const int n_pos = max(ctr_s[5] - q0 + 1, 0);                 // positions of the group's longest search range
             const uint32_t pos_recip = 0xFFFFFFFFu / (uint32_t)max(n_pos, 1) + 1u;   // i / n_pos == umulhi(i, recip) for i < 2^16
             const int n_pairs = R * n_pos;
+            if (threadIdx.x == 0) n_scan += (unsigned)n_pairs;
             for (int base = warp * 64; base < n_pairs; base += (kSvThreads / 32) * 64) {
                 uint32_t ea = 0, eb = 0, c4 = 0;   // first entries of (pair 0: table 0 | table 1 << 16), (pair 1: ...); the four bucket sizes, a byte each
                 int lane_total = 0;
@@ -514,7 +518,10 @@ k_seed_var(const __grid_constant__ DevParams P, const int pass, const int level,
                         const int dlo = max(0, min_end_rel - m) - K;
                         const int dhi = min(max_start_rel + a0, oL - m + K);
                         hit = delta >= dlo && delta <= dhi;
-                        if (hit && in_scan_filter) hit = sv_qgram_pass(planes_s, pl_words, bplanes_s, hr, b, m, K, delta);
+                        if (hit && in_scan_filter) {
+                            n_diag += 2u * (unsigned)K + 1u;
+                            hit = sv_qgram_pass(planes_s, pl_words, bplanes_s, hr, b, m, K, delta);
+                        }
                         rec = ((uint32_t)hr << 22) | ((uint32_t)b << 8) | (uint32_t)(delta + kSvDiagBias);
                     }
                     const uint32_t hm = __ballot_sync(0xFFFFFFFFu, hit);
@@ -537,7 +544,7 @@ k_seed_var(const __grid_constant__ DevParams P, const int pass, const int level,
         {
             int total = min(ctr_s[0], hit_cap), seg = 0;
             if (pl_words && !in_scan_filter) {
-                seg = sv_qgram_compact(hits_s, total, planes_s, pl_words, bplanes_s, binfo_s, ctr_s + 1);
+                seg = sv_qgram_compact(hits_s, total, planes_s, pl_words, bplanes_s, binfo_s, ctr_s + 1, n_diag);
                 __syncthreads();
                 total = ctr_s[1] + ctr_s[2] + ctr_s[3] + ctr_s[4];
             }
@@ -683,6 +690,11 @@ k_seed_var(const __grid_constant__ DevParams P, const int pass, const int level,
 #pragma unroll
         for (int o = 16; o >= 1; o >>= 1) n_cols += __shfl_down_sync(0xFFFFFFFFu, n_cols, o);
         if (lane == 0 && n_cols) atomicAdd(counters + 3, n_cols);
+        unsigned long long nd = n_diag;
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) nd += __shfl_down_sync(0xFFFFFFFFu, nd, o);
+        if (lane == 0 && nd) atomicAdd(counters + 8, nd);
+        if (threadIdx.x == 0 && n_scan) atomicAdd(counters + 7, n_scan);
         if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(counters + 4, (unsigned long long)n_items);
     }
 }

@@ -234,11 +234,17 @@ int bdx_stream_profile_read_stages(bdx_stream *s, double ms[BDX_PROFILE_STAGES],
  * since the last reset (syncs the stream). */
 int bdx_stream_path_counters(bdx_stream *s, int64_t *prefilter_reads, int64_t *seed_reads,
                              int64_t *automaton_reads, int reset);
-/* The same three counters plus the work of the seed-and-verify kernel k_seed_var: [3] window columns it stepped its
- * verified hits over -- one bit-parallel column step each, the unit of its integer-ALU roofline -- and [4] reads
- * it took in (summed over its launches).  out = {prefilter reads, seed reads, automaton reads, verified
- * hit-columns, k_seed_var input reads, 0}. */
-int bdx_stream_work_counters(bdx_stream *s, int64_t out[6], int reset);
+/* The same three counters plus the work units of the seed kernels (the unit counts of their integer-ALU rooflines,
+ * summed over their launches since the last reset):
+ *   out[0..2]  prefilter reads, seed reads, automaton reads
+ *   out[3]     k_seed_var: window columns it stepped its verified hits over (one bit-parallel column step each)
+ *   out[4]     k_seed_var: reads it took in
+ *   out[5]     k_seed: q-mers probed (one rolling-hash step and one bitmap test each)
+ *   out[6]     k_seed: window columns it verified its hits over
+ *   out[7]     k_seed_var: (read, position) pairs scanned (a q-mer code and one or two table look-ups each)
+ *   out[8]     k_seed_var: diagonals its 3-gram filter tested
+ *   out[9..11] 0 */
+int bdx_stream_work_counters(bdx_stream *s, int64_t out[12], int reset);
 /* number of kernel launches this stream has issued so far */
 int64_t bdx_stream_launch_count(const bdx_stream *s);
 

@@ -175,3 +175,46 @@ def test_seed_var_on_uniform_default_geometry(seed):
     for f in ("status", "bc1", "bc2", "keep_start", "keep_end"):
         bad = np.nonzero(got[f] != want[f])[0]
         assert bad.size == 0, (f, int(bad[0]), got[bad[0]], want[bad[0]], reads[bad[0]])
+
+
+def _classify_debug(cfg, blob, off, debug):
+    with capi.Engine(cfg, max_reads=len(off) - 1, max_bytes=int(off[-1]) + 16, debug=debug) as eng:
+        return eng.classify_packed(blob, off)
+
+
+@pytest.mark.parametrize("shape", ["dense_in_scan", "constrained_list", "short_reads_edges"])
+def test_qgram_filter_is_transparent(shape):
+    """The 3-gram filter (seed_var.cu, sv_qgram_pass) only drops hits that cannot verify: results with it, without it
+    (BDX_DEBUG_NO_QGRAM_FILTER) and the oracle's are the same -- in its in-scan mode (dense geometry), its list mode
+    (constrained start) and with reads barely longer than the barcode, where every window crosses a range edge."""
+    rng = np.random.default_rng({"dense_in_scan": 1, "constrained_list": 2, "short_reads_edges": 3}[shape])
+    debug = 0
+    if shape == "dense_in_scan":
+        bcs = synth.random_barcodes(rng, 96, 24, 24)
+        cfg = _cfg(bcs, min_delta=0.1)
+        reads = synth.random_reads(rng, 8000, bcs, min_len=120, max_len=160, max_edits=6, n_prob=0.02, lower_prob=0.02)
+        debug = capi.DEBUG_PREFER_SEED_VAR
+    elif shape == "constrained_list":
+        bcs = synth.random_barcodes(rng, 384, 16, 28)
+        cfg = _cfg(bcs, ref_search_range=R("1:40"), barcode_start_range=R("1:6"), min_delta=0.1)
+        reads = _reads(rng, 8000, bcs, start_hi=5)
+    else:
+        bcs = synth.random_barcodes(rng, 200, 20, 28)
+        cfg = _cfg(bcs, max_error_rate=0.25)
+        reads = []
+        for _ in range(8000):
+            bc = bcs[int(rng.integers(0, len(bcs)))].encode()
+            core = synth.mutate(rng, bc, int(rng.integers(0, 8)))
+            pre = bytes(rng.choice(list(b"ACGT"), size=int(rng.integers(0, 4))).astype(np.uint8))
+            post = bytes(rng.choice(list(b"ACGT"), size=int(rng.integers(0, 4))).astype(np.uint8))
+            cut = int(rng.integers(0, 3))
+            reads.append((pre + core + post)[cut:])
+        debug = capi.DEBUG_PREFER_SEED_VAR
+    blob, off = bdx.pack_reads(reads)
+    want = orc.Oracle(cfg).classify_mt(blob, off)
+    with_filter = _classify_debug(cfg, blob, off, debug)
+    without = _classify_debug(cfg, blob, off, debug | capi.DEBUG_NO_QGRAM_FILTER)
+    for f in ("status", "bc1", "bc2", "keep_start", "keep_end"):
+        for got, label in ((with_filter, "filter on"), (without, "filter off")):
+            bad = np.nonzero(got[f] != want[f])[0]
+            assert bad.size == 0, (label, f, int(bad[0]), got[bad[0]], want[bad[0]], reads[bad[0]])

@@ -93,13 +93,13 @@ __device__ __forceinline__ void sv_stage_warp(const uint8_t *__restrict__ seq, l
 // The block's hit list holds hit_rows rows of kSvThreads records; the decide phase reuses it as sg_literal's DP
 // columns [row][thread], max_m + 2 rows (sets whose geometry can bound the start get at least that many: tables.cu).
 
-enum { kSvPeq = 0, kSvHits, kSvCandL, kSvRinfo, kSvCandN, kSvCtr, kSvEntries, kSvBstart, kSvBinfo, kSvClass, kSvPlanes, kSvBplanes, kSvSlot, kSvParts };
+enum { kSvPeq = 0, kSvHits, kSvCandL, kSvRinfo, kSvCandN, kSvCtr, kSvBinfo, kSvClass, kSvPlanes, kSvBplanes, kSvSlot, kSvParts };
 
 // words of one bit plane of a read's search range (3-gram filter): the columns -32 .. slot_cols + 63, odd so that the
 // planes of consecutive reads start in different banks; 0 = no filter
 __host__ __device__ inline int sv_plane_words(int slot_cols, int qgram_filter) { return qgram_filter ? ((slot_cols + 32) / 32 + 3) | 1 : 0; }
 
-__host__ __device__ inline size_t sv_smem_layout(int W, int plane, int n_pad, int n_entries, int n_bstart, int tab_smem,
+__host__ __device__ inline size_t sv_smem_layout(int W, int plane, int n_pad,
                                                  int slot_stride, int R, int hit_rows, int pl_words, size_t off[kSvParts])
 {
     size_t o = 0;
@@ -109,8 +109,6 @@ __host__ __device__ inline size_t sv_smem_layout(int W, int plane, int n_pad, in
     off[kSvRinfo] = o; o += (size_t)kSvThreads * kSvRi * 4;               // per read: L, min_end_rel, max_start_rel, flags, n_rel
     off[kSvCandN] = o; o += ((size_t)kSvThreads + 4) * 4;                 // per read: number of candidates; later their offsets
     off[kSvCtr] = o; o += 32;
-    off[kSvEntries] = o; o += tab_smem ? (size_t)n_entries * 4 : 0;
-    off[kSvBstart] = o; o += tab_smem ? ((size_t)n_bstart * 2 + 3) / 4 * 4 : 0;
     off[kSvBinfo] = o; o += (size_t)n_pad * 4;                            // per barcode: m | K << 8 | allowed0 << 16
     off[kSvClass] = o; o += 256;
     off[kSvPlanes] = o; o += (size_t)R * 3 * pl_words * 4;                // per read: bit planes (absent, code bit 0, code bit 1) of the staged range
@@ -288,7 +286,7 @@ k_seed_var(const __grid_constant__ DevParams P, const int pass, const int level,
            const int *__restrict__ off, const int n_reads, PassOut *__restrict__ out,
            const PassOut *__restrict__ prev_pass, const int *__restrict__ wl_in, const int *__restrict__ n_in,
            int *__restrict__ wl_out, int *__restrict__ n_out, unsigned long long *__restrict__ counters,
-           const int slot_stride, const int slot_cols, const int tab_smem)
+           const int slot_stride, const int slot_cols)
 {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const DevSet &S = P.set[pass];
@@ -299,15 +297,17 @@ k_seed_var(const __grid_constant__ DevParams P, const int pass, const int level,
     const int plane = n_classes * n_pad;
     size_t lo[kSvParts];
     const int pl_words = sv_plane_words(slot_cols, W == 1 && V.qgram_filter);
-    sv_smem_layout(W, plane, n_pad, V.n_entries, V.n_bstart, tab_smem, slot_stride, R, V.hit_rows, pl_words, lo);
+    sv_smem_layout(W, plane, n_pad, slot_stride, R, V.hit_rows, pl_words, lo);
     uint32_t *peq_s = reinterpret_cast<uint32_t *>(smem_raw + lo[kSvPeq]);
     uint32_t *hits_s = reinterpret_cast<uint32_t *>(smem_raw + lo[kSvHits]);
     uint32_t *cand_s = reinterpret_cast<uint32_t *>(smem_raw + lo[kSvCandL]);
     int *rinfo_s = reinterpret_cast<int *>(smem_raw + lo[kSvRinfo]);
     int *cand_n_s = reinterpret_cast<int *>(smem_raw + lo[kSvCandN]);
     int *ctr_s = reinterpret_cast<int *>(smem_raw + lo[kSvCtr]);
-    const uint32_t *entries_s = tab_smem ? reinterpret_cast<const uint32_t *>(smem_raw + lo[kSvEntries]) : V.entries;
-    const uint16_t *bstart_s = tab_smem ? reinterpret_cast<const uint16_t *>(smem_raw + lo[kSvBstart]) : V.bstart;
+    // The seed tables (bucket starts + entries, a few KB) stay in global memory, i.e. in L1: copies in shared memory
+    // cost one or two resident blocks per SM and measured slower (config 3: 155 -> 173 M reads/s without them)
+    const uint32_t *entries_s = V.entries;
+    const uint16_t *bstart_s = V.bstart;
     uint32_t *binfo_s = reinterpret_cast<uint32_t *>(smem_raw + lo[kSvBinfo]);
     uint8_t *class_s = smem_raw + lo[kSvClass];
     uint8_t *slot_s = smem_raw + lo[kSvSlot];
@@ -319,12 +319,6 @@ k_seed_var(const __grid_constant__ DevParams P, const int pass, const int level,
     for (int k = threadIdx.x; k < W * plane; k += blockDim.x) {
         const int w = k / plane, rem = k - w * plane, c = rem / n_pad, b = rem - c * n_pad;
         peq_s[w * plane + b * n_classes + c] = S.peq[k];
-    }
-    if (tab_smem) {
-        uint32_t *en = reinterpret_cast<uint32_t *>(smem_raw + lo[kSvEntries]);
-        uint16_t *bs = reinterpret_cast<uint16_t *>(smem_raw + lo[kSvBstart]);
-        for (int k = threadIdx.x; k < V.n_entries; k += blockDim.x) en[k] = V.entries[k];
-        for (int k = threadIdx.x; k < V.n_bstart; k += blockDim.x) bs[k] = V.bstart[k];
     }
     for (int k = threadIdx.x; k < n_pad; k += blockDim.x) {
         uint32_t v = 0;
@@ -719,7 +713,7 @@ static bool sv_default_geometry(const DevSet &S)
 }
 
 struct SvLaunch {
-    int slot_cols, slot_stride, tab_smem;
+    int slot_cols, slot_stride;
     size_t smem;
 };
 
@@ -732,14 +726,8 @@ static SvLaunch sv_launch_params(const DevSet &S, const SeedVar &V)
     L.slot_stride = words * 4;
     size_t off[kSvParts];
     const int plane = S.n_classes * S.n_bc_pad;
-    L.tab_smem = 1;
-    L.smem = sv_smem_layout(S.words, plane, S.n_bc_pad, V.n_entries, V.n_bstart, 1, L.slot_stride, V.group_reads, V.hit_rows,
+    L.smem = sv_smem_layout(S.words, plane, S.n_bc_pad, L.slot_stride, V.group_reads, V.hit_rows,
                             sv_plane_words(L.slot_cols, S.words == 1 && V.qgram_filter), off);
-    if (L.smem > 100 * 1024) {
-        L.tab_smem = 0;
-        L.smem = sv_smem_layout(S.words, plane, S.n_bc_pad, V.n_entries, V.n_bstart, 0, L.slot_stride, V.group_reads, V.hit_rows,
-                            sv_plane_words(L.slot_cols, S.words == 1 && V.qgram_filter), off);
-    }
     return L;
 }
 
@@ -784,7 +772,7 @@ cudaError_t launch_seed_var(const DevParams &P, int pass, int level, const uint8
     e = cudaMemsetAsync(n_out, 0, sizeof(int), st);
     if (e != cudaSuccess) return e;
     kern<<<blocks, kSvThreads, L.smem, st>>>(P, pass, level, seq, off, n, sc.pass[pass], sc.pass[0], wl_in, n_in, wl_out, n_out,
-                                             counters, L.slot_stride, L.slot_cols, L.tab_smem);
+                                             counters, L.slot_stride, L.slot_cols);
     return cudaGetLastError();
 }
 

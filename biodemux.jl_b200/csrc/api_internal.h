@@ -44,7 +44,7 @@ struct HostSet {
     std::vector<uint16_t> hp_bstart, hp_entries;
     std::vector<uint2> hp_bcw;
     struct HostSeedLevel {
-        int k = 0, q = 0, log2 = 0, bm_log2 = 0;
+        int k = 0, q = 0, log2 = 0, bm_log2 = 0, max_hits = 0;
         uint32_t pow = 0;
         std::vector<uint32_t> bstart, entries, ekeys, bitmap;
     };

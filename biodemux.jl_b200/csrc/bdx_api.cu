@@ -235,6 +235,7 @@ static int get_tables(bdx_config *cfg, int device, DeviceTables **out)
             L.pow = H.pow;
             L.log2 = H.log2;
             L.bm_log2 = H.bm_log2;
+            L.max_hits = H.max_hits;
             L.n_entries = (int)H.entries.size();
             if (e == cudaSuccess) e = upload(t, H.bstart, &L.bstart);
             if (e == cudaSuccess) e = upload(t, H.entries, &L.entries);
@@ -251,6 +252,7 @@ static int get_tables(bdx_config *cfg, int device, DeviceTables **out)
             L.pow = H.pow;
             L.log2 = H.log2;
             L.bm_log2 = H.bm_log2;
+            L.max_hits = H.max_hits;
             L.n_entries = (int)H.entries.size();
             if (e == cudaSuccess) e = upload(t, H.bstart, &L.bstart);
             if (e == cudaSuccess) e = upload(t, H.entries, &L.entries);

@@ -35,6 +35,7 @@ struct SeedLevel {
     int log2;                     // buckets = 1 << log2
     int bm_log2;                  // first-level bitmap bits = 1 << bm_log2
     int n_entries;
+    int max_hits;                 // k_seed: rows of the per-read hit list (reads with more hits go to the next stage)
     const uint32_t *bstart;       // [buckets + 1]
     const uint32_t *entries;      // [n_entries] (barcode index << 8) | seed offset
     const uint32_t *ekeys;        // [n_entries] hash of the entry's q-mer

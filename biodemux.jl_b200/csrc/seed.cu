@@ -70,8 +70,9 @@ k_seed(const __grid_constant__ DevParams P, const int pass, const int level, con
     const uint32_t *bstart_s = TAB_SMEM ? tab_s : SL.bstart;    // [n_buckets + 1]
     const uint32_t *entries_s = TAB_SMEM ? tab_s + n_buckets + 1 : SL.entries;             // [n_entries]
     const uint32_t *ekeys_s = TAB_SMEM ? tab_s + n_buckets + 1 + SL.n_entries : SL.ekeys;  // [n_entries] full hashes
-    uint32_t *hits_s = TAB_SMEM ? tab_s + n_buckets + 1 + 2 * SL.n_entries : tab_s;        // [kSeedMaxHits][kSeedThreads]
-    uint8_t *wins_s = reinterpret_cast<uint8_t *>(hits_s + kSeedMaxHits * kSeedThreads);   // [kSeedMaxWins][threads]
+    const int max_hits = SL.max_hits;                           // rows of the per-read hit list (sized by the host per level)
+    uint32_t *hits_s = TAB_SMEM ? tab_s + n_buckets + 1 + 2 * SL.n_entries : tab_s;        // [max_hits][kSeedThreads]
+    uint8_t *wins_s = reinterpret_cast<uint8_t *>(hits_s + max_hits * kSeedThreads);   // [kSeedMaxWins][threads]
     uint8_t *class_s = wins_s + kSeedMaxWins * kSeedThreads;
     uint8_t *slot_s = class_s + 256;                            // [kSeedThreads][kSeedSlot] class codes
 
@@ -190,7 +191,7 @@ k_seed(const __grid_constant__ DevParams P, const int pass, const int level, con
                     // own window and the barcode's distance is the minimum over its records, so a missed merge
                     // only costs a verification.  (Searching ALL earlier records for a partner ran at 5 of 32
                     // lanes and cost 12 % of the kernel's instructions, profiles/r02_kernels_ncu_summary.txt.)
-                    if (n_hits > 0 && n_hits <= kSeedMaxHits) {
+                    if (n_hits > 0 && n_hits <= max_hits) {
                         const uint32_t old = hits_s[(n_hits - 1) * kSeedThreads + threadIdx.x];
                         if ((old >> 13) == b) {
                             const int dmin = (int)(old & 0x3FFu) - 256, span = (int)((old >> 10) & 0x7u);
@@ -201,15 +202,15 @@ k_seed(const __grid_constant__ DevParams P, const int pass, const int level, con
                             }
                         }
                     }
-                    if (n_hits < kSeedMaxHits) hits_s[n_hits * kSeedThreads + threadIdx.x] = hit_pack(b, 0, delta);
+                    if (n_hits < max_hits) hits_s[n_hits * kSeedThreads + threadIdx.x] = hit_pack(b, 0, delta);
                     n_hits++;
                 }
             }
-            if (n_hits > kSeedMaxHits) punt = true;
+            if (n_hits > max_hits) punt = true;
         }
 
         // ---- verify: the warp pools the hits of its 32 reads and spreads them evenly over the lanes
-        // (a lane's own read has 0..kSeedMaxHits hits; verifying per lane would leave most lanes idle) ----
+        // (a lane's own read has 0..max_hits hits; verifying per lane would leave most lanes idle) ----
         const int my_hits = punt ? 0 : n_hits;
         int incl = my_hits;                                      // inclusive prefix sum over the lanes
 #pragma unroll
@@ -337,7 +338,7 @@ static size_t seed_tab_words(const SeedLevel &L) { return ((size_t)1 << L.log2) 
 static size_t seed_smem(const DevSet &S, const SeedLevel &L, bool tab_smem)
 {
     size_t words = (size_t)S.words * S.n_classes * S.n_bc_pad + ((size_t)1 << (L.bm_log2 - 5)) + (tab_smem ? seed_tab_words(L) : 0) +
-                   (size_t)kSeedMaxHits * kSeedThreads;
+                   (size_t)L.max_hits * kSeedThreads;
     return words * 4 + (size_t)kSeedMaxWins * kSeedThreads + 256 + (size_t)kSeedThreads * kSeedSlot + 16;
 }
 

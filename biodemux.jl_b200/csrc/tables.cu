@@ -198,6 +198,10 @@ void build_seed_levels(const Build &B)
             const int seg = m / (K_l + 1), q = std::min(12, seg);
             L.k = K_l;
             L.q = q;
+            // rows of k_seed's per-read hit list: three times the chance hits expected on 150 columns + two records
+            // per true segment + slack.  (A fixed 28 rows cost 14 KB of shared memory per block -- one resident
+            // block per SM less for 96 barcodes, whose lists never hold more than a handful.)
+            L.max_hits = std::max(12, std::min(28, (int)std::ceil(3.0 * 150.0 * rate_of(K_l)) + 2 * (K_l + 1) + 4));
             uint32_t pw = 1;
             for (int i = 1; i < q; i++) pw *= kPfBase;
             L.pow = pw;

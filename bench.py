@@ -43,11 +43,11 @@ CHUNK = 4000                                               # reference chunk_siz
 # algorithmic 174 B: worklist-scattered 150-byte reads touch 6 32-byte sectors, offsets / PassOut one each.
 NCU_FILTER_DRAM_BYTES_PER_READ = (164.026880e6 + 16.110336e6) / 516667
 # the same for k_seed_var's complete level, the kernel that now takes those reads in config 2
-# (profiles/r02_kernels_ncu_summary.txt: 4 M-read step, 516 667 reads: 162.06 MB read + 14.85 MB written)
-NCU_SEEDVAR_DRAM_BYTES_PER_READ = (162.063104e6 + 14.851328e6) / 516667
+# (profiles/r02_kernels_ncu_summary.txt: 4 M-read step, 517 723 reads: 162.38 MB read + 17.05 MB written)
+NCU_SEEDVAR_DRAM_BYTES_PER_READ = (162.380800e6 + 17.052672e6) / 517723
 # k_seed, average of its two launches, per read of the first level's input (same capture: 4 M-read step, 2 155 000
-# reads left by the prefilter; level 1 496.77 + 38.71 MB, level 2 211.38 + 9.30 MB)
-NCU_SEED_DRAM_BYTES_PER_READ = (496.767744e6 + 38.713088e6 + 211.380224e6 + 9.296640e6) / 2 / 2155000
+# reads left by the prefilter; first level 497.05 + 36.03 MB, second level 211.38 + 8.73 MB)
+NCU_SEED_DRAM_BYTES_PER_READ = (497.048832e6 + 36.030208e6 + 211.384064e6 + 8.732672e6) / 2 / 2155000
 
 
 def make_config():

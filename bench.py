@@ -752,6 +752,8 @@ def run_ours(args):
                     "h2d_gbs_plain_memcpy": pcie_h2d_gbs,
                     "h2d_gbs_concurrent_per_rank": conc_per_rank, "h2d_gbs_concurrent_aggregate": sum(conc_per_rank),
                     "reads_per_sec_at_concurrent_h2d_ceiling": sum(conc_per_rank) * 1e9 / (READ_LEN + 4),
+                    # weak scaling gives every rank the same reads: the job ends with the rank whose link is slowest
+                    "reads_per_sec_at_slowest_rank_h2d": world * min(conc_per_rank) * 1e9 / (READ_LEN + 4),
                     "bound": "host link: every read is 154 B of H2D; a bare pinned cudaMemcpyAsync of the same "
                              "bytes runs at h2d_gbs_plain_memcpy on this box"},
             "gpu_launches": launches, "clocks": clocks,

@@ -1,8 +1,8 @@
 #!/usr/bin/env python
 """Extracts the hot inner loop of a kernel from `cuobjdump -sass` and counts its instructions per class.
 
-usage: python tools/sass_loop.py <libbdx.so> <substring of the mangled kernel name> [max loop length]
-The loop = the backward branch whose body (at most `max` instructions) holds the most LOP3s; printed with a
+usage: python tools/sass_loop.py <libbdx.so> <substring of the mangled kernel name> [max loop length] [mnemonic]
+The loop = the backward branch whose body (at most `max` instructions) holds the most LOP3s (or `mnemonic`s); printed with a
 per-mnemonic count so that the per-column instruction figures quoted in DESIGN.md can be checked."""
 import re
 import subprocess
@@ -13,6 +13,7 @@ from collections import Counter
 def main():
     lib, pat = sys.argv[1], sys.argv[2]
     max_len = int(sys.argv[3]) if len(sys.argv) > 3 else 260
+    rank_by = sys.argv[4] if len(sys.argv) > 4 else "LOP3"
     out = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True).stdout
     funcs = re.split(r"\n\s*Function : ", out)
     for f in funcs[1:]:
@@ -30,7 +31,7 @@ def main():
             tgt = int(m.group(1), 16)
             if tgt in idx and idx[tgt] < k and k - idx[tgt] <= max_len:
                 body = ins[idx[tgt]:k + 1]
-                lop = sum("LOP3" in t for _, t in body)
+                lop = sum(rank_by in t for _, t in body)
                 if best is None or lop > best[0]:
                     best = (lop, idx[tgt], k)
         print(f"== {name}")

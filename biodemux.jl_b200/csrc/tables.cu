@@ -514,6 +514,19 @@ void build_seed_var(const Build &B)
                     build_complete(q_lo, segs, e.chance);
             }
         }
+        // With a complete level behind them (score-only passes: seed_var_tail_level), k_seed's levels only have to
+        // be cheap, not deep: its second level is dropped when its seeds are short (> 0.02 chance hits per column,
+        // e.g. 96 x 24 nt at depth 3: 6-mers, 14 chance hits per read) -- the reads it resolved cost less in the
+        // complete level than the level costs on all of its input (config 2: 889 -> 910 M reads/s).  Sets without a
+        // complete level keep it: there its reads would fall to the lane-per-barcode automaton (config 5: 38 -> 24).
+        if (hs.sv_levels > 0 && hs.sv[hs.sv_levels - 1].complete && hs.sd_levels == 2 && hs.trim_side == 0 && !p.want_stats) {
+            const HostSet::HostSeedLevel &D = hs.sd[1];
+            const double rate = (double)hs.n_bc * (D.k + 1) / std::pow((double)std::max(2, hs.n_classes - 1), D.q);
+            if (rate > 0.02) {
+                hs.sd[1] = HostSet::HostSeedLevel();
+                hs.sd_levels = 1;
+            }
+        }
     }
 }
 

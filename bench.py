@@ -43,11 +43,11 @@ CHUNK = 4000                                               # reference chunk_siz
 # algorithmic 174 B: worklist-scattered 150-byte reads touch 6 32-byte sectors, offsets / PassOut one each.
 NCU_FILTER_DRAM_BYTES_PER_READ = (164.026880e6 + 16.110336e6) / 516667
 # the same for k_seed_var's complete level, the kernel that now takes those reads in config 2
-# (profiles/r02_kernels_ncu_summary.txt: 4 M-read step, 517 723 reads: 162.38 MB read + 17.05 MB written)
-NCU_SEEDVAR_DRAM_BYTES_PER_READ = (162.380800e6 + 17.052672e6) / 517723
-# k_seed, average of its two launches, per read of the first level's input (same capture: 4 M-read step, 2 155 000
-# reads left by the prefilter; first level 497.05 + 36.03 MB, second level 211.38 + 8.73 MB)
-NCU_SEED_DRAM_BYTES_PER_READ = (497.048832e6 + 36.030208e6 + 211.384064e6 + 8.732672e6) / 2 / 2155000
+# (profiles/r02_kernels_ncu_summary.txt: 4 M-read step, 746 917 reads: 222.07 MB read + 21.04 MB written)
+NCU_SEEDVAR_DRAM_BYTES_PER_READ = (222.070016e6 + 21.044992e6) / 746917
+# k_seed (config 2 runs one level of it), per read of its input (same capture: 2 155 000 reads left by the
+# prefilter; 497.53 MB read + 37.23 MB written)
+NCU_SEED_DRAM_BYTES_PER_READ = (497.526784e6 + 37.233920e6) / 2155000
 
 
 def make_config():
@@ -678,7 +678,7 @@ def run_ours(args):
         # The seed kernels do far LESS arithmetic than the automaton they replace -- that is their point -- so their
         # fraction of the ALU peak is small by construction; the reads they decide would have cost 244 800 int-ops
         # each in k_filter, which is reported next to it as the survey-convention figure.
-        stage_names = {"k_seed_deep": "k_seed_var (complete level)", "k_seed": "k_seed (levels 1-2)"}
+        stage_names = {"k_seed_deep": "k_seed_var (complete level)", "k_seed": "k_seed"}
         dom = max((k for k in stages if stages[k][1]), key=lambda k: stages[k][0])
         dom_ms, dom_n = stages[dom]
         dom_s = dom_ms * 1e-3 / max(dom_n, 1)             # average duration of one launch of it
@@ -697,8 +697,8 @@ def run_ours(args):
             units = (8.0 * seed_qmers + 17.0 * seed_ver_cols) / max(dom_n, 1)
             dom_reads = (n - pre_reads / max(stages["k_prefilter"][1], 1)) if stages.get("k_prefilter", (0, 0))[1] else n
             traffic = NCU_SEED_DRAM_BYTES_PER_READ * dom_reads
-            how = ("8 int-ops x q-mers probed + 17 x window columns verified, average of its launches (two levels per step; "
-                   "device counters bdx_stream_work_counters[5], [6]); reads_per_launch = the first level's input")
+            how = ("8 int-ops x q-mers probed + 17 x window columns verified, average of its launches "
+                   "(device counters bdx_stream_work_counters[5], [6]); reads_per_launch = the first level's input")
         else:
             units, dom_reads, traffic, how = None, None, None, "no algorithmic unit defined for this stage"
         achieved_ops = units / dom_s if units and dom_s > 0 else 0.0

@@ -229,3 +229,44 @@ def test_pack4_matches_numpy_reference():
     with pytest.raises(capi.BdxError):
         config.code_table()
     config.close()
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_table_builders_accept_any_set_shape(lib, seed):
+    """bdx_config_create builds every kernel family's tables on the host (csrc/tables.cu) -- no GPU needed.  Random
+    set shapes (1 .. 3000 barcodes, 4 .. 64 nt, uniform and mixed lengths, 2 .. 6 distinct bytes, wildcards, all
+    three algorithms, constrained ranges, odd thresholds) must give a config or a clean BDX_ERR_* -- never a
+    crash, and the same answer when asked twice."""
+    import synth
+    rng = np.random.default_rng(5150 + seed)
+    R = bdx.parse_dynamic_range
+    for _ in range(40):
+        n_bc = int(rng.choice([1, 2, 7, 8, 33, 96, 384, 1536, 3000]))
+        m_lo = int(rng.choice([4, 6, 8, 12, 16, 24, 32, 33, 48, 64]))
+        m_hi = min(64, m_lo + int(rng.choice([0, 0, 1, 4, 12])))
+        alphabet = [b"ACGT", b"AC", b"ACGTN", b"ACGTacgt", b"ACGTRY"][int(rng.integers(0, 5))]
+        bcs = synth.random_barcodes(rng, n_bc, m_lo, m_hi, alphabet=alphabet)
+        kw = dict(bc_seqs=bcs, bc_lengths_no_N=[max(1, len(b) - b.count("N")) for b in bcs],
+                  ids=[f"b{i}" for i in range(n_bc)],
+                  max_error_rate=float(rng.choice([0.0, 0.05, 0.2, 0.34, 0.5, 1.0])),
+                  min_delta=float(rng.choice([0.0, 0.0, 0.1])),
+                  matching_algorithm=str(rng.choice(["semiglobal", "semiglobal", "hamming", "exact"])),
+                  trim_side=[None, None, 3, 5][int(rng.integers(0, 4))], summary=bool(rng.random() < 0.2))
+        shape = int(rng.integers(0, 4))
+        if shape == 1:
+            kw.update(ref_search_range=R("1:40"), barcode_start_range=R(f"1:{int(rng.integers(1, 12))}"))
+        elif shape == 2:
+            kw.update(ref_search_range=R("end-49:end"), barcode_end_range=R(f"end-{int(rng.integers(0, 12))}:end"))
+        elif shape == 3:
+            kw.update(ref_search_range=R(f"{int(rng.integers(1, 9))}:{int(rng.integers(60, 200))}"))
+        if rng.random() < 0.2:
+            kw.update(indel=int(rng.choice([1, 2, 3])), mismatch=int(rng.choice([1, 2])), nindel=int(rng.choice([1, 2])))
+        outcomes = []
+        for _twice in range(2):
+            try:
+                c = capi.Config(bdx.DemuxConfig(**kw))
+                outcomes.append(("ok", c.layout.total_len))
+                c.close()
+            except capi.BdxError as e:
+                outcomes.append(("err", e.code))
+        assert outcomes[0] == outcomes[1], (kw, outcomes)

@@ -29,7 +29,7 @@ DEBUG_NO_QGRAM_FILTER = 256
 
 EXPORTS = [
     "bdx_last_error", "bdx_abi_version", "bdx_device_count", "bdx_config_create", "bdx_config_create_debug", "bdx_config_destroy",
-    "bdx_stream_work_counters", "bdx_config_code_table", "bdx_pack_reads4", "bdx_submit_packed4", "bdx_submit_packed4_pinned",
+    "bdx_stream_work_counters", "bdx_config_code_table", "bdx_config_describe", "bdx_pack_reads4", "bdx_submit_packed4", "bdx_submit_packed4_pinned",
     "bdx_stream_create", "bdx_stream_destroy", "bdx_submit", "bdx_acquire", "bdx_commit",
     "bdx_submit_pinned", "bdx_host_alloc", "bdx_host_free", "bdx_stream_enable_details",
     "bdx_fetch", "bdx_fetch_view", "bdx_classify", "bdx_classify_device", "bdx_stream_sync",
@@ -125,6 +125,7 @@ def load_library():
     L.bdx_config_create.argtypes = [C.POINTER(Params), C.POINTER(vp)]
     L.bdx_config_create_debug.argtypes = [C.POINTER(Params), C.c_uint32, C.POINTER(vp)]
     L.bdx_config_code_table.argtypes = [vp, vp]
+    L.bdx_config_describe.argtypes = [vp, C.c_int, C.c_char_p, C.c_int]
     L.bdx_pack_reads4.argtypes = [vp, vp, i64, vp]
     L.bdx_submit_packed4.argtypes = [vp, vp, vp, C.c_int32, C.c_uint64]
     L.bdx_submit_packed4_pinned.argtypes = [vp, vp, vp, C.c_int32, C.c_uint64]
@@ -293,6 +294,15 @@ class Config:
             _check(self.lib.bdx_config_create(C.byref(p), C.byref(self.handle)))
         self.layout = StatsLayout()
         _check(self.lib.bdx_stats_layout_get(self.handle, C.byref(self.layout)))
+
+    def describe(self, pass_: int = 0) -> str:
+        """bdx_config_describe: one line per table built for barcode set ``pass_`` (0 / 1) -- diagnostics and tests."""
+        n = self.lib.bdx_config_describe(self.handle, pass_, None, 0)
+        if n < 0:
+            _check(n)
+        buf = C.create_string_buffer(n + 1)
+        self.lib.bdx_config_describe(self.handle, pass_, buf, n + 1)
+        return buf.value.decode()
 
     def code_table(self) -> np.ndarray:
         """byte -> 4-bit code of the packed input (raises when the config has > 15 distinct barcode bytes)."""

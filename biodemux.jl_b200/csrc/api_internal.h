@@ -85,6 +85,7 @@ struct bdx_config {
 
 // Validates one barcode set and builds its host-side tables (tables.cu).  debug: BDX_DEBUG_* switches.
 int bdx_build_set(const bdx_params &p, const bdx_barcode_set &in, HostSet &hs, uint32_t debug, const char *name);
+std::string bdx_describe_set(const HostSet &hs);   // tables.cu: text description for bdx_config_describe
 
 // ---- streams ----
 struct Slot {

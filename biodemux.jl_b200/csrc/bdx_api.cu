@@ -779,6 +779,18 @@ extern "C" int bdx_config_code_table(const bdx_config *cfg, uint8_t table[256])
     return cfg->n_codes;
 }
 
+extern "C" int bdx_config_describe(const bdx_config *cfg, int pass, char *buf, int len)
+{
+    if (!cfg || pass < 0 || pass > 1 || len < 0 || (len > 0 && !buf)) return fail(BDX_ERR_INVALID, "bad argument");
+    const std::string text = cfg->set[pass].n_bc ? bdx_describe_set(cfg->set[pass]) : std::string();
+    if (len > 0) {
+        const size_t k = std::min(text.size(), (size_t)len - 1);
+        memcpy(buf, text.data(), k);
+        buf[k] = 0;
+    }
+    return (int)text.size();
+}
+
 extern "C" int bdx_pack_reads4(const bdx_config *cfg, const uint8_t *seq, int64_t n_bytes, uint8_t *packed)
 {
     if (!cfg || n_bytes < 0 || (n_bytes > 0 && (!seq || !packed))) return fail(BDX_ERR_INVALID, "bad argument");

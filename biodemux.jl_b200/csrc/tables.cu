@@ -4,7 +4,9 @@
 // the packed Hamming scan.  Pure host code.
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
 #include <cstring>
+#include <string>
 
 #include "api_internal.h"
 
@@ -642,3 +644,47 @@ int bdx_build_set(const bdx_params &p, const bdx_barcode_set &in, HostSet &hs, u
     build_hamming_packed(B);
     return BDX_OK;
 }
+
+// Text description of the tables built for one barcode set (bdx_config_describe): which shortcut stages exist and
+// with which parameters.  Host data only.
+std::string bdx_describe_set(const HostSet &hs)
+{
+    char line[256];
+    std::string out;
+    int min_m = hs.max_m;
+    for (int b = 0; b < hs.n_bc; b++) min_m = std::min(min_m, hs.off[b + 1] - hs.off[b]);
+    snprintf(line, sizeof line, "set: barcodes=%d length=%d..%d classes=%d words=%d filter=%d\n", hs.n_bc, hs.n_bc ? min_m : 0,
+             hs.max_m, hs.n_classes - 1, hs.words, hs.use_filter);
+    out += line;
+    if (hs.pf_enabled) {
+        snprintf(line, sizeof line, "prefilter: seed=%d log2=%d bitmap_log2=%d\n", hs.pf_seed, hs.pf_log2, hs.pf_bm_log2);
+        out += line;
+    }
+    for (int l = 0; l < hs.sd_levels; l++) {
+        snprintf(line, sizeof line, "k_seed level %d: K=%d q=%d entries=%zu max_hits=%d\n", l + 1, hs.sd[l].k, hs.sd[l].q,
+                 hs.sd[l].entries.size(), hs.sd[l].max_hits);
+        out += line;
+    }
+    for (int l = 0; l < hs.sdd_n; l++) {
+        snprintf(line, sizeof line, "k_seed_deep table %d: K=%d q=%d entries=%zu\n", l + 1, hs.sdd_k, hs.sdd[l].q, hs.sdd[l].entries.size());
+        out += line;
+    }
+    for (int l = 0; l < hs.sv_levels; l++) {
+        const HostSet::HostSeedVar &V = hs.sv[l];
+        int k_lo = 255, k_hi = 0;
+        for (uint8_t k : V.kdepth) {
+            k_lo = std::min<int>(k_lo, k);
+            k_hi = std::max<int>(k_hi, k);
+        }
+        snprintf(line, sizeof line, "k_seed_var level %d: q=%d q2=%d K=%d..%d complete=%d entries=%zu group_reads=%d hit_rows=%d qgram_filter=%d\n",
+                 l + 1, V.q, V.q2, V.kdepth.empty() ? 0 : k_lo, k_hi, V.complete, V.entries.size(), V.group_reads, V.hit_rows,
+                 V.qgram_filter);
+        out += line;
+    }
+    if (hs.hp_enabled) {
+        snprintf(line, sizeof line, "k_hamming_scan: m=%d allowed=%d segments=%d\n", hs.hp_m, hs.hp_allowed, hs.hp_n_seg);
+        out += line;
+    }
+    return out;
+}
+

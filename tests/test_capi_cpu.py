@@ -270,3 +270,55 @@ def test_table_builders_accept_any_set_shape(lib, seed):
             except capi.BdxError as e:
                 outcomes.append(("err", e.code))
         assert outcomes[0] == outcomes[1], (kw, outcomes)
+
+
+def _described(cfg, pass_=0):
+    c = capi.Config(cfg)
+    try:
+        return {ln.split(":", 1)[0]: dict(kv.split("=") for kv in ln.split(":", 1)[1].split())
+                for ln in c.describe(pass_).splitlines()}
+    finally:
+        c.close()
+
+
+def test_level_choices_for_the_benchmark_configs(lib):
+    """bdx_config_describe: the stage / level choices DESIGN.md sections 4.2b and 4.2c quote for BASELINE.json's configs
+    are what the table builders (csrc/tables.cu) really make -- checked on the host, no GPU."""
+    import synth
+    rng = np.random.default_rng(1)
+    R = bdx.parse_dynamic_range
+
+    def cfg(b1, b2=None, **kw):
+        c = bdx.DemuxConfig(bc_seqs=b1, bc_lengths_no_N=[len(x) for x in b1], ids=[f"a{i}" for i in range(len(b1))], **kw)
+        if b2:
+            c.is_dual = True
+            c.bc_seqs2, c.bc_lengths_no_N2, c.ids2 = b2, [len(x) for x in b2], [f"b{i}" for i in range(len(b2))]
+        return c
+
+    b96 = synth.random_barcodes(rng, 96, 24, 24)
+    # config 2: prefilter, ONE k_seed level (K = 2, 8-mers), complete k_seed_var level of 4- and 5-mers, filter inside the scan
+    d = _described(cfg(b96))
+    assert "prefilter" in d and d["k_seed level 1"]["K"] == "2" and d["k_seed level 1"]["q"] == "8"
+    assert "k_seed level 2" not in d
+    tail = d["k_seed_var level 2"]
+    assert (tail["complete"], tail["q"], tail["q2"], tail["K"], tail["qgram_filter"]) == ("1", "4", "5", "4..4", "1")
+    assert int(tail["group_reads"]) % 32 == 0
+    assert _described(cfg(b96), 1) == {}
+    # ... with trimming the complete level cannot take the tail: k_seed keeps its second level (K = 3, 6-mers)
+    d = _described(cfg(b96, trim_side=5))
+    assert d["k_seed level 2"]["K"] == "3" and d["k_seed level 2"]["q"] == "6"
+    # config 3: no k_seed (lengths differ); k_seed_var level 1 with 5-mers at depths 2..4, then the complete level;
+    # constrained geometry => the filter runs over the finished list (mode 2); a constrained START keeps >= m + 2 rows
+    b1, b2 = synth.random_barcodes(rng, 384, 16, 28), synth.random_barcodes(rng, 384, 16, 28)
+    c3 = cfg(b1, b2, ref_search_range=R("1:40"), barcode_start_range=R("1:6"), ref_search_range2=R("end-39:end"),
+             barcode_end_range2=R("end-5:end"), min_delta=0.1)
+    for p in (0, 1):
+        d = _described(c3, p)
+        assert "k_seed level 1" not in d
+        assert d["k_seed_var level 1"]["q"] == "5" and d["k_seed_var level 1"]["K"] == "2..4"
+        assert d["k_seed_var level 1"]["qgram_filter"] == "2" and d["k_seed_var level 2"]["complete"] == "1"
+    assert int(_described(c3, 0)["k_seed_var level 1"]["hit_rows"]) >= 28 + 2
+    # config 5: 1 536 barcodes keep both k_seed levels and get no complete level (its chance hits cost more than k_filter)
+    d = _described(cfg(synth.random_barcodes(rng, 1536, 24, 24)))
+    assert d["k_seed level 1"]["q"] == "12" and d["k_seed level 2"]["q"] == "8"
+    assert not any(v.get("complete") == "1" for v in d.values())
